@@ -1,0 +1,571 @@
+// asr_b200 -- persistent bidirectional GRU / LSTM recurrence (forward and backward) for sm_100a.
+//
+// Replaces the recurrent half of torch.nn.GRU / torch.nn.LSTM over packed sequences as the reference
+// calls it (asr_deepspeech/modules/blocks.py:87-89; cell equations: torch.nn docs, gate row order
+// [r|z|n] / [i|f|g|o]).  The input half (x W_ih^T + b_ih for all timesteps, both directions) is one big
+// tensor-core GEMM done beforehand (gemm.cu); this kernel runs the strictly sequential part.
+//
+// One launch covers all T steps of both directions.  CTA (dir, p) owns NJ hidden units:
+//   * its slice of W_hh (forward: NJ x gates rows of K=H; backward: NJ columns of W_hh, K=gates*H) is loaded
+//     ONCE by TMA into shared memory in the tcgen05 K-major/128B-swizzle layout and stays there;
+//   * per step it TMA-streams the previous state of ALL units (h_{t-1}: [B,H], or dgates_{t+1}: [B,G]) through
+//     a small mbarrier ring as the A operand, issues tcgen05.mma.kind::tf32 (M=128 batch rows, N=slice columns)
+//     into TMEM, and the 4 epilogue warps (one thread per batch row) apply the gate non-linearities, the
+//     sequence-length mask and write state / saved activations;
+//   * a per-direction release/acquire counter in global memory is the step barrier between CTAs.
+// Packed-sequence semantics (pack_padded_sequence / pad_packed_sequence, blocks.py:87,89): utterance b takes
+// part only while t < len[b]; outputs and states at t >= len[b] are written as zeros, which is also the correct
+// initial state for the reverse direction.
+//
+// State layout: hseq/cseq [2][T+2][B][H] with time slot t+1 holding step t and slots 0 / T+1 zero, so that
+// "previous step" is a pure pointer offset for both directions (used by the dW_hh GEMM as well).
+#include "ptx.cuh"
+
+namespace asrb {
+
+constexpr int kRnnThreads = 192;
+constexpr int kRnnBM = 128;      // batch rows per MMA (TMA zero-fills rows >= B)
+constexpr int kRnnStageBytes = kRnnBM * 128;
+constexpr int kRnnMaxSmem = 227 * 1024;
+
+struct RnnParams {
+    int T, B, H, G, P, kpad, use_simt, stages;
+    const int* lengths;
+    uint32_t* counters;
+    const float* wpack;  // packed weight slices (global copy, SIMT debug path)
+    // forward
+    const float* gi;     // [T,B,2,G]
+    const float* b_hh;   // [2,G]
+    float* hseq;         // [2,T+2,B,H]
+    float* cseq;         // [2,T+2,B,H] (LSTM)
+    float* saved;        // [2,T,B,4,H]
+    // backward
+    const float* dout;   // [T,B,H]
+    float* dgi;          // [T,B,2,G]
+    float* dgh;          // [2,T,B,G]
+};
+
+template <int CELL, int NJ>
+struct RnnShape {
+    static constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
+    static constexpr int kNpadF = ((kGates * NJ + 15) / 16) * 16;
+    static constexpr int kNpadB = 16;
+    static_assert(NJ <= 16 && kNpadF <= 64, "slice too wide");
+};
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: one contiguous, zero-padded [npad, kpad] K-major matrix per (direction, CTA)
+// ------------------------------------------------------------------------------------------------
+// forward : row c = gate (c / nj), unit p*nj + c % nj   ->  W_hh[dir][gate*H + unit][0..H)
+__global__ void rnn_pack_fwd_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, float* __restrict__ out,
+                                    int H, int gates, int nj, int P, int npad, int kpad) {
+    const long long total = 2LL * P * npad * kpad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % kpad);
+        long long r = i / kpad;
+        const int c = (int)(r % npad);
+        r /= npad;
+        const int p = (int)(r % P), dir = (int)(r / P);
+        const int g = c / nj, j = p * nj + c % nj;
+        float v = 0.f;
+        if (g < gates && j < H && k < H) v = (dir ? w_hh1 : w_hh0)[(size_t)(g * H + j) * H + k];
+        out[i] = v;
+    }
+}
+// backward: row c = unit p*nj + c  ->  W_hh[dir][0..G)[unit]   (a column of W_hh)
+__global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, float* __restrict__ out,
+                                    int H, int G, int nj, int P, int npad, int kpad) {
+    const long long total = 2LL * P * npad * kpad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % kpad);
+        long long r = i / kpad;
+        const int c = (int)(r % npad);
+        r /= npad;
+        const int p = (int)(r % P), dir = (int)(r / P);
+        const int j = p * nj + c;
+        float v = 0.f;
+        if (c < nj && j < H && k < G) v = (dir ? w_hh1 : w_hh0)[(size_t)k * H + j];
+        out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the recurrence
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int CELL, int NJ, bool BWD>
+__global__ void __launch_bounds__(kRnnThreads, 1)
+rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const RnnParams p) {
+    using S = RnnShape<CELL, NJ>;
+    constexpr int kGates = S::kGates;
+    constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
+    constexpr int kTmemCols = 64;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nkb = p.kpad / 32;
+    uint8_t* smem_w = smem;                                   // nkb x [NPAD rows x 128 B]
+    uint8_t* smem_a = smem_w + (size_t)nkb * NPAD * 128;      // stages x [128 rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * kRnnStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + 8;
+    uint64_t* w_bar = bars + 16;
+    uint64_t* tfull_bar = bars + 17;
+    uint64_t* tempty_bar = bars + 18;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.T, B = p.B, H = p.H, G = p.G, P = p.P;
+    const int dir = blockIdx.x / P, pidx = blockIdx.x % P;
+    const int j0 = pidx * NJ;
+    const bool tc = !p.use_simt;
+    uint32_t* counter = p.counters + dir;
+
+    // time index processed at sequential step s
+    auto t_of = [&](int s) { return (BWD ? (dir == 0) : (dir == 1)) ? (T - 1 - s) : s; };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmA);
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(w_bar, 1);
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0 && tc) {
+            mbar_arrive_expect_tx(w_bar, (uint32_t)(nkb * NPAD * 128));
+            for (int kb = 0; kb < nkb; ++kb)
+                tma_load_2d(smem_w + (size_t)kb * NPAD * 128, &tmW, w_bar, kb * 32, (dir * P + pidx) * NPAD);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int s = 1; s < T; ++s) {
+                const uint32_t need = (uint32_t)P * (uint32_t)s;
+                while (ld_acquire_u32(counter) < need) {
+                }
+                fence_proxy_async();  // other CTAs' generic-proxy stores -> visible to our async-proxy (TMA) reads
+                const int tp = t_of(s - 1);
+                const int slab = BWD ? (dir * T + tp) : (dir * (T + 2) + tp + 1);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], kRnnStageBytes);
+                    tma_load_3d(smem_a + (size_t)stage * kRnnStageBytes, &tmA, &full_bar[stage], kb * 32, 0, slab);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0 && tc) {
+            constexpr uint32_t idesc = umma_idesc(kFmtTF32, kRnnBM, NPAD);
+            mbar_wait(w_bar, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int s = 1; s < T; ++s) {
+                const uint32_t it = (uint32_t)(s - 1);
+                mbar_wait(tempty_bar, (it & 1) ^ 1);
+                tc_fence_after_sync();
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)stage * kRnnStageBytes));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + (size_t)kb * NPAD * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar);
+            }
+        }
+    } else {
+        // ===================== epilogue: one thread per batch row =====================
+        const int quad = warp & 3;
+        const int b = quad * 32 + lane;
+        const int etid = (warp - 2) * 32 + lane;  // 0..127
+        const bool rowok = b < B;
+        const bool warp_has_rows = quad * 32 < B;
+        const int len = rowok ? p.lengths[b] : 0;
+        const size_t slotHB = (size_t)B * H;
+
+        float state_h[NJ];   // fwd: h_{prev}[b, j0..] ; bwd: direct dh carry
+        float state_c[NJ];   // fwd LSTM: c_prev ; bwd LSTM: dc carry
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) state_h[jj] = state_c[jj] = 0.f;
+
+        if (!BWD && rowok) {  // zero boundary slots 0 and T+1 of our slice
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const int j = j0 + jj;
+                if (j < H) {
+                    float* h0 = p.hseq + ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j;
+                    h0[0] = 0.f;
+                    h0[(size_t)(T + 1) * slotHB] = 0.f;
+                    if constexpr (CELL == ASRB_RNN_LSTM) {
+                        float* c0 = p.cseq + ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j;
+                        c0[0] = 0.f;
+                        c0[(size_t)(T + 1) * slotHB] = 0.f;
+                    }
+                }
+            }
+        }
+
+        for (int s = 0; s < T; ++s) {
+            const int t = t_of(s);
+            const bool active = rowok && (t < len);
+            float acc[NPAD];
+#pragma unroll
+            for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
+
+            // ---- operand prefetch (independent of the MMA) ----
+            float in0[NJ], in1[NJ], in2[NJ], in3[NJ], in4[NJ], in5[NJ];
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) in0[jj] = in1[jj] = in2[jj] = in3[jj] = in4[jj] = in5[jj] = 0.f;
+            if (active) {
+                if constexpr (!BWD) {
+                    const float* g = p.gi + (((size_t)t * B + b) * 2 + dir) * G + j0;
+#pragma unroll
+                    for (int jj = 0; jj < NJ; ++jj)
+                        if (j0 + jj < H) {
+                            in0[jj] = __ldg(g + jj);
+                            in1[jj] = __ldg(g + H + jj);
+                            in2[jj] = __ldg(g + 2 * H + jj);
+                            if constexpr (kGates == 4) in3[jj] = __ldg(g + 3 * H + jj);
+                        }
+                } else {
+                    const float* sv = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0;
+                    const float* dop = p.dout + ((size_t)t * B + b) * H + j0;
+                    const int tprev_slot = (dir == 0) ? t : t + 2;  // slot of the step that preceded t in forward order
+                    const float* hp = p.hseq + ((size_t)dir * (T + 2) + tprev_slot) * slotHB + (size_t)b * H + j0;
+#pragma unroll
+                    for (int jj = 0; jj < NJ; ++jj)
+                        if (j0 + jj < H) {
+                            in0[jj] = sv[jj];
+                            in1[jj] = sv[H + jj];
+                            in2[jj] = sv[2 * H + jj];
+                            in3[jj] = sv[3 * H + jj];
+                            in4[jj] = dop[jj];
+                            if constexpr (CELL == ASRB_RNN_GRU) {
+                                in5[jj] = hp[jj];
+                            } else {
+                                in5[jj] = p.cseq[((size_t)dir * (T + 2) + tprev_slot) * slotHB + (size_t)b * H + j0 + jj];
+                            }
+                        }
+                }
+            }
+            float ct[NJ];  // bwd LSTM: c_t
+            if constexpr (BWD && CELL == ASRB_RNN_LSTM) {
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj)
+                    ct[jj] = (active && j0 + jj < H)
+                                 ? p.cseq[((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + jj] : 0.f;
+            }
+
+            // ---- recurrent product for this step ----
+            if (s > 0) {
+                if (tc) {
+                    mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
+                    tc_fence_after_sync();
+                    if (warp_has_rows) {
+#pragma unroll
+                        for (int c = 0; c < NPAD / 16; ++c)
+                            tmem_ld_32x16(tmem_base + (uint32_t(quad * 32) << 16) + c * 16, acc + c * 16);
+                        tmem_ld_wait();
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar);
+                } else {
+                    // DEBUG path (asrb_set_debug_flags bit 1): same algorithm, plain fp32 dot products
+                    if (etid == 0) {
+                        const uint32_t need = (uint32_t)P * (uint32_t)s;
+                        while (ld_acquire_u32(counter) < need) {
+                        }
+                    }
+                    named_bar_sync(1, 128);
+                    if (rowok) {
+                        const int tp = t_of(s - 1);
+                        const int K = BWD ? G : H;
+                        const float* arow = BWD ? p.dgh + (((size_t)dir * T + tp) * B + b) * G
+                                                : p.hseq + ((size_t)dir * (T + 2) + tp + 1) * slotHB + (size_t)b * H;
+                        const float* wrow = p.wpack + ((size_t)(dir * P + pidx) * NPAD) * p.kpad;
+                        for (int k = 0; k < K; ++k) {
+                            const float a = __ldcg(arow + k);
+#pragma unroll
+                            for (int c = 0; c < NPAD; ++c) acc[c] = fmaf(a, __ldg(wrow + (size_t)c * p.kpad + k), acc[c]);
+                        }
+                    }
+                }
+            }
+
+            // ---- cell math ----
+            if constexpr (!BWD) {
+                float* hout = p.hseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0;
+                float* cout = (CELL == ASRB_RNN_LSTM) ? p.cseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 : nullptr;
+                float* sv = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0;
+                const float* bh = p.b_hh + (size_t)dir * G + j0;
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    if (rowok && j0 + jj < H) {
+                        float hn = 0.f, cn = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                        if (active) {
+                            if constexpr (CELL == ASRB_RNN_GRU) {
+                                const float gr = acc[jj] + __ldg(bh + jj);
+                                const float gz = acc[NJ + jj] + __ldg(bh + H + jj);
+                                const float gn = acc[2 * NJ + jj] + __ldg(bh + 2 * H + jj);
+                                const float r = sigmoidf_(in0[jj] + gr);
+                                const float z = sigmoidf_(in1[jj] + gz);
+                                const float n = tanhf_(in2[jj] + r * gn);
+                                hn = (1.f - z) * n + z * state_h[jj];
+                                s0 = r; s1 = z; s2 = n; s3 = gn;
+                            } else {
+                                const float gi_ = sigmoidf_(in0[jj] + acc[jj] + __ldg(bh + jj));
+                                const float gf = sigmoidf_(in1[jj] + acc[NJ + jj] + __ldg(bh + H + jj));
+                                const float gg = tanhf_(in2[jj] + acc[2 * NJ + jj] + __ldg(bh + 2 * H + jj));
+                                const float go = sigmoidf_(in3[jj] + acc[(kGates - 1) * NJ + jj] + __ldg(bh + 3 * H + jj));
+                                cn = gf * state_c[jj] + gi_ * gg;
+                                hn = go * tanhf_(cn);
+                                s0 = gi_; s1 = gf; s2 = gg; s3 = go;
+                            }
+                        }
+                        hout[jj] = hn;
+                        if constexpr (CELL == ASRB_RNN_LSTM) cout[jj] = cn;
+                        sv[jj] = s0; sv[H + jj] = s1; sv[2 * H + jj] = s2; sv[3 * H + jj] = s3;
+                        state_h[jj] = hn;
+                        state_c[jj] = cn;
+                    }
+                }
+            } else {
+                float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0;
+                float* dgh = p.dgh + (((size_t)dir * T + t) * B + b) * G + j0;
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    if (rowok && j0 + jj < H) {
+                        const float carry = acc[jj] + state_h[jj];
+                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, e2 = 0.f;
+                        if (active) {
+                            const float dh = carry + in4[jj];
+                            if constexpr (CELL == ASRB_RNN_GRU) {
+                                const float r = in0[jj], z = in1[jj], n = in2[jj], gn = in3[jj], hp = in5[jj];
+                                const float dn = dh * (1.f - z) * (1.f - n * n);
+                                d2 = dn;                          // d gi_n
+                                e2 = dn * r;                      // d gh_n
+                                d1 = dh * (hp - n) * z * (1.f - z);
+                                d0 = dn * gn * r * (1.f - r);
+                                state_h[jj] = dh * z;
+                            } else {
+                                const float gi_ = in0[jj], gf = in1[jj], gg = in2[jj], go = in3[jj], cp = in5[jj];
+                                const float tcv = tanhf_(ct[jj]);
+                                const float dc = state_c[jj] + dh * go * (1.f - tcv * tcv);
+                                d0 = dc * gg * gi_ * (1.f - gi_);
+                                d1 = dc * cp * gf * (1.f - gf);
+                                d2 = dc * gi_ * (1.f - gg * gg);
+                                d3 = dh * tcv * go * (1.f - go);
+                                e2 = d2;
+                                state_c[jj] = dc * gf;
+                                state_h[jj] = 0.f;
+                            }
+                        } else {
+                            state_h[jj] = carry;  // gradient passes an inactive step untouched
+                        }
+                        dgi[jj] = d0; dgi[H + jj] = d1; dgi[2 * H + jj] = d2;
+                        dgh[jj] = d0; dgh[H + jj] = d1; dgh[2 * H + jj] = e2;
+                        if constexpr (kGates == 4) { dgi[3 * H + jj] = d3; dgh[3 * H + jj] = d3; }
+                    }
+                }
+            }
+
+            // ---- publish this step to the other CTAs of the direction ----
+            if (tc) fence_proxy_async();
+            named_bar_sync(2, 128);
+            if (etid == 0) {
+                __threadfence();
+                red_release_add_u32(counter, 1u);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// out[t,b,:] = hseq[0][t+1][b][:] + hseq[1][t+1][b][:]     (blocks.py:92 "sum(2)")
+__global__ void rnn_sum_dirs_kernel(const float* __restrict__ hseq, float* __restrict__ out, int T, long long BH) {
+    const long long n = (long long)T * BH;
+    const float* h0 = hseq + BH;
+    const float* h1 = hseq + (long long)(T + 2) * BH + BH;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = h0[i] + h1[i];
+}
+
+struct RnnPlan {
+    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b;
+    size_t smem_f, smem_b;
+};
+
+static int rnn_make_plan(int cell, int H, RnnPlan* pl) {
+    const int gates = cell == ASRB_RNN_GRU ? 3 : 4;
+    const int G = gates * H;
+    const int cands[3] = {8, 12, 16};
+    for (int ci = 0; ci < 3; ++ci) {
+        const int nj = cands[ci];
+        const int P = ceil_div(H, nj);
+        if (2 * P > kNumSMs) continue;
+        RnnPlan r;
+        r.nj = nj; r.P = P;
+        r.npad_f = round_up(gates * nj, 16); r.npad_b = 16;
+        r.kpad_f = round_up(H, 32); r.kpad_b = round_up(G, 32);
+        const size_t wf = (size_t)r.npad_f * r.kpad_f * 4, wb = (size_t)r.npad_b * r.kpad_b * 4;
+        const size_t fixed = 1024 + 256;
+        if (wf + fixed + kRnnStageBytes > (size_t)kRnnMaxSmem || wb + fixed + kRnnStageBytes > (size_t)kRnnMaxSmem) continue;
+        int sf = (int)((kRnnMaxSmem - fixed - wf) / kRnnStageBytes), sb = (int)((kRnnMaxSmem - fixed - wb) / kRnnStageBytes);
+        r.stages_f = sf > 6 ? 6 : sf; r.stages_b = sb > 6 ? 6 : sb;
+        r.smem_f = wf + fixed + (size_t)r.stages_f * kRnnStageBytes;
+        r.smem_b = wb + fixed + (size_t)r.stages_b * kRnnStageBytes;
+        *pl = r;
+        return 0;
+    }
+    return ASRB_ERR_UNSUPPORTED;
+}
+
+template <int CELL, int NJ, bool BWD>
+static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const float* wpack, const float* a_base, asrb_stream_t stream) {
+    using S = RnnShape<CELL, NJ>;
+    constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
+    const int kpad = BWD ? pl.kpad_b : pl.kpad_f;
+    const size_t smem = BWD ? pl.smem_b : pl.smem_f;
+    prm.kpad = kpad;
+    prm.stages = BWD ? pl.stages_b : pl.stages_f;
+    prm.wpack = wpack;
+    CUtensorMap tmW, tmA;
+    {
+        uint64_t d[2] = {(uint64_t)kpad, (uint64_t)2 * pl.P * NPAD}, s[1] = {(uint64_t)kpad * 4};
+        uint32_t bx[2] = {32, (uint32_t)NPAD};
+        int rc = make_tmap_f32(&tmW, wpack, 2, d, s, bx);
+        if (rc) return rc;
+    }
+    {
+        const int K = BWD ? prm.G : prm.H;
+        const int slabs = BWD ? 2 * prm.T : 2 * (prm.T + 2);
+        uint64_t d[3] = {(uint64_t)K, (uint64_t)prm.B, (uint64_t)slabs};
+        uint64_t s[2] = {(uint64_t)K * 4, (uint64_t)prm.B * K * 4};
+        uint32_t bx[3] = {32, (uint32_t)kRnnBM, 1};
+        int rc = make_tmap_f32(&tmA, a_base, 3, d, s, bx);
+        if (rc) return rc;
+    }
+    auto kern = rnn_rec_kernel<CELL, NJ, BWD>;
+    ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * sizeof(uint32_t), stream));
+    void* args[] = {(void*)&tmW, (void*)&tmA, (void*)&prm};
+    ASRB_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(2 * pl.P), dim3(kRnnThreads), args, smem, stream));
+    return 0;
+}
+
+template <bool BWD>
+static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const float* wpack, const float* a_base,
+                        asrb_stream_t stream) {
+#define ASRB_RNN_CASE(C, N) \
+    if (cell == C && pl.nj == N) return rnn_launch<C, N, BWD>(pl, prm, wpack, a_base, stream);
+    ASRB_RNN_CASE(ASRB_RNN_GRU, 8) ASRB_RNN_CASE(ASRB_RNN_GRU, 12) ASRB_RNN_CASE(ASRB_RNN_GRU, 16)
+    ASRB_RNN_CASE(ASRB_RNN_LSTM, 8) ASRB_RNN_CASE(ASRB_RNN_LSTM, 12) ASRB_RNN_CASE(ASRB_RNN_LSTM, 16)
+#undef ASRB_RNN_CASE
+    return ASRB_ERR_UNSUPPORTED;
+}
+
+}  // namespace asrb
+
+using namespace asrb;
+
+extern "C" {
+
+int asrb_rnn_plan(int cell, int H, int B, int* nj, int* P, size_t* wpack_fwd_floats, size_t* wpack_bwd_floats) {
+    ASRB_REQUIRE((cell == ASRB_RNN_GRU || cell == ASRB_RNN_LSTM) && H > 0 && B > 0, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(H % 4 == 0 && B <= kRnnBM, ASRB_ERR_UNSUPPORTED);
+    RnnPlan pl;
+    int rc = rnn_make_plan(cell, H, &pl);
+    if (rc) return rc;
+    if (nj) *nj = pl.nj;
+    if (P) *P = pl.P;
+    if (wpack_fwd_floats) *wpack_fwd_floats = (size_t)2 * pl.P * pl.npad_f * pl.kpad_f;
+    if (wpack_bwd_floats) *wpack_bwd_floats = (size_t)2 * pl.P * pl.npad_b * pl.kpad_b;
+    return 0;
+}
+
+int asrb_rnn_pack_weights(int cell, int H, const float* w_hh_fwd, const float* w_hh_rev, float* wpack_fwd,
+                          float* wpack_bwd, asrb_stream_t stream) {
+    RnnPlan pl;
+    int rc = rnn_make_plan(cell, H, &pl);
+    if (rc) return rc;
+    const int gates = cell == ASRB_RNN_GRU ? 3 : 4;
+    if (wpack_fwd) {
+        rnn_pack_fwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, wpack_fwd, H, gates, pl.nj, pl.P, pl.npad_f, pl.kpad_f);
+        ASRB_LAUNCH_OK();
+    }
+    if (wpack_bwd) {
+        rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
+        ASRB_LAUNCH_OK();
+    }
+    return 0;
+}
+
+int asrb_rnn_fwd(int cell, const float* gi, const float* b_hh, const float* wpack_fwd, const int32_t* lengths,
+                 float* hseq, float* cseq, float* saved, uint32_t* counters, int T, int B, int H, asrb_stream_t stream) {
+    ASRB_REQUIRE(gi && b_hh && wpack_fwd && lengths && hseq && saved && counters && T > 0, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(cell == ASRB_RNN_GRU || cseq, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(H % 4 == 0 && B <= kRnnBM, ASRB_ERR_UNSUPPORTED);
+    RnnPlan pl;
+    int rc = rnn_make_plan(cell, H, &pl);
+    if (rc) return rc;
+    RnnParams prm = {};
+    prm.T = T; prm.B = B; prm.H = H; prm.G = (cell == ASRB_RNN_GRU ? 3 : 4) * H; prm.P = pl.P;
+    prm.use_simt = (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 1 : 0;
+    prm.lengths = lengths; prm.counters = counters;
+    prm.gi = gi; prm.b_hh = b_hh; prm.hseq = hseq; prm.cseq = cseq; prm.saved = saved;
+    return rnn_dispatch<false>(cell, pl, prm, wpack_fwd, hseq, stream);
+}
+
+int asrb_rnn_bwd(int cell, const float* dout, const float* wpack_bwd, const int32_t* lengths, const float* hseq,
+                 const float* cseq, const float* saved, float* dgi, float* dgh, uint32_t* counters, int T, int B, int H,
+                 asrb_stream_t stream) {
+    ASRB_REQUIRE(dout && wpack_bwd && lengths && hseq && saved && dgi && dgh && counters && T > 0, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(cell == ASRB_RNN_GRU || cseq, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(H % 4 == 0 && B <= kRnnBM, ASRB_ERR_UNSUPPORTED);
+    RnnPlan pl;
+    int rc = rnn_make_plan(cell, H, &pl);
+    if (rc) return rc;
+    RnnParams prm = {};
+    prm.T = T; prm.B = B; prm.H = H; prm.G = (cell == ASRB_RNN_GRU ? 3 : 4) * H; prm.P = pl.P;
+    prm.use_simt = (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 1 : 0;
+    prm.lengths = lengths; prm.counters = counters;
+    prm.hseq = const_cast<float*>(hseq); prm.cseq = const_cast<float*>(cseq); prm.saved = const_cast<float*>(saved);
+    prm.dout = dout; prm.dgi = dgi; prm.dgh = dgh;
+    return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, dgh, stream);
+}
+
+int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream) {
+    ASRB_REQUIRE(hseq && out && T > 0 && B > 0 && H > 0, ASRB_ERR_BAD_ARG);
+    const long long n = (long long)T * B * H;
+    const int grid = (int)((n + 255) / 256 < kNumSMs * 8 ? (n + 255) / 256 : kNumSMs * 8);
+    rnn_sum_dirs_kernel<<<grid, 256, 0, stream>>>(hseq, out, T, (long long)B * H);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

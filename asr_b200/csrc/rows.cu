@@ -1,0 +1,240 @@
+// asr_b200 -- row-matrix kernels on [R = T*N, H] activations:
+//   * SequenceWise(BatchNorm1d) forward / backward (asr_deepspeech/modules/blocks.py:16-21,85-86 and the FC head's
+//     BatchNorm1d, modules/deepspeech.py:104): batch statistics over ALL T*N rows, padded (zero) rows included,
+//     exactly as the reference computes them.
+//   * column sums (bias gradients of the recurrent layers)
+//   * log_softmax / softmax / argmax over the class dimension (trainers/deepspeech_trainer.py:110,
+//     blocks.py:62, decoders/greedy_decoder.py:61) and the log_softmax backward.
+#include "common.cuh"
+
+namespace asrb {
+
+constexpr int kRowChunks = 296;  // 2 x 148 SMs worth of row chunks for the two-stage column reductions
+
+// partial[chunk][2][cols]: MODE 0 (sum x, sum x^2) ; MODE 1 (sum dy, sum dy*xhat) ; MODE 2 (sum x, -)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+rows_reduce_kernel(const float* __restrict__ a, int lda, const float* __restrict__ x, int ldx,
+                   const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial,
+                   long long R, int cols, int rows_per_chunk) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long r1 = r0 + rows_per_chunk < R ? r0 + rows_per_chunk : R;
+    float s0 = 0.f, s1 = 0.f;
+    if (col < cols) {
+        float mu = 0.f, is = 1.f;
+        if (MODE == 1) { mu = mean[col]; is = invstd[col]; }
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            const float v = a[r * lda + col];
+            if (MODE == 0) { s0 += v; s1 += v * v; }
+            else if (MODE == 2) { s0 += v; }
+            else { s0 += v; s1 += v * (x[r * ldx + col] - mu) * is; }
+        }
+    }
+    __shared__ float sh0[8][33], sh1[8][33];
+    sh0[ty][tx] = s0; sh1[ty][tx] = s1;
+    __syncthreads();
+    if (ty == 0 && col < cols) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { s0 += sh0[i][tx]; s1 += sh1[i][tx]; }
+        partial[((size_t)blockIdx.y * 2 + 0) * cols + col] = s0;
+        partial[((size_t)blockIdx.y * 2 + 1) * cols + col] = s1;
+    }
+}
+
+// kind 0: mean/invstd (+running stats) ; kind 1: raw sums
+__global__ void rows_finalize_kernel(const float* __restrict__ partial, int nchunks, int cols, double count, int kind,
+                                     float eps, float momentum, float* __restrict__ out0, float* __restrict__ out1,
+                                     float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double s0 = 0, s1 = 0;
+    for (int i = 0; i < nchunks; ++i) {
+        s0 += partial[((size_t)i * 2 + 0) * cols + c];
+        s1 += partial[((size_t)i * 2 + 1) * cols + c];
+    }
+    if (kind == 0) {
+        const double mean = s0 / count;
+        double var = s1 / count - mean * mean;
+        if (var < 0) var = 0;
+        out0[c] = (float)mean;
+        out1[c] = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            const double unb = count > 1 ? var * count / (count - 1) : var;
+            running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+            running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
+        }
+    } else {
+        if (out0) out0[c] = (float)s0;
+        if (out1) out1[c] = (float)s1;
+    }
+}
+
+__global__ void bn_rows_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* __restrict__ y, long long total, int cols) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols);
+        y[i] = (x[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+    }
+}
+
+__global__ void bn_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   const float* __restrict__ gamma, const float* __restrict__ s0,
+                                   const float* __restrict__ s1, float inv_count, int training, float* __restrict__ dx,
+                                   long long total, int cols) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols);
+        float g = dy[i];
+        if (training) g = g - s0[c] * inv_count - (x[i] - mean[c]) * invstd[c] * s1[c] * inv_count;
+        dx[i] = g * gamma[c] * invstd[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// class-dimension kernels: one warp per row
+// ------------------------------------------------------------------------------------------------
+// lp = log_softmax(logits) ; optional probs = softmax ; optional idx = argmax (first maximum)
+__global__ void __launch_bounds__(256)
+log_softmax_kernel(const float* __restrict__ logits, int ld, float* __restrict__ lp, float* __restrict__ probs,
+                   long long* __restrict__ idx, long long R, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const float* in = logits + row * ld;
+    float m = -INFINITY;
+    int mi = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+        const float v = in[c];
+        if (v > m) { m = v; mi = c; }   // strict > keeps the first maximum within a lane's stride
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    }
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(in[c] - m);
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    for (int c = lane; c < C; c += 32) {
+        const float v = in[c] - lse;
+        if (lp) lp[row * C + c] = v;
+        if (probs) probs[row * C + c] = expf(v);
+    }
+    if (idx && lane == 0) idx[row] = mi;
+}
+
+// dlogits = g - exp(lp) * sum_c g      (log_softmax backward)
+__global__ void __launch_bounds__(256)
+log_softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp, float* __restrict__ dlogits, int ld,
+                       long long R, int C) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= R) return;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += g[row * C + c];
+    s = warp_sum(s);
+    for (int c = lane; c < C; c += 32) dlogits[row * ld + c] = g[row * C + c] - expf(lp[row * C + c]) * s;
+}
+
+static inline int ew_grid(long long n) {
+    long long g = (n + 255) / 256;
+    return (int)(g < kNumSMs * 8 ? (g > 0 ? g : 1) : kNumSMs * 8);
+}
+
+template <int MODE>
+static int rows_reduce(const float* a, int lda, const float* x, int ldx, const float* mean, const float* invstd,
+                       float* ws, size_t ws_bytes, long long R, int cols, int* nchunks_out, asrb_stream_t stream) {
+    int nchunks = (int)(R < kRowChunks ? R : kRowChunks);
+    const int rpc = (int)((R + nchunks - 1) / nchunks);
+    nchunks = (int)((R + rpc - 1) / rpc);
+    if (ws_bytes < (size_t)nchunks * 2 * cols * sizeof(float)) return ASRB_ERR_WORKSPACE;
+    rows_reduce_kernel<MODE><<<dim3(ceil_div(cols, 32), nchunks), 256, 0, stream>>>(a, lda, x, ldx, mean, invstd, ws, R, cols, rpc);
+    ASRB_LAUNCH_OK();
+    *nchunks_out = nchunks;
+    return 0;
+}
+
+}  // namespace asrb
+
+using namespace asrb;
+
+extern "C" {
+
+size_t asrb_rows_workspace_bytes(int cols) { return (size_t)kRowChunks * 2 * cols * sizeof(float); }
+
+/* y = BatchNorm1d(x) over x[R, cols].  training: batch stats -> mean/invstd (saved for backward) and running stats
+ * update (momentum, unbiased variance); eval: mean/invstd from running stats.  y may alias x. */
+int asrb_bn_rows_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     int training, float momentum, float eps, float* mean, float* invstd, float* y, float* ws,
+                     size_t ws_bytes, long long R, int cols, asrb_stream_t stream) {
+    ASRB_REQUIRE(x && gamma && beta && mean && invstd && y && R > 0 && cols > 0, ASRB_ERR_BAD_ARG);
+    if (training) {
+        ASRB_REQUIRE(ws, ASRB_ERR_WORKSPACE);
+        int nchunks = 0;
+        int rc = rows_reduce<0>(x, cols, nullptr, 0, nullptr, nullptr, ws, ws_bytes, R, cols, &nchunks, stream);
+        if (rc) return rc;
+        rows_finalize_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(ws, nchunks, cols, (double)R, 0, eps, momentum, mean, invstd, running_mean, running_var);
+        ASRB_LAUNCH_OK();
+    } else {
+        ASRB_REQUIRE(running_mean && running_var, ASRB_ERR_BAD_ARG);
+        int rc = asrb_bn_eval_stats(running_mean, running_var, eps, cols, mean, invstd, stream);
+        if (rc) return rc;
+    }
+    const long long total = R * cols;
+    bn_rows_apply_kernel<<<ew_grid(total), 256, 0, stream>>>(x, mean, invstd, gamma, beta, y, total, cols);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* dx, dgamma, dbeta from dy and the saved x / mean / invstd.  dx may alias dy. */
+int asrb_bn_rows_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                     int training, float* dx, float* dgamma, float* dbeta, float* ws, size_t ws_bytes, long long R,
+                     int cols, asrb_stream_t stream) {
+    ASRB_REQUIRE(dy && x && mean && invstd && gamma && dx && dgamma && dbeta && ws && R > 0 && cols > 0, ASRB_ERR_BAD_ARG);
+    int nchunks = 0;
+    int rc = rows_reduce<1>(dy, cols, x, cols, mean, invstd, ws, ws_bytes, R, cols, &nchunks, stream);
+    if (rc) return rc;
+    rows_finalize_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(ws, nchunks, cols, 1.0, 1, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr);
+    ASRB_LAUNCH_OK();
+    const long long total = R * cols;
+    bn_rows_bwd_kernel<<<ew_grid(total), 256, 0, stream>>>(dy, x, mean, invstd, gamma, dbeta, dgamma, 1.0f / (float)R, training, dx, total, cols);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* out[c] = sum_r a[r*lda + c] */
+int asrb_col_sums(const float* a, int lda, float* out, float* ws, size_t ws_bytes, long long R, int cols,
+                  asrb_stream_t stream) {
+    ASRB_REQUIRE(a && out && ws && R > 0 && cols > 0 && lda >= cols, ASRB_ERR_BAD_ARG);
+    int nchunks = 0;
+    int rc = rows_reduce<2>(a, lda, nullptr, 0, nullptr, nullptr, ws, ws_bytes, R, cols, &nchunks, stream);
+    if (rc) return rc;
+    rows_finalize_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(ws, nchunks, cols, 1.0, 1, 0.f, 0.f, out, nullptr, nullptr, nullptr);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* logits[R, ld] (ld >= C) -> log_probs[R, C] (may be NULL), probs[R, C] (may be NULL), argmax int64[R] (may be NULL) */
+int asrb_log_softmax_fwd(const float* logits, int ld, float* log_probs, float* probs, long long* argmax, long long R,
+                         int C, asrb_stream_t stream) {
+    ASRB_REQUIRE(logits && R > 0 && C > 0 && ld >= C, ASRB_ERR_BAD_ARG);
+    log_softmax_kernel<<<(unsigned)((R + 7) / 8), 256, 0, stream>>>(logits, ld, log_probs, probs, argmax, R, C);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* dlogits[R, ld] = g - exp(log_probs) * rowsum(g) */
+int asrb_log_softmax_bwd(const float* g, const float* log_probs, float* dlogits, int ld, long long R, int C,
+                         asrb_stream_t stream) {
+    ASRB_REQUIRE(g && log_probs && dlogits && R > 0 && C > 0 && ld >= C, ASRB_ERR_BAD_ARG);
+    log_softmax_bwd_kernel<<<(unsigned)((R + 7) / 8), 256, 0, stream>>>(g, log_probs, dlogits, ld, R, C);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+/* asr_b200 -- C ABI of the B200-native DeepSpeech2 training-step kernels (libasr_b200.so).
+ *
+ * The reference (zakuro-ai/asr, package asr_deepspeech v0.4.10) is pure Python on top of torch; it has NO
+ * FFI of its own.  Its seam for this path is Python dependency injection (trainers/__main__.py:23,51-58:
+ * a `model` and a `criterion` are handed to DeepSpeechTrainer).  The entry points below are what the
+ * Python drop-in modules in asr_b200/ bind with ctypes -- one group per reference call site:
+ *
+ *   asrb_spectrogram*        data/parsers/spectrogram_parser.py:45-60  (librosa.stft -> |.| -> log1p -> normalise)
+ *   asrb_conv2d_mask_*       modules/blocks.py:48-55 on nn.Conv2d      (deepspeech.py:61,64)
+ *   asrb_bn_act_mask_*       modules/blocks.py:48-55 on nn.BatchNorm2d + nn.Hardtanh (deepspeech.py:62-63,65-66)
+ *   asrb_nchw_to_tnf*        modules/deepspeech.py:135-137              (view/transpose/contiguous)
+ *   asrb_bn_rows_*           modules/blocks.py:16-21,85-86 SequenceWise(BatchNorm1d) ; deepspeech.py:104
+ *   asrb_gemm_tn             every Linear-shaped product: GRU/LSTM input projection (blocks.py:88), FC head
+ *                            (deepspeech.py:105) and all of their dgrad / wgrad products
+ *   asrb_rnn_*               modules/blocks.py:87-92 pack -> nn.GRU / nn.LSTM (bidirectional) -> pad -> sum(2)
+ *   asrb_log_softmax_*       trainers/deepspeech_trainer.py:110 ; blocks.py:62 (softmax) ; greedy_decoder.py:61 (argmax)
+ *   asrb_ctc_*               trainers/deepspeech_trainer.py:111 with torch.nn.CTCLoss(reduction="sum") (trainers/__main__.py:53)
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes; every pointer is DEVICE memory of the current CUDA device unless a name ends in
+ *     `_host`; fp32 unless stated; tensors are dense row-major with the shape given in the comment.
+ *   - the caller owns every buffer including workspaces; the library allocates nothing and keeps no state
+ *     besides the process-wide debug flag word.
+ *   - asynchronous: work is enqueued on `stream`; no host synchronisation inside.
+ *   - return value: 0 = ok, negative = ASRB_ERR_* (bad argument / unsupported shape; nothing was launched),
+ *     positive = a cudaError_t.  Never throws, never falls back to another implementation.
+ */
+#ifndef ASR_B200_H_
+#define ASR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* asrb_stream_t; /* == cudaStream_t */
+
+#define ASRB_OK 0
+#define ASRB_ERR_BAD_ARG (-1)
+#define ASRB_ERR_ALIGNMENT (-2)
+#define ASRB_ERR_UNSUPPORTED (-3)
+#define ASRB_ERR_WORKSPACE (-4)
+#define ASRB_ERR_DRIVER (-5)
+#define ASRB_ERR_TENSORMAP (-6)
+
+#define ASRB_GEMM_ACCUMULATE 1 /* C += A*B^T instead of C = A*B^T */
+
+#define ASRB_RNN_GRU 0
+#define ASRB_RNN_LSTM 1
+
+/* Debug switches (tests only; default 0 = the tensor-core product path). */
+#define ASRB_DEBUG_SIMT_GEMM 1u /* asrb_gemm_tn runs a plain fp32 CUDA-core kernel */
+#define ASRB_DEBUG_SIMT_RNN 2u  /* asrb_rnn_{fwd,bwd} compute the recurrent product with fp32 CUDA-core dot products */
+
+int asrb_version(void);
+const char* asrb_strerror(int code);
+int asrb_set_debug_flags(unsigned flags);
+
+/* ---------------------------------------------------------------- GEMM (tcgen05, TF32 operands, fp32 accumulate)
+ * C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N]).  lda/ldb/ldc are row strides in elements; lda, ldb multiples of 4. */
+int asrb_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, int M,
+                 int N, int K, int flags, asrb_stream_t stream);
+/* out[c, r] = in[r, c] */
+int asrb_transpose(const float* in, long long rows, int cols, int ld_in, float* out, int ld_out, asrb_stream_t stream);
+/* 3xTF32 operand expansion: mode 0 -> [x_hi | x_lo | x_hi], mode 1 -> [x_hi | x_hi | x_lo]  (out: [rows, 3*cols]) */
+int asrb_split3(const float* in, long long rows, int cols, int ld_in, float* out, int ld_out, int mode,
+                asrb_stream_t stream);
+
+/* ---------------------------------------------------------------- recurrent layers
+ * Geometry of the persistent kernel for hidden size H (nj = hidden units per CTA, P = CTAs per direction) and the
+ * sizes (in floats) of the two packed-weight buffers. */
+int asrb_rnn_plan(int cell, int H, int B, int* nj, int* P, size_t* wpack_fwd_floats, size_t* wpack_bwd_floats);
+/* w_hh_*: [gates*H, H] (torch weight_hh_l0 / weight_hh_l0_reverse).  Either output may be NULL. */
+int asrb_rnn_pack_weights(int cell, int H, const float* w_hh_fwd, const float* w_hh_rev, float* wpack_fwd,
+                          float* wpack_bwd, asrb_stream_t stream);
+/* gi [T,B,2,G] = x W_ih^T + b_ih for both directions; b_hh [2,G]; lengths int32[B];
+ * out: hseq [2,T+2,B,H] (slot t+1 = step t; slots 0,T+1 zero), cseq same (LSTM only, else NULL),
+ * saved [2,T,B,4,H] (GRU: r,z,n,W_hn h+b_hn ; LSTM: i,f,g,o); counters: uint32[2] scratch. */
+int asrb_rnn_fwd(int cell, const float* gi, const float* b_hh, const float* wpack_fwd, const int32_t* lengths,
+                 float* hseq, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
+                 asrb_stream_t stream);
+/* dout [T,B,H] (gradient of the direction-summed output); out: dgi [T,B,2,G], dgh [2,T,B,G]. */
+int asrb_rnn_bwd(int cell, const float* dout, const float* wpack_bwd, const int32_t* lengths, const float* hseq,
+                 const float* cseq, const float* saved, float* dgi, float* dgh, uint32_t* counters, int T, int B,
+                 int H, asrb_stream_t stream);
+/* out[T,B,H] = hseq[0][1..T] + hseq[1][1..T] */
+int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream);
+
+/* ---------------------------------------------------------------- MaskConv pieces (NCHW; lengths int32[B] or NULL)
+ * y = mask(conv2d(x, w) + bias): zero for time index >= lengths[b].  Hout/Wout must equal the conv output size. */
+int asrb_conv2d_mask_fwd(const float* x, const float* w, const float* bias, const int32_t* lengths, float* y, int B,
+                         int Cin, int Hin, int Win, int Cout, int Hout, int Wout, int KH, int KW, int SH, int SW,
+                         int PH, int PW, asrb_stream_t stream);
+/* dx = conv2d^T(mask(dy), w) */
+int asrb_conv2d_mask_bwd_data(const float* dy, const float* w, const int32_t* lengths, float* dx, int B, int Cin,
+                              int Hin, int Win, int Cout, int Hout, int Wout, int KH, int KW, int SH, int SW, int PH,
+                              int PW, asrb_stream_t stream);
+/* dw[Cout,Cin,KH,KW], dbias[Cout] (may be NULL) from mask(dy) and x.  ws: asrb_nchw_reduce_workspace_bytes(B,Cout,Hout,Wout). */
+int asrb_conv2d_mask_bwd_weight(const float* dy, const float* x, const int32_t* lengths, float* dw, float* dbias,
+                                double* ws, size_t ws_bytes, int B, int Cin, int Hin, int Win, int Cout, int Hout,
+                                int Wout, int KH, int KW, int SH, int SW, int PH, int PW, asrb_stream_t stream);
+size_t asrb_nchw_reduce_workspace_bytes(int B, int C, int H, int W);
+/* BatchNorm2d batch statistics over ALL positions of y[B,C,H,W]; running stats updated when non-NULL. */
+int asrb_bn2d_stats(const float* y, float* mean, float* invstd, float* running_mean, float* running_var,
+                    float momentum, float eps, double* ws, size_t ws_bytes, int B, int C, int H, int W,
+                    asrb_stream_t stream);
+/* eval-mode statistics: mean = running_mean, invstd = rsqrt(running_var + eps) */
+int asrb_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
+                       float* invstd, asrb_stream_t stream);
+/* z = mask(hardtanh(mask(bn(y)), lo, hi)); has_bn / has_act switch the two stages off (plain mask when both 0). */
+int asrb_bn_act_mask_fwd(const float* y, const int32_t* lengths, const float* mean, const float* invstd,
+                         const float* gamma, const float* beta, int has_bn, int has_act, float lo, float hi, float* z,
+                         int B, int C, int H, int W, asrb_stream_t stream);
+int asrb_bn_act_mask_bwd(const float* dz, const float* y, const int32_t* lengths, const float* mean,
+                         const float* invstd, const float* gamma, const float* beta, int has_bn, int has_act, float lo,
+                         float hi, int training, float* dy, float* dgamma, float* dbeta, double* ws, size_t ws_bytes,
+                         int B, int C, int H, int W, asrb_stream_t stream);
+/* out[n][c][r] = in[n][r][c] with explicit leading dimensions / batch strides (elements) */
+int asrb_transpose_batched(const float* in, int rows, int cols, long long ld_in, long long batch_stride_in, float* out,
+                           long long ld_out, long long batch_stride_out, int nbatch, asrb_stream_t stream);
+
+/* ---------------------------------------------------------------- row-matrix kernels, x[R = T*N, cols] */
+size_t asrb_rows_workspace_bytes(int cols);
+int asrb_bn_rows_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     int training, float momentum, float eps, float* mean, float* invstd, float* y, float* ws,
+                     size_t ws_bytes, long long R, int cols, asrb_stream_t stream);
+int asrb_bn_rows_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                     int training, float* dx, float* dgamma, float* dbeta, float* ws, size_t ws_bytes, long long R,
+                     int cols, asrb_stream_t stream);
+int asrb_col_sums(const float* a, int lda, float* out, float* ws, size_t ws_bytes, long long R, int cols,
+                  asrb_stream_t stream);
+/* logits[R, ld] -> log_probs[R,C] / probs[R,C] / argmax int64[R] (each optional) */
+int asrb_log_softmax_fwd(const float* logits, int ld, float* log_probs, float* probs, long long* argmax, long long R,
+                         int C, asrb_stream_t stream);
+int asrb_log_softmax_bwd(const float* g, const float* log_probs, float* dlogits, int ld, long long R, int C,
+                         asrb_stream_t stream);
+
+/* ---------------------------------------------------------------- CTC (blank-extended alpha/beta, reduction = sum) */
+size_t asrb_ctc_workspace_bytes(int T, int N, int max_target_len);
+int asrb_ctc_fwd(const float* log_probs, const int32_t* targets, const int32_t* input_lengths,
+                 const int32_t* target_lengths, float* alpha_ws, size_t ws_bytes, float* nll, float* loss, int T, int N,
+                 int C, int max_target_len, int blank, asrb_stream_t stream);
+int asrb_ctc_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lengths,
+                 const int32_t* target_lengths, const float* alpha_ws, const float* nll, const float* grad_scale,
+                 float* grad, int T, int N, int C, int max_target_len, int blank, asrb_stream_t stream);
+
+/* ---------------------------------------------------------------- spectrogram (STFT -> |.| -> log1p -> normalise) */
+size_t asrb_spectrogram_workspace_bytes(int B, int max_samples, int n_fft, int hop);
+int asrb_dft_basis(float* basis_cat /* [2*(n_fft/2+1), 3*n_fft] */, int n_fft, asrb_stream_t stream);
+int asrb_spectrogram(const float* wav, long long wav_ld, const int32_t* n_samples, const float* window,
+                     const float* basis_cat, float* spec, int normalize, void* ws, size_t ws_bytes, int B,
+                     int max_samples, int n_fft, int hop, asrb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASR_B200_H_ */
