@@ -302,8 +302,8 @@ gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const float* __restric
 __global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, int ld_in, float* __restrict__ out,
                                  int ld_out) {
     __shared__ float tile[32][33];
-    const long long r0 = (long long)blockIdx.y * 32;
-    const int c0 = blockIdx.x * 32;
+    const long long r0 = (long long)blockIdx.x * 32;   // rows on grid.x (up to 2^31 blocks)
+    const int c0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += 8) {
         long long r = r0 + i;
         int c = c0 + threadIdx.x;
@@ -382,8 +382,8 @@ int asrb_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int
 
 int asrb_transpose(const float* in, long long rows, int cols, int ld_in, float* out, int ld_out, asrb_stream_t stream) {
     ASRB_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, ASRB_ERR_BAD_ARG);
-    dim3 grid(ceil_div(cols, 32), (unsigned)ceil_div64(rows, 32));
-    ASRB_REQUIRE(grid.y <= 65535u * 32u, ASRB_ERR_UNSUPPORTED);
+    dim3 grid((unsigned)ceil_div64(rows, 32), ceil_div(cols, 32));
+    ASRB_REQUIRE(grid.y <= 65535u && rows < (1LL << 31), ASRB_ERR_UNSUPPORTED);
     transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, (int)rows, cols, ld_in, out, ld_out);
     ASRB_LAUNCH_OK();
     return 0;

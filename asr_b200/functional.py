@@ -1,0 +1,309 @@
+"""Differentiable operators of the DeepSpeech2 step: torch.autograd.Function wrappers whose forward AND
+backward are our sm_100a kernels (asr_b200/ops.py -> libasr_b200.so).  No torch arithmetic on activations.
+
+Also the two pieces of host logic the reference keeps next to the path:
+`get_seq_lens` (asr_deepspeech/modules/deepspeech.py:275-288) and `check_loss`
+(asr_deepspeech/functional.py:45-61).
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+def _amp_fwd(fn):
+    # under torch.amp.autocast (the reference trains with fp16 autocast on CUDA, device.py:43-46) our kernels keep
+    # computing in fp32/TF32: inputs are cast to fp32 and autocast is disabled inside
+    return torch.amp.custom_fwd(fn, device_type="cuda", cast_inputs=torch.float32)
+
+
+def _amp_bwd(fn):
+    return torch.amp.custom_bwd(fn, device_type="cuda")
+
+
+# ----------------------------------------------------------------------------- host logic
+def conv_seq_len(lengths: torch.Tensor, convs) -> torch.Tensor:
+    """deepspeech.py:275-288: per Conv2d (L + 2p - d(k-1) - 1)/s + 1 in float, chained, one final int()."""
+    seq = lengths.cpu().int()
+    for m in convs:
+        seq = (seq + 2 * m.padding[1] - m.dilation[1] * (m.kernel_size[1] - 1) - 1) / m.stride[1] + 1
+    return seq.int()
+
+
+def check_loss(loss, loss_value):
+    """asr_deepspeech/functional.py:45-61 -- same verdicts and messages."""
+    loss_valid = True
+    error = ""
+    if loss_value == float("inf") or loss_value == float("-inf"):
+        loss_valid = False
+        error = "WARNING: received an inf loss"
+    elif torch.isnan(loss).sum() > 0:
+        loss_valid = False
+        error = "WARNING: received a nan loss, setting loss value to 0"
+    elif loss_value < 0:
+        loss_valid = False
+        error = "WARNING: received a negative loss"
+    return loss_valid, error
+
+
+# ----------------------------------------------------------------------------- MaskConv pieces
+class Conv2dMask(Function):
+    """mask(conv2d(x, w) + b): blocks.py:50-55 applied to an nn.Conv2d."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x, weight, bias, lengths_dev, stride, padding):
+        x = x.contiguous()
+        weight = weight.contiguous()
+        ctx.save_for_backward(x, weight, lengths_dev)
+        ctx.conf = (stride, padding, bias is not None)
+        return ops.conv2d_mask_fwd(x, weight, bias, lengths_dev, stride, padding)
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, dy):
+        x, weight, lengths_dev = ctx.saved_tensors
+        stride, padding, has_bias = ctx.conf
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv2d_mask_bwd_data(dy, weight, lengths_dev, x.shape, stride, padding)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.conv2d_mask_bwd_weight(dy, x, lengths_dev, weight.shape, stride, padding, has_bias)
+        return dx, dw, db, None, None, None
+
+
+class BnActMask(Function):
+    """mask(hardtanh(mask(batch_norm(y)))) -- blocks.py:50-55 applied to nn.BatchNorm2d then nn.Hardtanh
+    (either stage optional).  Batch statistics include the zeroed tail, like the reference."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, y, lengths_dev, gamma, beta, running_mean, running_var, has_bn, has_act, lo, hi, training,
+                momentum, eps):
+        y = y.contiguous()
+        mean = invstd = None
+        if has_bn:
+            mean, invstd = ops.bn2d_stats(y, running_mean, running_var, training, momentum, eps)
+        z = ops.bn_act_mask_fwd(y, lengths_dev, mean, invstd, gamma, beta, has_bn, has_act, lo, hi)
+        ctx.save_for_backward(y, lengths_dev, mean, invstd, gamma, beta)
+        ctx.conf = (has_bn, has_act, lo, hi, training)
+        return z
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, dz):
+        y, lengths_dev, mean, invstd, gamma, beta = ctx.saved_tensors
+        has_bn, has_act, lo, hi, training = ctx.conf
+        dy, dgamma, dbeta = ops.bn_act_mask_bwd(dz.contiguous(), y, lengths_dev, mean, invstd, gamma, beta, has_bn,
+                                                has_act, lo, hi, training)
+        return (dy, None, dgamma, dbeta) + (None,) * 9
+
+
+class NchwToTnf(Function):
+    """[B,C,D,T] -> [T,B,C*D]: view / transpose / contiguous of deepspeech.py:135-137."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x):
+        ctx.cd = (x.shape[1], x.shape[2])
+        return ops.nchw_to_tnf(x.contiguous())
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, g):
+        return ops.tnf_to_nchw(g.contiguous(), *ctx.cd)
+
+
+# ----------------------------------------------------------------------------- SequenceWise pieces
+class BatchNormRows(Function):
+    """SequenceWise(BatchNorm1d): x [T,N,H] normalised over all T*N rows (blocks.py:16-21,85-86)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps):
+        shape = x.shape
+        x2 = x.contiguous().view(-1, shape[-1])
+        y, mean, invstd = ops.bn_rows_fwd(x2, gamma, beta, running_mean, running_var, training, momentum, eps)
+        ctx.save_for_backward(x2, mean, invstd, gamma)
+        ctx.training = training
+        return y.view(shape)
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, dy):
+        x2, mean, invstd, gamma = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.bn_rows_bwd(dy.contiguous().view(x2.shape), x2, mean, invstd, gamma, ctx.training)
+        return dx.view(dy.shape), dgamma, dbeta, None, None, None, None, None
+
+
+class LinearRows(Function):
+    """SequenceWise(Linear): y [T,N,O] = x [T,N,H] W^T (+ b) on the tcgen05 GEMM; dgrad and wgrad likewise."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x, weight, bias):
+        shape = x.shape
+        x2 = x.contiguous().view(-1, shape[-1])
+        weight = weight.contiguous()
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        y = ops.gemm_tn(x2, weight, bias=bias)
+        return y.view(*shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        O, H = weight.shape
+        dy2 = dy.contiguous().view(-1, O)
+        R = dy2.shape[0]
+        dx = dw = db = None
+        dyt = _transpose_padded(dy2)                             # [O, R4]
+        if ctx.needs_input_grad[0]:
+            dy_k = dy2
+            if O % 4 != 0:                                       # TMA wants 16-byte row strides: re-lay dy as [R, O4]
+                dy_k = torch.empty(R, (O + 3) // 4 * 4, device=dy.device, dtype=torch.float32)[:, :O]
+                ops.transpose(dyt[:, :R], out=dy_k)
+            wt = _transpose_padded(weight)                       # [H, O4]
+            dx = ops.gemm_tn(dy_k, wt[:, :O]).view(*dy.shape[:-1], H)
+        if ctx.needs_input_grad[1]:
+            xt = _transpose_padded(x2)                           # [H, R4]
+            dw = ops.gemm_tn(dyt[:, :R], xt[:, :R])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.col_sums(dy2)
+        return dx, dw, db
+
+
+def _transpose_padded(a):
+    """a [R, C] -> a^T as a [C, R] view of a [C, R4] buffer (row stride multiple of 4 floats)."""
+    R, C = a.shape
+    R4 = (R + 3) // 4 * 4
+    buf = torch.empty(C, R4, device=a.device, dtype=torch.float32)
+    ops.transpose(a, out=buf)
+    return buf
+
+
+# ----------------------------------------------------------------------------- bidirectional recurrent layer
+class BiRnnLayer(Function):
+    """pack_padded_sequence -> 1-layer bidirectional nn.GRU / nn.LSTM -> pad_packed_sequence -> sum of the two
+    directions (blocks.py:87-92), for x [T,N,I] and CPU-side lengths already copied to the device."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x, lengths_dev, cell, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        T, B, I = x.shape
+        G, H = w_hh.shape
+        x2 = x.contiguous().view(T * B, I)
+        gi = torch.empty(T * B, 2 * G, device=x.device, dtype=torch.float32)
+        ops.gemm_tn(x2, w_ih.contiguous(), out=gi[:, :G], bias=b_ih)
+        ops.gemm_tn(x2, w_ih_r.contiguous(), out=gi[:, G:], bias=b_ih_r)
+        w_hh, w_hh_r = w_hh.contiguous(), w_hh_r.contiguous()
+        pack_f, _ = ops.rnn_pack_weights(cell, w_hh, w_hh_r, B, fwd=True, bwd=False)
+        b_hh2 = torch.empty(2, G, device=x.device, dtype=torch.float32)   # two D2D memcpys, no arithmetic
+        b_hh2[0].copy_(b_hh)
+        b_hh2[1].copy_(b_hh_r)
+        hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh2, pack_f, lengths_dev, T, B, H)
+        ctx.save_for_backward(x2, lengths_dev, w_ih, w_ih_r, w_hh, w_hh_r, hseq, cseq, saved)
+        ctx.dims = (cell, T, B, I, H, G)
+        return ops.rnn_sum_dirs(hseq, T, B, H)
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, dout):
+        x2, lengths_dev, w_ih, w_ih_r, w_hh, w_hh_r, hseq, cseq, saved = ctx.saved_tensors
+        cell, T, B, I, H, G = ctx.dims
+        R = T * B
+        _, pack_b = ops.rnn_pack_weights(cell, w_hh, w_hh_r, B, fwd=False, bwd=True)
+        dgi, dgh = ops.rnn_bwd(cell, dout.contiguous(), pack_b, lengths_dev, hseq, cseq, saved, T, B, H)
+        dgi2 = dgi.view(R, 2 * G)
+        # bias gradients
+        db_ih_cat = ops.col_sums(dgi2)
+        db_hh = [ops.col_sums(dgh[d].view(R, G)) for d in range(2)]
+        # input gradient: dx = dgi_f W_ih_f + dgi_r W_ih_r
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(R, I, device=dout.device, dtype=torch.float32)
+            ops.gemm_tn(dgi2[:, :G], _transpose_padded(w_ih.contiguous())[:, :G], out=dx)
+            ops.gemm_tn(dgi2[:, G:], _transpose_padded(w_ih_r.contiguous())[:, :G], out=dx, accumulate=True)
+            dx = dx.view(T, B, I)
+        # weight gradients (K = T*B): dW_ih = dgi^T x ; dW_hh = dgh^T h_prev
+        dgit = _transpose_padded(dgi2)                          # [2G, R4]
+        xt = _transpose_padded(x2)                              # [I, R4]
+        dw_ih = ops.gemm_tn(dgit[:G, :R], xt[:, :R])
+        dw_ih_r = ops.gemm_tn(dgit[G:, :R], xt[:, :R])
+        dw_hh = []
+        for d in range(2):
+            dght = _transpose_padded(dgh[d].view(R, G))         # [G, R4]
+            # previous state in forward order: slots 0..T-1 for the forward direction, 2..T+1 for the reverse one
+            first = 0 if d == 0 else 2
+            hprev = hseq[d, first:first + T].reshape(R, H)
+            hpt = _transpose_padded(hprev)                      # [H, R4]
+            dw_hh.append(ops.gemm_tn(dght[:, :R], hpt[:, :R]))
+        return (dx, None, None, dw_ih, dw_hh[0], db_ih_cat[:G], db_hh[0], dw_ih_r, dw_hh[1], db_ih_cat[G:], db_hh[1])
+
+
+# ----------------------------------------------------------------------------- log_softmax / CTC / argmax
+class LogSoftmaxLastDim(Function):
+    """x.float().log_softmax(-1) (trainers/deepspeech_trainer.py:109-110)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x):
+        C = x.shape[-1]
+        lp, _, _ = ops.log_softmax_fwd(x.contiguous().view(-1, C), C)
+        ctx.save_for_backward(lp)
+        return lp.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, g):
+        (lp,) = ctx.saved_tensors
+        return ops.log_softmax_bwd(g.contiguous().view(lp.shape), lp).view(g.shape)
+
+
+class CtcLossSum(Function):
+    """torch.nn.CTCLoss(blank, reduction='sum', zero_infinity=False) forward/backward (trainers/__main__.py:53)."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, log_probs, targets_dev, input_lengths_dev, target_lengths_dev, max_target_len, blank):
+        lp = log_probs.contiguous()
+        loss, nll, alpha = ops.ctc_fwd(lp, targets_dev, input_lengths_dev, target_lengths_dev, max_target_len, blank)
+        ctx.save_for_backward(lp, targets_dev, input_lengths_dev, target_lengths_dev, alpha, nll)
+        ctx.conf = (max_target_len, blank)
+        return loss.view(())
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, g):
+        lp, targets_dev, input_lengths_dev, target_lengths_dev, alpha, nll = ctx.saved_tensors
+        max_target_len, blank = ctx.conf
+        gscale = g.contiguous().float().view(1)
+        grad = ops.ctc_bwd(lp, targets_dev, input_lengths_dev, target_lengths_dev, alpha, nll, gscale, max_target_len, blank)
+        return grad, None, None, None, None, None
+
+
+def softmax_last_dim(x):
+    """Eval-mode InferenceBatchSoftmax (blocks.py:59-64); no gradient."""
+    C = x.shape[-1]
+    _, probs, _ = ops.log_softmax_fwd(x.contiguous().view(-1, C), C, want_lp=False, want_probs=True)
+    return probs.view(x.shape)
+
+
+def argmax_last_dim(x):
+    """torch.max(probs, 2)[1] of GreedyDecoder.decode (decoders/greedy_decoder.py:61): first maximum, int64."""
+    C = x.shape[-1]
+    _, _, idx = ops.log_softmax_fwd(x.contiguous().view(-1, C), C, want_lp=False, want_argmax=True)
+    return idx.view(x.shape[:-1])

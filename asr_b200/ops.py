@@ -1,0 +1,372 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point group).
+
+PyTorch is used here only as the owner of device memory and of the CUDA stream: every function
+checks that its tensors live on a CUDA device (there is no CPU implementation -- a CPU tensor raises),
+allocates outputs / workspaces through the caching allocator and enqueues our kernels on the current
+stream.  `LAUNCHES` counts kernel-launching calls (bench.py reports it as `gpu_launches`).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+GRU, LSTM = 0, 1
+LAUNCHES = 0
+BN_MOMENTUM = 0.1
+BN_EPS = 1e-5
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(*tensors, dtype=torch.float32):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("asr_b200 kernels need CUDA tensors (no CPU path exists)")
+        if t.dtype != dtype:
+            raise ValueError(f"expected {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError("expected a contiguous tensor")
+
+
+def require_cuda(t, who):
+    """The one guard every public entry point goes through: no CPU implementation exists."""
+    if not t.is_cuda:
+        raise RuntimeError(f"asr_b200.{who}: CUDA tensor required (this package has no CPU or PyTorch fallback)")
+
+
+PROFILE = None   # set to a dict to collect (start, end) CUDA-event pairs per entry point (bench.py)
+
+# kernels launched per call of an entry point (memsets not counted); used for the `gpu_launches` claim
+KERNELS_PER_CALL = {
+    "asrb_conv2d_mask_bwd_weight": 3, "asrb_bn2d_stats": 2, "asrb_bn_act_mask_bwd": 3, "asrb_bn_rows_fwd": 3,
+    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1,
+}
+
+
+def _call(name, *args):
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    if PROFILE is None:
+        _lib.call(name, *args, _stream())
+        return
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    _lib.call(name, *args, _stream())
+    end.record()
+    PROFILE.setdefault(name, []).append((start, end))
+
+
+def set_debug_flags(flags: int):
+    _lib.call("asrb_set_debug_flags", flags)
+
+
+def lengths_to_device(lengths, device):
+    """int32 lengths (CPU, as the reference keeps them) -> device int32 copy."""
+    return torch.as_tensor(lengths, dtype=torch.int32).to(device, non_blocking=True).contiguous()
+
+
+# ----------------------------------------------------------------------------- GEMM family
+def _ld(t):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("expected a 2-D tensor with unit inner stride")
+    return t.stride(0)
+
+
+def gemm_tn(A, B, out=None, bias=None, accumulate=False):
+    """out[M,N] (+)= A[M,K] @ B[N,K]^T (+ bias).  A, B, out may be row-strided views (unit inner stride)."""
+    for t in (A, B, out, bias):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError("gemm_tn needs fp32 CUDA tensors")
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2:
+        raise ValueError(f"inner dimensions differ: {K} vs {K2}")
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    _call("asrb_gemm_tn", _p(A), _ld(A), _p(B), _ld(B), _p(out), _ld(out), _p(bias), M, N, K, 1 if accumulate else 0)
+    return out
+
+
+def transpose(x, out=None):
+    """out[C,R] = x[R,C]^T (x may be a row-strided view)."""
+    R, C = x.shape
+    if out is None:
+        out = torch.empty(C, R, device=x.device, dtype=torch.float32)
+    _call("asrb_transpose", _p(x), R, C, _ld(x), _p(out), _ld(out))
+    return out
+
+
+def split3(x, mode):
+    R, C = x.shape
+    out = torch.empty(R, 3 * C, device=x.device, dtype=torch.float32)
+    _call("asrb_split3", _p(x), R, C, _ld(x), _p(out), 3 * C, mode)
+    return out
+
+
+def gemm_tn_3x(A, B, out=None, bias=None):
+    """~fp32-accurate product on TF32 tensor cores (3xTF32 operand expansion, K -> 3K)."""
+    return gemm_tn(split3(A, 0), split3(B, 1), out=out, bias=bias)
+
+
+def col_sums(a, cols=None):
+    R = a.shape[0]
+    cols = a.shape[1] if cols is None else cols
+    out = torch.empty(cols, device=a.device, dtype=torch.float32)
+    ws = torch.empty(_lib.query("asrb_rows_workspace_bytes", cols) // 4, device=a.device, dtype=torch.float32)
+    _call("asrb_col_sums", _p(a), _ld(a), _p(out), _p(ws), ws.numel() * 4, R, cols)
+    return out
+
+
+# ----------------------------------------------------------------------------- conv / BN2d / layout
+def conv_out_size(n, k, s, p):
+    return (n + 2 * p - k) // s + 1
+
+
+def conv2d_mask_fwd(x, w, bias, lengths, stride, padding):
+    _chk(x, w, bias)
+    _chk(lengths, dtype=torch.int32)
+    B, Cin, Hin, Win = x.shape
+    Cout, _, KH, KW = w.shape
+    Hout, Wout = conv_out_size(Hin, KH, stride[0], padding[0]), conv_out_size(Win, KW, stride[1], padding[1])
+    y = torch.empty(B, Cout, Hout, Wout, device=x.device, dtype=torch.float32)
+    _call("asrb_conv2d_mask_fwd", _p(x), _p(w), _p(bias), _p(lengths), _p(y), B, Cin, Hin, Win, Cout, Hout, Wout,
+          KH, KW, stride[0], stride[1], padding[0], padding[1])
+    return y
+
+
+def conv2d_mask_bwd_data(dy, w, lengths, x_shape, stride, padding):
+    _chk(dy, w)
+    B, Cin, Hin, Win = x_shape
+    Cout, _, KH, KW = w.shape
+    _, _, Hout, Wout = dy.shape
+    dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
+    _call("asrb_conv2d_mask_bwd_data", _p(dy), _p(w), _p(lengths), _p(dx), B, Cin, Hin, Win, Cout, Hout, Wout, KH, KW,
+          stride[0], stride[1], padding[0], padding[1])
+    return dx
+
+
+def conv2d_mask_bwd_weight(dy, x, lengths, w_shape, stride, padding, need_bias=True):
+    _chk(dy, x)
+    B, Cin, Hin, Win = x.shape
+    Cout, _, KH, KW = w_shape
+    _, _, Hout, Wout = dy.shape
+    dw = torch.empty(w_shape, device=dy.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=dy.device, dtype=torch.float32) if need_bias else None
+    nb = _lib.query("asrb_nchw_reduce_workspace_bytes", B, Cout, Hout, Wout)
+    ws = torch.empty(nb // 8, device=dy.device, dtype=torch.float64)
+    _call("asrb_conv2d_mask_bwd_weight", _p(dy), _p(x), _p(lengths), _p(dw), _p(db), _p(ws), nb, B, Cin, Hin, Win, Cout,
+          Hout, Wout, KH, KW, stride[0], stride[1], padding[0], padding[1])
+    return dw, db
+
+
+def bn2d_stats(y, running_mean, running_var, training, momentum=BN_MOMENTUM, eps=BN_EPS):
+    """-> (mean[C], invstd[C]); training: batch statistics (+ running-stat update), eval: from running stats."""
+    _chk(y)
+    B, C, H, W = y.shape
+    mean = torch.empty(C, device=y.device, dtype=torch.float32)
+    invstd = torch.empty(C, device=y.device, dtype=torch.float32)
+    if training:
+        nb = _lib.query("asrb_nchw_reduce_workspace_bytes", B, C, H, W)
+        ws = torch.empty(nb // 8, device=y.device, dtype=torch.float64)
+        _call("asrb_bn2d_stats", _p(y), _p(mean), _p(invstd), _p(running_mean), _p(running_var), momentum, eps, _p(ws),
+              nb, B, C, H, W)
+    else:
+        _call("asrb_bn_eval_stats", _p(running_mean), _p(running_var), eps, C, _p(mean), _p(invstd))
+    return mean, invstd
+
+
+def bn_act_mask_fwd(y, lengths, mean, invstd, gamma, beta, has_bn, has_act, lo, hi):
+    _chk(y, mean, invstd, gamma, beta)
+    B, C, H, W = y.shape
+    z = torch.empty_like(y)
+    _call("asrb_bn_act_mask_fwd", _p(y), _p(lengths), _p(mean), _p(invstd), _p(gamma), _p(beta), int(has_bn),
+          int(has_act), float(lo), float(hi), _p(z), B, C, H, W)
+    return z
+
+
+def bn_act_mask_bwd(dz, y, lengths, mean, invstd, gamma, beta, has_bn, has_act, lo, hi, training):
+    _chk(dz, y)
+    B, C, H, W = y.shape
+    dy = torch.empty_like(y)
+    dgamma = dbeta = ws = None
+    nb = 0
+    if has_bn:
+        dgamma = torch.empty(C, device=y.device, dtype=torch.float32)
+        dbeta = torch.empty(C, device=y.device, dtype=torch.float32)
+        nb = _lib.query("asrb_nchw_reduce_workspace_bytes", B, C, H, W)
+        ws = torch.empty(nb // 8, device=y.device, dtype=torch.float64)
+    _call("asrb_bn_act_mask_bwd", _p(dz), _p(y), _p(lengths), _p(mean), _p(invstd), _p(gamma), _p(beta), int(has_bn),
+          int(has_act), float(lo), float(hi), int(training), _p(dy), _p(dgamma), _p(dbeta), _p(ws), nb, B, C, H, W)
+    return dy, dgamma, dbeta
+
+
+def nchw_to_tnf(x):
+    """[B,C,D,T] -> [T,B,C*D] (deepspeech.py:135-137)."""
+    _chk(x)
+    B, C, D, T = x.shape
+    out = torch.empty(T, B, C * D, device=x.device, dtype=torch.float32)
+    _call("asrb_transpose_batched", _p(x), C * D, T, T, C * D * T, _p(out), B * C * D, C * D, B)
+    return out
+
+
+def tnf_to_nchw(x, C, D):
+    _chk(x)
+    T, B, F = x.shape
+    out = torch.empty(B, C, D, T, device=x.device, dtype=torch.float32)
+    _call("asrb_transpose_batched", _p(x), T, F, B * F, F, _p(out), T, F * T, B)
+    return out
+
+
+# ----------------------------------------------------------------------------- BatchNorm1d over rows
+def _rows_ws(cols, device):
+    return torch.empty(_lib.query("asrb_rows_workspace_bytes", cols) // 4, device=device, dtype=torch.float32)
+
+
+def bn_rows_fwd(x, gamma, beta, running_mean, running_var, training, momentum=BN_MOMENTUM, eps=BN_EPS):
+    """x [R, cols] -> (y, mean, invstd)"""
+    _chk(x, gamma, beta, running_mean, running_var)
+    R, cols = x.shape
+    mean = torch.empty(cols, device=x.device, dtype=torch.float32)
+    invstd = torch.empty(cols, device=x.device, dtype=torch.float32)
+    y = torch.empty_like(x)
+    ws = _rows_ws(cols, x.device)
+    _call("asrb_bn_rows_fwd", _p(x), _p(gamma), _p(beta), _p(running_mean), _p(running_var), int(training), momentum,
+          eps, _p(mean), _p(invstd), _p(y), _p(ws), ws.numel() * 4, R, cols)
+    return y, mean, invstd
+
+
+def bn_rows_bwd(dy, x, mean, invstd, gamma, training):
+    _chk(dy, x, mean, invstd, gamma)
+    R, cols = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(cols, device=x.device, dtype=torch.float32)
+    dbeta = torch.empty(cols, device=x.device, dtype=torch.float32)
+    ws = _rows_ws(cols, x.device)
+    _call("asrb_bn_rows_bwd", _p(dy), _p(x), _p(mean), _p(invstd), _p(gamma), int(training), _p(dx), _p(dgamma),
+          _p(dbeta), _p(ws), ws.numel() * 4, R, cols)
+    return dx, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------- recurrent layers
+def rnn_plan(cell, H, B):
+    nj, P = ctypes.c_int(), ctypes.c_int()
+    wf, wb = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.call("asrb_rnn_plan", cell, H, B, ctypes.byref(nj), ctypes.byref(P), ctypes.byref(wf), ctypes.byref(wb))
+    return nj.value, P.value, wf.value, wb.value
+
+
+def rnn_pack_weights(cell, w_hh_fwd, w_hh_rev, B, fwd=True, bwd=True):
+    _chk(w_hh_fwd, w_hh_rev)
+    H = w_hh_fwd.shape[1]
+    _, _, wf, wb = rnn_plan(cell, H, B)
+    pf = torch.empty(wf, device=w_hh_fwd.device, dtype=torch.float32) if fwd else None
+    pb = torch.empty(wb, device=w_hh_fwd.device, dtype=torch.float32) if bwd else None
+    _call("asrb_rnn_pack_weights", cell, H, _p(w_hh_fwd), _p(w_hh_rev), _p(pf), _p(pb))
+    return pf, pb
+
+
+def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
+    """gi [T,B,2,G], b_hh [2,G] -> hseq [2,T+2,B,H], cseq (LSTM) or None, saved [2,T,B,4,H]"""
+    _chk(gi, b_hh, wpack_fwd)
+    _chk(lengths, dtype=torch.int32)
+    dev = gi.device
+    hseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32)
+    cseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32) if cell == LSTM else None
+    saved = torch.empty(2, T, B, 4, H, device=dev, dtype=torch.float32)
+    counters = torch.empty(2, device=dev, dtype=torch.int32)
+    _call("asrb_rnn_fwd", cell, _p(gi), _p(b_hh), _p(wpack_fwd), _p(lengths), _p(hseq), _p(cseq), _p(saved),
+          _p(counters), T, B, H)
+    return hseq, cseq, saved
+
+
+def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
+    """dout [T,B,H] -> dgi [T,B,2,G], dgh [2,T,B,G]"""
+    _chk(dout, wpack_bwd, hseq, cseq, saved)
+    G = (3 if cell == GRU else 4) * H
+    dev = dout.device
+    dgi = torch.empty(T, B, 2, G, device=dev, dtype=torch.float32)
+    dgh = torch.empty(2, T, B, G, device=dev, dtype=torch.float32)
+    counters = torch.empty(2, device=dev, dtype=torch.int32)
+    _call("asrb_rnn_bwd", cell, _p(dout), _p(wpack_bwd), _p(lengths), _p(hseq), _p(cseq), _p(saved), _p(dgi), _p(dgh),
+          _p(counters), T, B, H)
+    return dgi, dgh
+
+
+def rnn_sum_dirs(hseq, T, B, H):
+    out = torch.empty(T, B, H, device=hseq.device, dtype=torch.float32)
+    _call("asrb_rnn_sum_dirs", _p(hseq), _p(out), T, B, H)
+    return out
+
+
+# ----------------------------------------------------------------------------- softmax / CTC
+def log_softmax_fwd(logits2d, C, want_lp=True, want_probs=False, want_argmax=False):
+    """logits2d [R, ld>=C] -> (log_probs [R,C] | None, probs | None, argmax int64 [R] | None)"""
+    R = logits2d.shape[0]
+    dev = logits2d.device
+    lp = torch.empty(R, C, device=dev, dtype=torch.float32) if want_lp else None
+    pr = torch.empty(R, C, device=dev, dtype=torch.float32) if want_probs else None
+    am = torch.empty(R, device=dev, dtype=torch.int64) if want_argmax else None
+    _call("asrb_log_softmax_fwd", _p(logits2d), _ld(logits2d), _p(lp), _p(pr), _p(am), R, C)
+    return lp, pr, am
+
+
+def log_softmax_bwd(g, lp):
+    _chk(g, lp)
+    R, C = lp.shape
+    d = torch.empty(R, C, device=lp.device, dtype=torch.float32)
+    _call("asrb_log_softmax_bwd", _p(g), _p(lp), _p(d), C, R, C)
+    return d
+
+
+def ctc_fwd(log_probs, targets, input_lengths, target_lengths, max_target_len, blank=0):
+    """log_probs [T,N,C]; int32 device tensors for the rest -> (loss[1], nll[N], alpha workspace)"""
+    _chk(log_probs)
+    _chk(targets, input_lengths, target_lengths, dtype=torch.int32)
+    T, N, C = log_probs.shape
+    nb = _lib.query("asrb_ctc_workspace_bytes", T, N, max_target_len)
+    alpha = torch.empty(nb // 4, device=log_probs.device, dtype=torch.float32)
+    nll = torch.empty(N, device=log_probs.device, dtype=torch.float32)
+    loss = torch.empty(1, device=log_probs.device, dtype=torch.float32)
+    _call("asrb_ctc_fwd", _p(log_probs), _p(targets), _p(input_lengths), _p(target_lengths), _p(alpha), nb, _p(nll),
+          _p(loss), T, N, C, max_target_len, blank)
+    return loss, nll, alpha
+
+
+def ctc_bwd(log_probs, targets, input_lengths, target_lengths, alpha, nll, grad_scale, max_target_len, blank=0):
+    T, N, C = log_probs.shape
+    grad = torch.empty_like(log_probs)
+    _call("asrb_ctc_bwd", _p(log_probs), _p(targets), _p(input_lengths), _p(target_lengths), _p(alpha), _p(nll),
+          _p(grad_scale), _p(grad), T, N, C, max_target_len, blank)
+    return grad
+
+
+# ----------------------------------------------------------------------------- spectrogram
+def dft_basis(n_fft, device):
+    basis = torch.empty(2 * (n_fft // 2 + 1), 3 * n_fft, device=device, dtype=torch.float32)
+    _call("asrb_dft_basis", _p(basis), n_fft)
+    return basis
+
+
+def spectrogram(wav, n_samples, window, basis, n_fft, hop, normalize=True):
+    """wav [B, S] zero padded, n_samples int32[B] -> [B,1,n_fft/2+1, 1+S//hop]"""
+    _chk(wav, window, basis)
+    _chk(n_samples, dtype=torch.int32)
+    B, S = wav.shape
+    F, Tmax = n_fft // 2 + 1, 1 + S // hop
+    nb = _lib.query("asrb_spectrogram_workspace_bytes", B, S, n_fft, hop)
+    ws = torch.empty((nb + 3) // 4, device=wav.device, dtype=torch.float32)
+    spec = torch.empty(B, 1, F, Tmax, device=wav.device, dtype=torch.float32)
+    _call("asrb_spectrogram", _p(wav), S, _p(n_samples), _p(window), _p(basis), _p(spec), int(normalize), _p(ws), nb, B,
+          S, n_fft, hop)
+    return spec

@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py -- utterance-seconds of audio per second through the DeepSpeech2 hot path
+(spectrogram -> MaskConv -> biGRU x5 -> FC -> log_softmax -> CTC, forward + backward to every parameter gradient
+[+ one NCCL all-reduce of the flat gradient bucket when N > 1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our sm_100a path
+  python bench.py --impl reference ...                           the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): 5 x biGRU-800, batch 64 per GPU, 10 s @ 16 kHz (161 bins x 1001 frames),
+29 labels, 100-character targets, synthetic randn spectrograms (seed 1234+2), reference default init (seed 123456).
+One JSON line on stdout (rank 0).  The optimizer step is not part of the metric (fwd-bwd), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(rnn_type="gru", hidden=800, layers=5, C=29, B=64, seconds=10, T=1001, U=100, seed=1236)
+CPU_SAMPLE_B = 4   # utterances of the 64 used for the bounded CPU runs (about 10 s of CPU work per step on 8 cores)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def flops_per_step(B, Tp, H, L, C, layers_in=1312):
+    """Algorithmic FLOPs of SURVEY.md section 8d for fwd (x3 for fwd+bwd), padded frames counted."""
+    G = 3 * H
+    rows = Tp * B
+    inproj = sum(2 * rows * (layers_in if l == 0 else H) * G * 2 for l in range(L))
+    rec = 2 * rows * H * G * 2 * L
+    conv1 = 2 * B * 32 * 81 * Tp * 451
+    conv2 = 2 * B * 32 * 41 * Tp * 32 * 231
+    fc = 2 * rows * H * C
+    return dict(inproj=inproj, rec=rec, conv1=conv1, conv2=conv2, fc=fc)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows and self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_batch(B, cfg=CFG):
+    from oracle.make_golden import synth_batch
+
+    return synth_batch(cfg["seed"], B, cfg["T"], cfg["U"], cfg["C"])
+
+
+def run_cpu_port(steps, warmup, cfg=CFG):
+    """The reference's CPU implementation of the path (oracle/torch_path.py: the same torch calls the reference
+    makes, pinned to the reference's golden vectors) on a bounded sample, all host threads."""
+    from oracle import torch_path
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = torch_path.init_params(cfg["rnn_type"], cfg["hidden"], cfg["layers"], cfg["C"])
+    batch = make_batch(CPU_SAMPLE_B)
+    for _ in range(warmup):
+        torch_path.loss_and_grads(p, *batch, rnn_type=cfg["rnn_type"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        torch_path.loss_and_grads(p, *batch, rnn_type=cfg["rnn_type"])
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    sample = (f"{CPU_SAMPLE_B} of the {cfg['B']} utterances (full 10 s length, same model), fwd+CTC+bwd, "
+              f"{steps} step(s) after {warmup} warm-up, torch {torch.__version__} CPU")
+    return CPU_SAMPLE_B * cfg["seconds"] / dt, dt, cores, sample
+
+
+def build_model(cfg, device):
+    import pandas as pd
+
+    from asr_b200.modules import DeepSpeech
+    from oracle import torch_path
+    from oracle.make_golden import LABELS29
+
+    conf = SimpleNamespace(sample_rate=16000, window_size=0.02, window_stride=0.01, window="hamming")
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "labels.csv")
+        pd.DataFrame({"label": LABELS29[:cfg["C"]]}).to_csv(path, index=False)
+        model = DeepSpeech(audio_conf=conf, decoder=None, label_path=path, rnn_type=f"nn.{cfg['rnn_type'].upper()}",
+                           rnn_hidden_size=cfg["hidden"], rnn_hidden_layers=cfg["layers"])
+    model.load_state_dict(torch_path.init_params(cfg["rnn_type"], cfg["hidden"], cfg["layers"], cfg["C"]), strict=True)
+    return model.to(device).train()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = CFG
+    workload = (f"configs[1]: 5xbiGRU-800, batch {cfg['B']}/GPU, 10 s @16 kHz (161x1001 spectrogram), 29 labels, "
+                f"U=100, fwd+CTC+bwd to all parameter gradients")
+    base = {"metric": "utterance-sec/s through conv+biRNN+CTC fwd-bwd", "unit": "utterance-sec/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "data": "synthetic",
+            "config": {"workload": workload, "global_batch": cfg["B"] * max(args.gpus, 1), "frames": cfg["T"],
+                       "optimizer_step": "excluded (metric is fwd-bwd)", "l2_policy": "activations (GBs) far exceed the 126 MB L2"}}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, args.steps), args.warmup
+        v, dt, cores, sample = run_cpu_port(steps, warmup)
+        line = dict(base, impl="reference", value=v, ms_per_step=dt * 1e3, dtype="f32",
+                    cpu_baseline={"value": v, "unit": "utterance-sec/s", "cores": cores, "kind": "port", "sample": sample},
+                    e2e={"value": v, "unit": "utterance-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch.distributed as dist
+
+    from asr_b200 import ops
+    from asr_b200.distributed import FlatGradBucket
+    from asr_b200.trainers import CTCLoss, fit
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = build_model(cfg, dev)
+    criterion = CTCLoss(reduction="sum")
+    bucket = FlatGradBucket(model.parameters())
+    host = make_batch(cfg["B"])
+    pinned = host[0].pin_memory()
+    resident = host[0].to(dev)
+    stream = torch.cuda.current_stream()
+
+    def step(inputs):
+        bucket.zero()
+        valid, loss, loss_value = fit(model, criterion, (inputs, host[1], host[2], host[3]), dev)
+        loss.backward()
+        bucket.all_reduce_mean()
+        return loss_value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(inputs, steps, profile=False):
+        barrier()
+        ops.PROFILE = {} if profile else None
+        l0 = ops.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            lv = step(inputs)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof, ops.PROFILE = ops.PROFILE, None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / steps, lv, ops.LAUNCHES - l0, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev, loss_value, launches, prof = timed(resident, args.steps, profile=True)
+    ms_e2e, _, _, _ = timed(pinned, args.steps)          # host buffers: pinned H2D + loss D2H inside the region
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_sec = cfg["B"] * cfg["seconds"] * world
+    hbm_peak, tf_peak, peak_src = peaks()
+    # per-entry-point device time over the timed region (CUDA events on the launching stream)
+    per_op = {k: (sum(s.elapsed_time(e) for s, e in v) / args.steps, len(v) // args.steps) for k, v in prof.items()}
+    Tp = (cfg["T"] - 1) // 2 + 1
+    fl = flops_per_step(cfg["B"], Tp, cfg["hidden"], cfg["layers"], cfg["C"])
+    top = max(per_op, key=lambda k: per_op[k][0])
+    if top in ("asrb_rnn_fwd", "asrb_rnn_bwd"):
+        launch_flops = fl["rec"] / cfg["layers"] * (1 if top == "asrb_rnn_fwd" else 1)   # one layer per launch
+        what = f"{top}: 2*T'*B*H*G*2dirs FLOP per launch (one layer, both directions)"
+    elif top == "asrb_gemm_tn":
+        launch_flops = (3 * fl["inproj"] + 2 * fl["rec"] + 3 * fl["fc"]) / per_op[top][1]
+        what = f"{top}: mean over the {per_op[top][1]} GEMM launches of a step (in-proj fwd/dgrad/wgrad, dW_hh, FC)"
+    else:
+        launch_flops = {"asrb_conv2d_mask_fwd": (fl["conv1"] + fl["conv2"]) / 2, "asrb_conv2d_mask_bwd_data": fl["conv2"],
+                        "asrb_conv2d_mask_bwd_weight": (fl["conv1"] + fl["conv2"]) / 2}.get(top, 0.0)
+        what = f"{top}: mean conv FLOP per launch"
+    avg_ms = per_op[top][0] / per_op[top][1]
+    achieved = launch_flops / (avg_ms * 1e-3) / 1e12
+    line = dict(base, value=total_sec / (ms_dev * 1e-3), ms_per_step=ms_dev, dtype="tf32 operands, f32 accumulate/storage",
+                loss=loss_value, gpu_launches=launches,
+                e2e={"value": total_sec / (ms_e2e * 1e-3), "unit": "utterance-sec/s", "ms_per_step": ms_e2e,
+                     "h2d_bytes_per_step": pinned.numel() * 4 + host[1].numel() * 4 + 2 * cfg["B"] * 4 + 3 * cfg["B"] * 4,
+                     "d2h_bytes_per_step": 4},
+                clocks=clocks,
+                roofline={"bound": "tensor", "kernel": top, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                          "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src, "algorithmic": what,
+                          "avg_launch_ms": avg_ms,
+                          "note": "peak is the measured bf16 rate; tf32 operands run at half of it"},
+                kernel_ms_per_step={k: round(v[0], 3) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1][0])})
+    if not args.no_cpu_baseline and world == 1:
+        v, dt, cores, sample = run_cpu_port(1, 0)
+        line["cpu_baseline"] = {"value": v, "unit": "utterance-sec/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,52 @@
+"""CPU: the C-ABI shared library builds/loads and exports exactly what include/asr_b200.h declares
+(no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+
+import pytest
+
+
+def test_library_exports_every_header_symbol():
+    from asr_b200 import _lib
+
+    assert os.path.exists(_lib.LIBRARY), "run __graft_entry__.build() first"
+    names = set(_lib.PROTOTYPES)
+    expected = {"asrb_version", "asrb_strerror", "asrb_set_debug_flags", "asrb_gemm_tn", "asrb_rnn_fwd",
+                "asrb_rnn_bwd", "asrb_conv2d_mask_fwd", "asrb_bn_act_mask_fwd", "asrb_bn_rows_fwd",
+                "asrb_log_softmax_fwd", "asrb_ctc_fwd", "asrb_ctc_bwd", "asrb_spectrogram"}
+    assert expected <= names
+    dll = ctypes.CDLL(_lib.LIBRARY)
+    for n in names:
+        assert hasattr(dll, n), f"{n} declared in include/asr_b200.h but not exported"
+    assert _lib.query("asrb_version") >= 100
+
+
+def test_error_contract_without_a_gpu():
+    """negative status = bad argument / unsupported shape, decoded by asrb_strerror; nothing is launched"""
+    from asr_b200 import _lib
+
+    assert "bad argument" in _lib.strerror(-1)
+    assert "unsupported" in _lib.strerror(-3)
+    with pytest.raises(ValueError):           # NULL pointers are rejected before any CUDA call
+        _lib.call("asrb_gemm_tn", None, 4, None, 4, None, 4, None, 1, 1, 4, 0, None)
+    nj, P = ctypes.c_int(), ctypes.c_int()
+    _lib.call("asrb_rnn_plan", 0, 800, 64, ctypes.byref(nj), ctypes.byref(P), None, None)
+    assert 2 * P.value <= 148 and nj.value * P.value >= 800      # one CTA per SM, both directions co-resident
+    with pytest.raises(ValueError):           # hidden size that is not a multiple of 4 floats (16-byte TMA rows)
+        _lib.call("asrb_rnn_plan", 0, 801, 64, None, None, None, None)
+    assert _lib.query("asrb_ctc_workspace_bytes", 2000, 256, 200) == 2000 * 256 * 401 * 4
+
+
+def test_sass_contains_tcgen05_and_tma():
+    """The product GEMM / recurrence really are Blackwell-native: UTC*MMA (tcgen05.mma), LDTM (tcgen05.ld),
+    UTMALDG (TMA) in the SASS of the shipped library."""
+    import shutil
+    import subprocess
+
+    from asr_b200 import _lib
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIBRARY], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic

@@ -1,0 +1,321 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (asr_b200.ops -> libasr_b200.so) against the CPU oracle
+(oracle/explicit.py, oracle/torch_path.py) on the same seeded inputs.
+
+Tolerances (stated per test): integer / index outputs bit-exact; fp32 CUDA-core kernels ~1e-5 relative;
+tensor-core products carry TF32 operand rounding (10-bit mantissa, fp32 accumulate): |err| <= 2e-3 * sqrt(K) * rms(a)*rms(b).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import explicit, torch_path
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from asr_b200 import ops as _ops
+
+    _ops.set_debug_flags(0)
+    yield _ops
+    _ops.set_debug_flags(0)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def report(name, got, ref):
+    err = (got.double().cpu() - ref.double()).abs()
+    print(f"[{name}] max_abs_err={err.max().item():.3e} ref_max={ref.abs().max().item():.3e} "
+          f"argmax={np.unravel_index(int(err.argmax()), err.shape)}")
+    return err.max().item()
+
+
+# ----------------------------------------------------------------------------- GEMM
+GEMM_SHAPES = [(128, 128, 32), (128, 64, 64), (256, 256, 256), (300, 200, 100), (1000, 29, 800), (77, 2400, 800),
+               (2048, 4800, 1312), (36, 40, 32064)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_tn_tcgen05(ops, M, N, K):
+    A, B, bias = rnd(M, K, seed=1), rnd(N, K, seed=2), rnd(N, seed=3)
+    ref = A.double() @ B.double().t() + bias.double()
+    out = ops.gemm_tn(A.to(DEV), B.to(DEV), bias=bias.to(DEV))
+    torch.cuda.synchronize()
+    err = report(f"gemm_tc {M}x{N}x{K}", out, ref)
+    assert err <= 2e-3 * math.sqrt(K)
+    # accumulate flag: C += A B^T
+    out2 = ops.gemm_tn(A.to(DEV), B.to(DEV), out=out.clone(), accumulate=True)
+    assert report("gemm_tc accumulate", out2, 2 * ref - bias.double()) <= 4e-3 * math.sqrt(K)
+
+
+def test_gemm_tn_strided_views_and_3x(ops):
+    M, N, K = 500, 96, 160
+    Abuf, Bbuf = rnd(M, K + 8, seed=4).to(DEV), rnd(N, K + 4, seed=5).to(DEV)
+    Cbuf = torch.zeros(M, N + 12, device=DEV)
+    A, B = Abuf[:, :K], Bbuf[:, :K]
+    ref = A.double().cpu() @ B.double().cpu().t()
+    ops.gemm_tn(A, B, out=Cbuf[:, 4:4 + N])
+    assert report("gemm_tc strided", Cbuf[:, 4:4 + N], ref) <= 2e-3 * math.sqrt(K)
+    assert Cbuf[:, :4].abs().max() == 0 and Cbuf[:, 4 + N:].abs().max() == 0
+    out3 = ops.gemm_tn_3x(A.contiguous(), B.contiguous())
+    assert report("gemm 3xTF32", out3, ref) <= 2e-6 * math.sqrt(K) * 4
+
+
+def test_gemm_simt_debug_path_and_transpose(ops):
+    M, N, K = 200, 130, 70
+    A, B = rnd(M, K, seed=6), rnd(N, K, seed=7)
+    ops.set_debug_flags(1)
+    try:
+        out = ops.gemm_tn(A.to(DEV), B.to(DEV))
+    finally:
+        ops.set_debug_flags(0)
+    assert report("gemm_simt", out, A.double() @ B.double().t()) <= 1e-4
+    t = ops.transpose(A.to(DEV))
+    assert torch.equal(t.cpu(), A.t().contiguous())
+
+
+# ----------------------------------------------------------------------------- MaskConv pieces
+CONV_CASES = [
+    dict(B=2, Cin=1, H=8, W=10, Cout=2, k=(3, 3), s=(1, 1), p=(1, 1), lens=[10, 4]),
+    dict(B=3, Cin=1, H=161, W=61, Cout=32, k=(41, 11), s=(2, 2), p=(20, 5), lens=[31, 24, 15]),
+    dict(B=2, Cin=32, H=81, W=150, Cout=32, k=(21, 11), s=(2, 1), p=(10, 5), lens=[150, 77]),
+    dict(B=2, Cin=3, H=9, W=140, Cout=5, k=(3, 5), s=(1, 2), p=(1, 2), lens=[68, 30]),
+]
+
+
+@pytest.mark.parametrize("c", CONV_CASES)
+def test_conv2d_mask_fwd_bwd(ops, c):
+    x = rnd(c["B"], c["Cin"], c["H"], c["W"], seed=10).requires_grad_(True)
+    w = (rnd(c["Cout"], c["Cin"], *c["k"], seed=11) * 0.1).requires_grad_(True)
+    b = rnd(c["Cout"], seed=12).requires_grad_(True)
+    lens = torch.tensor(c["lens"], dtype=torch.int32)
+    y_ref = explicit.time_mask(F.conv2d(x.double(), w.double(), b.double(), stride=c["s"], padding=c["p"]), lens.long())
+    dy = rnd(*y_ref.shape, seed=13)
+    y_ref.backward(dy.double())
+    ld = lens.to(DEV)
+    y = ops.conv2d_mask_fwd(x.detach().to(DEV), w.detach().to(DEV), b.detach().to(DEV), ld, c["s"], c["p"])
+    scale = y_ref.abs().max().item()
+    assert report("conv fwd", y, y_ref.detach()) <= 2e-5 * scale
+    dx = ops.conv2d_mask_bwd_data(dy.to(DEV), w.detach().to(DEV), ld, tuple(x.shape), c["s"], c["p"])
+    assert report("conv bwd_data", dx, x.grad) <= 2e-5 * x.grad.abs().max().item()
+    dw, db = ops.conv2d_mask_bwd_weight(dy.to(DEV), x.detach().to(DEV), ld, tuple(w.shape), c["s"], c["p"])
+    assert report("conv bwd_weight", dw, w.grad) <= 5e-5 * w.grad.abs().max().item()
+    assert report("conv bwd_bias", db, b.grad) <= 5e-5 * b.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act_mask_fwd_bwd(ops, training):
+    B, C, H, W = 3, 5, 7, 40
+    lens = torch.tensor([40, 25, 9])
+    y = (rnd(B, C, H, W, seed=20) * 3 + 1)
+    y = explicit.time_mask(y, lens).requires_grad_(True)
+    gamma, beta = (rnd(C, seed=21) + 2).requires_grad_(True), rnd(C, seed=22).requires_grad_(True)
+    rm, rv = rnd(C, seed=23) * 0.1, rnd(C, seed=24).abs() + 0.5
+    yd = y.double()
+    z_ref, rm_ref, rv_ref = explicit.batch_norm(yd, gamma.double(), beta.double(), rm.double(), rv.double(), training)
+    z_ref = explicit.time_mask(torch.clamp(explicit.time_mask(z_ref, lens), 0.0, 20.0), lens)
+    dz = rnd(B, C, H, W, seed=25)
+    z_ref.backward(dz.double())
+    ld = lens.int().to(DEV)
+    rm_d, rv_d = rm.clone().to(DEV), rv.clone().to(DEV)
+    mean, invstd = ops.bn2d_stats(y.detach().to(DEV), rm_d, rv_d, training)
+    z = ops.bn_act_mask_fwd(y.detach().to(DEV), ld, mean, invstd, gamma.detach().to(DEV), beta.detach().to(DEV), True, True, 0.0, 20.0)
+    assert report("bn2d fwd", z, z_ref.detach()) <= 1e-5 * 20
+    assert report("bn2d running_mean", rm_d, rm_ref) <= 1e-6 and report("bn2d running_var", rv_d, rv_ref) <= 1e-5
+    dy, dgamma, dbeta = ops.bn_act_mask_bwd(dz.to(DEV), y.detach().to(DEV), ld, mean, invstd, gamma.detach().to(DEV),
+                                            beta.detach().to(DEV), True, True, 0.0, 20.0, training)
+    assert report("bn2d dy", dy, y.grad) <= 2e-5 * max(1.0, y.grad.abs().max().item())
+    assert report("bn2d dgamma", dgamma, gamma.grad) <= 1e-4 * max(1.0, gamma.grad.abs().max().item())
+    assert report("bn2d dbeta", dbeta, beta.grad) <= 1e-4 * max(1.0, beta.grad.abs().max().item())
+
+
+def test_layout_change_roundtrip(ops):
+    x = rnd(3, 4, 5, 37, seed=30)
+    t = ops.nchw_to_tnf(x.to(DEV))
+    ref = x.view(3, 20, 37).transpose(1, 2).transpose(0, 1).contiguous()   # deepspeech.py:135-137
+    assert torch.equal(t.cpu(), ref)
+    assert torch.equal(ops.tnf_to_nchw(t, 4, 5).cpu(), x)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_rows_fwd_bwd(ops, training):
+    R, H = 777, 44
+    x = (rnd(R, H, seed=31) * 2 + 0.5).requires_grad_(True)
+    gamma, beta = (rnd(H, seed=32) + 1.5).requires_grad_(True), rnd(H, seed=33).requires_grad_(True)
+    rm, rv = rnd(H, seed=34) * 0.1, rnd(H, seed=35).abs() + 0.5
+    y_ref, rm_ref, rv_ref = explicit.batch_norm(x.double(), gamma.double(), beta.double(), rm.double(), rv.double(), training)
+    dy = rnd(R, H, seed=36)
+    y_ref.backward(dy.double())
+    rm_d, rv_d = rm.clone().to(DEV), rv.clone().to(DEV)
+    y, mean, invstd = ops.bn_rows_fwd(x.detach().to(DEV), gamma.detach().to(DEV), beta.detach().to(DEV), rm_d, rv_d, training)
+    assert report("bn rows fwd", y, y_ref.detach()) <= 2e-5
+    assert report("bn rows rm", rm_d, rm_ref) <= 1e-6 and report("bn rows rv", rv_d, rv_ref) <= 1e-5
+    dx, dgamma, dbeta = ops.bn_rows_bwd(dy.to(DEV), x.detach().to(DEV), mean, invstd, gamma.detach().to(DEV), training)
+    assert report("bn rows dx", dx, x.grad) <= 2e-5 * max(1.0, x.grad.abs().max().item())
+    assert report("bn rows dgamma", dgamma, gamma.grad) <= 1e-4 * max(1.0, gamma.grad.abs().max().item())
+    assert report("bn rows dbeta", dbeta, beta.grad) <= 1e-4 * max(1.0, beta.grad.abs().max().item())
+    assert report("col sums", ops.col_sums(dy.to(DEV)), dy.double().sum(0)) <= 1e-4
+
+
+# ----------------------------------------------------------------------------- recurrence
+RNN_CASES = [
+    dict(cell="gru", T=7, B=3, H=16, lens=[7, 5, 2]),
+    dict(cell="lstm", T=7, B=3, H=16, lens=[7, 5, 2]),
+    dict(cell="gru", T=12, B=5, H=24, lens=[12, 12, 9, 4, 1]),
+    dict(cell="lstm", T=9, B=2, H=40, lens=[9, 6]),
+    dict(cell="gru", T=20, B=64, H=800, lens=None),
+    dict(cell="lstm", T=10, B=33, H=800, lens=None),
+    dict(cell="gru", T=6, B=128, H=160, lens=None),
+]
+
+
+def _rnn_reference(c, gi, w_hh, b_hh, lens, dout):
+    """explicit oracle: the two directions on precomputed input projections, summed; autograd for the grads."""
+    fn = explicit.gru_direction if c["cell"] == "gru" else explicit.lstm_direction
+    gi = gi.double().requires_grad_(True)
+    w = [w_hh[d].double().requires_grad_(True) for d in range(2)]
+    b = [b_hh[d].double().requires_grad_(True) for d in range(2)]
+    outs = [fn(gi[:, :, d], w[d], b[d], lens.long(), bool(d)) for d in range(2)]
+    out = outs[0] + outs[1]
+    out.backward(dout.double())
+    return out.detach(), gi.grad, [x.grad for x in w], [x.grad for x in b], [o.detach() for o in outs]
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["simt_debug", "tcgen05"])
+@pytest.mark.parametrize("c", RNN_CASES, ids=lambda c: f"{c['cell']}_T{c['T']}_B{c['B']}_H{c['H']}")
+def test_rnn_fwd_bwd(ops, c, simt):
+    T, B, H = c["T"], c["B"], c["H"]
+    if simt and H >= 800 and T > 10:
+        T = 8
+    cell = ops.GRU if c["cell"] == "gru" else ops.LSTM
+    G = (3 if c["cell"] == "gru" else 4) * H
+    lens = torch.tensor(c["lens"] if c["lens"] else sorted([max(1, T - (i * 7) % T) for i in range(B)], reverse=True),
+                        dtype=torch.int32).clamp(max=T)
+    k = 1.0 / math.sqrt(H)
+    gi = rnd(T, B, 2, G, seed=40)
+    w_hh = (torch.rand(2, G, H, generator=torch.Generator().manual_seed(41)) * 2 - 1) * k
+    b_hh = (torch.rand(2, G, generator=torch.Generator().manual_seed(42)) * 2 - 1) * k
+    dout = rnd(T, B, H, seed=43)
+    out_ref, dgi_ref, dw_ref, db_ref, dirs_ref = _rnn_reference(c, gi, w_hh, b_hh, lens, dout)
+
+    ops.set_debug_flags(2 if simt else 0)
+    try:
+        ld = lens.to(DEV)
+        pf, pb = ops.rnn_pack_weights(cell, w_hh[0].contiguous().to(DEV), w_hh[1].contiguous().to(DEV), B)
+        hseq, cseq, saved = ops.rnn_fwd(cell, gi.to(DEV), b_hh.to(DEV), pf, ld, T, B, H)
+        out = ops.rnn_sum_dirs(hseq, T, B, H)
+        torch.cuda.synchronize()
+        tol = 1e-5 if simt else 3e-3       # TF32 recurrent products feed back through T steps
+        for d in range(2):
+            assert report(f"rnn fwd dir{d}", hseq[d, 1:T + 1], dirs_ref[d]) <= tol
+        assert hseq[:, 0].abs().max() == 0 and hseq[:, T + 1].abs().max() == 0
+        assert report("rnn fwd sum", out, out_ref) <= 2 * tol
+        # zero output past each length (pad_packed_sequence semantics)
+        for bi, l in enumerate(lens.tolist()):
+            assert out[l:, bi].abs().max().item() == 0 if l < T else True
+        dgi, dgh = ops.rnn_bwd(cell, dout.to(DEV), pb, ld, hseq, cseq, saved, T, B, H)
+        torch.cuda.synchronize()
+        gscale = dgi_ref.abs().max().item()
+        assert report("rnn bwd dgi", dgi, dgi_ref) <= (2e-5 if simt else 1e-2) * gscale
+        # parameter gradients from the kernel outputs, assembled on the host in fp64
+        R = T * B
+        for d in range(2):
+            first = 0 if d == 0 else 2
+            hprev = hseq[d, first:first + T].reshape(R, H).double().cpu()
+            dw = dgh[d].reshape(R, G).double().cpu().t() @ hprev
+            assert report(f"rnn dW_hh dir{d}", dw, dw_ref[d]) <= (5e-5 if simt else 1e-2) * max(1.0, dw_ref[d].abs().max().item())
+            assert report(f"rnn db_hh dir{d}", dgh[d].reshape(R, G).double().cpu().sum(0), db_ref[d]) <= \
+                (5e-5 if simt else 1e-2) * max(1.0, db_ref[d].abs().max().item())
+    finally:
+        ops.set_debug_flags(0)
+
+
+# ----------------------------------------------------------------------------- softmax / argmax / CTC
+@pytest.mark.parametrize("R,C", [(100, 29), (33, 90), (17, 5000), (5, 1)])
+def test_log_softmax_argmax(ops, R, C):
+    x = rnd(R, C, seed=50) * 3
+    x[0, : min(C, 3)] = 7.0          # exact tie: first maximum must win (torch.max semantics)
+    xd = x.to(DEV)
+    lp, pr, am = ops.log_softmax_fwd(xd, C, want_lp=True, want_probs=True, want_argmax=True)
+    assert report("log_softmax", lp, x.double().log_softmax(-1)) <= 2e-6 * max(1.0, math.log(C))
+    assert report("softmax", pr, x.double().softmax(-1)) <= 1e-6
+    assert torch.equal(am.cpu(), torch.max(x, 1)[1])                 # bit-exact indices
+    g = rnd(R, C, seed=51)
+    ref = g.double() - x.double().softmax(-1) * g.double().sum(-1, keepdim=True)
+    assert report("log_softmax bwd", ops.log_softmax_bwd(g.to(DEV), lp), ref) <= 1e-5
+
+
+def _ctc_gpu(ops, logits, targets, in_len, tgt_len, scale=1.0):
+    lp = logits.float().log_softmax(2).contiguous().to(DEV)
+    max_u = int(tgt_len.max()) if tgt_len.numel() else 0
+    t, i, u = targets.int().to(DEV), in_len.int().to(DEV), tgt_len.int().to(DEV)
+    loss, nll, alpha = ops.ctc_fwd(lp, t, i, u, max_u)
+    grad = ops.ctc_bwd(lp, t, i, u, alpha, nll, torch.tensor([scale], device=DEV), max_u)
+    torch.cuda.synchronize()
+    return loss.cpu(), nll.cpu(), grad.cpu(), lp.cpu()
+
+
+def test_ctc_reference_golden_cases(ops, golden):
+    """the reference's own criterion (torch.nn.CTCLoss(reduction='sum')) on fixed cases incl. repeats, empty and
+    infeasible targets -- tests/golden/ctc_cases.pt"""
+    for c in golden("ctc_cases"):
+        loss, nll, grad, _ = _ctc_gpu(ops, c["logits"], c["targets"], c["input_lengths"], c["target_lengths"])
+        ref = c["nll"].double()
+        assert torch.equal(torch.isinf(nll), torch.isinf(ref))
+        fin = torch.isfinite(ref)
+        assert report("ctc nll", nll[fin], ref[fin]) <= 1e-5 * max(1.0, ref[fin].abs().max().item())
+        if c["grad_logits"] is not None:
+            assert abs(loss.item() - c["loss"].item()) <= 1e-5 * abs(c["loss"].item())
+            assert report("ctc grad", grad, c["grad_log_probs"]) <= 2e-5
+
+
+@pytest.mark.parametrize("T,N,C,U", [(50, 8, 29, 10), (120, 4, 90, 30), (64, 3, 5000, 20), (300, 2, 29, 100)])
+def test_ctc_vs_oracle(ops, T, N, C, U):
+    g = torch.Generator().manual_seed(60 + C)
+    logits = torch.randn(T, N, C, generator=g) * 2
+    in_len = torch.tensor(sorted([T - (3 * i) % (T // 3) for i in range(N)], reverse=True))
+    tgt_len = torch.tensor([max(1, U - 2 * i) for i in range(N)])
+    tgts = torch.randint(1, C, (int(tgt_len.sum()),), generator=g)
+    if U >= 10:
+        tgts[1] = tgts[0]                                            # a repeated label (needs the blank between)
+    loss, nll, grad, lp = _ctc_gpu(ops, logits, tgts, in_len, tgt_len, scale=0.25)
+    nll_ref, grad_ref = explicit.ctc(lp.double().numpy(), tgts.numpy(), in_len.numpy(), tgt_len.numpy())
+    assert report("ctc nll", nll, torch.from_numpy(nll_ref)) <= 1e-5 * nll_ref.max()
+    assert abs(loss.item() - nll_ref.sum()) <= 1e-5 * nll_ref.sum()
+    assert report("ctc grad", grad, torch.from_numpy(grad_ref) * 0.25) <= 1e-5
+    for n in range(N):
+        assert grad[int(in_len[n]):, n].abs().max().item() == 0 if in_len[n] < T else True
+
+
+# ----------------------------------------------------------------------------- spectrogram
+def test_spectrogram_vs_oracle(ops):
+    import scipy.signal
+
+    lens = [16000, 12345, 8000]
+    rng = np.random.default_rng(0)
+    t = np.linspace(0, 1, 16000, endpoint=False, dtype=np.float32)
+    waves = [np.sin(2 * np.pi * 440 * t).astype(np.float32),                 # the reference's own fixture signal
+             (rng.standard_normal(12345) * 0.1).astype(np.float32),
+             (rng.standard_normal(8000) * 0.3).astype(np.float32)]
+    wav = torch.zeros(3, 16000)
+    for i, w in enumerate(waves):
+        wav[i, : len(w)] = torch.from_numpy(w)
+    window = torch.from_numpy(scipy.signal.get_window("hamming", 320, fftbins=True)).float().to(DEV)
+    basis = ops.dft_basis(320, DEV)
+    for normalize in (False, True):
+        spec = ops.spectrogram(wav.to(DEV), torch.tensor(lens, dtype=torch.int32).to(DEV), window, basis, 320, 160, normalize)
+        assert spec.shape == (3, 1, 161, 101)
+        for i, w in enumerate(waves):
+            ref = explicit.spectrogram(w, normalize=normalize)
+            nf = ref.shape[1]
+            assert report(f"spectrogram utt{i} norm={normalize}", spec[i, 0, :, :nf], ref) <= (2e-4 if normalize else 2e-5)
+            assert spec[i, 0, :, nf:].abs().max().item() == 0 if nf < 101 else True
