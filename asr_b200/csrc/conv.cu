@@ -371,6 +371,17 @@ __global__ void transpose_batched_kernel(const float* __restrict__ in, int rows,
     }
 }
 
+// out[r][0..cols) = in[r][0..cols), out[r][cols..ld_out) = 0
+__global__ void copy_rows_padded_kernel(const float* __restrict__ in, long long ld_in, float* __restrict__ out,
+                                        long long ld_out, long long rows, int cols) {
+    const long long total = rows * ld_out;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ld_out;
+        const int c = (int)(i % ld_out);
+        out[i] = c < cols ? in[r * ld_in + c] : 0.f;
+    }
+}
+
 static int conv_dims_ok(const ConvDims& d) {
     if (d.B <= 0 || d.Cin <= 0 || d.Cout <= 0 || d.KH <= 0 || d.KW <= 0 || d.SH <= 0 || d.SW <= 0) return 0;
     if (d.Hout != (d.Hin + 2 * d.PH - d.KH) / d.SH + 1 || d.Wout != (d.Win + 2 * d.PW - d.KW) / d.SW + 1) return 0;
@@ -443,6 +454,28 @@ int asrb_conv2d_mask_bwd_weight(const float* dy, const float* x, const int32_t* 
         reduce_finalize_kernel<<<ceil_div(Cout, 128), 128, 0, stream>>>(ws, B * nsplit, Cout, 1.0, 1, 0.f, 0.f, dbias, nullptr, nullptr, nullptr);
         ASRB_LAUNCH_OK();
     }
+    return 0;
+}
+
+int asrb_copy_rows_padded(const float* in, long long ld_in, float* out, long long ld_out, long long rows, int cols,
+                          asrb_stream_t stream) {
+    ASRB_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= cols, ASRB_ERR_BAD_ARG);
+    copy_rows_padded_kernel<<<ew_grid(rows * ld_out), 256, 0, stream>>>(in, ld_in, out, ld_out, rows, cols);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* out[c] = sum over (b, h, w < lengths[b]) of a[b,c,h,w] */
+int asrb_nchw_channel_sums(const float* a, const int32_t* lengths, float* out, double* ws, size_t ws_bytes, int B, int C,
+                           int H, int W, asrb_stream_t stream) {
+    ASRB_REQUIRE(a && out && ws && B > 0 && C > 0 && H > 0 && W > 0, ASRB_ERR_BAD_ARG);
+    const int HW = H * W, nsplit = HW >= 4096 ? 4 : 1;
+    ASRB_REQUIRE(ws_bytes >= (size_t)C * B * nsplit * 2 * sizeof(double), ASRB_ERR_WORKSPACE);
+    BnAct p = {};
+    nchw_reduce_kernel<2><<<dim3(C, B * nsplit), 256, 0, stream>>>(a, nullptr, lengths, p, ws, B, C, HW, W, nsplit);
+    ASRB_LAUNCH_OK();
+    reduce_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(ws, B * nsplit, C, 1.0, 1, 0.f, 0.f, out, nullptr, nullptr, nullptr);
+    ASRB_LAUNCH_OK();
     return 0;
 }
 

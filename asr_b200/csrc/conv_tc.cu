@@ -1,0 +1,442 @@
+// asr_b200 -- 32->32-channel 2-D convolution (the DeepSpeech2 "conv2": nn.Conv2d(32, 32, (21,11), stride (2,1),
+// padding (10,5)), asr_deepspeech/modules/deepspeech.py:64) on the tcgen05 tensor cores, as an implicit GEMM with
+// no im2col buffer.  Forward, data gradient and weight gradient; time stride must be 1, channels 32/32.
+//
+// forward / dgrad ("row" kernel).  Activations are NHWC, so one pixel = 32 channels = 128 bytes = exactly one
+// row of the 128B-swizzled K-major operand layout.  For an output row (b, d) and a kernel row kh the A operand of
+// EVERY kernel column kw is the same strip of input pixels shifted by kw pixels, i.e. by kw smem rows: the strip
+// (128 + KW - 1 pixels) is fetched ONCE per kh by TMA (out-of-image pixels zero-filled = the conv padding) and the
+// KW taps are issued as tcgen05.mma with the shared-memory descriptor start address advanced by kw*128 B (matrix
+// base offset = kw & 7 keeps the swizzle phase).  M = 128 pixels, N = 32 output channels, K = 32 input channels per
+// tap, fp32 accumulation in TMEM over all KH*KW taps; 2 pixel tiles per work item share the per-kh weight tiles.
+//   dgrad is the same kernel on dy (NHWC) with the kernel-column shift reversed and only the kh of matching stride
+//   parity contributing.
+// wgrad.  dW[co,ci,kh,kw] = sum_{b,d,t} dy[b,co,d,t] * x[b,ci,d*SH+kh-PH,t+kw-PW]: K runs over time (contiguous in
+// NCHW rows), M = (kw, ci) (KW shifted TMA boxes of the same input row), N = co; one CTA per (kh, chunk of rows),
+// partial sums combined with fp32 atomics.
+#include "ptx.cuh"
+
+namespace asrb {
+
+constexpr int kCtThreads = 192;
+constexpr int kCtC = 32;                 // channels (in and out)
+constexpr int kCtStrip = 18432;          // bytes reserved per A strip (144 rows x 128 B, 1024-aligned)
+constexpr int kCtWTile = 4096;           // 32 x 32 fp32 weight tile
+
+struct ConvRowParams {
+    int B, Hs, Ws, Ho, Wo, KH, KW, SH, PH, PW, mode;   // mode 0 = forward, 1 = data gradient
+    const float* bias;
+    const int* lengths;
+    float* out;                                        // NCHW [B][32][Ho][Wo]
+    int num_items, tpairs;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_shift(uint32_t smem_addr, int shift_rows) {
+    return umma_desc_sw128(smem_addr + shift_rows * 128) | (static_cast<uint64_t>(shift_rows & 7) << 49);
+}
+
+// source row feeding output row `drow` through kernel row kh, or -1
+__device__ __forceinline__ int conv_src_row(const ConvRowParams& p, int drow, int kh) {
+    if (p.mode == 0) {
+        const int hs = drow * p.SH + kh - p.PH;
+        return (hs >= 0 && hs < p.Hs) ? hs : -1;
+    }
+    const int num = drow + p.PH - kh;
+    if (num < 0 || num % p.SH != 0) return -1;
+    const int hs = num / p.SH;
+    return hs < p.Hs ? hs : -1;
+}
+
+__global__ void __launch_bounds__(kCtThreads, 1)
+conv_row_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmW,
+                   const ConvRowParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = 2 * kCtStrip + p.KW * kCtWTile;
+    constexpr int kStages = 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tfull_bar = bars + 2 * kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    constexpr int kTmemCols = 128;        // 2 accumulator buffers x 2 pixel tiles x 32 channels
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmS);
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int strip_rows = 128 + p.KW - 1;
+    const uint32_t strip_bytes = (uint32_t)strip_rows * 128u;
+
+    auto decode = [&](int item, int& b, int& drow, int& t0, int& n_mt) {
+        const int tp = item % p.tpairs;
+        const int r = item / p.tpairs;
+        drow = r % p.Ho;
+        b = r / p.Ho;
+        t0 = tp * 256;
+        n_mt = (t0 + 128 < p.Wo) ? 2 : 1;
+    };
+    auto num_groups = [&](int drow) {
+        int n = 0;
+        for (int kh = 0; kh < p.KH; ++kh) n += conv_src_row(p, drow, kh) >= 0;
+        return n;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                int b, drow, t0, n_mt;
+                decode(item, b, drow, t0, n_mt);
+                // first source column of the strip: forward x col = t + kw - PW ; dgrad dy col = t + PW - kw
+                const int col0 = p.mode == 0 ? t0 - p.PW : t0 + p.PW - (p.KW - 1);
+                for (int kh = 0; kh < p.KH; ++kh) {
+                    const int hs = conv_src_row(p, drow, kh);
+                    if (hs < 0) continue;
+                    uint8_t* st = smem + stage * stage_bytes;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], n_mt * strip_bytes + p.KW * kCtWTile);
+                    for (int mt = 0; mt < n_mt; ++mt)
+                        tma_load_4d(st + mt * kCtStrip, &tmS, &full_bar[stage], 0, col0 + mt * 128, hs, b);
+                    for (int kw = 0; kw < p.KW; ++kw)
+                        tma_load_2d(st + 2 * kCtStrip + kw * kCtWTile, &tmW, &full_bar[stage], 0, (kh * p.KW + kw) * kCtC);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kFmtTF32, 128, kCtC);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                int b, drow, t0, n_mt;
+                decode(item, b, drow, t0, n_mt);
+                if (num_groups(drow) == 0) continue;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after_sync();
+                bool first = true;
+                for (int kh = 0; kh < p.KH; ++kh) {
+                    if (conv_src_row(p, drow, kh) < 0) continue;
+                    uint8_t* st = smem + stage * stage_bytes;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    for (int kw = 0; kw < p.KW; ++kw) {
+                        const int shift = p.mode == 0 ? kw : p.KW - 1 - kw;
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(st + 2 * kCtStrip + kw * kCtWTile));
+                        for (int mt = 0; mt < n_mt; ++mt) {
+                            const uint64_t adesc = umma_desc_sw128_shift(smem_u32(st + mt * kCtStrip), shift);
+                            const uint32_t d_tmem = tmem_base + acc * 64 + mt * 32;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, !(first && kw == 0 && k == 0));
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    first = false;
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5): thread = pixel, 32 channels in registers =====================
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            int b, drow, t0, n_mt;
+            decode(item, b, drow, t0, n_mt);
+            const bool have = num_groups(drow) > 0;
+            if (have) {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after_sync();
+            }
+            const int len = (p.mode == 0 && p.lengths) ? p.lengths[b] : p.Wo;
+            for (int mt = 0; mt < n_mt; ++mt) {
+                float v[32];
+                if (have) {
+                    tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * 64 + mt * 32, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = 0.f;
+                }
+                const int t = t0 + mt * 128 + quad * 32 + lane;
+                if (t < p.Wo) {
+                    float* o = p.out + (((size_t)b * kCtC) * p.Ho + drow) * p.Wo + t;
+                    const size_t cstride = (size_t)p.Ho * p.Wo;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float r = v[c];
+                        if (p.mode == 0) r = t < len ? r + (p.bias ? __ldg(p.bias + c) : 0.f) : 0.f;
+                        o[c * cstride] = r;
+                    }
+                }
+            }
+            if (have) {
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------
+struct ConvWgradParams {
+    int B, Hin, Win, Hout, Wout, KH, KW, SH, PH, PW;
+    int rows_per_chunk, m_tiles;
+    float* dw;                                          // [32][32][KH][KW]
+};
+
+__global__ void __launch_bounds__(kCtThreads, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                     const ConvWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = p.m_tiles * 16384;                 // m_tiles x [128 rows = 4 kernel columns x 32 ci][32 t]
+    const int stage_bytes = a_bytes + kCtWTile;            // + dy tile [32 co][32 t]
+    const int stages = (200 * 1024) / stage_bytes < 6 ? (200 * 1024) / stage_bytes : 6;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + 8;
+    uint64_t* tfull_bar = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    constexpr int kTmemCols = 128;                         // up to 4 M-tiles x 32 columns
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kh = blockIdx.x % p.KH, chunk = blockIdx.x / p.KH;
+    const int nrows = p.B * p.Hout;
+    const int r0 = chunk * p.rows_per_chunk;
+    const int r1 = min(nrows, r0 + p.rows_per_chunk);
+    const int n_kb = ceil_div(p.Wout, 32);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmDy);
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // number of (row, k-block) steps this CTA performs (rows whose input row falls outside the image are skipped)
+    int total_rows = 0;
+    for (int r = r0; r < r1; ++r) {
+        const int hi = (r % p.Hout) * p.SH + kh - p.PH;
+        total_rows += (hi >= 0 && hi < p.Hin);
+    }
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int r = r0; r < r1; ++r) {
+                const int b = r / p.Hout, ho = r % p.Hout;
+                const int hi = ho * p.SH + kh - p.PH;
+                if (hi < 0 || hi >= p.Hin) continue;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    uint8_t* st = smem + stage * stage_bytes;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.m_tiles * 4 + 1) * kCtWTile);
+                    for (int j = 0; j < p.m_tiles * 4; ++j)   // kernel column j (columns >= KW are never read back)
+                        tma_load_4d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * 32 + j - p.PW, hi, 0, b);
+                    tma_load_4d(st + a_bytes, &tmDy, &full_bar[stage], kb * 32, ho, 0, b);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && total_rows > 0) {
+            constexpr uint32_t idesc = umma_idesc(kFmtTF32, 128, kCtC);
+            int stage = 0;
+            uint32_t phase = 0;
+            const int steps = total_rows * n_kb;
+            for (int s = 0; s < steps; ++s) {
+                uint8_t* st = smem + stage * stage_bytes;
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after_sync();
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(st + a_bytes));
+                for (int mt = 0; mt < p.m_tiles; ++mt) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(st + mt * 16384));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_tf32(tmem_base + mt * 32, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull_bar);
+        }
+    } else {
+        const int quad = warp & 3;
+        if (total_rows > 0) {
+            mbar_wait(tfull_bar, 0);
+            tc_fence_after_sync();
+            for (int mt = 0; mt < p.m_tiles; ++mt) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + mt * 32, v);
+                tmem_ld_wait();
+                const int kw = mt * 4 + quad, ci = lane;     // accumulator row = (kernel column, input channel)
+                if (kw < p.KW) {
+#pragma unroll
+                    for (int co = 0; co < 32; ++co)
+                        atomicAdd(p.dw + (((size_t)co * kCtC + ci) * p.KH + kh) * p.KW + kw, v[co]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// w [32][32][KH][KW] -> fwd pack [kh][kw][co][ci], dgrad pack [kh][kw][ci][co]
+__global__ void conv_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ pf, float* __restrict__ pd,
+                                         int KH, int KW) {
+    const int total = KH * KW * 32 * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int kw = i % KW, kh = (i / KW) % KH, ci = (i / (KW * KH)) % 32, co = i / (KW * KH * 32);
+        const float v = w[i];
+        const size_t tap = (size_t)(kh * KW + kw) * 1024;
+        if (pf) pf[tap + co * 32 + ci] = v;
+        if (pd) pd[tap + ci * 32 + co] = v;
+    }
+}
+
+static int conv_row_launch(const float* src_nhwc, const float* wpack, ConvRowParams& p, asrb_stream_t stream) {
+    CUtensorMap tmS, tmW;
+    {
+        uint64_t d[4] = {32, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
+        uint64_t s[3] = {128, (uint64_t)p.Ws * 128, (uint64_t)p.Hs * p.Ws * 128};
+        uint32_t bx[4] = {32, (uint32_t)(128 + p.KW - 1), 1, 1};
+        int rc = make_tmap_f32(&tmS, src_nhwc, 4, d, s, bx);
+        if (rc) return rc;
+    }
+    {
+        uint64_t d[2] = {32, (uint64_t)p.KH * p.KW * 32}, s[1] = {128};
+        uint32_t bx[2] = {32, 32};
+        int rc = make_tmap_f32(&tmW, wpack, 2, d, s, bx);
+        if (rc) return rc;
+    }
+    p.tpairs = ceil_div(p.Wo, 256);
+    p.num_items = p.B * p.Ho * p.tpairs;
+    const size_t smem = 2 * (size_t)(2 * kCtStrip + p.KW * kCtWTile) + 1024 + 256;
+    ASRB_CUDA_OK(cudaFuncSetAttribute(conv_row_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = p.num_items < kNumSMs ? p.num_items : kNumSMs;
+    conv_row_tc_kernel<<<grid, kCtThreads, smem, stream>>>(tmS, tmW, p);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace asrb
+
+using namespace asrb;
+
+extern "C" {
+
+int asrb_conv32_supported(int Cin, int Cout, int KH, int KW, int SH, int SW, int PH, int PW) {
+    return Cin == 32 && Cout == 32 && SW == 1 && KW >= 1 && KW <= 16 && KH >= 1 && SH >= 1 && PH >= 0 && PW >= 0 &&
+           (2 * (2 * kCtStrip + KW * kCtWTile) + 2048 <= 227 * 1024);
+}
+
+int asrb_conv32_pack_weights(const float* w, float* pack_fwd, float* pack_dgrad, int KH, int KW, asrb_stream_t stream) {
+    ASRB_REQUIRE(w && (pack_fwd || pack_dgrad) && KH > 0 && KW > 0, ASRB_ERR_BAD_ARG);
+    conv_pack_weights_kernel<<<kNumSMs, 256, 0, stream>>>(w, pack_fwd, pack_dgrad, KH, KW);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* y[B,32,Hout,Wout] (NCHW) = mask(conv(x) + bias), x given as NHWC [B,Hin,Win,32], weights from asrb_conv32_pack_weights */
+int asrb_conv32_fwd(const float* x_nhwc, const float* pack_fwd, const float* bias, const int32_t* lengths, float* y,
+                    int B, int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW,
+                    asrb_stream_t stream) {
+    ASRB_REQUIRE(x_nhwc && pack_fwd && y && B > 0, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(asrb_conv32_supported(32, 32, KH, KW, SH, 1, PH, PW), ASRB_ERR_UNSUPPORTED);
+    ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
+    ConvRowParams p = {B, Hin, Win, Hout, Wout, KH, KW, SH, PH, PW, 0, bias, lengths, y, 0, 0};
+    return conv_row_launch(x_nhwc, pack_fwd, p, stream);
+}
+
+/* dx[B,32,Hin,Win] (NCHW) from dy given as NHWC [B,Hout,Wout,32] (already masked) */
+int asrb_conv32_bwd_data(const float* dy_nhwc, const float* pack_dgrad, float* dx, int B, int Hin, int Win, int Hout,
+                         int Wout, int KH, int KW, int SH, int PH, int PW, asrb_stream_t stream) {
+    ASRB_REQUIRE(dy_nhwc && pack_dgrad && dx && B > 0, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(asrb_conv32_supported(32, 32, KH, KW, SH, 1, PH, PW), ASRB_ERR_UNSUPPORTED);
+    ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
+    ConvRowParams p = {B, Hout, Wout, Hin, Win, KH, KW, SH, PH, PW, 1, nullptr, nullptr, dx, 0, 0};
+    return conv_row_launch(dy_nhwc, pack_dgrad, p, stream);
+}
+
+/* dw[32,32,KH,KW] from x (NCHW) and dy (NCHW, already masked).  ldx / lddy: row strides (elements) of the two
+ * tensors, multiples of 4 (TMA needs 16-byte strides; pad odd widths with asrb_copy_rows_padded). */
+int asrb_conv32_bwd_weight(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int Hin, int Win,
+                           int Hout, int Wout, int KH, int KW, int SH, int PH, int PW, asrb_stream_t stream) {
+    ASRB_REQUIRE(x && dy && dw && B > 0, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(asrb_conv32_supported(32, 32, KH, KW, SH, 1, PH, PW), ASRB_ERR_UNSUPPORTED);
+    ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(ldx >= Win && lddy >= Wout && ldx % 4 == 0 && lddy % 4 == 0, ASRB_ERR_ALIGNMENT);
+    CUtensorMap tmX, tmDy;
+    {
+        uint64_t d[4] = {(uint64_t)Win, (uint64_t)Hin, 32, (uint64_t)B};
+        uint64_t s[3] = {(uint64_t)ldx * 4, (uint64_t)Hin * ldx * 4, (uint64_t)32 * Hin * ldx * 4};
+        uint32_t bx[4] = {32, 1, 32, 1};
+        int rc = make_tmap_f32(&tmX, x, 4, d, s, bx);
+        if (rc) return rc;
+    }
+    {
+        uint64_t d[4] = {(uint64_t)Wout, (uint64_t)Hout, 32, (uint64_t)B};
+        uint64_t s[3] = {(uint64_t)lddy * 4, (uint64_t)Hout * lddy * 4, (uint64_t)32 * Hout * lddy * 4};
+        uint32_t bx[4] = {32, 1, 32, 1};
+        int rc = make_tmap_f32(&tmDy, dy, 4, d, s, bx);
+        if (rc) return rc;
+    }
+    ConvWgradParams p = {B, Hin, Win, Hout, Wout, KH, KW, SH, PH, PW, 0, ceil_div(KW, 4), dw};
+    int chunks = kNumSMs / KH;
+    if (chunks < 1) chunks = 1;
+    const int nrows = B * Hout;
+    if (chunks > nrows) chunks = nrows;
+    p.rows_per_chunk = ceil_div(nrows, chunks);
+    chunks = ceil_div(nrows, p.rows_per_chunk);
+    ASRB_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)32 * 32 * KH * KW * sizeof(float), stream));
+    const size_t smem = 200 * 1024 + 1024 + 256;
+    ASRB_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_wgrad_tc_kernel<<<KH * chunks, kCtThreads, smem, stream>>>(tmX, tmDy, p);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

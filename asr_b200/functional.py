@@ -59,7 +59,11 @@ class Conv2dMask(Function):
         x = x.contiguous()
         weight = weight.contiguous()
         ctx.save_for_backward(x, weight, lengths_dev)
-        ctx.conf = (stride, padding, bias is not None)
+        tc = ops.conv32_supported(weight.shape, stride, padding)
+        ctx.conf = (stride, padding, bias is not None, tc)
+        if tc:   # 32->32 channels, time stride 1: implicit GEMM on the tensor cores (NHWC source)
+            pack_f, _ = ops.conv32_pack_weights(weight, fwd=True, dgrad=False)
+            return ops.conv32_fwd(ops.nchw_to_nhwc(x), pack_f, bias, lengths_dev, weight.shape, stride, padding)
         return ops.conv2d_mask_fwd(x, weight, bias, lengths_dev, stride, padding)
 
     @staticmethod
@@ -67,9 +71,19 @@ class Conv2dMask(Function):
     @_amp_bwd
     def backward(ctx, dy):
         x, weight, lengths_dev = ctx.saved_tensors
-        stride, padding, has_bias = ctx.conf
+        stride, padding, has_bias, tc = ctx.conf
         dy = dy.contiguous()
         dx = dw = db = None
+        if tc:
+            dym = ops.mask_time(dy, lengths_dev)
+            if ctx.needs_input_grad[0]:
+                _, pack_d = ops.conv32_pack_weights(weight, fwd=False, dgrad=True)
+                dx = ops.conv32_bwd_data(ops.nchw_to_nhwc(dym), pack_d, x.shape, weight.shape, stride, padding)
+            if ctx.needs_input_grad[1]:
+                dw = ops.conv32_bwd_weight(x, dym, weight.shape, stride, padding)
+            if has_bias and ctx.needs_input_grad[2]:
+                db = ops.nchw_channel_sums(dym, None)
+            return dx, dw, db, None, None, None
         if ctx.needs_input_grad[0]:
             dx = ops.conv2d_mask_bwd_data(dy, weight, lengths_dev, x.shape, stride, padding)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):

@@ -67,7 +67,12 @@ def _call(name, *args):
     PROFILE.setdefault(name, []).append((start, end))
 
 
+DEBUG_FLAGS = 0   # bit 0: CUDA-core GEMM, bit 1: CUDA-core recurrent product, bit 2: CUDA-core conv2 (tests only)
+
+
 def set_debug_flags(flags: int):
+    global DEBUG_FLAGS
+    DEBUG_FLAGS = flags
     _lib.call("asrb_set_debug_flags", flags)
 
 
@@ -168,6 +173,95 @@ def conv2d_mask_bwd_weight(dy, x, lengths, w_shape, stride, padding, need_bias=T
     _call("asrb_conv2d_mask_bwd_weight", _p(dy), _p(x), _p(lengths), _p(dw), _p(db), _p(ws), nb, B, Cin, Hin, Win, Cout,
           Hout, Wout, KH, KW, stride[0], stride[1], padding[0], padding[1])
     return dw, db
+
+
+def conv32_supported(w_shape, stride, padding):
+    """True when the tcgen05 implicit-GEMM conv applies (32->32 channels, time stride 1)."""
+    Cout, Cin, KH, KW = w_shape
+    if DEBUG_FLAGS & 4:
+        return False
+    return bool(_lib.query("asrb_conv32_supported", Cin, Cout, KH, KW, stride[0], stride[1], padding[0], padding[1]))
+
+
+def nchw_to_nhwc(x):
+    _chk(x)
+    B, C, H, W = x.shape
+    out = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32)
+    _call("asrb_transpose_batched", _p(x), C, H * W, H * W, C * H * W, _p(out), C, H * W * C, B)
+    return out
+
+
+def pad_rows4(x):
+    """NCHW tensor whose last dim is not a multiple of 4 -> (buffer [..., W4], W4) with zero-filled padding
+    (TMA needs 16-byte row strides); returns (x, W) unchanged when already aligned."""
+    W = x.shape[-1]
+    if W % 4 == 0:
+        return x, W
+    W4 = (W + 3) // 4 * 4
+    out = torch.empty(*x.shape[:-1], W4, device=x.device, dtype=torch.float32)
+    rows = x.numel() // W
+    _call("asrb_copy_rows_padded", _p(x), W, _p(out), W4, rows, W)
+    return out, W4
+
+
+def mask_time(x, lengths):
+    """x[b, :, :, t >= lengths[b]] = 0 (a copy)."""
+    return bn_act_mask_fwd(x, lengths, None, None, None, None, False, False, 0.0, 0.0)
+
+
+def nchw_channel_sums(a, lengths):
+    _chk(a)
+    B, C, H, W = a.shape
+    out = torch.empty(C, device=a.device, dtype=torch.float32)
+    nb = _lib.query("asrb_nchw_reduce_workspace_bytes", B, C, H, W)
+    ws = torch.empty(nb // 8, device=a.device, dtype=torch.float64)
+    _call("asrb_nchw_channel_sums", _p(a), _p(lengths), _p(out), _p(ws), nb, B, C, H, W)
+    return out
+
+
+def conv32_pack_weights(w, fwd=True, dgrad=True):
+    _chk(w)
+    _, _, KH, KW = w.shape
+    pf = torch.empty(KH * KW * 1024, device=w.device, dtype=torch.float32) if fwd else None
+    pd = torch.empty(KH * KW * 1024, device=w.device, dtype=torch.float32) if dgrad else None
+    _call("asrb_conv32_pack_weights", _p(w), _p(pf), _p(pd), KH, KW)
+    return pf, pd
+
+
+def conv32_fwd(x_nhwc, pack_fwd, bias, lengths, w_shape, stride, padding):
+    _chk(x_nhwc, pack_fwd, bias)
+    B, Hin, Win, _ = x_nhwc.shape
+    _, _, KH, KW = w_shape
+    Hout, Wout = conv_out_size(Hin, KH, stride[0], padding[0]), conv_out_size(Win, KW, 1, padding[1])
+    y = torch.empty(B, 32, Hout, Wout, device=x_nhwc.device, dtype=torch.float32)
+    _call("asrb_conv32_fwd", _p(x_nhwc), _p(pack_fwd), _p(bias), _p(lengths), _p(y), B, Hin, Win, Hout, Wout, KH, KW,
+          stride[0], padding[0], padding[1])
+    return y
+
+
+def conv32_bwd_data(dy_nhwc, pack_dgrad, x_shape, w_shape, stride, padding):
+    _chk(dy_nhwc, pack_dgrad)
+    B, _, Hin, Win = x_shape
+    _, Hout, Wout, _ = dy_nhwc.shape
+    _, _, KH, KW = w_shape
+    dx = torch.empty(x_shape, device=dy_nhwc.device, dtype=torch.float32)
+    _call("asrb_conv32_bwd_data", _p(dy_nhwc), _p(pack_dgrad), _p(dx), B, Hin, Win, Hout, Wout, KH, KW, stride[0],
+          padding[0], padding[1])
+    return dx
+
+
+def conv32_bwd_weight(x, dy_masked, w_shape, stride, padding):
+    """x, dy NCHW (dy already masked) -> dw"""
+    _chk(x, dy_masked)
+    B, _, Hin, Win = x.shape
+    _, _, Hout, Wout = dy_masked.shape
+    _, _, KH, KW = w_shape
+    xp, ldx = pad_rows4(x)
+    dyp, lddy = pad_rows4(dy_masked)
+    dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
+    _call("asrb_conv32_bwd_weight", _p(xp), ldx, _p(dyp), lddy, _p(dw), B, Hin, Win, Hout, Wout, KH, KW, stride[0],
+          padding[0], padding[1])
+    return dw
 
 
 def bn2d_stats(y, running_mean, running_var, training, momentum=BN_MOMENTUM, eps=BN_EPS):

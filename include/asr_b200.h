@@ -121,6 +121,23 @@ int asrb_bn_act_mask_bwd(const float* dz, const float* y, const int32_t* lengths
 int asrb_transpose_batched(const float* in, int rows, int cols, long long ld_in, long long batch_stride_in, float* out,
                            long long ld_out, long long batch_stride_out, int nbatch, asrb_stream_t stream);
 
+int asrb_copy_rows_padded(const float* in, long long ld_in, float* out, long long ld_out, long long rows, int cols,
+                          asrb_stream_t stream);
+int asrb_nchw_channel_sums(const float* a, const int32_t* lengths, float* out, double* ws, size_t ws_bytes, int B, int C,
+                           int H, int W, asrb_stream_t stream);
+
+/* ---------------------------------------------------------------- 32->32 channel conv on tcgen05 (implicit GEMM, TF32)
+ * (deepspeech.py:64 "conv2").  Time stride 1, KW <= 16.  Activations NHWC for fwd/dgrad sources, NCHW elsewhere. */
+int asrb_conv32_supported(int Cin, int Cout, int KH, int KW, int SH, int SW, int PH, int PW);
+int asrb_conv32_pack_weights(const float* w, float* pack_fwd, float* pack_dgrad, int KH, int KW, asrb_stream_t stream);
+int asrb_conv32_fwd(const float* x_nhwc, const float* pack_fwd, const float* bias, const int32_t* lengths, float* y,
+                    int B, int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW,
+                    asrb_stream_t stream);
+int asrb_conv32_bwd_data(const float* dy_nhwc, const float* pack_dgrad, float* dx, int B, int Hin, int Win, int Hout,
+                         int Wout, int KH, int KW, int SH, int PH, int PW, asrb_stream_t stream);
+int asrb_conv32_bwd_weight(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int Hin, int Win,
+                           int Hout, int Wout, int KH, int KW, int SH, int PH, int PW, asrb_stream_t stream);
+
 /* ---------------------------------------------------------------- row-matrix kernels, x[R = T*N, cols] */
 size_t asrb_rows_workspace_bytes(int cols);
 int asrb_bn_rows_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,

@@ -73,6 +73,44 @@ def conv2d_mask_bwd_weight(dy, x, lengths, w_shape, stride, padding, need_bias=T
     return dw, (dym.sum((0, 2, 3)) if need_bias else None)
 
 
+def conv32_supported(w_shape, stride, padding):
+    return w_shape[0] == 32 and w_shape[1] == 32 and stride[1] == 1 and w_shape[3] <= 16
+
+
+def nchw_to_nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def pad_rows4(x):
+    W = x.shape[-1]
+    W4 = (W + 3) // 4 * 4
+    return (x, W) if W4 == W else (F.pad(x, (0, W4 - W)), W4)
+
+
+def mask_time(x, lengths):
+    return x * _tmask(x, lengths)
+
+
+def nchw_channel_sums(a, lengths):
+    return (a * _tmask(a, lengths)).sum((0, 2, 3))
+
+
+def conv32_pack_weights(w, fwd=True, dgrad=True):
+    return (w if fwd else None), (w if dgrad else None)
+
+
+def conv32_fwd(x_nhwc, pack_fwd, bias, lengths, w_shape, stride, padding):
+    return conv2d_mask_fwd(x_nhwc.permute(0, 3, 1, 2), pack_fwd, bias, lengths, stride, padding)
+
+
+def conv32_bwd_data(dy_nhwc, pack_dgrad, x_shape, w_shape, stride, padding):
+    return torch.nn.grad.conv2d_input(x_shape, pack_dgrad, dy_nhwc.permute(0, 3, 1, 2), stride=stride, padding=padding)
+
+
+def conv32_bwd_weight(x, dy_masked, w_shape, stride, padding):
+    return torch.nn.grad.conv2d_weight(x, w_shape, dy_masked, stride=stride, padding=padding)
+
+
 def _finalize_stats(s0, s1, count, running_mean, running_var, momentum, eps):
     mean = s0 / count
     var = (s1 / count - mean * mean).clamp_min(0)

@@ -113,6 +113,42 @@ def test_conv2d_mask_fwd_bwd(ops, c):
     assert report("conv bwd_bias", db, b.grad) <= 5e-5 * b.grad.abs().max().item()
 
 
+CONV32_CASES = [
+    dict(B=2, H=81, W=150, k=(21, 11), s=(2, 1), p=(10, 5), lens=[150, 77]),     # the DeepSpeech2 conv2 geometry
+    dict(B=1, H=81, W=501, k=(21, 11), s=(2, 1), p=(10, 5), lens=[501]),         # 2 tile pairs, ragged tail, W % 4 != 0
+    dict(B=3, H=20, W=31, k=(5, 3), s=(1, 1), p=(2, 1), lens=[31, 20, 7]),
+    dict(B=2, H=17, W=260, k=(3, 7), s=(3, 1), p=(0, 3), lens=[260, 129]),
+]
+
+
+@pytest.mark.parametrize("c", CONV32_CASES, ids=lambda c: f"H{c['H']}_W{c['W']}_k{c['k'][0]}x{c['k'][1]}")
+def test_conv32_tensor_core_fwd_bwd(ops, c):
+    """32->32 channel conv as a tcgen05 implicit GEMM (TF32 operands) vs the fp64 oracle."""
+    x = rnd(c["B"], 32, c["H"], c["W"], seed=14).requires_grad_(True)
+    w = (rnd(32, 32, *c["k"], seed=15) * 0.05).requires_grad_(True)
+    b = rnd(32, seed=16).requires_grad_(True)
+    lens = torch.tensor(c["lens"], dtype=torch.int32)
+    assert ops.conv32_supported(tuple(w.shape), c["s"], c["p"])
+    y_ref = explicit.time_mask(F.conv2d(x.double(), w.double(), b.double(), stride=c["s"], padding=c["p"]), lens.long())
+    dy = explicit.time_mask(rnd(*y_ref.shape, seed=17), lens.long())
+    y_ref.backward(dy.double())
+    K = 32 * c["k"][0] * c["k"][1]
+    ld = lens.to(DEV)
+    xd, wd = x.detach().to(DEV), w.detach().to(DEV)
+    pf, pd = ops.conv32_pack_weights(wd)
+    y = ops.conv32_fwd(ops.nchw_to_nhwc(xd), pf, b.detach().to(DEV), ld, tuple(w.shape), c["s"], c["p"])
+    torch.cuda.synchronize()
+    assert report("conv32 fwd", y, y_ref.detach()) <= 2e-3 * math.sqrt(K) * 0.05
+    dx = ops.conv32_bwd_data(ops.nchw_to_nhwc(dy.to(DEV)), pd, tuple(x.shape), tuple(w.shape), c["s"], c["p"])
+    torch.cuda.synchronize()
+    assert report("conv32 dgrad", dx, x.grad) <= 2e-3 * math.sqrt(K) * 0.05
+    dw = ops.conv32_bwd_weight(xd, dy.to(DEV), tuple(w.shape), c["s"], c["p"])
+    torch.cuda.synchronize()
+    npix = c["B"] * y_ref.shape[2] * y_ref.shape[3]
+    assert report("conv32 wgrad", dw, w.grad) <= 2e-3 * math.sqrt(npix)
+    assert report("channel sums", ops.nchw_channel_sums(dy.to(DEV), ld), b.grad) <= 1e-4 * max(1.0, b.grad.abs().max().item())
+
+
 @pytest.mark.parametrize("training", [True, False])
 def test_bn_act_mask_fwd_bwd(ops, training):
     B, C, H, W = 3, 5, 7, 40

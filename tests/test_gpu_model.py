@@ -6,7 +6,7 @@ Stated tolerances
   * CTC loss: |loss - reference| <= 1e-4 * |reference|   (BASELINE.json north_star)
   * logits / gradients, tensor-core path (TF32 operands, fp32 accumulate): gradient norms within 1 %,
     sampled entries within 2 % of the tensor's rms + 1 % of the entry;
-    debug CUDA-core path (asrb_set_debug_flags(3), fp32 everywhere): 2e-3 / 5e-3 -- the golden values are the
+    debug CUDA-core path (asrb_set_debug_flags(7), fp32 everywhere): 2e-3 / 5e-3 -- the golden values are the
     reference's own fp32 results, whose conv weight gradients (sums of ~1e4 mixed-sign terms) are themselves only
     good to ~1e-3 of their rms; the fp64 comparisons in test_gpu_kernels.py are the tight ones.
   * greedy-decode indices: bit-exact wherever the reference's top-2 probability margin exceeds 1e-3 (TF32) --
@@ -45,7 +45,7 @@ def build_model(tmp_path, g):
     return model.to(DEV), p
 
 
-@pytest.mark.parametrize("flags", [3, 0], ids=["fp32_debug", "tcgen05"])
+@pytest.mark.parametrize("flags", [7, 0], ids=["fp32_debug", "tcgen05"])
 @pytest.mark.parametrize("name", ["gru_small", "lstm_small", "lstm_c90", "cfg1_gru800x5"])
 def test_training_step_matches_reference_golden(golden, tmp_path, name, flags):
     from asr_b200 import ops

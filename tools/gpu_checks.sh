@@ -17,6 +17,7 @@ for g in $groups; do
   case $g in
     gemm)     run gemm 300 tests/test_gpu_kernels.py -k "gemm" ;;
     conv)     run conv 300 tests/test_gpu_kernels.py -k "conv2d or bn_act or layout" ;;
+    conv32)   run conv32 300 tests/test_gpu_kernels.py -k "conv32" ;;
     rows)     run rows 300 tests/test_gpu_kernels.py -k "bn_rows or log_softmax" ;;
     rnn_simt) run rnn_simt 600 tests/test_gpu_kernels.py -k "rnn and simt_debug" ;;
     rnn_tc)   run rnn_tc 300 tests/test_gpu_kernels.py -k "rnn and tcgen05" ;;
