@@ -7,12 +7,13 @@
 // EVERY kernel column kw is the same strip of input pixels shifted by kw pixels, i.e. by kw smem rows: the strip
 // (128 + KW - 1 pixels) is fetched ONCE per kh by TMA (out-of-image pixels zero-filled = the conv padding) and the
 // KW taps are issued as tcgen05.mma with the shared-memory descriptor start address advanced by kw*128 B (matrix
-// base offset = kw & 7 keeps the swizzle phase).  M = 128 pixels, N = 32 output channels, K = 32 input channels per
+// the swizzle is address-based, so no other descriptor field changes).  M = 128 pixels, N = 32 output channels, K = 32 input channels per
 // tap, fp32 accumulation in TMEM over all KH*KW taps; 2 pixel tiles per work item share the per-kh weight tiles.
 //   dgrad is the same kernel on dy (NHWC) with the kernel-column shift reversed and only the kh of matching stride
 //   parity contributing.
 // wgrad.  dW[co,ci,kh,kw] = sum_{b,d,t} dy[b,co,d,t] * x[b,ci,d*SH+kh-PH,t+kw-PW]: K runs over time (contiguous in
-// NCHW rows), M = (kw, ci) (KW shifted TMA boxes of the same input row), N = co; one CTA per (kh, chunk of rows),
+// NCHW rows), M = (kw, ci) (KW time-shifted TMA boxes of the same input row; TMA needs 16-byte aligned inner coordinates, so
+// the boxes come from 4 copies of x pre-shifted by 0..3 samples), N = co; one CTA per (kh, chunk of rows),
 // partial sums combined with fp32 atomics.
 #include "ptx.cuh"
 
@@ -31,8 +32,12 @@ struct ConvRowParams {
     int num_items, tpairs;
 };
 
+// Operand view that starts `shift_rows` pixels (128-byte rows) into a strip.  The 128B swizzle is a function of
+// the absolute shared-memory address bits (TMA writes it that way and tcgen05.mma reads it that way -- measured
+// on B200: results are exact with the descriptor's "matrix base offset" field left at 0), so advancing the start
+// address is all it takes.
 __device__ __forceinline__ uint64_t umma_desc_sw128_shift(uint32_t smem_addr, int shift_rows) {
-    return umma_desc_sw128(smem_addr + shift_rows * 128) | (static_cast<uint64_t>(shift_rows & 7) << 49);
+    return umma_desc_sw128(smem_addr + shift_rows * 128);
 }
 
 // source row feeding output row `drow` through kernel row kh, or -1
@@ -269,8 +274,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     uint8_t* st = smem + stage * stage_bytes;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.m_tiles * 4 + 1) * kCtWTile);
-                    for (int j = 0; j < p.m_tiles * 4; ++j)   // kernel column j (columns >= KW are never read back)
-                        tma_load_4d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * 32 + j - p.PW, hi, 0, b);
+                    for (int j = 0; j < p.m_tiles * 4; ++j) { // kernel column j (columns >= KW are never read back)
+                        const int off = j - p.PW;             // time shift; copy r holds x shifted left by r samples
+                        const int r = ((off % 4) + 4) % 4;
+                        tma_load_5d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * 32 + off - r, hi, 0, b, r);
+                    }
                     tma_load_4d(st + a_bytes, &tmDy, &full_bar[stage], kb * 32, ho, 0, b);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -321,6 +329,18 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// xs[r][row][w] = x[row][w + r] (zero past the end), r = 0..3, row stride ldo (multiple of 4)
+__global__ void conv_shift_copies_kernel(const float* __restrict__ x, float* __restrict__ xs, long long rows, int W, int ldo) {
+    const long long per = rows * ldo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / ldo;
+        const int w = (int)(i % ldo);
+        const float* xr = x + row * W;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xs[r * per + i] = (w + r < W) ? xr[w + r] : 0.f;
     }
 }
 
@@ -401,20 +421,34 @@ int asrb_conv32_bwd_data(const float* dy_nhwc, const float* pack_dgrad, float* d
     return conv_row_launch(dy_nhwc, pack_dgrad, p, stream);
 }
 
-/* dw[32,32,KH,KW] from x (NCHW) and dy (NCHW, already masked).  ldx / lddy: row strides (elements) of the two
- * tensors, multiples of 4 (TMA needs 16-byte strides; pad odd widths with asrb_copy_rows_padded). */
-int asrb_conv32_bwd_weight(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int Hin, int Win,
-                           int Hout, int Wout, int KH, int KW, int SH, int PH, int PW, asrb_stream_t stream) {
-    ASRB_REQUIRE(x && dy && dw && B > 0, ASRB_ERR_BAD_ARG);
+size_t asrb_conv32_bwd_weight_workspace_bytes(int B, int Hin, int Win) {
+    return (size_t)4 * B * 32 * Hin * round_up(Win, 4) * sizeof(float);
+}
+
+/* dw[32,32,KH,KW] from x (NCHW, dense) and dy (NCHW, already masked, row stride lddy = multiple of 4: TMA needs
+ * 16-byte strides; pad odd widths with asrb_copy_rows_padded).  ws: asrb_conv32_bwd_weight_workspace_bytes. */
+int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw, float* ws, size_t ws_bytes, int B,
+                           int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW,
+                           asrb_stream_t stream) {
+    ASRB_REQUIRE(x && dy && dw && ws && B > 0, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(asrb_conv32_supported(32, 32, KH, KW, SH, 1, PH, PW), ASRB_ERR_UNSUPPORTED);
     ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
-    ASRB_REQUIRE(ldx >= Win && lddy >= Wout && ldx % 4 == 0 && lddy % 4 == 0, ASRB_ERR_ALIGNMENT);
+    ASRB_REQUIRE(lddy >= Wout && lddy % 4 == 0, ASRB_ERR_ALIGNMENT);
+    ASRB_REQUIRE(ws_bytes >= asrb_conv32_bwd_weight_workspace_bytes(B, Hin, Win), ASRB_ERR_WORKSPACE);
+    const int ldx = round_up(Win, 4);
+    const long long xrows = (long long)B * 32 * Hin;
+    {
+        const long long n = xrows * ldx;
+        const int g = (int)((n + 255) / 256 < kNumSMs * 8 ? (n + 255) / 256 : kNumSMs * 8);
+        conv_shift_copies_kernel<<<g, 256, 0, stream>>>(x, ws, xrows, Win, ldx);
+        ASRB_LAUNCH_OK();
+    }
     CUtensorMap tmX, tmDy;
     {
-        uint64_t d[4] = {(uint64_t)Win, (uint64_t)Hin, 32, (uint64_t)B};
-        uint64_t s[3] = {(uint64_t)ldx * 4, (uint64_t)Hin * ldx * 4, (uint64_t)32 * Hin * ldx * 4};
-        uint32_t bx[4] = {32, 1, 32, 1};
-        int rc = make_tmap_f32(&tmX, x, 4, d, s, bx);
+        uint64_t d[5] = {(uint64_t)Win, (uint64_t)Hin, 32, (uint64_t)B, 4};
+        uint64_t s[4] = {(uint64_t)ldx * 4, (uint64_t)Hin * ldx * 4, (uint64_t)32 * Hin * ldx * 4, (uint64_t)xrows * ldx * 4};
+        uint32_t bx[5] = {32, 1, 32, 1, 1};
+        int rc = make_tmap_f32(&tmX, ws, 5, d, s, bx);
         if (rc) return rc;
     }
     {

@@ -50,7 +50,7 @@ PROFILE = None   # set to a dict to collect (start, end) CUDA-event pairs per en
 # kernels launched per call of an entry point (memsets not counted); used for the `gpu_launches` claim
 KERNELS_PER_CALL = {
     "asrb_conv2d_mask_bwd_weight": 3, "asrb_bn2d_stats": 2, "asrb_bn_act_mask_bwd": 3, "asrb_bn_rows_fwd": 3,
-    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1,
+    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_conv32_bwd_weight": 2,
 }
 
 
@@ -256,11 +256,12 @@ def conv32_bwd_weight(x, dy_masked, w_shape, stride, padding):
     B, _, Hin, Win = x.shape
     _, _, Hout, Wout = dy_masked.shape
     _, _, KH, KW = w_shape
-    xp, ldx = pad_rows4(x)
     dyp, lddy = pad_rows4(dy_masked)
     dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
-    _call("asrb_conv32_bwd_weight", _p(xp), ldx, _p(dyp), lddy, _p(dw), B, Hin, Win, Hout, Wout, KH, KW, stride[0],
-          padding[0], padding[1])
+    nb = _lib.query("asrb_conv32_bwd_weight_workspace_bytes", B, Hin, Win)
+    ws = torch.empty(nb // 4, device=x.device, dtype=torch.float32)
+    _call("asrb_conv32_bwd_weight", _p(x), _p(dyp), lddy, _p(dw), _p(ws), nb, B, Hin, Win, Hout, Wout, KH, KW,
+          stride[0], padding[0], padding[1])
     return dw
 
 
