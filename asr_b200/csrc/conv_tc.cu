@@ -13,7 +13,7 @@
 //   parity contributing.
 // wgrad.  dW[co,ci,kh,kw] = sum_{b,d,t} dy[b,co,d,t] * x[b,ci,d*SH+kh-PH,t+kw-PW]: K runs over time (contiguous in
 // NCHW rows), M = (kw, ci) (KW time-shifted TMA boxes of the same input row; TMA needs 16-byte aligned inner coordinates, so
-// the boxes come from 4 copies of x pre-shifted by 0..3 samples), N = co; one CTA per (kh, chunk of rows),
+// the boxes come from 4 copies of x delayed by 0..3 samples), N = co; one CTA per (kh, chunk of rows),
 // partial sums combined with fp32 atomics.
 #include "ptx.cuh"
 
@@ -275,9 +275,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.m_tiles * 4 + 1) * kCtWTile);
                     for (int j = 0; j < p.m_tiles * 4; ++j) { // kernel column j (columns >= KW are never read back)
-                        const int off = j - p.PW;             // time shift; copy r holds x shifted left by r samples
-                        const int r = ((off % 4) + 4) % 4;
-                        tma_load_5d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * 32 + off - r, hi, 0, b, r);
+                        const int off = j - p.PW;             // time shift; copy r holds x delayed by r samples
+                        const int r = (((-off) % 4) + 4) % 4; // so that the box start kb*32 + off + r is 16-byte aligned
+                        tma_load_5d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * 32 + off + r, hi, 0, b, r);
                     }
                     tma_load_4d(st + a_bytes, &tmDy, &full_bar[stage], kb * 32, ho, 0, b);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -332,7 +332,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
 }
 
-// xs[r][row][w] = x[row][w + r] (zero past the end), r = 0..3, row stride ldo (multiple of 4)
+// xs[r][row][w] = x[row][w - r] (zero outside the row), r = 0..3, row stride ldo >= W + 3 (multiple of 4)
 __global__ void conv_shift_copies_kernel(const float* __restrict__ x, float* __restrict__ xs, long long rows, int W, int ldo) {
     const long long per = rows * ldo;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
@@ -340,7 +340,7 @@ __global__ void conv_shift_copies_kernel(const float* __restrict__ x, float* __r
         const int w = (int)(i % ldo);
         const float* xr = x + row * W;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) xs[r * per + i] = (w + r < W) ? xr[w + r] : 0.f;
+        for (int r = 0; r < 4; ++r) xs[r * per + i] = (w - r >= 0 && w - r < W) ? xr[w - r] : 0.f;
     }
 }
 
@@ -422,7 +422,7 @@ int asrb_conv32_bwd_data(const float* dy_nhwc, const float* pack_dgrad, float* d
 }
 
 size_t asrb_conv32_bwd_weight_workspace_bytes(int B, int Hin, int Win) {
-    return (size_t)4 * B * 32 * Hin * round_up(Win, 4) * sizeof(float);
+    return (size_t)4 * B * 32 * Hin * round_up(Win + 3, 4) * sizeof(float);
 }
 
 /* dw[32,32,KH,KW] from x (NCHW, dense) and dy (NCHW, already masked, row stride lddy = multiple of 4: TMA needs
@@ -435,7 +435,7 @@ int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw,
     ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(lddy >= Wout && lddy % 4 == 0, ASRB_ERR_ALIGNMENT);
     ASRB_REQUIRE(ws_bytes >= asrb_conv32_bwd_weight_workspace_bytes(B, Hin, Win), ASRB_ERR_WORKSPACE);
-    const int ldx = round_up(Win, 4);
+    const int ldx = round_up(Win + 3, 4);
     const long long xrows = (long long)B * 32 * Hin;
     {
         const long long n = xrows * ldx;
@@ -445,7 +445,7 @@ int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw,
     }
     CUtensorMap tmX, tmDy;
     {
-        uint64_t d[5] = {(uint64_t)Win, (uint64_t)Hin, 32, (uint64_t)B, 4};
+        uint64_t d[5] = {(uint64_t)Win + 3, (uint64_t)Hin, 32, (uint64_t)B, 4};
         uint64_t s[4] = {(uint64_t)ldx * 4, (uint64_t)Hin * ldx * 4, (uint64_t)32 * Hin * ldx * 4, (uint64_t)xrows * ldx * 4};
         uint32_t bx[5] = {32, 1, 32, 1, 1};
         int rc = make_tmap_f32(&tmX, ws, 5, d, s, bx);
