@@ -9,9 +9,12 @@
 //   * its slice of W_hh (forward: NJ x gates rows of K=H; backward: NJ columns of W_hh, K=gates*H) is loaded
 //     ONCE by TMA into shared memory in the tcgen05 K-major/128B-swizzle layout and stays there;
 //   * per step it TMA-streams the previous state of ALL units (h_{t-1}: [B,H], or dgates_{t+1}: [B,G]) through
-//     a small mbarrier ring as the A operand, issues tcgen05.mma.kind::tf32 (M=128 batch rows, N=slice columns)
-//     into TMEM, and the 4 epilogue warps (one thread per batch row) apply the gate non-linearities, the
-//     sequence-length mask and write state / saved activations;
+//     an mbarrier ring as the A operand, issues tcgen05.mma (M = 64 or 128 batch rows, N = slice columns) into TMEM,
+//     and the 4 epilogue warps (one thread per batch row) apply the gate non-linearities, the sequence-length mask
+//     and write state / saved activations;
+//   * operand precision of the recurrent product: bf16 (default: kind::f16, whole previous state in flight at once,
+//     the step is latency-bound and bf16 halves both the bytes and the shared-memory footprint) or tf32 (fp32 state
+//     read directly); accumulation, gate math, stored states and all gradients are fp32 either way;
 //   * a per-direction release/acquire counter in global memory is the step barrier between CTAs.
 // Packed-sequence semantics (pack_padded_sequence / pad_packed_sequence, blocks.py:87,89): utterance b takes
 // part only while t < len[b]; outputs and states at t >= len[b] are written as zeros, which is also the correct
@@ -19,20 +22,25 @@
 //
 // State layout: hseq/cseq [2][T+2][B][H] with time slot t+1 holding step t and slots 0 / T+1 zero, so that
 // "previous step" is a pure pointer offset for both directions (used by the dW_hh GEMM as well).
+#include <cuda_bf16.h>
+
 #include "ptx.cuh"
 
 namespace asrb {
 
 constexpr int kRnnThreads = 192;
-constexpr int kRnnBM = 128;      // batch rows per MMA (TMA zero-fills rows >= B)
-constexpr int kRnnStageBytes = kRnnBM * 128;
+constexpr int kRnnMaxRows = 128;   // batch rows per CTA (one MMA M tile; TMA zero-fills rows >= B)
 constexpr int kRnnMaxSmem = 227 * 1024;
+constexpr int kRnnMaxStages = 40;
+constexpr int kRnnBarBytes = 1024;
 
 struct RnnParams {
     int T, B, H, G, P, kpad, use_simt, stages;
     const int* lengths;
     uint32_t* counters;
-    const float* wpack;  // packed weight slices (global copy, SIMT debug path)
+    const float* wpack;  // packed fp32 weight slices (global copy, SIMT debug path)
+    __nv_bfloat16* hbf;   // [2,T+2,B,H] bf16 copy of hseq (forward, bf16 mode): the next step's MMA operand
+    __nv_bfloat16* dghbf; // [2,T,B,G]  bf16 copy of dgh  (backward, bf16 mode)
     // forward
     const float* gi;     // [T,B,2,G]
     const float* b_hh;   // [2,G]
@@ -57,7 +65,11 @@ struct RnnShape {
 // weight packing: one contiguous, zero-padded [npad, kpad] K-major matrix per (direction, CTA)
 // ------------------------------------------------------------------------------------------------
 // forward : row c = gate (c / nj), unit p*nj + c % nj   ->  W_hh[dir][gate*H + unit][0..H)
-__global__ void rnn_pack_fwd_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, float* __restrict__ out,
+__device__ __forceinline__ void pack_store(float* o, float v) { *o = v; }
+__device__ __forceinline__ void pack_store(__nv_bfloat16* o, float v) { *o = __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void rnn_pack_fwd_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, OutT* __restrict__ out,
                                     int H, int gates, int nj, int P, int npad, int kpad) {
     const long long total = 2LL * P * npad * kpad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -69,11 +81,12 @@ __global__ void rnn_pack_fwd_kernel(const float* __restrict__ w_hh0, const float
         const int g = c / nj, j = p * nj + c % nj;
         float v = 0.f;
         if (g < gates && j < H && k < H) v = (dir ? w_hh1 : w_hh0)[(size_t)(g * H + j) * H + k];
-        out[i] = v;
+        pack_store(out + i, v);
     }
 }
 // backward: row c = unit p*nj + c  ->  W_hh[dir][0..G)[unit]   (a column of W_hh)
-__global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, float* __restrict__ out,
+template <typename OutT>
+__global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, OutT* __restrict__ out,
                                     int H, int G, int nj, int P, int npad, int kpad) {
     const long long total = 2LL * P * npad * kpad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -85,7 +98,7 @@ __global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float
         const int j = p * nj + c;
         float v = 0.f;
         if (c < nj && j < H && k < G) v = (dir ? w_hh1 : w_hh0)[(size_t)k * H + j];
-        out[i] = v;
+        pack_store(out + i, v);
     }
 }
 
@@ -96,26 +109,30 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int CELL, int NJ, bool BWD>
+template <int CELL, int NJ, bool BWD, bool BF16, int MROWS>
 __global__ void __launch_bounds__(kRnnThreads, 1)
 rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const RnnParams p) {
     using S = RnnShape<CELL, NJ>;
     constexpr int kGates = S::kGates;
     constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
     constexpr int kTmemCols = 64;
+    constexpr int KBE = BF16 ? 64 : 32;          // elements per 128-byte K block
+    constexpr int kStageBytes = MROWS * 128;
+    // TMEM lane of batch row m: M=128 -> m ; M=64 -> (m % 16) + 32 * (m / 16)  (half of every lane quarter)
+    constexpr int kRowsPerWarp = MROWS / 4;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int nkb = p.kpad / 32;
+    const int nkb = p.kpad / KBE;
     uint8_t* smem_w = smem;                                   // nkb x [NPAD rows x 128 B]
-    uint8_t* smem_a = smem_w + (size_t)nkb * NPAD * 128;      // stages x [128 rows x 128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * kRnnStageBytes);
+    uint8_t* smem_a = smem_w + (size_t)nkb * NPAD * 128;      // stages x [MROWS rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * kStageBytes);
     uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + 8;
-    uint64_t* w_bar = bars + 16;
-    uint64_t* tfull_bar = bars + 17;
-    uint64_t* tempty_bar = bars + 18;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* empty_bar = bars + kRnnMaxStages;
+    uint64_t* w_bar = bars + 2 * kRnnMaxStages;
+    uint64_t* tfull_bar = w_bar + 1;
+    uint64_t* tempty_bar = w_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, B = p.B, H = p.H, G = p.G, P = p.P;
@@ -150,7 +167,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         if (lane == 0 && tc) {
             mbar_arrive_expect_tx(w_bar, (uint32_t)(nkb * NPAD * 128));
             for (int kb = 0; kb < nkb; ++kb)
-                tma_load_2d(smem_w + (size_t)kb * NPAD * 128, &tmW, w_bar, kb * 32, (dir * P + pidx) * NPAD);
+                tma_load_2d(smem_w + (size_t)kb * NPAD * 128, &tmW, w_bar, kb * KBE, (dir * P + pidx) * NPAD);
             int stage = 0;
             uint32_t phase = 0;
             for (int s = 1; s < T; ++s) {
@@ -162,8 +179,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const int slab = BWD ? (dir * T + tp) : (dir * (T + 2) + tp + 1);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], kRnnStageBytes);
-                    tma_load_3d(smem_a + (size_t)stage * kRnnStageBytes, &tmA, &full_bar[stage], kb * 32, 0, slab);
+                    mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                    tma_load_3d(smem_a + (size_t)stage * kStageBytes, &tmA, &full_bar[stage], kb * KBE, 0, slab);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -171,7 +188,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0 && tc) {
-            constexpr uint32_t idesc = umma_idesc(kFmtTF32, kRnnBM, NPAD);
+            constexpr uint32_t idesc = umma_idesc(BF16 ? kFmtBF16 : kFmtTF32, MROWS, NPAD);
             mbar_wait(w_bar, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -182,10 +199,13 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after_sync();
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)stage * kRnnStageBytes));
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)stage * kStageBytes));
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + (size_t)kb * NPAD * 128));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices per 128-byte block (K=8 tf32 / K=16 bf16)
+                        if constexpr (BF16) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else                umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -195,10 +215,10 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     } else {
         // ===================== epilogue: one thread per batch row =====================
         const int quad = warp & 3;
-        const int b = quad * 32 + lane;
+        const int b = quad * kRowsPerWarp + lane;
         const int etid = (warp - 2) * 32 + lane;  // 0..127
-        const bool rowok = b < B;
-        const bool warp_has_rows = quad * 32 < B;
+        const bool rowok = lane < kRowsPerWarp && b < B;
+        const bool warp_has_rows = quad * kRowsPerWarp < B;
         const int len = rowok ? p.lengths[b] : 0;
         const size_t slotHB = (size_t)B * H;
 
@@ -215,6 +235,11 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     float* h0 = p.hseq + ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j;
                     h0[0] = 0.f;
                     h0[(size_t)(T + 1) * slotHB] = 0.f;
+                    if constexpr (BF16) {
+                        __nv_bfloat16* q0 = p.hbf + ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j;
+                        q0[0] = __float2bfloat16_rn(0.f);
+                        q0[(size_t)(T + 1) * slotHB] = __float2bfloat16_rn(0.f);
+                    }
                     if constexpr (CELL == ASRB_RNN_LSTM) {
                         float* c0 = p.cseq + ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j;
                         c0[0] = 0.f;
@@ -343,6 +368,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             }
                         }
                         hout[jj] = hn;
+                        if constexpr (BF16)
+                            p.hbf[((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + jj] = __float2bfloat16_rn(hn);
                         if constexpr (CELL == ASRB_RNN_LSTM) cout[jj] = cn;
                         sv[jj] = s0; sv[H + jj] = s1; sv[2 * H + jj] = s2; sv[3 * H + jj] = s3;
                         state_h[jj] = hn;
@@ -385,6 +412,11 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         dgi[jj] = d0; dgi[H + jj] = d1; dgi[2 * H + jj] = d2;
                         dgh[jj] = d0; dgh[H + jj] = d1; dgh[2 * H + jj] = e2;
                         if constexpr (kGates == 4) { dgi[3 * H + jj] = d3; dgh[3 * H + jj] = d3; }
+                        if constexpr (BF16) {
+                            __nv_bfloat16* q = p.dghbf + (((size_t)dir * T + t) * B + b) * G + j0 + jj;
+                            q[0] = __float2bfloat16_rn(d0); q[H] = __float2bfloat16_rn(d1); q[2 * H] = __float2bfloat16_rn(e2);
+                            if constexpr (kGates == 4) q[3 * H] = __float2bfloat16_rn(d3);
+                        }
                     }
                 }
             }
@@ -416,61 +448,72 @@ __global__ void rnn_sum_dirs_kernel(const float* __restrict__ hseq, float* __res
 }
 
 struct RnnPlan {
-    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b;
+    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, mrows, bf16;
     size_t smem_f, smem_b;
 };
 
-static int rnn_make_plan(int cell, int H, RnnPlan* pl) {
+// bf16 != 0: bf16 operands for the recurrent product (needs H % 8 == 0); else tf32 (H % 4 == 0)
+static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
     const int gates = cell == ASRB_RNN_GRU ? 3 : 4;
     const int G = gates * H;
+    const int esize = bf16 ? 2 : 4, kbe = 128 / esize;
+    if (B > kRnnMaxRows || H % (16 / esize) != 0) return ASRB_ERR_UNSUPPORTED;
+    const int mrows = B <= 64 ? 64 : 128;
+    const int stage = mrows * 128;
     const int cands[3] = {8, 12, 16};
     for (int ci = 0; ci < 3; ++ci) {
         const int nj = cands[ci];
         const int P = ceil_div(H, nj);
         if (2 * P > kNumSMs) continue;
         RnnPlan r;
-        r.nj = nj; r.P = P;
+        r.nj = nj; r.P = P; r.mrows = mrows; r.bf16 = bf16;
         r.npad_f = round_up(gates * nj, 16); r.npad_b = 16;
-        r.kpad_f = round_up(H, 32); r.kpad_b = round_up(G, 32);
-        const size_t wf = (size_t)r.npad_f * r.kpad_f * 4, wb = (size_t)r.npad_b * r.kpad_b * 4;
-        const size_t fixed = 1024 + 256;
-        if (wf + fixed + kRnnStageBytes > (size_t)kRnnMaxSmem || wb + fixed + kRnnStageBytes > (size_t)kRnnMaxSmem) continue;
-        int sf = (int)((kRnnMaxSmem - fixed - wf) / kRnnStageBytes), sb = (int)((kRnnMaxSmem - fixed - wb) / kRnnStageBytes);
-        r.stages_f = sf > 6 ? 6 : sf; r.stages_b = sb > 6 ? 6 : sb;
-        r.smem_f = wf + fixed + (size_t)r.stages_f * kRnnStageBytes;
-        r.smem_b = wb + fixed + (size_t)r.stages_b * kRnnStageBytes;
+        r.kpad_f = round_up(H, kbe); r.kpad_b = round_up(G, kbe);
+        const size_t wf = (size_t)r.npad_f * r.kpad_f * esize, wb = (size_t)r.npad_b * r.kpad_b * esize;
+        const size_t fixed = 1024 + kRnnBarBytes;
+        if (wf + fixed + stage > (size_t)kRnnMaxSmem || wb + fixed + stage > (size_t)kRnnMaxSmem) continue;
+        // as many K blocks in flight as fit (the whole previous state when possible): the step is latency-bound
+        int sf = (int)((kRnnMaxSmem - fixed - wf) / stage), sb = (int)((kRnnMaxSmem - fixed - wb) / stage);
+        const int nkb_f = r.kpad_f / kbe, nkb_b = r.kpad_b / kbe;
+        r.stages_f = sf < nkb_f ? sf : nkb_f; r.stages_b = sb < nkb_b ? sb : nkb_b;
+        if (r.stages_f > kRnnMaxStages) r.stages_f = kRnnMaxStages;
+        if (r.stages_b > kRnnMaxStages) r.stages_b = kRnnMaxStages;
+        r.smem_f = wf + fixed + (size_t)r.stages_f * stage;
+        r.smem_b = wb + fixed + (size_t)r.stages_b * stage;
         *pl = r;
         return 0;
     }
     return ASRB_ERR_UNSUPPORTED;
 }
 
-template <int CELL, int NJ, bool BWD>
-static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const float* wpack, const float* a_base, asrb_stream_t stream) {
+template <int CELL, int NJ, bool BWD, bool BF16, int MROWS>
+static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, const void* a_base, asrb_stream_t stream) {
     using S = RnnShape<CELL, NJ>;
     constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
+    constexpr int KBE = BF16 ? 64 : 32;
+    constexpr int ES = BF16 ? 2 : 4;
     const int kpad = BWD ? pl.kpad_b : pl.kpad_f;
     const size_t smem = BWD ? pl.smem_b : pl.smem_f;
     prm.kpad = kpad;
     prm.stages = BWD ? pl.stages_b : pl.stages_f;
-    prm.wpack = wpack;
+    prm.wpack = BF16 ? nullptr : reinterpret_cast<const float*>(wpack);
     CUtensorMap tmW, tmA;
     {
-        uint64_t d[2] = {(uint64_t)kpad, (uint64_t)2 * pl.P * NPAD}, s[1] = {(uint64_t)kpad * 4};
-        uint32_t bx[2] = {32, (uint32_t)NPAD};
-        int rc = make_tmap_f32(&tmW, wpack, 2, d, s, bx);
+        uint64_t d[2] = {(uint64_t)kpad, (uint64_t)2 * pl.P * NPAD}, s[1] = {(uint64_t)kpad * ES};
+        uint32_t bx[2] = {KBE, (uint32_t)NPAD};
+        int rc = BF16 ? make_tmap_bf16(&tmW, wpack, 2, d, s, bx) : make_tmap_f32(&tmW, wpack, 2, d, s, bx);
         if (rc) return rc;
     }
     {
         const int K = BWD ? prm.G : prm.H;
         const int slabs = BWD ? 2 * prm.T : 2 * (prm.T + 2);
         uint64_t d[3] = {(uint64_t)K, (uint64_t)prm.B, (uint64_t)slabs};
-        uint64_t s[2] = {(uint64_t)K * 4, (uint64_t)prm.B * K * 4};
-        uint32_t bx[3] = {32, (uint32_t)kRnnBM, 1};
-        int rc = make_tmap_f32(&tmA, a_base, 3, d, s, bx);
+        uint64_t s[2] = {(uint64_t)K * ES, (uint64_t)prm.B * K * ES};
+        uint32_t bx[3] = {KBE, (uint32_t)MROWS, 1};
+        int rc = BF16 ? make_tmap_bf16(&tmA, a_base, 3, d, s, bx) : make_tmap_f32(&tmA, a_base, 3, d, s, bx);
         if (rc) return rc;
     }
-    auto kern = rnn_rec_kernel<CELL, NJ, BWD>;
+    auto kern = rnn_rec_kernel<CELL, NJ, BWD, BF16, MROWS>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * sizeof(uint32_t), stream));
     void* args[] = {(void*)&tmW, (void*)&tmA, (void*)&prm};
@@ -479,15 +522,25 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const float* wpack, con
 }
 
 template <bool BWD>
-static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const float* wpack, const float* a_base,
+static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, const void* a_base,
                         asrb_stream_t stream) {
-#define ASRB_RNN_CASE(C, N) \
-    if (cell == C && pl.nj == N) return rnn_launch<C, N, BWD>(pl, prm, wpack, a_base, stream);
+#define ASRB_RNN_CASE(C, N)                                                                              \
+    if (cell == C && pl.nj == N) {                                                                       \
+        if (pl.bf16) {                                                                                   \
+            if (pl.mrows == 64) return rnn_launch<C, N, BWD, true, 64>(pl, prm, wpack, a_base, stream);  \
+            return rnn_launch<C, N, BWD, true, 128>(pl, prm, wpack, a_base, stream);                     \
+        }                                                                                                \
+        if (pl.mrows == 64) return rnn_launch<C, N, BWD, false, 64>(pl, prm, wpack, a_base, stream);     \
+        return rnn_launch<C, N, BWD, false, 128>(pl, prm, wpack, a_base, stream);                        \
+    }
     ASRB_RNN_CASE(ASRB_RNN_GRU, 8) ASRB_RNN_CASE(ASRB_RNN_GRU, 12) ASRB_RNN_CASE(ASRB_RNN_GRU, 16)
     ASRB_RNN_CASE(ASRB_RNN_LSTM, 8) ASRB_RNN_CASE(ASRB_RNN_LSTM, 12) ASRB_RNN_CASE(ASRB_RNN_LSTM, 16)
 #undef ASRB_RNN_CASE
     return ASRB_ERR_UNSUPPORTED;
 }
+
+// the CUDA-core debug product reads fp32 operands: it always runs the tf32-layout variant
+static inline int rnn_effective_bf16(int bf16) { return (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 0 : (bf16 ? 1 : 0); }
 
 }  // namespace asrb
 
@@ -495,68 +548,74 @@ using namespace asrb;
 
 extern "C" {
 
-int asrb_rnn_plan(int cell, int H, int B, int* nj, int* P, size_t* wpack_fwd_floats, size_t* wpack_bwd_floats) {
+int asrb_rnn_plan(int cell, int H, int B, int bf16, int* nj, int* P, size_t* wpack_fwd_bytes, size_t* wpack_bwd_bytes) {
     ASRB_REQUIRE((cell == ASRB_RNN_GRU || cell == ASRB_RNN_LSTM) && H > 0 && B > 0, ASRB_ERR_BAD_ARG);
-    ASRB_REQUIRE(H % 4 == 0 && B <= kRnnBM, ASRB_ERR_UNSUPPORTED);
     RnnPlan pl;
-    int rc = rnn_make_plan(cell, H, &pl);
+    int rc = rnn_make_plan(cell, H, B, rnn_effective_bf16(bf16), &pl);
     if (rc) return rc;
+    const size_t es = pl.bf16 ? 2 : 4;
     if (nj) *nj = pl.nj;
     if (P) *P = pl.P;
-    if (wpack_fwd_floats) *wpack_fwd_floats = (size_t)2 * pl.P * pl.npad_f * pl.kpad_f;
-    if (wpack_bwd_floats) *wpack_bwd_floats = (size_t)2 * pl.P * pl.npad_b * pl.kpad_b;
+    if (wpack_fwd_bytes) *wpack_fwd_bytes = (size_t)2 * pl.P * pl.npad_f * pl.kpad_f * es;
+    if (wpack_bwd_bytes) *wpack_bwd_bytes = (size_t)2 * pl.P * pl.npad_b * pl.kpad_b * es;
     return 0;
 }
 
-int asrb_rnn_pack_weights(int cell, int H, const float* w_hh_fwd, const float* w_hh_rev, float* wpack_fwd,
-                          float* wpack_bwd, asrb_stream_t stream) {
+int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fwd, const float* w_hh_rev,
+                          void* wpack_fwd, void* wpack_bwd, asrb_stream_t stream) {
+    ASRB_REQUIRE(w_hh_fwd && w_hh_rev, ASRB_ERR_BAD_ARG);
     RnnPlan pl;
-    int rc = rnn_make_plan(cell, H, &pl);
+    int rc = rnn_make_plan(cell, H, B, rnn_effective_bf16(bf16), &pl);
     if (rc) return rc;
     const int gates = cell == ASRB_RNN_GRU ? 3 : 4;
     if (wpack_fwd) {
-        rnn_pack_fwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, wpack_fwd, H, gates, pl.nj, pl.P, pl.npad_f, pl.kpad_f);
+        if (pl.bf16) rnn_pack_fwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_fwd, H, gates, pl.nj, pl.P, pl.npad_f, pl.kpad_f);
+        else         rnn_pack_fwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (float*)wpack_fwd, H, gates, pl.nj, pl.P, pl.npad_f, pl.kpad_f);
         ASRB_LAUNCH_OK();
     }
     if (wpack_bwd) {
-        rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
+        if (pl.bf16) rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
+        else         rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (float*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
         ASRB_LAUNCH_OK();
     }
     return 0;
 }
 
-int asrb_rnn_fwd(int cell, const float* gi, const float* b_hh, const float* wpack_fwd, const int32_t* lengths,
-                 float* hseq, float* cseq, float* saved, uint32_t* counters, int T, int B, int H, asrb_stream_t stream) {
+int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
+                 float* hseq, void* hseq_bf16, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
+                 asrb_stream_t stream) {
     ASRB_REQUIRE(gi && b_hh && wpack_fwd && lengths && hseq && saved && counters && T > 0, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(cell == ASRB_RNN_GRU || cseq, ASRB_ERR_BAD_ARG);
-    ASRB_REQUIRE(H % 4 == 0 && B <= kRnnBM, ASRB_ERR_UNSUPPORTED);
     RnnPlan pl;
-    int rc = rnn_make_plan(cell, H, &pl);
+    int rc = rnn_make_plan(cell, H, B, rnn_effective_bf16(bf16), &pl);
     if (rc) return rc;
+    ASRB_REQUIRE(!pl.bf16 || hseq_bf16, ASRB_ERR_BAD_ARG);
     RnnParams prm = {};
     prm.T = T; prm.B = B; prm.H = H; prm.G = (cell == ASRB_RNN_GRU ? 3 : 4) * H; prm.P = pl.P;
     prm.use_simt = (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 1 : 0;
     prm.lengths = lengths; prm.counters = counters;
     prm.gi = gi; prm.b_hh = b_hh; prm.hseq = hseq; prm.cseq = cseq; prm.saved = saved;
-    return rnn_dispatch<false>(cell, pl, prm, wpack_fwd, hseq, stream);
+    prm.hbf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16);
+    return rnn_dispatch<false>(cell, pl, prm, wpack_fwd, pl.bf16 ? (const void*)hseq_bf16 : (const void*)hseq, stream);
 }
 
-int asrb_rnn_bwd(int cell, const float* dout, const float* wpack_bwd, const int32_t* lengths, const float* hseq,
-                 const float* cseq, const float* saved, float* dgi, float* dgh, uint32_t* counters, int T, int B, int H,
-                 asrb_stream_t stream) {
+int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
+                 const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
+                 uint32_t* counters, int T, int B, int H, asrb_stream_t stream) {
     ASRB_REQUIRE(dout && wpack_bwd && lengths && hseq && saved && dgi && dgh && counters && T > 0, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(cell == ASRB_RNN_GRU || cseq, ASRB_ERR_BAD_ARG);
-    ASRB_REQUIRE(H % 4 == 0 && B <= kRnnBM, ASRB_ERR_UNSUPPORTED);
     RnnPlan pl;
-    int rc = rnn_make_plan(cell, H, &pl);
+    int rc = rnn_make_plan(cell, H, B, rnn_effective_bf16(bf16), &pl);
     if (rc) return rc;
+    ASRB_REQUIRE(!pl.bf16 || dgh_bf16, ASRB_ERR_BAD_ARG);
     RnnParams prm = {};
     prm.T = T; prm.B = B; prm.H = H; prm.G = (cell == ASRB_RNN_GRU ? 3 : 4) * H; prm.P = pl.P;
     prm.use_simt = (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 1 : 0;
     prm.lengths = lengths; prm.counters = counters;
     prm.hseq = const_cast<float*>(hseq); prm.cseq = const_cast<float*>(cseq); prm.saved = const_cast<float*>(saved);
     prm.dout = dout; prm.dgi = dgi; prm.dgh = dgh;
-    return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, dgh, stream);
+    prm.dghbf = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
+    return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, pl.bf16 ? (const void*)dgh_bf16 : (const void*)dgh, stream);
 }
 
 int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream) {

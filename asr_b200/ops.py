@@ -354,47 +354,60 @@ def bn_rows_bwd(dy, x, mean, invstd, gamma, training):
 
 
 # ----------------------------------------------------------------------------- recurrent layers
-def rnn_plan(cell, H, B):
+RNN_BF16 = True   # operand precision of the recurrent product: bf16 (default) or tf32; see include/asr_b200.h
+
+
+def rnn_use_bf16(H):
+    """bf16 recurrent operands need 16-byte rows of bf16 (H % 8 == 0); the CUDA-core debug path reads fp32."""
+    return bool(RNN_BF16 and H % 8 == 0 and not (DEBUG_FLAGS & 2))
+
+
+def rnn_plan(cell, H, B, bf16):
     nj, P = ctypes.c_int(), ctypes.c_int()
     wf, wb = ctypes.c_size_t(), ctypes.c_size_t()
-    _lib.call("asrb_rnn_plan", cell, H, B, ctypes.byref(nj), ctypes.byref(P), ctypes.byref(wf), ctypes.byref(wb))
+    _lib.call("asrb_rnn_plan", cell, H, B, int(bf16), ctypes.byref(nj), ctypes.byref(P), ctypes.byref(wf), ctypes.byref(wb))
     return nj.value, P.value, wf.value, wb.value
 
 
 def rnn_pack_weights(cell, w_hh_fwd, w_hh_rev, B, fwd=True, bwd=True):
     _chk(w_hh_fwd, w_hh_rev)
     H = w_hh_fwd.shape[1]
-    _, _, wf, wb = rnn_plan(cell, H, B)
-    pf = torch.empty(wf, device=w_hh_fwd.device, dtype=torch.float32) if fwd else None
-    pb = torch.empty(wb, device=w_hh_fwd.device, dtype=torch.float32) if bwd else None
-    _call("asrb_rnn_pack_weights", cell, H, _p(w_hh_fwd), _p(w_hh_rev), _p(pf), _p(pb))
+    bf16 = rnn_use_bf16(H)
+    _, _, wf, wb = rnn_plan(cell, H, B, bf16)
+    pf = torch.empty(wf, device=w_hh_fwd.device, dtype=torch.uint8) if fwd else None
+    pb = torch.empty(wb, device=w_hh_fwd.device, dtype=torch.uint8) if bwd else None
+    _call("asrb_rnn_pack_weights", cell, H, B, int(bf16), _p(w_hh_fwd), _p(w_hh_rev), _p(pf), _p(pb))
     return pf, pb
 
 
 def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
     """gi [T,B,2,G], b_hh [2,G] -> hseq [2,T+2,B,H], cseq (LSTM) or None, saved [2,T,B,4,H]"""
-    _chk(gi, b_hh, wpack_fwd)
+    _chk(gi, b_hh)
     _chk(lengths, dtype=torch.int32)
     dev = gi.device
+    bf16 = rnn_use_bf16(H)
     hseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32)
+    hbf = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.bfloat16) if bf16 else None
     cseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32) if cell == LSTM else None
     saved = torch.empty(2, T, B, 4, H, device=dev, dtype=torch.float32)
     counters = torch.empty(2, device=dev, dtype=torch.int32)
-    _call("asrb_rnn_fwd", cell, _p(gi), _p(b_hh), _p(wpack_fwd), _p(lengths), _p(hseq), _p(cseq), _p(saved),
-          _p(counters), T, B, H)
+    _call("asrb_rnn_fwd", cell, int(bf16), _p(gi), _p(b_hh), _p(wpack_fwd), _p(lengths), _p(hseq), _p(hbf), _p(cseq),
+          _p(saved), _p(counters), T, B, H)
     return hseq, cseq, saved
 
 
 def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
     """dout [T,B,H] -> dgi [T,B,2,G], dgh [2,T,B,G]"""
-    _chk(dout, wpack_bwd, hseq, cseq, saved)
+    _chk(dout, hseq, cseq, saved)
     G = (3 if cell == GRU else 4) * H
     dev = dout.device
+    bf16 = rnn_use_bf16(H)
     dgi = torch.empty(T, B, 2, G, device=dev, dtype=torch.float32)
     dgh = torch.empty(2, T, B, G, device=dev, dtype=torch.float32)
+    dghbf = torch.empty(2, T, B, G, device=dev, dtype=torch.bfloat16) if bf16 else None
     counters = torch.empty(2, device=dev, dtype=torch.int32)
-    _call("asrb_rnn_bwd", cell, _p(dout), _p(wpack_bwd), _p(lengths), _p(hseq), _p(cseq), _p(saved), _p(dgi), _p(dgh),
-          _p(counters), T, B, H)
+    _call("asrb_rnn_bwd", cell, int(bf16), _p(dout), _p(wpack_bwd), _p(lengths), _p(hseq), _p(cseq), _p(saved), _p(dgi),
+          _p(dgh), _p(dghbf), _p(counters), T, B, H)
     return dgi, dgh
 
 

@@ -69,22 +69,26 @@ int asrb_split3(const float* in, long long rows, int cols, int ld_in, float* out
                 asrb_stream_t stream);
 
 /* ---------------------------------------------------------------- recurrent layers
- * Geometry of the persistent kernel for hidden size H (nj = hidden units per CTA, P = CTAs per direction) and the
- * sizes (in floats) of the two packed-weight buffers. */
-int asrb_rnn_plan(int cell, int H, int B, int* nj, int* P, size_t* wpack_fwd_floats, size_t* wpack_bwd_floats);
+ * `bf16` selects the operand precision of the recurrent product h W_hh^T (1: bf16 weights + bf16 copy of the state,
+ * needs H % 8 == 0; 0: tf32 straight from the fp32 state, needs H % 4 == 0).  Accumulation, gate math, stored
+ * states and gradients are fp32 in both modes.  B <= 128.
+ * Geometry of the persistent kernel (nj = hidden units per CTA, P = CTAs per direction) and the sizes in BYTES of
+ * the two packed-weight buffers: */
+int asrb_rnn_plan(int cell, int H, int B, int bf16, int* nj, int* P, size_t* wpack_fwd_bytes, size_t* wpack_bwd_bytes);
 /* w_hh_*: [gates*H, H] (torch weight_hh_l0 / weight_hh_l0_reverse).  Either output may be NULL. */
-int asrb_rnn_pack_weights(int cell, int H, const float* w_hh_fwd, const float* w_hh_rev, float* wpack_fwd,
-                          float* wpack_bwd, asrb_stream_t stream);
+int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fwd, const float* w_hh_rev,
+                          void* wpack_fwd, void* wpack_bwd, asrb_stream_t stream);
 /* gi [T,B,2,G] = x W_ih^T + b_ih for both directions; b_hh [2,G]; lengths int32[B];
- * out: hseq [2,T+2,B,H] (slot t+1 = step t; slots 0,T+1 zero), cseq same (LSTM only, else NULL),
- * saved [2,T,B,4,H] (GRU: r,z,n,W_hn h+b_hn ; LSTM: i,f,g,o); counters: uint32[2] scratch. */
-int asrb_rnn_fwd(int cell, const float* gi, const float* b_hh, const float* wpack_fwd, const int32_t* lengths,
-                 float* hseq, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
+ * out: hseq [2,T+2,B,H] (slot t+1 = step t; slots 0,T+1 zero), hseq_bf16 same shape in bf16 (bf16 mode, else NULL),
+ * cseq like hseq (LSTM only, else NULL), saved [2,T,B,4,H] (GRU: r,z,n,W_hn h+b_hn ; LSTM: i,f,g,o);
+ * counters: uint32[2] scratch. */
+int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
+                 float* hseq, void* hseq_bf16, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream);
-/* dout [T,B,H] (gradient of the direction-summed output); out: dgi [T,B,2,G], dgh [2,T,B,G]. */
-int asrb_rnn_bwd(int cell, const float* dout, const float* wpack_bwd, const int32_t* lengths, const float* hseq,
-                 const float* cseq, const float* saved, float* dgi, float* dgh, uint32_t* counters, int T, int B,
-                 int H, asrb_stream_t stream);
+/* dout [T,B,H] (gradient of the direction-summed output); out: dgi [T,B,2,G], dgh [2,T,B,G], dgh_bf16 (bf16 mode). */
+int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
+                 const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
+                 uint32_t* counters, int T, int B, int H, asrb_stream_t stream);
 /* out[T,B,H] = hseq[0][1..T] + hseq[1][1..T] */
 int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream);
 

@@ -191,7 +191,11 @@ def bn_rows_bwd(dy, x, mean, invstd, gamma, training):
 
 
 # ----------------------------------------------------------------------------- recurrence (mirrors rnn.cu)
-def rnn_plan(cell, H, B):
+def rnn_use_bf16(H):
+    return False
+
+
+def rnn_plan(cell, H, B, bf16):
     return 8, (H + 7) // 8, 0, 0
 
 

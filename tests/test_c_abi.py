@@ -30,10 +30,15 @@ def test_error_contract_without_a_gpu():
     with pytest.raises(ValueError):           # NULL pointers are rejected before any CUDA call
         _lib.call("asrb_gemm_tn", None, 4, None, 4, None, 4, None, 1, 1, 4, 0, None)
     nj, P = ctypes.c_int(), ctypes.c_int()
-    _lib.call("asrb_rnn_plan", 0, 800, 64, ctypes.byref(nj), ctypes.byref(P), None, None)
-    assert 2 * P.value <= 148 and nj.value * P.value >= 800      # one CTA per SM, both directions co-resident
-    with pytest.raises(ValueError):           # hidden size that is not a multiple of 4 floats (16-byte TMA rows)
-        _lib.call("asrb_rnn_plan", 0, 801, 64, None, None, None, None)
+    for bf16 in (0, 1):
+        _lib.call("asrb_rnn_plan", 0, 800, 64, bf16, ctypes.byref(nj), ctypes.byref(P), None, None)
+        assert 2 * P.value <= 148 and nj.value * P.value >= 800  # one CTA per SM, both directions co-resident
+    with pytest.raises(ValueError):           # hidden size whose rows are not 16-byte multiples (TMA)
+        _lib.call("asrb_rnn_plan", 0, 801, 64, 0, None, None, None, None)
+    with pytest.raises(ValueError):           # fp32/tf32 LSTM-1024 slices do not fit shared memory: bf16 only
+        _lib.call("asrb_rnn_plan", 1, 1024, 128, 0, None, None, None, None)
+    _lib.call("asrb_rnn_plan", 1, 1024, 128, 1, ctypes.byref(nj), ctypes.byref(P), None, None)
+    assert 2 * P.value <= 148
     assert _lib.query("asrb_ctc_workspace_bytes", 2000, 256, 200) == 2000 * 256 * 401 * 4
 
 

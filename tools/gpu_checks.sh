@@ -20,7 +20,7 @@ for g in $groups; do
     conv32)   run conv32 300 tests/test_gpu_kernels.py -k "conv32" ;;
     rows)     run rows 300 tests/test_gpu_kernels.py -k "bn_rows or log_softmax" ;;
     rnn_simt) run rnn_simt 600 tests/test_gpu_kernels.py -k "rnn and simt_debug" ;;
-    rnn_tc)   run rnn_tc 300 tests/test_gpu_kernels.py -k "rnn and tcgen05" ;;
+    rnn_tc)   run rnn_tc 300 tests/test_gpu_kernels.py -k "rnn and (tf32 or bf16)" ;;
     ctc)      run ctc 300 tests/test_gpu_kernels.py -k "ctc" ;;
     stft)     run stft 300 tests/test_gpu_kernels.py -k "spectrogram" ;;
     model)    run model 900 tests/test_gpu_model.py ;;
