@@ -41,6 +41,7 @@ struct RnnParams {
     const float* wpack;  // packed fp32 weight slices (global copy, SIMT debug path)
     __nv_bfloat16* hbf;   // [2,T+2,B,H] bf16 copy of hseq (forward, bf16 mode): the next step's MMA operand
     __nv_bfloat16* dghbf; // [2,T,B,G]  bf16 copy of dgh  (backward, bf16 mode)
+    long long* trace;     // DEBUG: [gridDim][T][12] SM-clock stamps per step (asrb_debug_rnn_trace), else NULL
     // forward
     const float* gi;     // [T,B,2,G]
     const float* b_hh;   // [2,G]
@@ -105,6 +106,13 @@ __global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float
 // ------------------------------------------------------------------------------------------------
 // the recurrence
 // ------------------------------------------------------------------------------------------------
+long long* g_rnn_trace = nullptr;
+
+#define ASRB_TRACE(slot, step)                                                                   \
+    do {                                                                                         \
+        if (p.trace) p.trace[((size_t)blockIdx.x * p.T + (step)) * 12 + (slot)] = clock64();     \
+    } while (0)
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -174,6 +182,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const uint32_t need = (uint32_t)P * (uint32_t)s;
                 while (ld_acquire_u32(counter) < need) {
                 }
+                ASRB_TRACE(0, s);
                 fence_proxy_async();  // other CTAs' generic-proxy stores -> visible to our async-proxy (TMA) reads
                 const int tp = t_of(s - 1);
                 const int slab = BWD ? (dir * T + tp) : (dir * (T + 2) + tp + 1);
@@ -183,6 +192,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     tma_load_3d(smem_a + (size_t)stage * kStageBytes, &tmA, &full_bar[stage], kb * KBE, 0, slab);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
+                ASRB_TRACE(1, s);
             }
         }
     } else if (warp == 1) {
@@ -198,6 +208,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 tc_fence_after_sync();
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (kb == 0) ASRB_TRACE(2, s);
                     tc_fence_after_sync();
                     const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)stage * kStageBytes));
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + (size_t)kb * NPAD * 128));
@@ -210,6 +221,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tfull_bar);
+                ASRB_TRACE(3, s);
             }
         }
     } else {
@@ -252,6 +264,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int s = 0; s < T; ++s) {
             const int t = t_of(s);
             const bool active = rowok && (t < len);
+            if (etid == 0) ASRB_TRACE(4, s);
             float acc[NPAD];
 #pragma unroll
             for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
@@ -304,6 +317,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if (s > 0) {
                 if (tc) {
                     mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
+                    if (etid == 0) ASRB_TRACE(5, s);
                     tc_fence_after_sync();
                     if (warp_has_rows) {
 #pragma unroll
@@ -314,6 +328,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar);
+                    if (etid == 0) ASRB_TRACE(6, s);
                 } else {
                     // DEBUG path (asrb_set_debug_flags bit 1): same algorithm, plain fp32 dot products
                     if (etid == 0) {
@@ -422,11 +437,15 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
 
             // ---- publish this step to the other CTAs of the direction ----
+            if (etid == 0) ASRB_TRACE(7, s);
             if (tc) fence_proxy_async();
             named_bar_sync(2, 128);
             if (etid == 0) {
+                ASRB_TRACE(8, s);
                 __threadfence();
+                ASRB_TRACE(9, s);
                 red_release_add_u32(counter, 1u);
+                ASRB_TRACE(10, s);
             }
         }
     }
@@ -596,6 +615,7 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
     prm.lengths = lengths; prm.counters = counters;
     prm.gi = gi; prm.b_hh = b_hh; prm.hseq = hseq; prm.cseq = cseq; prm.saved = saved;
     prm.hbf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16);
+    prm.trace = g_rnn_trace;
     return rnn_dispatch<false>(cell, pl, prm, wpack_fwd, pl.bf16 ? (const void*)hseq_bf16 : (const void*)hseq, stream);
 }
 
@@ -615,7 +635,14 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
     prm.hseq = const_cast<float*>(hseq); prm.cseq = const_cast<float*>(cseq); prm.saved = const_cast<float*>(saved);
     prm.dout = dout; prm.dgi = dgi; prm.dgh = dgh;
     prm.dghbf = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
+    prm.trace = g_rnn_trace;
     return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, pl.bf16 ? (const void*)dgh_bf16 : (const void*)dgh, stream);
+}
+
+/* DEBUG: per-step SM-clock stamps of the next asrb_rnn_fwd / asrb_rnn_bwd launches into trace[grid][T][12] (NULL = off) */
+int asrb_debug_rnn_trace(long long* trace) {
+    g_rnn_trace = trace;
+    return 0;
 }
 
 int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream) {

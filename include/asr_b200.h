@@ -89,6 +89,7 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
                  const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
                  uint32_t* counters, int T, int B, int H, asrb_stream_t stream);
+int asrb_debug_rnn_trace(long long* trace);
 /* out[T,B,H] = hseq[0][1..T] + hseq[1][1..T] */
 int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream);
 
