@@ -35,7 +35,7 @@ constexpr int kRnnMaxStages = 40;
 constexpr int kRnnBarBytes = 1024;
 
 struct RnnParams {
-    int T, B, H, G, P, kpad, use_simt, stages;
+    int T, B, H, G, P, kpad, use_simt, stages, chunk;   // chunk = K blocks per pipeline stage / barrier
     const int* lengths;
     uint32_t* counters;
     const float* wpack;  // packed fp32 weight slices (global copy, SIMT debug path)
@@ -108,6 +108,29 @@ __global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float
 // ------------------------------------------------------------------------------------------------
 long long* g_rnn_trace = nullptr;
 
+// fast gate non-linearities (ex2.approx + approximate division): ~1e-6 absolute error
+__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+__device__ __forceinline__ void ld4(float* dst, const float* src) {
+    const float4 t = *reinterpret_cast<const float4*>(src);
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+}
+__device__ __forceinline__ void ldg4(float* dst, const float* src) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+}
+__device__ __forceinline__ void st4(float* dst, const float* v) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* dst, const float* v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst) = u;
+}
+
 #define ASRB_TRACE(slot, step)                                                                   \
     do {                                                                                         \
         if (p.trace) p.trace[((size_t)blockIdx.x * p.T + (step)) * 12 + (slot)] = clock64();     \
@@ -133,8 +156,11 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nkb = p.kpad / KBE;
     uint8_t* smem_w = smem;                                   // nkb x [NPAD rows x 128 B]
-    uint8_t* smem_a = smem_w + (size_t)nkb * NPAD * 128;      // stages x [MROWS rows x 128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * kStageBytes);
+    uint8_t* smem_a = smem_w + (size_t)nkb * NPAD * 128;      // stages x chunk x [MROWS rows x 128 B]
+    const int stage_bytes = p.chunk * kStageBytes;
+    const int nchunks = ceil_div(nkb, p.chunk);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * stage_bytes);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 704);   // [kGates][NJ] (forward)
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kRnnMaxStages;
     uint64_t* w_bar = bars + 2 * kRnnMaxStages;
@@ -186,10 +212,14 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 fence_proxy_async();  // other CTAs' generic-proxy stores -> visible to our async-proxy (TMA) reads
                 const int tp = t_of(s - 1);
                 const int slab = BWD ? (dir * T + tp) : (dir * (T + 2) + tp + 1);
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int c = 0; c < nchunks; ++c) {
+                    const int kb0 = c * p.chunk;
+                    const int nblk = min(p.chunk, nkb - kb0);
+                    uint8_t* st = smem_a + (size_t)stage * stage_bytes;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-                    tma_load_3d(smem_a + (size_t)stage * kStageBytes, &tmA, &full_bar[stage], kb * KBE, 0, slab);
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nblk * kStageBytes));
+                    for (int i = 0; i < nblk; ++i)
+                        tma_load_3d(st + (size_t)i * kStageBytes, &tmA, &full_bar[stage], (kb0 + i) * KBE, 0, slab);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 ASRB_TRACE(1, s);
@@ -206,16 +236,21 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const uint32_t it = (uint32_t)(s - 1);
                 mbar_wait(tempty_bar, (it & 1) ^ 1);
                 tc_fence_after_sync();
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int c = 0; c < nchunks; ++c) {
+                    const int kb0 = c * p.chunk;
+                    const int nblk = min(p.chunk, nkb - kb0);
+                    uint8_t* st = smem_a + (size_t)stage * stage_bytes;
                     mbar_wait(&full_bar[stage], phase);
-                    if (kb == 0) ASRB_TRACE(2, s);
+                    if (c == 0) ASRB_TRACE(2, s);
                     tc_fence_after_sync();
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)stage * kStageBytes));
-                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + (size_t)kb * NPAD * 128));
+                    for (int i = 0; i < nblk; ++i) {
+                        const uint64_t adesc = umma_desc_sw128(smem_u32(st + (size_t)i * kStageBytes));
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + (size_t)(kb0 + i) * NPAD * 128));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices per 128-byte block (K=8 tf32 / K=16 bf16)
-                        if constexpr (BF16) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                        else                umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices per 128-byte block (K=8 tf32 / K=16 bf16)
+                            if constexpr (BF16) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                            else                umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -261,6 +296,18 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
         }
 
+        constexpr int NV = NJ / 4;               // 4-wide groups: all global traffic is 16-byte vectors
+        bool gvalid[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) gvalid[v] = j0 + 4 * v < H;
+        if constexpr (!BWD) {                    // recurrent biases of our slice -> shared memory (broadcast reads)
+            for (int i = etid; i < kGates * NJ; i += 128) {
+                const int g = i / NJ, jj = i % NJ;
+                s_bias[i] = (j0 + jj < H) ? p.b_hh[(size_t)dir * G + g * H + j0 + jj] : 0.f;
+            }
+            named_bar_sync(3, 128);
+        }
+
         for (int s = 0; s < T; ++s) {
             const int t = t_of(s);
             const bool active = rowok && (t < len);
@@ -269,48 +316,47 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
 
-            // ---- operand prefetch (independent of the MMA) ----
-            float in0[NJ], in1[NJ], in2[NJ], in3[NJ], in4[NJ], in5[NJ];
+            // ---- operand prefetch (independent of the MMA): issued before we wait for the accumulator ----
+            float in[6][NJ];
 #pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) in0[jj] = in1[jj] = in2[jj] = in3[jj] = in4[jj] = in5[jj] = 0.f;
+            for (int q = 0; q < 6; ++q)
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) in[q][jj] = 0.f;
             if (active) {
                 if constexpr (!BWD) {
                     const float* g = p.gi + (((size_t)t * B + b) * 2 + dir) * G + j0;
 #pragma unroll
-                    for (int jj = 0; jj < NJ; ++jj)
-                        if (j0 + jj < H) {
-                            in0[jj] = __ldg(g + jj);
-                            in1[jj] = __ldg(g + H + jj);
-                            in2[jj] = __ldg(g + 2 * H + jj);
-                            if constexpr (kGates == 4) in3[jj] = __ldg(g + 3 * H + jj);
+                    for (int v = 0; v < NV; ++v)
+                        if (gvalid[v]) {
+#pragma unroll
+                            for (int q = 0; q < kGates; ++q) ldg4(&in[q][4 * v], g + (size_t)q * H + 4 * v);
                         }
                 } else {
                     const float* sv = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0;
                     const float* dop = p.dout + ((size_t)t * B + b) * H + j0;
                     const int tprev_slot = (dir == 0) ? t : t + 2;  // slot of the step that preceded t in forward order
-                    const float* hp = p.hseq + ((size_t)dir * (T + 2) + tprev_slot) * slotHB + (size_t)b * H + j0;
+                    const float* prevp = (CELL == ASRB_RNN_GRU ? p.hseq : p.cseq) +
+                                         ((size_t)dir * (T + 2) + tprev_slot) * slotHB + (size_t)b * H + j0;
 #pragma unroll
-                    for (int jj = 0; jj < NJ; ++jj)
-                        if (j0 + jj < H) {
-                            in0[jj] = sv[jj];
-                            in1[jj] = sv[H + jj];
-                            in2[jj] = sv[2 * H + jj];
-                            in3[jj] = sv[3 * H + jj];
-                            in4[jj] = dop[jj];
-                            if constexpr (CELL == ASRB_RNN_GRU) {
-                                in5[jj] = hp[jj];
-                            } else {
-                                in5[jj] = p.cseq[((size_t)dir * (T + 2) + tprev_slot) * slotHB + (size_t)b * H + j0 + jj];
-                            }
+                    for (int v = 0; v < NV; ++v)
+                        if (gvalid[v]) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) ld4(&in[q][4 * v], sv + (size_t)q * H + 4 * v);
+                            ldg4(&in[4][4 * v], dop + 4 * v);
+                            ld4(&in[5][4 * v], prevp + 4 * v);
                         }
                 }
             }
             float ct[NJ];  // bwd LSTM: c_t
-            if constexpr (BWD && CELL == ASRB_RNN_LSTM) {
 #pragma unroll
-                for (int jj = 0; jj < NJ; ++jj)
-                    ct[jj] = (active && j0 + jj < H)
-                                 ? p.cseq[((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + jj] : 0.f;
+            for (int jj = 0; jj < NJ; ++jj) ct[jj] = 0.f;
+            if constexpr (BWD && CELL == ASRB_RNN_LSTM) {
+                if (active) {
+                    const float* cp = p.cseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        if (gvalid[v]) ld4(&ct[4 * v], cp + 4 * v);
+                }
             }
 
             // ---- recurrent product for this step ----
@@ -352,87 +398,97 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
             }
 
-            // ---- cell math ----
+            // ---- cell math (registers only), then 16-byte vector stores ----
             if constexpr (!BWD) {
-                float* hout = p.hseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0;
-                float* cout = (CELL == ASRB_RNN_LSTM) ? p.cseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 : nullptr;
-                float* sv = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0;
-                const float* bh = p.b_hh + (size_t)dir * G + j0;
+                float hn[NJ], cn[NJ], sv[4][NJ];
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) {
-                    if (rowok && j0 + jj < H) {
-                        float hn = 0.f, cn = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                        if (active) {
-                            if constexpr (CELL == ASRB_RNN_GRU) {
-                                const float gr = acc[jj] + __ldg(bh + jj);
-                                const float gz = acc[NJ + jj] + __ldg(bh + H + jj);
-                                const float gn = acc[2 * NJ + jj] + __ldg(bh + 2 * H + jj);
-                                const float r = sigmoidf_(in0[jj] + gr);
-                                const float z = sigmoidf_(in1[jj] + gz);
-                                const float n = tanhf_(in2[jj] + r * gn);
-                                hn = (1.f - z) * n + z * state_h[jj];
-                                s0 = r; s1 = z; s2 = n; s3 = gn;
-                            } else {
-                                const float gi_ = sigmoidf_(in0[jj] + acc[jj] + __ldg(bh + jj));
-                                const float gf = sigmoidf_(in1[jj] + acc[NJ + jj] + __ldg(bh + H + jj));
-                                const float gg = tanhf_(in2[jj] + acc[2 * NJ + jj] + __ldg(bh + 2 * H + jj));
-                                const float go = sigmoidf_(in3[jj] + acc[(kGates - 1) * NJ + jj] + __ldg(bh + 3 * H + jj));
-                                cn = gf * state_c[jj] + gi_ * gg;
-                                hn = go * tanhf_(cn);
-                                s0 = gi_; s1 = gf; s2 = gg; s3 = go;
-                            }
+                    float h_ = 0.f, c_ = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    if (active) {
+                        if constexpr (CELL == ASRB_RNN_GRU) {
+                            const float gr = acc[jj] + s_bias[jj];
+                            const float gz = acc[NJ + jj] + s_bias[NJ + jj];
+                            const float gn = acc[2 * NJ + jj] + s_bias[2 * NJ + jj];
+                            const float r = fsigmoid(in[0][jj] + gr);
+                            const float z = fsigmoid(in[1][jj] + gz);
+                            const float n = ftanh(in[2][jj] + r * gn);
+                            h_ = (1.f - z) * n + z * state_h[jj];
+                            s0 = r; s1 = z; s2 = n; s3 = gn;
+                        } else {
+                            const float gi_ = fsigmoid(in[0][jj] + acc[jj] + s_bias[jj]);
+                            const float gf = fsigmoid(in[1][jj] + acc[NJ + jj] + s_bias[NJ + jj]);
+                            const float gg = ftanh(in[2][jj] + acc[2 * NJ + jj] + s_bias[2 * NJ + jj]);
+                            const float go = fsigmoid(in[3][jj] + acc[(kGates - 1) * NJ + jj] + s_bias[(kGates - 1) * NJ + jj]);
+                            c_ = gf * state_c[jj] + gi_ * gg;
+                            h_ = go * ftanh(c_);
+                            s0 = gi_; s1 = gf; s2 = gg; s3 = go;
                         }
-                        hout[jj] = hn;
-                        if constexpr (BF16)
-                            p.hbf[((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + jj] = __float2bfloat16_rn(hn);
-                        if constexpr (CELL == ASRB_RNN_LSTM) cout[jj] = cn;
-                        sv[jj] = s0; sv[H + jj] = s1; sv[2 * H + jj] = s2; sv[3 * H + jj] = s3;
-                        state_h[jj] = hn;
-                        state_c[jj] = cn;
                     }
+                    hn[jj] = h_; cn[jj] = c_;
+                    sv[0][jj] = s0; sv[1][jj] = s1; sv[2][jj] = s2; sv[3][jj] = s3;
+                    state_h[jj] = h_;
+                    state_c[jj] = c_;
+                }
+                if (rowok) {
+                    const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0;
+                    float* svp = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        if (gvalid[v]) {
+                            st4(p.hseq + o + 4 * v, &hn[4 * v]);
+                            if constexpr (BF16) st4_bf16(p.hbf + o + 4 * v, &hn[4 * v]);
+                            if constexpr (CELL == ASRB_RNN_LSTM) st4(p.cseq + o + 4 * v, &cn[4 * v]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) st4(svp + (size_t)q * H + 4 * v, &sv[q][4 * v]);
+                        }
                 }
             } else {
-                float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0;
-                float* dgh = p.dgh + (((size_t)dir * T + t) * B + b) * G + j0;
+                float dg[4][NJ], eg2[NJ];
 #pragma unroll
                 for (int jj = 0; jj < NJ; ++jj) {
-                    if (rowok && j0 + jj < H) {
-                        const float carry = acc[jj] + state_h[jj];
-                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, e2 = 0.f;
-                        if (active) {
-                            const float dh = carry + in4[jj];
-                            if constexpr (CELL == ASRB_RNN_GRU) {
-                                const float r = in0[jj], z = in1[jj], n = in2[jj], gn = in3[jj], hp = in5[jj];
-                                const float dn = dh * (1.f - z) * (1.f - n * n);
-                                d2 = dn;                          // d gi_n
-                                e2 = dn * r;                      // d gh_n
-                                d1 = dh * (hp - n) * z * (1.f - z);
-                                d0 = dn * gn * r * (1.f - r);
-                                state_h[jj] = dh * z;
-                            } else {
-                                const float gi_ = in0[jj], gf = in1[jj], gg = in2[jj], go = in3[jj], cp = in5[jj];
-                                const float tcv = tanhf_(ct[jj]);
-                                const float dc = state_c[jj] + dh * go * (1.f - tcv * tcv);
-                                d0 = dc * gg * gi_ * (1.f - gi_);
-                                d1 = dc * cp * gf * (1.f - gf);
-                                d2 = dc * gi_ * (1.f - gg * gg);
-                                d3 = dh * tcv * go * (1.f - go);
-                                e2 = d2;
-                                state_c[jj] = dc * gf;
-                                state_h[jj] = 0.f;
-                            }
+                    const float carry = acc[jj] + state_h[jj];
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, e2 = 0.f;
+                    if (active) {
+                        const float dh = carry + in[4][jj];
+                        if constexpr (CELL == ASRB_RNN_GRU) {
+                            const float r = in[0][jj], z = in[1][jj], n = in[2][jj], gn = in[3][jj], hp = in[5][jj];
+                            const float dn = dh * (1.f - z) * (1.f - n * n);
+                            d2 = dn;                          // d gi_n
+                            e2 = dn * r;                      // d gh_n
+                            d1 = dh * (hp - n) * z * (1.f - z);
+                            d0 = dn * gn * r * (1.f - r);
+                            state_h[jj] = dh * z;
                         } else {
-                            state_h[jj] = carry;  // gradient passes an inactive step untouched
+                            const float gi_ = in[0][jj], gf = in[1][jj], gg = in[2][jj], go = in[3][jj], cp = in[5][jj];
+                            const float tcv = ftanh(ct[jj]);
+                            const float dc = state_c[jj] + dh * go * (1.f - tcv * tcv);
+                            d0 = dc * gg * gi_ * (1.f - gi_);
+                            d1 = dc * cp * gf * (1.f - gf);
+                            d2 = dc * gi_ * (1.f - gg * gg);
+                            d3 = dh * tcv * go * (1.f - go);
+                            e2 = d2;
+                            state_c[jj] = dc * gf;
+                            state_h[jj] = 0.f;
                         }
-                        dgi[jj] = d0; dgi[H + jj] = d1; dgi[2 * H + jj] = d2;
-                        dgh[jj] = d0; dgh[H + jj] = d1; dgh[2 * H + jj] = e2;
-                        if constexpr (kGates == 4) { dgi[3 * H + jj] = d3; dgh[3 * H + jj] = d3; }
-                        if constexpr (BF16) {
-                            __nv_bfloat16* q = p.dghbf + (((size_t)dir * T + t) * B + b) * G + j0 + jj;
-                            q[0] = __float2bfloat16_rn(d0); q[H] = __float2bfloat16_rn(d1); q[2 * H] = __float2bfloat16_rn(e2);
-                            if constexpr (kGates == 4) q[3 * H] = __float2bfloat16_rn(d3);
-                        }
+                    } else {
+                        state_h[jj] = carry;  // gradient passes an inactive step untouched
                     }
+                    dg[0][jj] = d0; dg[1][jj] = d1; dg[2][jj] = d2; dg[3][jj] = d3; eg2[jj] = e2;
+                }
+                if (rowok) {
+                    float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0;
+                    const size_t oh = (((size_t)dir * T + t) * B + b) * G + j0;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        if (gvalid[v]) {
+#pragma unroll
+                            for (int q = 0; q < kGates; ++q) {
+                                const float* hv = (q == 2) ? &eg2[4 * v] : &dg[q][4 * v];
+                                st4(dgi + (size_t)q * H + 4 * v, &dg[q][4 * v]);
+                                st4(p.dgh + oh + (size_t)q * H + 4 * v, hv);
+                                if constexpr (BF16) st4_bf16(p.dghbf + oh + (size_t)q * H + 4 * v, hv);
+                            }
+                        }
                 }
             }
 
@@ -442,9 +498,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             named_bar_sync(2, 128);
             if (etid == 0) {
                 ASRB_TRACE(8, s);
-                __threadfence();
-                ASRB_TRACE(9, s);
-                red_release_add_u32(counter, 1u);
+                red_release_add_u32(counter, 1u);   // release: orders the CTA's stores (observed through the barrier)
                 ASRB_TRACE(10, s);
             }
         }
@@ -467,7 +521,7 @@ __global__ void rnn_sum_dirs_kernel(const float* __restrict__ hseq, float* __res
 }
 
 struct RnnPlan {
-    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, mrows, bf16;
+    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, chunk_f, chunk_b, mrows, bf16;
     size_t smem_f, smem_b;
 };
 
@@ -492,13 +546,19 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
         const size_t fixed = 1024 + kRnnBarBytes;
         if (wf + fixed + stage > (size_t)kRnnMaxSmem || wb + fixed + stage > (size_t)kRnnMaxSmem) continue;
         // as many K blocks in flight as fit (the whole previous state when possible): the step is latency-bound
-        int sf = (int)((kRnnMaxSmem - fixed - wf) / stage), sb = (int)((kRnnMaxSmem - fixed - wb) / stage);
+        // K blocks that fit next to the resident weights; up to 4 blocks share one barrier / pipeline stage
+        const int bf = (int)((kRnnMaxSmem - fixed - wf) / stage), bb = (int)((kRnnMaxSmem - fixed - wb) / stage);
         const int nkb_f = r.kpad_f / kbe, nkb_b = r.kpad_b / kbe;
-        r.stages_f = sf < nkb_f ? sf : nkb_f; r.stages_b = sb < nkb_b ? sb : nkb_b;
+        r.chunk_f = bf >= 8 ? 4 : (bf >= 4 ? 2 : 1);
+        r.chunk_b = bb >= 8 ? 4 : (bb >= 4 ? 2 : 1);
+        r.stages_f = bf / r.chunk_f; r.stages_b = bb / r.chunk_b;
+        const int cf = ceil_div(nkb_f, r.chunk_f), cb = ceil_div(nkb_b, r.chunk_b);
+        if (r.stages_f > cf) r.stages_f = cf;
+        if (r.stages_b > cb) r.stages_b = cb;
         if (r.stages_f > kRnnMaxStages) r.stages_f = kRnnMaxStages;
         if (r.stages_b > kRnnMaxStages) r.stages_b = kRnnMaxStages;
-        r.smem_f = wf + fixed + (size_t)r.stages_f * stage;
-        r.smem_b = wb + fixed + (size_t)r.stages_b * stage;
+        r.smem_f = wf + fixed + (size_t)r.stages_f * r.chunk_f * stage;
+        r.smem_b = wb + fixed + (size_t)r.stages_b * r.chunk_b * stage;
         *pl = r;
         return 0;
     }
@@ -515,6 +575,7 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
     const size_t smem = BWD ? pl.smem_b : pl.smem_f;
     prm.kpad = kpad;
     prm.stages = BWD ? pl.stages_b : pl.stages_f;
+    prm.chunk = BWD ? pl.chunk_b : pl.chunk_f;
     prm.wpack = BF16 ? nullptr : reinterpret_cast<const float*>(wpack);
     CUtensorMap tmW, tmA;
     {
