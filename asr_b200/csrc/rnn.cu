@@ -28,7 +28,8 @@
 
 namespace asrb {
 
-constexpr int kRnnThreads = 192;
+constexpr int kRnnThreads = 320;   // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two warps per TMEM lane quarter)
+constexpr int kRnnEpiThreads = 256;
 constexpr int kRnnMaxRows = 128;   // batch rows per CTA (one MMA M tile; TMA zero-fills rows >= B)
 constexpr int kRnnMaxSmem = 227 * 1024;
 constexpr int kRnnMaxStages = 40;
@@ -187,7 +188,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         }
         mbar_init(w_bar, 1);
         mbar_init(tfull_bar, 1);
-        mbar_init(tempty_bar, 4);
+        mbar_init(tempty_bar, 8);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -260,85 +261,89 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue: one thread per batch row =====================
+        // ===================== epilogue: thread = (batch row, half of the slice's hidden units) =====================
+        // Two warps share each TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31) and split the columns.
+        constexpr int NV = NJ / 4;               // 4-wide unit groups of the slice: all global traffic is 16-byte vectors
+        constexpr int NVH = (NV + 1) / 2;        // groups per thread
+        constexpr int NJH = 4 * NVH;             // units per thread
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int b = quad * kRowsPerWarp + lane;
-        const int etid = (warp - 2) * 32 + lane;  // 0..127
+        const int etid = (warp - 2) * 32 + lane;  // 0..255
         const bool rowok = lane < kRowsPerWarp && b < B;
         const bool warp_has_rows = quad * kRowsPerWarp < B;
         const int len = rowok ? p.lengths[b] : 0;
         const size_t slotHB = (size_t)B * H;
-
-        float state_h[NJ];   // fwd: h_{prev}[b, j0..] ; bwd: direct dh carry
-        float state_c[NJ];   // fwd LSTM: c_prev ; bwd LSTM: dc carry
+        const int u0 = half * NJH;               // first unit (within the slice) owned by this thread
+        bool gvalid[NVH];
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) state_h[jj] = state_c[jj] = 0.f;
+        for (int v = 0; v < NVH; ++v) gvalid[v] = (half * NVH + v < NV) && (j0 + u0 + 4 * v < H);
 
-        if (!BWD && rowok) {  // zero boundary slots 0 and T+1 of our slice
+        float state_h[NJH];   // fwd: h_prev of our units ; bwd: direct dh carry
+        float state_c[NJH];   // fwd LSTM: c_prev ; bwd LSTM: dc carry
 #pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) {
-                const int j = j0 + jj;
-                if (j < H) {
-                    float* h0 = p.hseq + ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j;
-                    h0[0] = 0.f;
-                    h0[(size_t)(T + 1) * slotHB] = 0.f;
+        for (int jj = 0; jj < NJH; ++jj) state_h[jj] = state_c[jj] = 0.f;
+
+        if (!BWD && rowok) {  // zero boundary slots 0 and T+1 of our part of the slice
+            float z4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int v = 0; v < NVH; ++v)
+                if (gvalid[v]) {
+                    const size_t o = ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j0 + u0 + 4 * v;
+                    st4(p.hseq + o, z4);
+                    st4(p.hseq + o + (size_t)(T + 1) * slotHB, z4);
                     if constexpr (BF16) {
-                        __nv_bfloat16* q0 = p.hbf + ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j;
-                        q0[0] = __float2bfloat16_rn(0.f);
-                        q0[(size_t)(T + 1) * slotHB] = __float2bfloat16_rn(0.f);
+                        st4_bf16(p.hbf + o, z4);
+                        st4_bf16(p.hbf + o + (size_t)(T + 1) * slotHB, z4);
                     }
                     if constexpr (CELL == ASRB_RNN_LSTM) {
-                        float* c0 = p.cseq + ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j;
-                        c0[0] = 0.f;
-                        c0[(size_t)(T + 1) * slotHB] = 0.f;
+                        st4(p.cseq + o, z4);
+                        st4(p.cseq + o + (size_t)(T + 1) * slotHB, z4);
                     }
                 }
-            }
         }
-
-        constexpr int NV = NJ / 4;               // 4-wide groups: all global traffic is 16-byte vectors
-        bool gvalid[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) gvalid[v] = j0 + 4 * v < H;
-        if constexpr (!BWD) {                    // recurrent biases of our slice -> shared memory (broadcast reads)
-            for (int i = etid; i < kGates * NJ; i += 128) {
+        if constexpr (!BWD) {                    // recurrent biases of the slice -> shared memory (broadcast reads)
+            for (int i = etid; i < kGates * NJ; i += kRnnEpiThreads) {
                 const int g = i / NJ, jj = i % NJ;
                 s_bias[i] = (j0 + jj < H) ? p.b_hh[(size_t)dir * G + g * H + j0 + jj] : 0.f;
             }
-            named_bar_sync(3, 128);
+            named_bar_sync(3, kRnnEpiThreads);
         }
 
         for (int s = 0; s < T; ++s) {
             const int t = t_of(s);
             const bool active = rowok && (t < len);
             if (etid == 0) ASRB_TRACE(4, s);
-            float acc[NPAD];
+            constexpr int kAccG = BWD ? 1 : kGates;      // accumulator column groups we read: gates (fwd) / units (bwd)
+            float acc[kAccG][NJH];
 #pragma unroll
-            for (int c = 0; c < NPAD; ++c) acc[c] = 0.f;
+            for (int g = 0; g < kAccG; ++g)
+#pragma unroll
+                for (int jj = 0; jj < NJH; ++jj) acc[g][jj] = 0.f;
 
             // ---- operand prefetch (independent of the MMA): issued before we wait for the accumulator ----
-            float in[6][NJ];
+            float in[6][NJH];
 #pragma unroll
             for (int q = 0; q < 6; ++q)
 #pragma unroll
-                for (int jj = 0; jj < NJ; ++jj) in[q][jj] = 0.f;
+                for (int jj = 0; jj < NJH; ++jj) in[q][jj] = 0.f;
             if (active) {
                 if constexpr (!BWD) {
-                    const float* g = p.gi + (((size_t)t * B + b) * 2 + dir) * G + j0;
+                    const float* g = p.gi + (((size_t)t * B + b) * 2 + dir) * G + j0 + u0;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v)
+                    for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
 #pragma unroll
                             for (int q = 0; q < kGates; ++q) ldg4(&in[q][4 * v], g + (size_t)q * H + 4 * v);
                         }
                 } else {
-                    const float* sv = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0;
-                    const float* dop = p.dout + ((size_t)t * B + b) * H + j0;
+                    const float* sv = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0 + u0;
+                    const float* dop = p.dout + ((size_t)t * B + b) * H + j0 + u0;
                     const int tprev_slot = (dir == 0) ? t : t + 2;  // slot of the step that preceded t in forward order
                     const float* prevp = (CELL == ASRB_RNN_GRU ? p.hseq : p.cseq) +
-                                         ((size_t)dir * (T + 2) + tprev_slot) * slotHB + (size_t)b * H + j0;
+                                         ((size_t)dir * (T + 2) + tprev_slot) * slotHB + (size_t)b * H + j0 + u0;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v)
+                    for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) ld4(&in[q][4 * v], sv + (size_t)q * H + 4 * v);
@@ -347,14 +352,14 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         }
                 }
             }
-            float ct[NJ];  // bwd LSTM: c_t
+            float ct[NJH];  // bwd LSTM: c_t
 #pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) ct[jj] = 0.f;
+            for (int jj = 0; jj < NJH; ++jj) ct[jj] = 0.f;
             if constexpr (BWD && CELL == ASRB_RNN_LSTM) {
                 if (active) {
-                    const float* cp = p.cseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0;
+                    const float* cp = p.cseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v)
+                    for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) ld4(&ct[4 * v], cp + 4 * v);
                 }
             }
@@ -366,9 +371,13 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     if (etid == 0) ASRB_TRACE(5, s);
                     tc_fence_after_sync();
                     if (warp_has_rows) {
+                        const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
 #pragma unroll
-                        for (int c = 0; c < NPAD / 16; ++c)
-                            tmem_ld_32x16(tmem_base + (uint32_t(quad * 32) << 16) + c * 16, acc + c * 16);
+                        for (int g = 0; g < kAccG; ++g)
+#pragma unroll
+                            for (int v = 0; v < NVH; ++v)
+                                if (half * NVH + v < NV)      // warp-uniform
+                                    tmem_ld_32x4(lane_base + (BWD ? 0 : g * NJ) + u0 + 4 * v, &acc[g][4 * v]);
                         tmem_ld_wait();
                     }
                     tc_fence_before_sync();
@@ -382,7 +391,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         while (ld_acquire_u32(counter) < need) {
                         }
                     }
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1, kRnnEpiThreads);
                     if (rowok) {
                         const int tp = t_of(s - 1);
                         const int K = BWD ? G : H;
@@ -392,7 +401,12 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         for (int k = 0; k < K; ++k) {
                             const float a = __ldcg(arow + k);
 #pragma unroll
-                            for (int c = 0; c < NPAD; ++c) acc[c] = fmaf(a, __ldg(wrow + (size_t)c * p.kpad + k), acc[c]);
+                            for (int g = 0; g < kAccG; ++g)
+#pragma unroll
+                                for (int jj = 0; jj < NJH; ++jj) {
+                                    const int col = (BWD ? 0 : g * NJ) + u0 + jj;
+                                    if (col < NPAD) acc[g][jj] = fmaf(a, __ldg(wrow + (size_t)col * p.kpad + k), acc[g][jj]);
+                                }
                         }
                     }
                 }
@@ -400,25 +414,26 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
             // ---- cell math (registers only), then 16-byte vector stores ----
             if constexpr (!BWD) {
-                float hn[NJ], cn[NJ], sv[4][NJ];
+                float hn[NJH], cn[NJH], sv[4][NJH];
 #pragma unroll
-                for (int jj = 0; jj < NJ; ++jj) {
+                for (int jj = 0; jj < NJH; ++jj) {
                     float h_ = 0.f, c_ = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                     if (active) {
+                        const float* bs = s_bias + u0 + jj;
                         if constexpr (CELL == ASRB_RNN_GRU) {
-                            const float gr = acc[jj] + s_bias[jj];
-                            const float gz = acc[NJ + jj] + s_bias[NJ + jj];
-                            const float gn = acc[2 * NJ + jj] + s_bias[2 * NJ + jj];
+                            const float gr = acc[0][jj] + bs[0];
+                            const float gz = acc[1][jj] + bs[NJ];
+                            const float gn = acc[2][jj] + bs[2 * NJ];
                             const float r = fsigmoid(in[0][jj] + gr);
                             const float z = fsigmoid(in[1][jj] + gz);
                             const float n = ftanh(in[2][jj] + r * gn);
                             h_ = (1.f - z) * n + z * state_h[jj];
                             s0 = r; s1 = z; s2 = n; s3 = gn;
                         } else {
-                            const float gi_ = fsigmoid(in[0][jj] + acc[jj] + s_bias[jj]);
-                            const float gf = fsigmoid(in[1][jj] + acc[NJ + jj] + s_bias[NJ + jj]);
-                            const float gg = ftanh(in[2][jj] + acc[2 * NJ + jj] + s_bias[2 * NJ + jj]);
-                            const float go = fsigmoid(in[3][jj] + acc[(kGates - 1) * NJ + jj] + s_bias[(kGates - 1) * NJ + jj]);
+                            const float gi_ = fsigmoid(in[0][jj] + acc[0][jj] + bs[0]);
+                            const float gf = fsigmoid(in[1][jj] + acc[1][jj] + bs[NJ]);
+                            const float gg = ftanh(in[2][jj] + acc[2][jj] + bs[2 * NJ]);
+                            const float go = fsigmoid(in[3][jj] + acc[kGates - 1][jj] + bs[(kGates - 1) * NJ]);
                             c_ = gf * state_c[jj] + gi_ * gg;
                             h_ = go * ftanh(c_);
                             s0 = gi_; s1 = gf; s2 = gg; s3 = go;
@@ -430,10 +445,10 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     state_c[jj] = c_;
                 }
                 if (rowok) {
-                    const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0;
-                    float* svp = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0;
+                    const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0;
+                    float* svp = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0 + u0;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v)
+                    for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
                             st4(p.hseq + o + 4 * v, &hn[4 * v]);
                             if constexpr (BF16) st4_bf16(p.hbf + o + 4 * v, &hn[4 * v]);
@@ -443,10 +458,10 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         }
                 }
             } else {
-                float dg[4][NJ], eg2[NJ];
+                float dg[4][NJH], eg2[NJH];
 #pragma unroll
-                for (int jj = 0; jj < NJ; ++jj) {
-                    const float carry = acc[jj] + state_h[jj];
+                for (int jj = 0; jj < NJH; ++jj) {
+                    const float carry = acc[0][jj] + state_h[jj];
                     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, e2 = 0.f;
                     if (active) {
                         const float dh = carry + in[4][jj];
@@ -476,10 +491,10 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     dg[0][jj] = d0; dg[1][jj] = d1; dg[2][jj] = d2; dg[3][jj] = d3; eg2[jj] = e2;
                 }
                 if (rowok) {
-                    float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0;
-                    const size_t oh = (((size_t)dir * T + t) * B + b) * G + j0;
+                    float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0 + u0;
+                    const size_t oh = (((size_t)dir * T + t) * B + b) * G + j0 + u0;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v)
+                    for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
 #pragma unroll
                             for (int q = 0; q < kGates; ++q) {
@@ -495,7 +510,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             // ---- publish this step to the other CTAs of the direction ----
             if (etid == 0) ASRB_TRACE(7, s);
             if (tc) fence_proxy_async();
-            named_bar_sync(2, 128);
+            named_bar_sync(2, kRnnEpiThreads);
             if (etid == 0) {
                 ASRB_TRACE(8, s);
                 red_release_add_u32(counter, 1u);   // release: orders the CTA's stores (observed through the barrier)
@@ -533,7 +548,8 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
     if (B > kRnnMaxRows || H % (16 / esize) != 0) return ASRB_ERR_UNSUPPORTED;
     const int mrows = B <= 64 ? 64 : 128;
     const int stage = mrows * 128;
-    const int cands[3] = {8, 12, 16};
+    // widest slice first: fewer CTAs mean less replicated state traffic and a cheaper step barrier
+    const int cands[3] = {16, 12, 8};
     for (int ci = 0; ci < 3; ++ci) {
         const int nj = cands[ci];
         const int P = ceil_div(H, nj);
