@@ -147,7 +147,12 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     using S = RnnShape<CELL, NJ>;
     constexpr int kGates = S::kGates;
     constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
-    constexpr int kTmemCols = 64;
+    // The per-step product is a chain of tiny MMAs (M x N x 16/8); accumulating all of them into ONE TMEM tile makes
+    // the step latency-bound on the tensor pipe (~90 cycles per dependent MMA, measured).  So the K slices are dealt
+    // round-robin to KS independent accumulators that the epilogue adds up.
+    constexpr int KS = BWD ? 8 : 4;
+    constexpr int kTmemCols = BWD ? 128 : 256;   // KS x NPAD columns
+    static_assert(KS * NPAD <= kTmemCols, "accumulators exceed the TMEM allocation");
     constexpr int KBE = BF16 ? 64 : 32;          // elements per 128-byte K block
     constexpr int kStageBytes = MROWS * 128;
     // TMEM lane of batch row m: M=128 -> m ; M=64 -> (m % 16) + 32 * (m / 16)  (half of every lane quarter)
@@ -160,6 +165,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint8_t* smem_a = smem_w + (size_t)nkb * NPAD * 128;      // stages x chunk x [MROWS rows x 128 B]
     const int stage_bytes = p.chunk * kStageBytes;
     const int nchunks = ceil_div(nkb, p.chunk);
+    const int ks_eff = min(KS, nkb * 4);                      // accumulators that receive at least one MMA
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * stage_bytes);
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 704);   // [kGates][NJ] (forward)
     uint64_t* full_bar = bars;
@@ -249,8 +255,10 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + (size_t)(kb0 + i) * NPAD * 128));
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices per 128-byte block (K=8 tf32 / K=16 bf16)
-                            if constexpr (BF16) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (c | i | k) != 0);
-                            else                umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                            const int m = (kb0 + i) * 4 + k;                     // running MMA index of this step
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(m % KS) * NPAD;
+                            if constexpr (BF16) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, m >= KS);
+                            else                umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, m >= KS);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
@@ -322,9 +330,10 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 for (int jj = 0; jj < NJH; ++jj) acc[g][jj] = 0.f;
 
             // ---- operand prefetch (independent of the MMA): issued before we wait for the accumulator ----
-            float in[6][NJH];
+            constexpr int kIn = BWD ? 6 : kGates;        // fwd: gi gates ; bwd: 4 saved + dout + previous state
+            float in[kIn][NJH];
 #pragma unroll
-            for (int q = 0; q < 6; ++q)
+            for (int q = 0; q < kIn; ++q)
 #pragma unroll
                 for (int jj = 0; jj < NJH; ++jj) in[q][jj] = 0.f;
             if (active) {
@@ -352,9 +361,9 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         }
                 }
             }
-            float ct[NJH];  // bwd LSTM: c_t
+            float ct[(BWD && CELL == ASRB_RNN_LSTM) ? NJH : 1];  // bwd LSTM: c_t
 #pragma unroll
-            for (int jj = 0; jj < NJH; ++jj) ct[jj] = 0.f;
+            for (int jj = 0; jj < ((BWD && CELL == ASRB_RNN_LSTM) ? NJH : 1); ++jj) ct[jj] = 0.f;
             if constexpr (BWD && CELL == ASRB_RNN_LSTM) {
                 if (active) {
                     const float* cp = p.cseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0;
@@ -372,13 +381,35 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     tc_fence_after_sync();
                     if (warp_has_rows) {
                         const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
+                        constexpr int KSB = BWD ? KS / 2 : 1;   // partial accumulators fetched per round (register budget)
 #pragma unroll
-                        for (int g = 0; g < kAccG; ++g)
+                        for (int r0 = 0; r0 < KS; r0 += KSB) {
+                            float part[KSB][kAccG][NJH];
 #pragma unroll
-                            for (int v = 0; v < NVH; ++v)
-                                if (half * NVH + v < NV)      // warp-uniform
-                                    tmem_ld_32x4(lane_base + (BWD ? 0 : g * NJ) + u0 + 4 * v, &acc[g][4 * v]);
-                        tmem_ld_wait();
+                            for (int ks = 0; ks < KSB; ++ks)
+                                if (r0 + ks < ks_eff) {   // uniform
+#pragma unroll
+                                    for (int g = 0; g < kAccG; ++g)
+#pragma unroll
+                                        for (int v = 0; v < NVH; ++v)
+                                            if (half * NVH + v < NV)      // warp-uniform
+                                                tmem_ld_32x4(lane_base + (r0 + ks) * NPAD + (BWD ? 0 : g * NJ) + u0 + 4 * v,
+                                                             &part[ks][g][4 * v]);
+                                }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int ks = 0; ks < KSB; ++ks)
+                                if (r0 + ks < ks_eff) {
+#pragma unroll
+                                    for (int g = 0; g < kAccG; ++g)
+#pragma unroll
+                                        for (int v = 0; v < NVH; ++v)
+                                            if (half * NVH + v < NV) {
+#pragma unroll
+                                                for (int e = 0; e < 4; ++e) acc[g][4 * v + e] += part[ks][g][4 * v + e];
+                                            }
+                                }
+                        }
                     }
                     tc_fence_before_sync();
                     __syncwarp();
@@ -475,7 +506,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             state_h[jj] = dh * z;
                         } else {
                             const float gi_ = in[0][jj], gf = in[1][jj], gg = in[2][jj], go = in[3][jj], cp = in[5][jj];
-                            const float tcv = ftanh(ct[jj]);
+                            const float tcv = ftanh(ct[(BWD && CELL == ASRB_RNN_LSTM) ? jj : 0]);
                             const float dc = state_c[jj] + dh * go * (1.f - tcv * tcv);
                             d0 = dc * gg * gi_ * (1.f - gi_);
                             d1 = dc * cp * gf * (1.f - gf);
