@@ -98,49 +98,51 @@ conv_row_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
     };
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-                int b, drow, t0, n_mt;
-                decode(item, b, drow, t0, n_mt);
-                // first source column of the strip: forward x col = t + kw - PW ; dgrad dy col = t + PW - kw
-                const int col0 = p.mode == 0 ? t0 - p.PW : t0 + p.PW - (p.KW - 1);
-                for (int kh = 0; kh < p.KH; ++kh) {
-                    const int hs = conv_src_row(p, drow, kh);
-                    if (hs < 0) continue;
-                    uint8_t* st = smem + stage * stage_bytes;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            int b, drow, t0, n_mt;
+            decode(item, b, drow, t0, n_mt);
+            // first source column of the strip: forward x col = t + kw - PW ; dgrad dy col = t + PW - kw
+            const int col0 = p.mode == 0 ? t0 - p.PW : t0 + p.PW - (p.KW - 1);
+            for (int kh = 0; kh < p.KH; ++kh) {
+                const int hs = conv_src_row(p, drow, kh);
+                if (hs < 0) continue;
+                uint8_t* st = smem + stage * stage_bytes;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], n_mt * strip_bytes + p.KW * kCtWTile);
                     for (int mt = 0; mt < n_mt; ++mt)
                         tma_load_4d(st + mt * kCtStrip, &tmS, &full_bar[stage], 0, col0 + mt * 128, hs, b);
                     for (int kw = 0; kw < p.KW; ++kw)
                         tma_load_2d(st + 2 * kCtStrip + kw * kCtWTile, &tmW, &full_bar[stage], 0, (kh * p.KW + kw) * kCtC);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(kFmtTF32, 128, kCtC);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-                int b, drow, t0, n_mt;
-                decode(item, b, drow, t0, n_mt);
-                if (num_groups(drow) == 0) continue;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = umma_idesc(kFmtTF32, 128, kCtC);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            int b, drow, t0, n_mt;
+            decode(item, b, drow, t0, n_mt);
+            const int ngroups = num_groups(drow);
+            if (ngroups == 0) continue;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after_sync();
+            int gdone = 0;
+            for (int kh = 0; kh < p.KH; ++kh) {
+                if (conv_src_row(p, drow, kh) < 0) continue;
+                uint8_t* st = smem + stage * stage_bytes;
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after_sync();
-                bool first = true;
-                for (int kh = 0; kh < p.KH; ++kh) {
-                    if (conv_src_row(p, drow, kh) < 0) continue;
-                    uint8_t* st = smem + stage * stage_bytes;
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after_sync();
+                if (elect_one()) {
                     for (int kw = 0; kw < p.KW; ++kw) {
                         const int shift = p.mode == 0 ? kw : p.KW - 1 - kw;
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(st + 2 * kCtStrip + kw * kCtWTile));
@@ -149,16 +151,17 @@ conv_row_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
                             const uint32_t d_tmem = tmem_base + acc * 64 + mt * 32;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, !(first && kw == 0 && k == 0));
+                                umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (gdone | kw | k) != 0);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
-                    first = false;
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (gdone == ngroups - 1) umma_commit(&tfull_bar[acc]);
                 }
-                umma_commit(&tfull_bar[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                ++gdone;
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..5): thread = pixel, 32 channels in registers =====================
@@ -263,29 +266,32 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int r = r0; r < r1; ++r) {
-                const int b = r / p.Hout, ho = r % p.Hout;
-                const int hi = ho * p.SH + kh - p.PH;
-                if (hi < 0 || hi >= p.Hin) continue;
-                for (int kb = 0; kb < n_kb; ++kb) {
-                    uint8_t* st = smem + stage * stage_bytes;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // TMA producer: warp-uniform loop, one elected lane issues
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int r = r0; r < r1; ++r) {
+            const int b = r / p.Hout, ho = r % p.Hout;
+            const int hi = ho * p.SH + kh - p.PH;
+            if (hi < 0 || hi >= p.Hin) continue;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                uint8_t* st = smem + stage * stage_bytes;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.m_tiles * 4 + 1) * kCtWTile);
                     for (int j = 0; j < p.m_tiles * 4; ++j) { // kernel column j (columns >= KW are never read back)
-                        const int off = j - p.PW;             // time shift; copy r holds x delayed by r samples
-                        const int r = (((-off) % 4) + 4) % 4; // so that the box start kb*32 + off + r is 16-byte aligned
-                        tma_load_5d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * 32 + off + r, hi, 0, b, r);
+                        const int off = j - p.PW;             // time shift; copy q holds x delayed by q samples
+                        const int q = (((-off) % 4) + 4) % 4; // so that the box start kb*32 + off + q is 16-byte aligned
+                        tma_load_5d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * 32 + off + q, hi, 0, b, q);
                     }
                     tma_load_4d(st + a_bytes, &tmDy, &full_bar[stage], kb * 32, ho, 0, b);
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && total_rows > 0) {
+        // MMA issuer: warp-uniform loop, one elected lane issues
+        if (total_rows > 0) {
             constexpr uint32_t idesc = umma_idesc(kFmtTF32, 128, kCtC);
             int stage = 0;
             uint32_t phase = 0;
@@ -294,17 +300,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 uint8_t* st = smem + stage * stage_bytes;
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after_sync();
-                const uint64_t bdesc = umma_desc_sw128(smem_u32(st + a_bytes));
-                for (int mt = 0; mt < p.m_tiles; ++mt) {
-                    const uint64_t adesc = umma_desc_sw128(smem_u32(st + mt * 16384));
+                if (elect_one()) {
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(st + a_bytes));
+                    for (int mt = 0; mt < p.m_tiles; ++mt) {
+                        const uint64_t adesc = umma_desc_sw128(smem_u32(st + mt * 16384));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_tf32(tmem_base + mt * 32, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+                        for (int k = 0; k < 4; ++k)
+                            umma_tf32(tmem_base + mt * 32, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (s == steps - 1) umma_commit(tfull_bar);
                 }
-                umma_commit(&empty_bar[stage]);
+                __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(tfull_bar);
         }
     } else {
         const int quad = warp & 3;

@@ -131,46 +131,50 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // The whole warp runs the (warp-uniform) loop and ONE elected lane issues, so the loop state lives in uniform
+        // registers -- which is what TMA / tcgen05 instructions take.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kBK, m0);
                     tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], kb * kBK, n0);
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(kFmtTF32, kBM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = umma_idesc(kFmtTF32, kBM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after_sync();
+                if (elect_one()) {
                     const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k)  // UMMA_K = 8 for tf32: advance 32 B inside the swizzle row
                         umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
                 }
-                umma_commit(&tfull_bar[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================

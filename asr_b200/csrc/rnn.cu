@@ -147,12 +147,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     using S = RnnShape<CELL, NJ>;
     constexpr int kGates = S::kGates;
     constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
-    // The per-step product is a chain of tiny MMAs (M x N x 16/8); accumulating all of them into ONE TMEM tile makes
-    // the step latency-bound on the tensor pipe (~90 cycles per dependent MMA, measured).  So the K slices are dealt
-    // round-robin to KS independent accumulators that the epilogue adds up.
-    constexpr int KS = BWD ? 8 : 4;
-    constexpr int kTmemCols = BWD ? 128 : 256;   // KS x NPAD columns
-    static_assert(KS * NPAD <= kTmemCols, "accumulators exceed the TMEM allocation");
+    constexpr int kTmemCols = 64;
     constexpr int KBE = BF16 ? 64 : 32;          // elements per 128-byte K block
     constexpr int kStageBytes = MROWS * 128;
     // TMEM lane of batch row m: M=128 -> m ; M=64 -> (m % 16) + 32 * (m / 16)  (half of every lane quarter)
@@ -165,7 +160,6 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint8_t* smem_a = smem_w + (size_t)nkb * NPAD * 128;      // stages x chunk x [MROWS rows x 128 B]
     const int stage_bytes = p.chunk * kStageBytes;
     const int nchunks = ceil_div(nkb, p.chunk);
-    const int ks_eff = min(KS, nkb * 4);                      // accumulators that receive at least one MMA
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * stage_bytes);
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 704);   // [kGates][NJ] (forward)
     uint64_t* full_bar = bars;
@@ -204,18 +198,21 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0 && tc) {
-            mbar_arrive_expect_tx(w_bar, (uint32_t)(nkb * NPAD * 128));
-            for (int kb = 0; kb < nkb; ++kb)
-                tma_load_2d(smem_w + (size_t)kb * NPAD * 128, &tmW, w_bar, kb * KBE, (dir * P + pidx) * NPAD);
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        if (tc) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(w_bar, (uint32_t)(nkb * NPAD * 128));
+                for (int kb = 0; kb < nkb; ++kb)
+                    tma_load_2d(smem_w + (size_t)kb * NPAD * 128, &tmW, w_bar, kb * KBE, (dir * P + pidx) * NPAD);
+            }
+            __syncwarp();
             int stage = 0;
             uint32_t phase = 0;
             for (int s = 1; s < T; ++s) {
                 const uint32_t need = (uint32_t)P * (uint32_t)s;
                 while (ld_acquire_u32(counter) < need) {
                 }
-                ASRB_TRACE(0, s);
+                if (lane == 0) ASRB_TRACE(0, s);
                 fence_proxy_async();  // other CTAs' generic-proxy stores -> visible to our async-proxy (TMA) reads
                 const int tp = t_of(s - 1);
                 const int slab = BWD ? (dir * T + tp) : (dir * (T + 2) + tp + 1);
@@ -224,17 +221,20 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     const int nblk = min(p.chunk, nkb - kb0);
                     uint8_t* st = smem_a + (size_t)stage * stage_bytes;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nblk * kStageBytes));
-                    for (int i = 0; i < nblk; ++i)
-                        tma_load_3d(st + (size_t)i * kStageBytes, &tmA, &full_bar[stage], (kb0 + i) * KBE, 0, slab);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nblk * kStageBytes));
+                        for (int i = 0; i < nblk; ++i)
+                            tma_load_3d(st + (size_t)i * kStageBytes, &tmA, &full_bar[stage], (kb0 + i) * KBE, 0, slab);
+                    }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                ASRB_TRACE(1, s);
+                if (lane == 0) ASRB_TRACE(1, s);
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0 && tc) {
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        if (tc) {
             constexpr uint32_t idesc = umma_idesc(BF16 ? kFmtBF16 : kFmtTF32, MROWS, NPAD);
             mbar_wait(w_bar, 0);
             int stage = 0;
@@ -246,26 +246,28 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 for (int c = 0; c < nchunks; ++c) {
                     const int kb0 = c * p.chunk;
                     const int nblk = min(p.chunk, nkb - kb0);
-                    uint8_t* st = smem_a + (size_t)stage * stage_bytes;
                     mbar_wait(&full_bar[stage], phase);
-                    if (c == 0) ASRB_TRACE(2, s);
+                    if (c == 0 && lane == 0) ASRB_TRACE(2, s);
                     tc_fence_after_sync();
-                    for (int i = 0; i < nblk; ++i) {
-                        const uint64_t adesc = umma_desc_sw128(smem_u32(st + (size_t)i * kStageBytes));
-                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_w + (size_t)(kb0 + i) * NPAD * 128));
+                    if (elect_one()) {
+                        const uint32_t a0 = smem_u32(smem_a + (size_t)stage * stage_bytes);
+                        const uint32_t b0 = smem_u32(smem_w + (size_t)kb0 * NPAD * 128);
+                        for (int i = 0; i < nblk; ++i) {
+                            const uint64_t adesc = umma_desc_sw128(a0 + i * kStageBytes);
+                            const uint64_t bdesc = umma_desc_sw128(b0 + i * NPAD * 128);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices per 128-byte block (K=8 tf32 / K=16 bf16)
-                            const int m = (kb0 + i) * 4 + k;                     // running MMA index of this step
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(m % KS) * NPAD;
-                            if constexpr (BF16) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, m >= KS);
-                            else                umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, m >= KS);
+                            for (int k = 0; k < 4; ++k) {   // 4 x 32-byte K slices per 128-byte block (K=8 tf32 / K=16 bf16)
+                                if constexpr (BF16) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                                else                umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                            }
                         }
+                        umma_commit(&empty_bar[stage]);
+                        if (c == nchunks - 1) umma_commit(tfull_bar);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar);
-                ASRB_TRACE(3, s);
+                if (lane == 0) ASRB_TRACE(3, s);
             }
         }
     } else {
@@ -381,35 +383,13 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     tc_fence_after_sync();
                     if (warp_has_rows) {
                         const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
-                        constexpr int KSB = BWD ? KS / 2 : 1;   // partial accumulators fetched per round (register budget)
 #pragma unroll
-                        for (int r0 = 0; r0 < KS; r0 += KSB) {
-                            float part[KSB][kAccG][NJH];
+                        for (int g = 0; g < kAccG; ++g)
 #pragma unroll
-                            for (int ks = 0; ks < KSB; ++ks)
-                                if (r0 + ks < ks_eff) {   // uniform
-#pragma unroll
-                                    for (int g = 0; g < kAccG; ++g)
-#pragma unroll
-                                        for (int v = 0; v < NVH; ++v)
-                                            if (half * NVH + v < NV)      // warp-uniform
-                                                tmem_ld_32x4(lane_base + (r0 + ks) * NPAD + (BWD ? 0 : g * NJ) + u0 + 4 * v,
-                                                             &part[ks][g][4 * v]);
-                                }
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int ks = 0; ks < KSB; ++ks)
-                                if (r0 + ks < ks_eff) {
-#pragma unroll
-                                    for (int g = 0; g < kAccG; ++g)
-#pragma unroll
-                                        for (int v = 0; v < NVH; ++v)
-                                            if (half * NVH + v < NV) {
-#pragma unroll
-                                                for (int e = 0; e < 4; ++e) acc[g][4 * v + e] += part[ks][g][4 * v + e];
-                                            }
-                                }
-                        }
+                            for (int v = 0; v < NVH; ++v)
+                                if (half * NVH + v < NV)      // warp-uniform
+                                    tmem_ld_32x4(lane_base + (BWD ? 0 : g * NJ) + u0 + 4 * v, &acc[g][4 * v]);
+                        tmem_ld_wait();
                     }
                     tc_fence_before_sync();
                     __syncwarp();

@@ -14,6 +14,21 @@ pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
 nj, P, _, _ = ops.rnn_plan(cell, H, B, ops.rnn_use_bf16(H))
 grid = 2 * P
 names = ["P:counter ok", "P:loads issued", "M:first full", "M:commit", "E:step top", "E:tfull", "E:ld done", "E:math+stores", "E:bar done", "E:membar", "E:red"]
+def timed(fn, n=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+for flags in (0, 16):
+    ops.set_debug_flags(flags)
+    hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
+    dout = torch.randn(T, B, H, device=dev)
+    tf = timed(lambda: ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H))
+    tb = timed(lambda: ops.rnn_bwd(cell, dout, pb, lens, hseq, cseq, saved, T, B, H))
+    print(f"flags={flags} (no trace): fwd {tf:.3f} ms ({tf*1e3/T:.2f} us/step)  bwd {tb:.3f} ms ({tb*1e3/T:.2f} us/step)")
+ops.set_debug_flags(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 for which in ("fwd", "bwd"):
     for _ in range(2):
         hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
