@@ -59,11 +59,15 @@ class Conv2dMask(Function):
         x = x.contiguous()
         weight = weight.contiguous()
         ctx.save_for_backward(x, weight, lengths_dev)
-        tc = ops.conv32_supported(weight.shape, stride, padding)
+        # tensor-core paths: 2 = 32->32 channels, time stride 1 (conv2); 1 = 1->32 channels, stride (2,2) (conv1)
+        tc = 2 if ops.conv32_supported(weight.shape, stride, padding) else (
+            1 if ops.conv1_supported(x.shape, weight.shape, stride, padding) else 0)
         ctx.conf = (stride, padding, bias is not None, tc)
-        if tc:   # 32->32 channels, time stride 1: implicit GEMM on the tensor cores (NHWC source)
+        if tc == 2:   # implicit GEMM over an NHWC source
             pack_f, _ = ops.conv32_pack_weights(weight, fwd=True, dgrad=False)
             return ops.conv32_fwd(ops.nchw_to_nhwc(x), pack_f, bias, lengths_dev, weight.shape, stride, padding)
+        if tc == 1:   # polyphase implicit GEMM
+            return ops.conv1_fwd(x, weight, bias, lengths_dev, stride, padding)
         return ops.conv2d_mask_fwd(x, weight, bias, lengths_dev, stride, padding)
 
     @staticmethod
@@ -77,10 +81,14 @@ class Conv2dMask(Function):
         if tc:
             dym = ops.mask_time(dy, lengths_dev)
             if ctx.needs_input_grad[0]:
-                _, pack_d = ops.conv32_pack_weights(weight, fwd=False, dgrad=True)
-                dx = ops.conv32_bwd_data(ops.nchw_to_nhwc(dym), pack_d, x.shape, weight.shape, stride, padding)
+                if tc == 2:
+                    _, pack_d = ops.conv32_pack_weights(weight, fwd=False, dgrad=True)
+                    dx = ops.conv32_bwd_data(ops.nchw_to_nhwc(dym), pack_d, x.shape, weight.shape, stride, padding)
+                else:     # a gradient w.r.t. the spectrogram is never needed on the training path: generic kernel
+                    dx = ops.conv2d_mask_bwd_data(dym, weight, None, x.shape, stride, padding)
             if ctx.needs_input_grad[1]:
-                dw = ops.conv32_bwd_weight(x, dym, weight.shape, stride, padding)
+                dw = (ops.conv32_bwd_weight(x, dym, weight.shape, stride, padding) if tc == 2
+                      else ops.conv1_bwd_weight(x, dym, weight.shape, padding))
             if has_bias and ctx.needs_input_grad[2]:
                 db = ops.nchw_channel_sums(dym, None)
             return dx, dw, db, None, None, None

@@ -50,7 +50,7 @@ PROFILE = None   # set to a dict to collect (start, end) CUDA-event pairs per en
 # kernels launched per call of an entry point (memsets not counted); used for the `gpu_launches` claim
 KERNELS_PER_CALL = {
     "asrb_conv2d_mask_bwd_weight": 3, "asrb_bn2d_stats": 2, "asrb_bn_act_mask_bwd": 3, "asrb_bn_rows_fwd": 3,
-    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_conv32_bwd_weight": 2,
+    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_conv32_bwd_weight": 2, "asrb_conv1_fwd": 3, "asrb_conv1_bwd_weight": 2,
 }
 
 
@@ -262,6 +262,39 @@ def conv32_bwd_weight(x, dy_masked, w_shape, stride, padding):
     ws = torch.empty(nb // 4, device=x.device, dtype=torch.float32)
     _call("asrb_conv32_bwd_weight", _p(x), _p(dyp), lddy, _p(dw), _p(ws), nb, B, Hin, Win, Hout, Wout, KH, KW,
           stride[0], padding[0], padding[1])
+    return dw
+
+
+def conv1_supported(x_shape, w_shape, stride, padding):
+    """True when the tcgen05 polyphase conv applies (1->32 channels, (KH,11) kernel, stride (2,2), padding (even,5))."""
+    Cout, Cin, KH, KW = w_shape
+    if DEBUG_FLAGS & 4:
+        return False
+    return bool(_lib.query("asrb_conv1_supported", Cin, Cout, x_shape[2], KH, KW, stride[0], stride[1], padding[0], padding[1]))
+
+
+def conv1_fwd(x, w, bias, lengths, stride, padding):
+    _chk(x, w, bias)
+    B, _, F, T = x.shape
+    Cout, _, KH, KW = w.shape
+    Hout, Wout = conv_out_size(F, KH, 2, padding[0]), conv_out_size(T, KW, 2, padding[1])
+    y = torch.empty(B, Cout, Hout, Wout, device=x.device, dtype=torch.float32)
+    nb = _lib.query("asrb_conv1_workspace_bytes", B, F, T, 0)
+    ws = torch.empty(nb // 4, device=x.device, dtype=torch.float32)
+    _call("asrb_conv1_fwd", _p(x), _p(w), _p(bias), _p(lengths), _p(y), _p(ws), nb, B, F, T, Hout, Wout, KH, padding[0])
+    return y
+
+
+def conv1_bwd_weight(x, dy_masked, w_shape, padding):
+    _chk(x, dy_masked)
+    B, _, F, T = x.shape
+    _, _, Hout, Wout = dy_masked.shape
+    _, _, KH, KW = w_shape
+    dyp, lddy = pad_rows4(dy_masked)
+    dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
+    nb = _lib.query("asrb_conv1_workspace_bytes", B, F, T, 1)
+    ws = torch.empty(nb // 4, device=x.device, dtype=torch.float32)
+    _call("asrb_conv1_bwd_weight", _p(x), _p(dyp), lddy, _p(dw), _p(ws), nb, B, F, T, Hout, Wout, KH, padding[0])
     return dw
 
 

@@ -145,6 +145,15 @@ int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw,
                            int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW,
                            asrb_stream_t stream);
 
+/* ---------------------------------------------------------------- 1->32 channel, time-stride-2 conv on tcgen05
+ * (deepspeech.py:61 "conv1": kernel (KH,11), stride (2,2), padding (PH,5)); forward and weight gradient. */
+int asrb_conv1_supported(int Cin, int Cout, int F, int KH, int KW, int SH, int SW, int PH, int PW);
+size_t asrb_conv1_workspace_bytes(int B, int F, int T, int for_wgrad);
+int asrb_conv1_fwd(const float* x, const float* w, const float* bias, const int32_t* lengths, float* y, float* ws,
+                   size_t ws_bytes, int B, int F, int T, int Hout, int Wout, int KH, int PH, asrb_stream_t stream);
+int asrb_conv1_bwd_weight(const float* x, const float* dy, int lddy, float* dw, float* ws, size_t ws_bytes, int B,
+                          int F, int T, int Hout, int Wout, int KH, int PH, asrb_stream_t stream);
+
 /* ---------------------------------------------------------------- row-matrix kernels, x[R = T*N, cols] */
 size_t asrb_rows_workspace_bytes(int cols);
 int asrb_bn_rows_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,

@@ -77,6 +77,18 @@ def conv32_supported(w_shape, stride, padding):
     return w_shape[0] == 32 and w_shape[1] == 32 and stride[1] == 1 and w_shape[3] <= 16
 
 
+def conv1_supported(x_shape, w_shape, stride, padding):
+    return w_shape[1] == 1 and w_shape[0] == 32 and w_shape[3] == 11 and tuple(stride) == (2, 2) and padding[1] == 5
+
+
+def conv1_fwd(x, w, bias, lengths, stride, padding):
+    return conv2d_mask_fwd(x, w, bias, lengths, stride, padding)
+
+
+def conv1_bwd_weight(x, dy_masked, w_shape, padding):
+    return torch.nn.grad.conv2d_weight(x, w_shape, dy_masked, stride=(2, 2), padding=padding)
+
+
 def nchw_to_nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous()
 

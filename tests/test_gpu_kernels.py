@@ -149,6 +149,36 @@ def test_conv32_tensor_core_fwd_bwd(ops, c):
     assert report("channel sums", ops.nchw_channel_sums(dy.to(DEV), ld), b.grad) <= 1e-4 * max(1.0, b.grad.abs().max().item())
 
 
+CONV1_CASES = [
+    dict(B=3, F=161, T=61, KH=41, PH=20, lens=[31, 24, 15]),
+    dict(B=1, F=161, T=1001, KH=41, PH=20, lens=[501]),
+    dict(B=2, F=161, T=300, KH=41, PH=20, lens=[150, 99]),
+    dict(B=2, F=40, T=77, KH=7, PH=2, lens=[39, 20]),
+]
+
+
+@pytest.mark.parametrize("c", CONV1_CASES, ids=lambda c: f"F{c['F']}_T{c['T']}_KH{c['KH']}")
+def test_conv1_tensor_core_fwd_wgrad(ops, c):
+    """1->32 channel, stride-(2,2) conv as a polyphase tcgen05 implicit GEMM (TF32 operands) vs the fp64 oracle."""
+    x = rnd(c["B"], 1, c["F"], c["T"], seed=18)
+    w = (rnd(32, 1, c["KH"], 11, seed=19) * 0.1).requires_grad_(True)
+    b = rnd(32, seed=20).requires_grad_(True)
+    lens = torch.tensor(c["lens"], dtype=torch.int32)
+    stride, pad = (2, 2), (c["PH"], 5)
+    assert ops.conv1_supported(tuple(x.shape), tuple(w.shape), stride, pad)
+    y_ref = explicit.time_mask(F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad), lens.long())
+    dy = explicit.time_mask(rnd(*y_ref.shape, seed=21), lens.long())
+    y_ref.backward(dy.double())
+    K = c["KH"] * 11
+    y = ops.conv1_fwd(x.to(DEV), w.detach().to(DEV), b.detach().to(DEV), lens.to(DEV), stride, pad)
+    torch.cuda.synchronize()
+    assert report("conv1 fwd", y, y_ref.detach()) <= 2e-3 * math.sqrt(K) * 0.1
+    dw = ops.conv1_bwd_weight(x.to(DEV), dy.to(DEV), tuple(w.shape), pad)
+    torch.cuda.synchronize()
+    npix = c["B"] * y_ref.shape[2] * y_ref.shape[3]
+    assert report("conv1 wgrad", dw, w.grad) <= 2e-3 * math.sqrt(npix)
+
+
 @pytest.mark.parametrize("training", [True, False])
 def test_bn_act_mask_fwd_bwd(ops, training):
     B, C, H, W = 3, 5, 7, 40

@@ -18,6 +18,7 @@ for g in $groups; do
     gemm)     run gemm 300 tests/test_gpu_kernels.py -k "gemm" ;;
     conv)     run conv 300 tests/test_gpu_kernels.py -k "conv2d or bn_act or layout" ;;
     conv32)   run conv32 300 tests/test_gpu_kernels.py -k "conv32" ;;
+    conv1)    run conv1 300 tests/test_gpu_kernels.py -k "conv1_tensor" ;;
     rows)     run rows 300 tests/test_gpu_kernels.py -k "bn_rows or log_softmax" ;;
     rnn_simt) run rnn_simt 600 tests/test_gpu_kernels.py -k "rnn and simt_debug" ;;
     rnn_tc)   run rnn_tc 300 tests/test_gpu_kernels.py -k "rnn and (tf32 or bf16)" ;;
