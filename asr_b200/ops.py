@@ -390,9 +390,12 @@ def bn_rows_bwd(dy, x, mean, invstd, gamma, training):
 RNN_BF16 = True   # operand precision of the recurrent product: bf16 (default) or tf32; see include/asr_b200.h
 
 
+RNN_BF16_MIN_HIDDEN = 256   # below this the tf32 state fits in flight anyway: keep the extra mantissa bits
+
+
 def rnn_use_bf16(H):
     """bf16 recurrent operands need 16-byte rows of bf16 (H % 8 == 0); the CUDA-core debug path reads fp32."""
-    return bool(RNN_BF16 and H % 8 == 0 and not (DEBUG_FLAGS & 2))
+    return bool(RNN_BF16 and H % 8 == 0 and H >= RNN_BF16_MIN_HIDDEN and not (DEBUG_FLAGS & 2))
 
 
 def rnn_plan(cell, H, B, bf16):

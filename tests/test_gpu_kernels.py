@@ -281,6 +281,7 @@ def test_rnn_fwd_bwd(ops, c, mode):
 
     ops.set_debug_flags(2 if simt else 0)
     old_bf16, ops.RNN_BF16 = ops.RNN_BF16, mode == "bf16"
+    old_min, ops.RNN_BF16_MIN_HIDDEN = ops.RNN_BF16_MIN_HIDDEN, 0
     try:
         ld = lens.to(DEV)
         pf, pb = ops.rnn_pack_weights(cell, w_hh[0].contiguous().to(DEV), w_hh[1].contiguous().to(DEV), B)
@@ -312,6 +313,7 @@ def test_rnn_fwd_bwd(ops, c, mode):
     finally:
         ops.set_debug_flags(0)
         ops.RNN_BF16 = old_bf16
+        ops.RNN_BF16_MIN_HIDDEN = old_min
 
 
 # ----------------------------------------------------------------------------- softmax / argmax / CTC
