@@ -52,7 +52,10 @@ struct RnnParams {
     // backward
     const float* dout;   // [T,B,H]
     float* dgi;          // [T,B,2,G]
-    float* dgh;          // [2,T,B,G]
+    float* dgh;          // [2,T,B,G]  (tf32 / debug modes: MMA operand; NULL in bf16 mode)
+    float* dgiT;         // [2G, ldT]  transposed gate gradients (row = dir*G + gate*H + unit, column = t*B + b)
+    float* dghTn;        // [2, H, ldT] GRU: transposed gradient of the hidden-side n gate (the r,z rows equal dgiT's)
+    long long ldT;
 };
 
 template <int CELL, int NJ>
@@ -348,7 +351,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             for (int q = 0; q < kGates; ++q) ldg4(&in[q][4 * v], g + (size_t)q * H + 4 * v);
                         }
                 } else {
-                    const float* sv = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0 + u0;
+                    const float* sv = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) + (size_t)b * 4;
                     const float* dop = p.dout + ((size_t)t * B + b) * H + j0 + u0;
                     const int tprev_slot = (dir == 0) ? t : t + 2;  // slot of the step that preceded t in forward order
                     const float* prevp = (CELL == ASRB_RNN_GRU ? p.hseq : p.cseq) +
@@ -357,7 +360,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) ld4(&in[q][4 * v], sv + (size_t)q * H + 4 * v);
+                            for (int q = 0; q < 4; ++q)
+                                ld4(&in[q][4 * v], sv + ((size_t)q * NV + half * NVH + v) * (size_t)(B * 4));
                             ldg4(&in[4][4 * v], dop + 4 * v);
                             ld4(&in[5][4 * v], prevp + 4 * v);
                         }
@@ -457,7 +461,9 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
                 if (rowok) {
                     const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0;
-                    float* svp = p.saved + (((size_t)dir * T + t) * B + b) * 4 * H + j0 + u0;
+                    // saved gates, slice-major [dir][t][slice][gate][group][b][4]: consecutive batch rows (= lanes) are
+                    // 16 bytes apart, so a warp store covers 2 lines instead of 16
+                    float* svp = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) + (size_t)b * 4;
 #pragma unroll
                     for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
@@ -465,7 +471,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             if constexpr (BF16) st4_bf16(p.hbf + o + 4 * v, &hn[4 * v]);
                             if constexpr (CELL == ASRB_RNN_LSTM) st4(p.cseq + o + 4 * v, &cn[4 * v]);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) st4(svp + (size_t)q * H + 4 * v, &sv[q][4 * v]);
+                            for (int q = 0; q < 4; ++q)
+                                st4(svp + ((size_t)q * NV + half * NVH + v) * (size_t)(B * 4), &sv[q][4 * v]);
                         }
                 }
             } else {
@@ -504,6 +511,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 if (rowok) {
                     float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0 + u0;
                     const size_t oh = (((size_t)dir * T + t) * B + b) * G + j0 + u0;
+                    // transposed copies for the weight-gradient GEMMs: lanes (batch rows) are contiguous -> coalesced
+                    float* gT = p.dgiT + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b;
 #pragma unroll
                     for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
@@ -511,8 +520,15 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             for (int q = 0; q < kGates; ++q) {
                                 const float* hv = (q == 2) ? &eg2[4 * v] : &dg[q][4 * v];
                                 st4(dgi + (size_t)q * H + 4 * v, &dg[q][4 * v]);
-                                st4(p.dgh + oh + (size_t)q * H + 4 * v, hv);
+                                if (p.dgh) st4(p.dgh + oh + (size_t)q * H + 4 * v, hv);
                                 if constexpr (BF16) st4_bf16(p.dghbf + oh + (size_t)q * H + 4 * v, hv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) gT[((size_t)q * H + 4 * v + e) * p.ldT] = dg[q][4 * v + e];
+                            }
+                            if constexpr (CELL == ASRB_RNN_GRU) {
+                                float* hT = p.dghTn + ((size_t)dir * H + j0 + u0) * p.ldT + (size_t)t * B + b;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) hT[(size_t)(4 * v + e) * p.ldT] = eg2[4 * v + e];
                             }
                         }
                 }
@@ -655,6 +671,13 @@ using namespace asrb;
 
 extern "C" {
 
+/* floats in the saved-gates buffer (slice-major layout private to asrb_rnn_fwd / asrb_rnn_bwd) */
+size_t asrb_rnn_saved_floats(int cell, int H, int B, int bf16, int T) {
+    RnnPlan pl;
+    if (rnn_make_plan(cell, H, B, rnn_effective_bf16(bf16), &pl)) return 0;
+    return (size_t)2 * T * pl.P * 4 * pl.nj * B;
+}
+
 int asrb_rnn_plan(int cell, int H, int B, int bf16, int* nj, int* P, size_t* wpack_fwd_bytes, size_t* wpack_bwd_bytes) {
     ASRB_REQUIRE((cell == ASRB_RNN_GRU || cell == ASRB_RNN_LSTM) && H > 0 && B > 0, ASRB_ERR_BAD_ARG);
     RnnPlan pl;
@@ -709,19 +732,22 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
 
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
                  const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
-                 uint32_t* counters, int T, int B, int H, asrb_stream_t stream) {
-    ASRB_REQUIRE(dout && wpack_bwd && lengths && hseq && saved && dgi && dgh && counters && T > 0, ASRB_ERR_BAD_ARG);
+                 float* dgiT, float* dghTn, long long ldT, uint32_t* counters, int T, int B, int H,
+                 asrb_stream_t stream) {
+    ASRB_REQUIRE(dout && wpack_bwd && lengths && hseq && saved && dgi && dgiT && counters && T > 0, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(cell == ASRB_RNN_GRU || cseq, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(cell == ASRB_RNN_LSTM || dghTn, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(ldT >= (long long)T * B, ASRB_ERR_BAD_ARG);
     RnnPlan pl;
     int rc = rnn_make_plan(cell, H, B, rnn_effective_bf16(bf16), &pl);
     if (rc) return rc;
-    ASRB_REQUIRE(!pl.bf16 || dgh_bf16, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(pl.bf16 ? (dgh_bf16 != nullptr) : (dgh != nullptr), ASRB_ERR_BAD_ARG);
     RnnParams prm = {};
     prm.T = T; prm.B = B; prm.H = H; prm.G = (cell == ASRB_RNN_GRU ? 3 : 4) * H; prm.P = pl.P;
     prm.use_simt = (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 1 : 0;
     prm.lengths = lengths; prm.counters = counters;
     prm.hseq = const_cast<float*>(hseq); prm.cseq = const_cast<float*>(cseq); prm.saved = const_cast<float*>(saved);
-    prm.dout = dout; prm.dgi = dgi; prm.dgh = dgh;
+    prm.dout = dout; prm.dgi = dgi; prm.dgh = dgh; prm.dgiT = dgiT; prm.dghTn = dghTn; prm.ldT = ldT;
     prm.dghbf = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
     prm.trace = g_rnn_trace;
     return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, pl.bf16 ? (const void*)dgh_bf16 : (const void*)dgh, stream);

@@ -93,6 +93,23 @@ __global__ void bn_rows_bwd_kernel(const float* __restrict__ dy, const float* __
     }
 }
 
+// out[r] = sum_c a[r*ld + c]   (one block per row, fixed reduction order)
+__global__ void __launch_bounds__(256)
+row_sums_kernel(const float* __restrict__ a, long long ld, float* __restrict__ out, long long cols) {
+    const float* row = a + (size_t)blockIdx.x * ld;
+    float s = 0.f;
+    for (long long c = threadIdx.x; c < cols; c += 256) s += row[c];
+    __shared__ float red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        out[blockIdx.x] = t;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // class-dimension kernels: one warp per row
 // ------------------------------------------------------------------------------------------------
@@ -215,6 +232,14 @@ int asrb_col_sums(const float* a, int lda, float* out, float* ws, size_t ws_byte
     int rc = rows_reduce<2>(a, lda, nullptr, 0, nullptr, nullptr, ws, ws_bytes, R, cols, &nchunks, stream);
     if (rc) return rc;
     rows_finalize_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(ws, nchunks, cols, 1.0, 1, 0.f, 0.f, out, nullptr, nullptr, nullptr);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* out[r] = sum_c a[r*ld + c] */
+int asrb_row_sums(const float* a, long long ld, float* out, int rows, long long cols, asrb_stream_t stream) {
+    ASRB_REQUIRE(a && out && rows > 0 && cols > 0 && ld >= cols, ASRB_ERR_BAD_ARG);
+    row_sums_kernel<<<rows, 256, 0, stream>>>(a, ld, out, cols);
     ASRB_LAUNCH_OK();
     return 0;
 }

@@ -246,11 +246,16 @@ class BiRnnLayer(Function):
         cell, T, B, I, H, G = ctx.dims
         R = T * B
         _, pack_b = ops.rnn_pack_weights(cell, w_hh, w_hh_r, B, fwd=False, bwd=True)
-        dgi, dgh = ops.rnn_bwd(cell, dout.contiguous(), pack_b, lengths_dev, hseq, cseq, saved, T, B, H)
+        dgi, dgiT, dghTn = ops.rnn_bwd(cell, dout.contiguous(), pack_b, lengths_dev, hseq, cseq, saved, T, B, H)
         dgi2 = dgi.view(R, 2 * G)
-        # bias gradients
-        db_ih_cat = ops.col_sums(dgi2)
-        db_hh = [ops.col_sums(dgh[d].view(R, G)) for d in range(2)]
+        gru = cell == ops.GRU
+        # bias gradients = row sums of the transposed gate gradients
+        db_ih_cat = ops.row_sums(dgiT, R)
+        if gru:   # hidden-side gradients equal the input-side ones for r,z; the n gate has its own (x r)
+            db_hn = ops.row_sums(dghTn.view(2 * H, -1), R)
+            db_hh = [torch.cat([db_ih_cat[d * G:d * G + 2 * H], db_hn[d * H:(d + 1) * H]]) for d in range(2)]
+        else:
+            db_hh = [db_ih_cat[d * G:(d + 1) * G] for d in range(2)]
         # input gradient: dx = dgi_f W_ih_f + dgi_r W_ih_r
         dx = None
         if ctx.needs_input_grad[0]:
@@ -258,19 +263,23 @@ class BiRnnLayer(Function):
             ops.gemm_tn(dgi2[:, :G], _transpose_padded(w_ih.contiguous())[:, :G], out=dx)
             ops.gemm_tn(dgi2[:, G:], _transpose_padded(w_ih_r.contiguous())[:, :G], out=dx, accumulate=True)
             dx = dx.view(T, B, I)
-        # weight gradients (K = T*B): dW_ih = dgi^T x ; dW_hh = dgh^T h_prev
-        dgit = _transpose_padded(dgi2)                          # [2G, R4]
+        # weight gradients (K = T*B): dW_ih = dgi^T x ; dW_hh = dgh^T h_prev -- the transposed gate gradients come
+        # straight from the recurrent kernel, only x and h_prev are transposed here
         xt = _transpose_padded(x2)                              # [I, R4]
-        dw_ih = ops.gemm_tn(dgit[:G, :R], xt[:, :R])
-        dw_ih_r = ops.gemm_tn(dgit[G:, :R], xt[:, :R])
+        dw_ih = ops.gemm_tn(dgiT[:G, :R], xt[:, :R])
+        dw_ih_r = ops.gemm_tn(dgiT[G:, :R], xt[:, :R])
         dw_hh = []
         for d in range(2):
-            dght = _transpose_padded(dgh[d].view(R, G))         # [G, R4]
             # previous state in forward order: slots 0..T-1 for the forward direction, 2..T+1 for the reverse one
             first = 0 if d == 0 else 2
-            hprev = hseq[d, first:first + T].reshape(R, H)
-            hpt = _transpose_padded(hprev)                      # [H, R4]
-            dw_hh.append(ops.gemm_tn(dght[:, :R], hpt[:, :R]))
+            hpt = _transpose_padded(hseq[d, first:first + T].reshape(R, H))   # [H, R4]
+            out = torch.empty(G, H, device=dout.device, dtype=torch.float32)
+            if gru:
+                ops.gemm_tn(dgiT[d * G:d * G + 2 * H, :R], hpt[:, :R], out=out[:2 * H])
+                ops.gemm_tn(dghTn[d][:, :R], hpt[:, :R], out=out[2 * H:])
+            else:
+                ops.gemm_tn(dgiT[d * G:(d + 1) * G, :R], hpt[:, :R], out=out)
+            dw_hh.append(out)
         return (dx, None, None, dw_ih, dw_hh[0], db_ih_cat[:G], db_hh[0], dw_ih_r, dw_hh[1], db_ih_cat[G:], db_hh[1])
 
 

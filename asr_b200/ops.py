@@ -425,7 +425,7 @@ def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
     hseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32)
     hbf = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.bfloat16) if bf16 else None
     cseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32) if cell == LSTM else None
-    saved = torch.empty(2, T, B, 4, H, device=dev, dtype=torch.float32)
+    saved = torch.empty(_lib.query("asrb_rnn_saved_floats", cell, H, B, int(bf16), T), device=dev, dtype=torch.float32)
     counters = torch.empty(2, device=dev, dtype=torch.int32)
     _call("asrb_rnn_fwd", cell, int(bf16), _p(gi), _p(b_hh), _p(wpack_fwd), _p(lengths), _p(hseq), _p(hbf), _p(cseq),
           _p(saved), _p(counters), T, B, H)
@@ -433,18 +433,31 @@ def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
 
 
 def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
-    """dout [T,B,H] -> dgi [T,B,2,G], dgh [2,T,B,G]"""
+    """dout [T,B,H] -> (dgi [T,B,2,G], dgiT [2G, R4], dghTn [2,H,R4] | None): the gate gradients row-major (operand of
+    the input-gradient GEMM) and transposed (operands of the weight-gradient GEMMs; R4 = T*B rounded up to 4)."""
     _chk(dout, hseq, cseq, saved)
     G = (3 if cell == GRU else 4) * H
     dev = dout.device
     bf16 = rnn_use_bf16(H)
+    R4 = (T * B + 3) // 4 * 4
     dgi = torch.empty(T, B, 2, G, device=dev, dtype=torch.float32)
-    dgh = torch.empty(2, T, B, G, device=dev, dtype=torch.float32)
+    dgh = None if bf16 else torch.empty(2, T, B, G, device=dev, dtype=torch.float32)
     dghbf = torch.empty(2, T, B, G, device=dev, dtype=torch.bfloat16) if bf16 else None
+    dgiT = torch.empty(2 * G, R4, device=dev, dtype=torch.float32)
+    dghTn = torch.empty(2, H, R4, device=dev, dtype=torch.float32) if cell == GRU else None
     counters = torch.empty(2, device=dev, dtype=torch.int32)
     _call("asrb_rnn_bwd", cell, int(bf16), _p(dout), _p(wpack_bwd), _p(lengths), _p(hseq), _p(cseq), _p(saved), _p(dgi),
-          _p(dgh), _p(dghbf), _p(counters), T, B, H)
-    return dgi, dgh
+          _p(dgh), _p(dghbf), _p(dgiT), _p(dghTn), R4, _p(counters), T, B, H)
+    return dgi, dgiT, dghTn
+
+
+def row_sums(a, cols=None):
+    """out[r] = sum_c a[r, :cols] for a row-strided 2-D view."""
+    rows = a.shape[0]
+    cols = a.shape[1] if cols is None else cols
+    out = torch.empty(rows, device=a.device, dtype=torch.float32)
+    _call("asrb_row_sums", _p(a), _ld(a), _p(out), rows, cols)
+    return out
 
 
 def rnn_sum_dirs(hseq, T, B, H):

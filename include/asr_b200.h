@@ -80,15 +80,22 @@ int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fw
                           void* wpack_fwd, void* wpack_bwd, asrb_stream_t stream);
 /* gi [T,B,2,G] = x W_ih^T + b_ih for both directions; b_hh [2,G]; lengths int32[B];
  * out: hseq [2,T+2,B,H] (slot t+1 = step t; slots 0,T+1 zero), hseq_bf16 same shape in bf16 (bf16 mode, else NULL),
- * cseq like hseq (LSTM only, else NULL), saved [2,T,B,4,H] (GRU: r,z,n,W_hn h+b_hn ; LSTM: i,f,g,o);
+ * cseq like hseq (LSTM only, else NULL), saved: asrb_rnn_saved_floats floats (GRU: r,z,n,W_hn h+b_hn ; LSTM: i,f,g,o);
  * counters: uint32[2] scratch. */
 int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
                  float* hseq, void* hseq_bf16, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream);
-/* dout [T,B,H] (gradient of the direction-summed output); out: dgi [T,B,2,G], dgh [2,T,B,G], dgh_bf16 (bf16 mode). */
+/* dout [T,B,H] (gradient of the direction-summed output).  out: dgi [T,B,2,G] (for the input-gradient GEMM);
+ * dgiT [2G, ldT] = its transpose (row = dir*G + gate*H + unit, column = t*B + b; ldT >= T*B, multiple of 4) and, for
+ * GRU, dghTn [2, H, ldT] = transposed gradient of the hidden-side n gate -- the K-major operands of the weight-
+ * gradient GEMMs, written directly so no transpose pass is needed; the recurrent operand of the next step is
+ * dgh_bf16 [2,T,B,G] (bf16 mode, dgh may be NULL) or dgh [2,T,B,G] fp32 (tf32 mode, dgh_bf16 may be NULL). */
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
                  const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
-                 uint32_t* counters, int T, int B, int H, asrb_stream_t stream);
+                 float* dgiT, float* dghTn, long long ldT, uint32_t* counters, int T, int B, int H,
+                 asrb_stream_t stream);
+/* floats in the saved-gates buffer (slice-major layout private to asrb_rnn_fwd / asrb_rnn_bwd) */
+size_t asrb_rnn_saved_floats(int cell, int H, int B, int bf16, int T);
 int asrb_debug_rnn_trace(long long* trace);
 /* out[T,B,H] = hseq[0][1..T] + hseq[1][1..T] */
 int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream);
@@ -164,6 +171,7 @@ int asrb_bn_rows_bwd(const float* dy, const float* x, const float* mean, const f
                      int cols, asrb_stream_t stream);
 int asrb_col_sums(const float* a, int lda, float* out, float* ws, size_t ws_bytes, long long R, int cols,
                   asrb_stream_t stream);
+int asrb_row_sums(const float* a, long long ld, float* out, int rows, long long cols, asrb_stream_t stream);
 /* logits[R, ld] -> log_probs[R,C] / probs[R,C] / argmax int64[R] (each optional) */
 int asrb_log_softmax_fwd(const float* logits, int ld, float* log_probs, float* probs, long long* argmax, long long R,
                          int C, asrb_stream_t stream);

@@ -307,7 +307,20 @@ def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
             dgi[t, :, d] = gi_g
             dgh[d, t] = gh_g
             prev_dgh = gh_g
-    return dgi, dgh
+    R = T * B
+    R4 = (R + 3) // 4 * 4
+    dgiT = torch.zeros(2 * G, R4)
+    dgiT[:, :R] = dgi.view(R, 2 * G).t()
+    dghTn = None
+    if cell == GRU:
+        dghTn = torch.zeros(2, H, R4)
+        for d in range(2):
+            dghTn[d, :, :R] = dgh[d].view(R, G)[:, 2 * H:].t()
+    return dgi, dgiT, dghTn
+
+
+def row_sums(a, cols=None):
+    return a[:, :cols].sum(1) if cols is not None else a.sum(1)
 
 
 def rnn_sum_dirs(hseq, T, B, H):

@@ -297,18 +297,25 @@ def test_rnn_fwd_bwd(ops, c, mode):
         # zero output past each length (pad_packed_sequence semantics)
         for bi, l in enumerate(lens.tolist()):
             assert out[l:, bi].abs().max().item() == 0 if l < T else True
-        dgi, dgh = ops.rnn_bwd(cell, dout.to(DEV), pb, ld, hseq, cseq, saved, T, B, H)
+        dgi, dgiT, dghTn = ops.rnn_bwd(cell, dout.to(DEV), pb, ld, hseq, cseq, saved, T, B, H)
         torch.cuda.synchronize()
         gscale = dgi_ref.abs().max().item()
         assert report("rnn bwd dgi", dgi, dgi_ref) <= gtol * gscale
-        # parameter gradients from the kernel outputs, assembled on the host in fp64
         R = T * B
+        # the transposed copy the kernel writes for the weight-gradient GEMMs must be the same numbers
+        assert torch.equal(dgiT[:, :R].cpu(), dgi.view(R, 2 * G).t().cpu())
+        # parameter gradients from the kernel outputs, assembled on the host in fp64
         for d in range(2):
             first = 0 if d == 0 else 2
             hprev = hseq[d, first:first + T].reshape(R, H).double().cpu()
-            dw = dgh[d].reshape(R, G).double().cpu().t() @ hprev
+            dghT = dgiT[d * G:(d + 1) * G, :R].double().cpu().clone()        # hidden-side gate gradients, [G, R]
+            if c["cell"] == "gru":
+                dghT[2 * H:] = dghTn[d][:, :R].double().cpu()
+            dgh = [None, None]
+            dgh[d] = dghT.t()
+            dw = dghT @ hprev
             assert report(f"rnn dW_hh dir{d}", dw, dw_ref[d]) <= gtol * max(1.0, dw_ref[d].abs().max().item())
-            assert report(f"rnn db_hh dir{d}", dgh[d].reshape(R, G).double().cpu().sum(0), db_ref[d]) <= \
+            assert report(f"rnn db_hh dir{d}", dgh[d].sum(0), db_ref[d]) <= \
                 gtol * max(1.0, db_ref[d].abs().max().item())
     finally:
         ops.set_debug_flags(0)
