@@ -54,7 +54,7 @@ struct RnnParams {
     float* dgi;          // [T,B,2,G]
     float* dgh;          // [2,T,B,G]  (tf32 / debug modes: MMA operand; NULL in bf16 mode)
     float* dgiT;         // [2G, ldT]  transposed gate gradients (row = dir*G + gate*H + unit, column = t*B + b)
-    float* dghTn;        // [2, H, ldT] GRU: transposed gradient of the hidden-side n gate (the r,z rows equal dgiT's)
+    float* dghT;         // [2G, ldT]  GRU: transposed hidden-side gate gradients (n rows differ from dgiT); NULL for LSTM
     long long ldT;
 };
 
@@ -459,16 +459,33 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     state_h[jj] = h_;
                     state_c[jj] = c_;
                 }
+                // (1) the next step's MMA operand goes out first and is published; (2) the stores nobody waits for
+                //     (fp32 state, saved gates) follow AFTER the release and overlap the wait for the next step
+                const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0;
                 if (rowok) {
-                    const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0;
+#pragma unroll
+                    for (int v = 0; v < NVH; ++v)
+                        if (gvalid[v]) {
+                            if constexpr (BF16) st4_bf16(p.hbf + o + 4 * v, &hn[4 * v]);
+                            else                st4(p.hseq + o + 4 * v, &hn[4 * v]);
+                        }
+                }
+                if (etid == 0) ASRB_TRACE(7, s);
+                if (tc) fence_proxy_async();
+                named_bar_sync(2, kRnnEpiThreads);
+                if (etid == 0) {
+                    ASRB_TRACE(8, s);
+                    red_release_add_u32(counter, 1u);   // release: orders the CTA's stores (observed through the barrier)
+                    ASRB_TRACE(10, s);
+                }
+                if (rowok) {
                     // saved gates, slice-major [dir][t][slice][gate][group][b][4]: consecutive batch rows (= lanes) are
                     // 16 bytes apart, so a warp store covers 2 lines instead of 16
                     float* svp = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) + (size_t)b * 4;
 #pragma unroll
                     for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
-                            st4(p.hseq + o + 4 * v, &hn[4 * v]);
-                            if constexpr (BF16) st4_bf16(p.hbf + o + 4 * v, &hn[4 * v]);
+                            if constexpr (BF16) st4(p.hseq + o + 4 * v, &hn[4 * v]);
                             if constexpr (CELL == ASRB_RNN_LSTM) st4(p.cseq + o + 4 * v, &cn[4 * v]);
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
@@ -508,11 +525,32 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     }
                     dg[0][jj] = d0; dg[1][jj] = d1; dg[2][jj] = d2; dg[3][jj] = d3; eg2[jj] = e2;
                 }
-                if (rowok) {
+                const size_t oh = (((size_t)dir * T + t) * B + b) * G + j0 + u0;
+                if (rowok) {   // (1) next step's MMA operand first
+#pragma unroll
+                    for (int v = 0; v < NVH; ++v)
+                        if (gvalid[v]) {
+#pragma unroll
+                            for (int q = 0; q < kGates; ++q) {
+                                const float* hv = (q == 2) ? &eg2[4 * v] : &dg[q][4 * v];
+                                if constexpr (BF16) st4_bf16(p.dghbf + oh + (size_t)q * H + 4 * v, hv);
+                                if (p.dgh) st4(p.dgh + oh + (size_t)q * H + 4 * v, hv);
+                            }
+                        }
+                }
+                if (etid == 0) ASRB_TRACE(7, s);
+                if (tc) fence_proxy_async();
+                named_bar_sync(2, kRnnEpiThreads);
+                if (etid == 0) {
+                    ASRB_TRACE(8, s);
+                    red_release_add_u32(counter, 1u);
+                    ASRB_TRACE(10, s);
+                }
+                if (rowok) {   // (2) outputs only later kernels read
                     float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0 + u0;
-                    const size_t oh = (((size_t)dir * T + t) * B + b) * G + j0 + u0;
                     // transposed copies for the weight-gradient GEMMs: lanes (batch rows) are contiguous -> coalesced
                     float* gT = p.dgiT + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b;
+                    float* hT = p.dghT ? p.dghT + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b : nullptr;
 #pragma unroll
                     for (int v = 0; v < NVH; ++v)
                         if (gvalid[v]) {
@@ -520,28 +558,15 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             for (int q = 0; q < kGates; ++q) {
                                 const float* hv = (q == 2) ? &eg2[4 * v] : &dg[q][4 * v];
                                 st4(dgi + (size_t)q * H + 4 * v, &dg[q][4 * v]);
-                                if (p.dgh) st4(p.dgh + oh + (size_t)q * H + 4 * v, hv);
-                                if constexpr (BF16) st4_bf16(p.dghbf + oh + (size_t)q * H + 4 * v, hv);
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) gT[((size_t)q * H + 4 * v + e) * p.ldT] = dg[q][4 * v + e];
-                            }
-                            if constexpr (CELL == ASRB_RNN_GRU) {
-                                float* hT = p.dghTn + ((size_t)dir * H + j0 + u0) * p.ldT + (size_t)t * B + b;
+                                if (hT) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) hT[(size_t)(4 * v + e) * p.ldT] = eg2[4 * v + e];
+                                    for (int e = 0; e < 4; ++e) hT[((size_t)q * H + 4 * v + e) * p.ldT] = hv[e];
+                                }
                             }
                         }
                 }
-            }
-
-            // ---- publish this step to the other CTAs of the direction ----
-            if (etid == 0) ASRB_TRACE(7, s);
-            if (tc) fence_proxy_async();
-            named_bar_sync(2, kRnnEpiThreads);
-            if (etid == 0) {
-                ASRB_TRACE(8, s);
-                red_release_add_u32(counter, 1u);   // release: orders the CTA's stores (observed through the barrier)
-                ASRB_TRACE(10, s);
             }
         }
     }
@@ -732,11 +757,11 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
 
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
                  const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
-                 float* dgiT, float* dghTn, long long ldT, uint32_t* counters, int T, int B, int H,
+                 float* dgiT, float* dghT, long long ldT, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream) {
     ASRB_REQUIRE(dout && wpack_bwd && lengths && hseq && saved && dgi && dgiT && counters && T > 0, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(cell == ASRB_RNN_GRU || cseq, ASRB_ERR_BAD_ARG);
-    ASRB_REQUIRE(cell == ASRB_RNN_LSTM || dghTn, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(cell == ASRB_RNN_LSTM || dghT, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(ldT >= (long long)T * B, ASRB_ERR_BAD_ARG);
     RnnPlan pl;
     int rc = rnn_make_plan(cell, H, B, rnn_effective_bf16(bf16), &pl);
@@ -747,7 +772,7 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
     prm.use_simt = (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 1 : 0;
     prm.lengths = lengths; prm.counters = counters;
     prm.hseq = const_cast<float*>(hseq); prm.cseq = const_cast<float*>(cseq); prm.saved = const_cast<float*>(saved);
-    prm.dout = dout; prm.dgi = dgi; prm.dgh = dgh; prm.dgiT = dgiT; prm.dghTn = dghTn; prm.ldT = ldT;
+    prm.dout = dout; prm.dgi = dgi; prm.dgh = dgh; prm.dgiT = dgiT; prm.dghT = (cell == ASRB_RNN_GRU) ? dghT : nullptr; prm.ldT = ldT;
     prm.dghbf = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
     prm.trace = g_rnn_trace;
     return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, pl.bf16 ? (const void*)dgh_bf16 : (const void*)dgh, stream);

@@ -246,16 +246,14 @@ class BiRnnLayer(Function):
         cell, T, B, I, H, G = ctx.dims
         R = T * B
         _, pack_b = ops.rnn_pack_weights(cell, w_hh, w_hh_r, B, fwd=False, bwd=True)
-        dgi, dgiT, dghTn = ops.rnn_bwd(cell, dout.contiguous(), pack_b, lengths_dev, hseq, cseq, saved, T, B, H)
+        dgi, dgiT, dghT = ops.rnn_bwd(cell, dout.contiguous(), pack_b, lengths_dev, hseq, cseq, saved, T, B, H)
         dgi2 = dgi.view(R, 2 * G)
-        gru = cell == ops.GRU
+        if dghT is None:      # LSTM: hidden-side gate gradients are the input-side ones
+            dghT = dgiT
         # bias gradients = row sums of the transposed gate gradients
         db_ih_cat = ops.row_sums(dgiT, R)
-        if gru:   # hidden-side gradients equal the input-side ones for r,z; the n gate has its own (x r)
-            db_hn = ops.row_sums(dghTn.view(2 * H, -1), R)
-            db_hh = [torch.cat([db_ih_cat[d * G:d * G + 2 * H], db_hn[d * H:(d + 1) * H]]) for d in range(2)]
-        else:
-            db_hh = [db_ih_cat[d * G:(d + 1) * G] for d in range(2)]
+        db_hh_cat = db_ih_cat if dghT is dgiT else ops.row_sums(dghT, R)
+        db_hh = [db_hh_cat[d * G:(d + 1) * G] for d in range(2)]
         # input gradient: dx = dgi_f W_ih_f + dgi_r W_ih_r
         dx = None
         if ctx.needs_input_grad[0]:
@@ -273,13 +271,7 @@ class BiRnnLayer(Function):
             # previous state in forward order: slots 0..T-1 for the forward direction, 2..T+1 for the reverse one
             first = 0 if d == 0 else 2
             hpt = _transpose_padded(hseq[d, first:first + T].reshape(R, H))   # [H, R4]
-            out = torch.empty(G, H, device=dout.device, dtype=torch.float32)
-            if gru:
-                ops.gemm_tn(dgiT[d * G:d * G + 2 * H, :R], hpt[:, :R], out=out[:2 * H])
-                ops.gemm_tn(dghTn[d][:, :R], hpt[:, :R], out=out[2 * H:])
-            else:
-                ops.gemm_tn(dgiT[d * G:(d + 1) * G, :R], hpt[:, :R], out=out)
-            dw_hh.append(out)
+            dw_hh.append(ops.gemm_tn(dghT[d * G:(d + 1) * G, :R], hpt[:, :R]))
         return (dx, None, None, dw_ih, dw_hh[0], db_ih_cat[:G], db_hh[0], dw_ih_r, dw_hh[1], db_ih_cat[G:], db_hh[1])
 
 

@@ -433,8 +433,9 @@ def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
 
 
 def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
-    """dout [T,B,H] -> (dgi [T,B,2,G], dgiT [2G, R4], dghTn [2,H,R4] | None): the gate gradients row-major (operand of
-    the input-gradient GEMM) and transposed (operands of the weight-gradient GEMMs; R4 = T*B rounded up to 4)."""
+    """dout [T,B,H] -> (dgi [T,B,2,G], dgiT [2G, R4], dghT [2G, R4] | None): the gate gradients row-major (operand of
+    the input-gradient GEMM) and transposed (operands of the weight-gradient GEMMs; R4 = T*B rounded up to 4).
+    dghT (hidden-side gradients) exists for GRU only; for LSTM it equals dgiT."""
     _chk(dout, hseq, cseq, saved)
     G = (3 if cell == GRU else 4) * H
     dev = dout.device
@@ -444,11 +445,11 @@ def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
     dgh = None if bf16 else torch.empty(2, T, B, G, device=dev, dtype=torch.float32)
     dghbf = torch.empty(2, T, B, G, device=dev, dtype=torch.bfloat16) if bf16 else None
     dgiT = torch.empty(2 * G, R4, device=dev, dtype=torch.float32)
-    dghTn = torch.empty(2, H, R4, device=dev, dtype=torch.float32) if cell == GRU else None
+    dghT = torch.empty(2 * G, R4, device=dev, dtype=torch.float32) if cell == GRU else None
     counters = torch.empty(2, device=dev, dtype=torch.int32)
     _call("asrb_rnn_bwd", cell, int(bf16), _p(dout), _p(wpack_bwd), _p(lengths), _p(hseq), _p(cseq), _p(saved), _p(dgi),
-          _p(dgh), _p(dghbf), _p(dgiT), _p(dghTn), R4, _p(counters), T, B, H)
-    return dgi, dgiT, dghTn
+          _p(dgh), _p(dghbf), _p(dgiT), _p(dghT), R4, _p(counters), T, B, H)
+    return dgi, dgiT, dghT
 
 
 def row_sums(a, cols=None):

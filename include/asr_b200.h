@@ -87,12 +87,13 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
                  asrb_stream_t stream);
 /* dout [T,B,H] (gradient of the direction-summed output).  out: dgi [T,B,2,G] (for the input-gradient GEMM);
  * dgiT [2G, ldT] = its transpose (row = dir*G + gate*H + unit, column = t*B + b; ldT >= T*B, multiple of 4) and, for
- * GRU, dghTn [2, H, ldT] = transposed gradient of the hidden-side n gate -- the K-major operands of the weight-
- * gradient GEMMs, written directly so no transpose pass is needed; the recurrent operand of the next step is
+ * GRU, dghT [2G, ldT] = the transposed hidden-side gate gradients (they differ from dgiT in the n gate; LSTM: NULL)
+ * -- the K-major operands of the weight-gradient GEMMs, written directly so no transpose pass is needed; the
+ * recurrent operand of the next step is
  * dgh_bf16 [2,T,B,G] (bf16 mode, dgh may be NULL) or dgh [2,T,B,G] fp32 (tf32 mode, dgh_bf16 may be NULL). */
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
                  const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
-                 float* dgiT, float* dghTn, long long ldT, uint32_t* counters, int T, int B, int H,
+                 float* dgiT, float* dghT, long long ldT, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream);
 /* floats in the saved-gates buffer (slice-major layout private to asrb_rnn_fwd / asrb_rnn_bwd) */
 size_t asrb_rnn_saved_floats(int cell, int H, int B, int bf16, int T);

@@ -311,12 +311,12 @@ def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
     R4 = (R + 3) // 4 * 4
     dgiT = torch.zeros(2 * G, R4)
     dgiT[:, :R] = dgi.view(R, 2 * G).t()
-    dghTn = None
+    dghT = None
     if cell == GRU:
-        dghTn = torch.zeros(2, H, R4)
+        dghT = torch.zeros(2 * G, R4)
         for d in range(2):
-            dghTn[d, :, :R] = dgh[d].view(R, G)[:, 2 * H:].t()
-    return dgi, dgiT, dghTn
+            dghT[d * G:(d + 1) * G, :R] = dgh[d].view(R, G).t()
+    return dgi, dgiT, dghT
 
 
 def row_sums(a, cols=None):

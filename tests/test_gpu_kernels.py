@@ -297,7 +297,7 @@ def test_rnn_fwd_bwd(ops, c, mode):
         # zero output past each length (pad_packed_sequence semantics)
         for bi, l in enumerate(lens.tolist()):
             assert out[l:, bi].abs().max().item() == 0 if l < T else True
-        dgi, dgiT, dghTn = ops.rnn_bwd(cell, dout.to(DEV), pb, ld, hseq, cseq, saved, T, B, H)
+        dgi, dgiT, dghT_k = ops.rnn_bwd(cell, dout.to(DEV), pb, ld, hseq, cseq, saved, T, B, H)
         torch.cuda.synchronize()
         gscale = dgi_ref.abs().max().item()
         assert report("rnn bwd dgi", dgi, dgi_ref) <= gtol * gscale
@@ -308,9 +308,8 @@ def test_rnn_fwd_bwd(ops, c, mode):
         for d in range(2):
             first = 0 if d == 0 else 2
             hprev = hseq[d, first:first + T].reshape(R, H).double().cpu()
-            dghT = dgiT[d * G:(d + 1) * G, :R].double().cpu().clone()        # hidden-side gate gradients, [G, R]
-            if c["cell"] == "gru":
-                dghT[2 * H:] = dghTn[d][:, :R].double().cpu()
+            src = dghT_k if c["cell"] == "gru" else dgiT                     # hidden-side gate gradients, [G, R]
+            dghT = src[d * G:(d + 1) * G, :R].double().cpu().clone()
             dgh = [None, None]
             dgh[d] = dghT.t()
             dw = dghT @ hprev
