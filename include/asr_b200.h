@@ -185,7 +185,7 @@ int asrb_ctc_fwd(const float* log_probs, const int32_t* targets, const int32_t* 
                  const int32_t* target_lengths, float* alpha_ws, size_t ws_bytes, float* nll, float* loss, int T, int N,
                  int C, int max_target_len, int blank, asrb_stream_t stream);
 int asrb_ctc_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lengths,
-                 const int32_t* target_lengths, const float* alpha_ws, const float* nll, const float* grad_scale,
+                 const int32_t* target_lengths, float* alpha_ws, const float* nll, const float* grad_scale,
                  float* grad, int T, int N, int C, int max_target_len, int blank, asrb_stream_t stream);
 
 /* ---------------------------------------------------------------- spectrogram (STFT -> |.| -> log1p -> normalise) */
