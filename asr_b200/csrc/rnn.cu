@@ -28,20 +28,30 @@
 
 namespace asrb {
 
-constexpr int kRnnThreads = 320;   // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two warps per TMEM lane quarter)
-constexpr int kRnnEpiThreads = 256;
+// warp 0: TMA producer; warp 1: MMA issuer; warps 2,3: idle (keep warp % 4 == TMEM lane quarter for the rest);
+// warps 4..19: epilogue, lane quarter = warp % 4, four 4-unit groups per quarter
+constexpr int kRnnCtrlWarps = 4;
+constexpr int kRnnEpiWarps = 16;
+constexpr int kRnnThreads = (kRnnCtrlWarps + kRnnEpiWarps) * 32;
+constexpr int kRnnEpiThreads = kRnnEpiWarps * 32;
+constexpr int kRnnCounterStride = 32;                  // step counters [dir], one 128-byte line each
 constexpr int kRnnMaxRows = 128;   // batch rows per CTA (one MMA M tile; TMA zero-fills rows >= B)
 constexpr int kRnnMaxSmem = 227 * 1024;
 constexpr int kRnnMaxStages = 40;
-constexpr int kRnnBarBytes = 1024;
+constexpr int kRnnBarBytes = 1024;  // 2 x kRnnMaxStages ring barriers + 3 + TMEM slot, then the bias slice
+constexpr int kRnnBiasOffset = 704;
 
 struct RnnParams {
     int T, B, H, G, P, kpad, use_simt, stages, chunk;   // chunk = K blocks per pipeline stage / barrier
     const int* lengths;
-    uint32_t* counters;
+    uint32_t* counters;   // [2 dirs] step counters, kRnnCounterStride words apart
+    int dbg;              // DEBUG timing experiments: 1 = drop the non-critical stores, 2 = drop the operand prefetch
     const float* wpack;  // packed fp32 weight slices (global copy, SIMT debug path)
-    __nv_bfloat16* hbf;   // [2,T+2,B,H] bf16 copy of hseq (forward, bf16 mode): the next step's MMA operand
-    __nv_bfloat16* dghbf; // [2,T,B,G]  bf16 copy of dgh  (backward, bf16 mode)
+    // bf16 MMA operands; rows padded to a multiple of 64 elements (128 bytes) so that every 128-byte box row TMA
+    // fetches is ONE aligned L2 line (H=800 rows of 1600 bytes would put every odd row across two lines)
+    __nv_bfloat16* hbf;   // [2,T+2,B,Hp] bf16 copy of hseq (forward, bf16 mode): the next step's MMA operand
+    __nv_bfloat16* dghbf; // [2,T,B,Gp]  bf16 copy of dgh  (backward, bf16 mode)
+    int Hp, Gp;
     long long* trace;     // DEBUG: [gridDim][T][12] SM-clock stamps per step (asrb_debug_rnn_trace), else NULL
     // forward
     const float* gi;     // [T,B,2,G]
@@ -111,6 +121,8 @@ __global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float
 // the recurrence
 // ------------------------------------------------------------------------------------------------
 long long* g_rnn_trace = nullptr;
+int g_rnn_dbg = 0;
+int g_rnn_chunk = 0;   // DEBUG: K blocks per pipeline barrier (0 = automatic)
 
 // fast gate non-linearities (ex2.approx + approximate division): ~1e-6 absolute error
 __device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
@@ -152,8 +164,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
     constexpr int kTmemCols = 64;
     constexpr int KBE = BF16 ? 64 : 32;          // elements per 128-byte K block
-    constexpr int kStageBytes = MROWS * 128;
-    // TMEM lane of batch row m: M=128 -> m ; M=64 -> (m % 16) + 32 * (m / 16)  (half of every lane quarter)
+    constexpr int kStageBytes = MROWS * 128;     // one K block of the A tile: MROWS rows x 128 B
+    // TMEM lane of tile row m: M=128 -> m ; M=64 -> (m % 16) + 32 * (m / 16)  (16 lanes of every lane quarter)
     constexpr int kRowsPerWarp = MROWS / 4;
 
     extern __shared__ uint8_t smem_raw[];
@@ -164,7 +176,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const int stage_bytes = p.chunk * kStageBytes;
     const int nchunks = ceil_div(nkb, p.chunk);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * stage_bytes);
-    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 704);   // [kGates][NJ] (forward)
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kRnnBiasOffset);   // [kGates][NJ] (forward)
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kRnnMaxStages;
     uint64_t* w_bar = bars + 2 * kRnnMaxStages;
@@ -177,8 +189,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const int dir = blockIdx.x / P, pidx = blockIdx.x % P;
     const int j0 = pidx * NJ;
     const bool tc = !p.use_simt;
-    uint32_t* counter = p.counters + dir;
-
+    uint32_t* counter = p.counters + dir * kRnnCounterStride;
     // time index processed at sequential step s
     auto t_of = [&](int s) { return (BWD ? (dir == 0) : (dir == 1)) ? (T - 1 - s) : s; };
 
@@ -191,7 +202,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         }
         mbar_init(w_bar, 1);
         mbar_init(tfull_bar, 1);
-        mbar_init(tempty_bar, 8);
+        mbar_init(tempty_bar, kRnnEpiWarps);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -212,11 +223,15 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int s = 1; s < T; ++s) {
+                // step barrier: every CTA of this direction has published step s-1
                 const uint32_t need = (uint32_t)P * (uint32_t)s;
                 while (ld_acquire_u32(counter) < need) {
                 }
                 if (lane == 0) ASRB_TRACE(0, s);
-                fence_proxy_async();  // other CTAs' generic-proxy stores -> visible to our async-proxy (TMA) reads
+                // other CTAs' generic-proxy stores (acquired above) -> visible to our async-proxy (TMA) reads.
+                // The .global form is a bare FENCE.VIEW.ASYNC.G; the unqualified one adds a MEMBAR.ALL.GPU.
+                fence_proxy_async_global();
+                if (lane == 0) ASRB_TRACE(9, s);
                 const int tp = t_of(s - 1);
                 const int slab = BWD ? (dir * T + tp) : (dir * (T + 2) + tp + 1);
                 for (int c = 0; c < nchunks; ++c) {
@@ -237,6 +252,11 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        // Measured (tools/trace_rnn.py, tools/ubench): this phase is bound by shared-memory bandwidth -- every step the
+        // whole previous state is written to SMEM by TMA and read back by the tensor core together with the weight slice
+        // (fwd 286 KB, bwd 684 KB per CTA per step at ~90 B/clk) -- not by L2 (TMA multicast over clusters of 2/5 CTAs and
+        // replicated operands changed nothing), not by the accumulator dependency (4 independent accumulators: same
+        // time) and not by the number of MMAs (two half-batch passes cost the same as one).
         if (tc) {
             constexpr uint32_t idesc = umma_idesc(BF16 ? kFmtBF16 : kFmtTF32, MROWS, NPAD);
             mbar_wait(w_bar, 0);
@@ -273,50 +293,43 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 if (lane == 0) ASRB_TRACE(3, s);
             }
         }
-    } else {
-        // ===================== epilogue: thread = (batch row, half of the slice's hidden units) =====================
-        // Two warps share each TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31) and split the columns.
+    } else if (warp >= kRnnCtrlWarps) {
+        // ===================== epilogue: thread = (batch row, one 4-wide group of the slice's hidden units) ==========
+        // 16 warps: lane quarter q = warp % 4 (a warp may only read TMEM lanes 32*(warp%4)..+31), unit group ug.
         constexpr int NV = NJ / 4;               // 4-wide unit groups of the slice: all global traffic is 16-byte vectors
-        constexpr int NVH = (NV + 1) / 2;        // groups per thread
-        constexpr int NJH = 4 * NVH;             // units per thread
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int ug = (warp - kRnnCtrlWarps) >> 2;
         const int b = quad * kRowsPerWarp + lane;
-        const int etid = (warp - 2) * 32 + lane;  // 0..255
-        const bool rowok = lane < kRowsPerWarp && b < B;
-        const bool warp_has_rows = quad * kRowsPerWarp < B;
+        const int hl = (warp - kRnnCtrlWarps) * 32 + lane;    // epilogue thread index: 0..511
+        const bool gvalid = (ug < NV) && (j0 + 4 * ug < H);
+        const bool rowok = lane < kRowsPerWarp && b < B && gvalid;
+        const bool warp_ld = (quad * kRowsPerWarp < B) && (ug < NV);   // warp-uniform: this warp reads the accumulator
         const int len = rowok ? p.lengths[b] : 0;
         const size_t slotHB = (size_t)B * H;
-        const int u0 = half * NJH;               // first unit (within the slice) owned by this thread
-        bool gvalid[NVH];
-#pragma unroll
-        for (int v = 0; v < NVH; ++v) gvalid[v] = (half * NVH + v < NV) && (j0 + u0 + 4 * v < H);
+        const int u0 = 4 * ug;                   // first unit (within the slice) owned by this thread
 
-        float state_h[NJH];   // fwd: h_prev of our units ; bwd: direct dh carry
-        float state_c[NJH];   // fwd LSTM: c_prev ; bwd LSTM: dc carry
+        float state_h[4];   // fwd: h_prev of our units ; bwd: direct dh carry
+        float state_c[4];   // fwd LSTM: c_prev ; bwd LSTM: dc carry
 #pragma unroll
-        for (int jj = 0; jj < NJH; ++jj) state_h[jj] = state_c[jj] = 0.f;
+        for (int jj = 0; jj < 4; ++jj) state_h[jj] = state_c[jj] = 0.f;
 
         if (!BWD && rowok) {  // zero boundary slots 0 and T+1 of our part of the slice
             float z4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int v = 0; v < NVH; ++v)
-                if (gvalid[v]) {
-                    const size_t o = ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j0 + u0 + 4 * v;
-                    st4(p.hseq + o, z4);
-                    st4(p.hseq + o + (size_t)(T + 1) * slotHB, z4);
-                    if constexpr (BF16) {
-                        st4_bf16(p.hbf + o, z4);
-                        st4_bf16(p.hbf + o + (size_t)(T + 1) * slotHB, z4);
-                    }
-                    if constexpr (CELL == ASRB_RNN_LSTM) {
-                        st4(p.cseq + o, z4);
-                        st4(p.cseq + o + (size_t)(T + 1) * slotHB, z4);
-                    }
-                }
+            const size_t o = ((size_t)dir * (T + 2)) * slotHB + (size_t)b * H + j0 + u0;
+            st4(p.hseq + o, z4);
+            st4(p.hseq + o + (size_t)(T + 1) * slotHB, z4);
+            if constexpr (BF16) {
+                const size_t ob = (((size_t)dir * (T + 2)) * B + b) * p.Hp + j0 + u0;
+                st4_bf16(p.hbf + ob, z4);
+                st4_bf16(p.hbf + ob + (size_t)(T + 1) * B * p.Hp, z4);
+            }
+            if constexpr (CELL == ASRB_RNN_LSTM) {
+                st4(p.cseq + o, z4);
+                st4(p.cseq + o + (size_t)(T + 1) * slotHB, z4);
+            }
         }
         if constexpr (!BWD) {                    // recurrent biases of the slice -> shared memory (broadcast reads)
-            for (int i = etid; i < kGates * NJ; i += kRnnEpiThreads) {
+            for (int i = hl; i < kGates * NJ; i += kRnnEpiThreads) {
                 const int g = i / NJ, jj = i % NJ;
                 s_bias[i] = (j0 + jj < H) ? p.b_hh[(size_t)dir * G + g * H + j0 + jj] : 0.f;
             }
@@ -326,30 +339,27 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int s = 0; s < T; ++s) {
             const int t = t_of(s);
             const bool active = rowok && (t < len);
-            if (etid == 0) ASRB_TRACE(4, s);
+            if (hl == 0) ASRB_TRACE(4, s);
             constexpr int kAccG = BWD ? 1 : kGates;      // accumulator column groups we read: gates (fwd) / units (bwd)
-            float acc[kAccG][NJH];
+            float acc[kAccG][4];
 #pragma unroll
             for (int g = 0; g < kAccG; ++g)
 #pragma unroll
-                for (int jj = 0; jj < NJH; ++jj) acc[g][jj] = 0.f;
+                for (int jj = 0; jj < 4; ++jj) acc[g][jj] = 0.f;
 
             // ---- operand prefetch (independent of the MMA): issued before we wait for the accumulator ----
             constexpr int kIn = BWD ? 6 : kGates;        // fwd: gi gates ; bwd: 4 saved + dout + previous state
-            float in[kIn][NJH];
+            float in[kIn][4];
 #pragma unroll
             for (int q = 0; q < kIn; ++q)
 #pragma unroll
-                for (int jj = 0; jj < NJH; ++jj) in[q][jj] = 0.f;
-            if (active) {
+                for (int jj = 0; jj < 4; ++jj) in[q][jj] = 0.f;
+            float ct[4] = {0.f, 0.f, 0.f, 0.f};          // bwd LSTM: c_t
+            if (active && !(p.dbg & 2)) {
                 if constexpr (!BWD) {
                     const float* g = p.gi + (((size_t)t * B + b) * 2 + dir) * G + j0 + u0;
 #pragma unroll
-                    for (int v = 0; v < NVH; ++v)
-                        if (gvalid[v]) {
-#pragma unroll
-                            for (int q = 0; q < kGates; ++q) ldg4(&in[q][4 * v], g + (size_t)q * H + 4 * v);
-                        }
+                    for (int q = 0; q < kGates; ++q) ldg4(in[q], g + (size_t)q * H);
                 } else {
                     const float* sv = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) + (size_t)b * 4;
                     const float* dop = p.dout + ((size_t)t * B + b) * H + j0 + u0;
@@ -357,25 +367,11 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     const float* prevp = (CELL == ASRB_RNN_GRU ? p.hseq : p.cseq) +
                                          ((size_t)dir * (T + 2) + tprev_slot) * slotHB + (size_t)b * H + j0 + u0;
 #pragma unroll
-                    for (int v = 0; v < NVH; ++v)
-                        if (gvalid[v]) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                ld4(&in[q][4 * v], sv + ((size_t)q * NV + half * NVH + v) * (size_t)(B * 4));
-                            ldg4(&in[4][4 * v], dop + 4 * v);
-                            ld4(&in[5][4 * v], prevp + 4 * v);
-                        }
-                }
-            }
-            float ct[(BWD && CELL == ASRB_RNN_LSTM) ? NJH : 1];  // bwd LSTM: c_t
-#pragma unroll
-            for (int jj = 0; jj < ((BWD && CELL == ASRB_RNN_LSTM) ? NJH : 1); ++jj) ct[jj] = 0.f;
-            if constexpr (BWD && CELL == ASRB_RNN_LSTM) {
-                if (active) {
-                    const float* cp = p.cseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0;
-#pragma unroll
-                    for (int v = 0; v < NVH; ++v)
-                        if (gvalid[v]) ld4(&ct[4 * v], cp + 4 * v);
+                    for (int q = 0; q < 4; ++q) ld4(in[q], sv + ((size_t)q * NV + ug) * (size_t)(B * 4));
+                    ldg4(in[4], dop);
+                    ld4(in[5], prevp);
+                    if constexpr (CELL == ASRB_RNN_LSTM)
+                        ld4(ct, p.cseq + ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0);
                 }
             }
 
@@ -383,25 +379,21 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if (s > 0) {
                 if (tc) {
                     mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
-                    if (etid == 0) ASRB_TRACE(5, s);
+                    if (hl == 0) ASRB_TRACE(5, s);
                     tc_fence_after_sync();
-                    if (warp_has_rows) {
-                        const uint32_t lane_base = tmem_base + (uint32_t(quad * 32) << 16);
+                    if (warp_ld) {
+                        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + u0;
 #pragma unroll
-                        for (int g = 0; g < kAccG; ++g)
-#pragma unroll
-                            for (int v = 0; v < NVH; ++v)
-                                if (half * NVH + v < NV)      // warp-uniform
-                                    tmem_ld_32x4(lane_base + (BWD ? 0 : g * NJ) + u0 + 4 * v, &acc[g][4 * v]);
+                        for (int g = 0; g < kAccG; ++g) tmem_ld_32x4(taddr + (BWD ? 0 : g * NJ), acc[g]);
                         tmem_ld_wait();
                     }
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar);
-                    if (etid == 0) ASRB_TRACE(6, s);
+                    if (hl == 0) ASRB_TRACE(6, s);
                 } else {
                     // DEBUG path (asrb_set_debug_flags bit 1): same algorithm, plain fp32 dot products
-                    if (etid == 0) {
+                    if (hl == 0) {
                         const uint32_t need = (uint32_t)P * (uint32_t)s;
                         while (ld_acquire_u32(counter) < need) {
                         }
@@ -418,9 +410,9 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 #pragma unroll
                             for (int g = 0; g < kAccG; ++g)
 #pragma unroll
-                                for (int jj = 0; jj < NJH; ++jj) {
+                                for (int jj = 0; jj < 4; ++jj) {
                                     const int col = (BWD ? 0 : g * NJ) + u0 + jj;
-                                    if (col < NPAD) acc[g][jj] = fmaf(a, __ldg(wrow + (size_t)col * p.kpad + k), acc[g][jj]);
+                                    acc[g][jj] = fmaf(a, __ldg(wrow + (size_t)col * p.kpad + k), acc[g][jj]);
                                 }
                         }
                     }
@@ -429,9 +421,9 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
             // ---- cell math (registers only), then 16-byte vector stores ----
             if constexpr (!BWD) {
-                float hn[NJH], cn[NJH], sv[4][NJH];
+                float hn[4], cn[4], sv[4][4];
 #pragma unroll
-                for (int jj = 0; jj < NJH; ++jj) {
+                for (int jj = 0; jj < 4; ++jj) {
                     float h_ = 0.f, c_ = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                     if (active) {
                         const float* bs = s_bias + u0 + jj;
@@ -463,39 +455,35 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 //     (fp32 state, saved gates) follow AFTER the release and overlap the wait for the next step
                 const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)b * H + j0 + u0;
                 if (rowok) {
-#pragma unroll
-                    for (int v = 0; v < NVH; ++v)
-                        if (gvalid[v]) {
-                            if constexpr (BF16) st4_bf16(p.hbf + o + 4 * v, &hn[4 * v]);
-                            else                st4(p.hseq + o + 4 * v, &hn[4 * v]);
-                        }
+                    if constexpr (BF16) st4_bf16(p.hbf + (((size_t)dir * (T + 2) + t + 1) * B + b) * p.Hp + j0 + u0, hn);
+                    else                st4(p.hseq + o, hn);
                 }
-                if (etid == 0) ASRB_TRACE(7, s);
-                if (tc) fence_proxy_async();
+                if (hl == 0) ASRB_TRACE(7, s);
+                // Step barrier, cooperative-groups style: CTA barrier, then ONE thread fences (the MEMBAR.ALL.GPU inside
+                // red.release covers the stores it observed through the barrier) and bumps the counter.  The consumers'
+                // TMA reads are ordered by their own acquire + fence.proxy.async.global; no per-thread fence here (an
+                // unqualified fence.proxy.async is a MEMBAR.ALL.GPU in every warp: measured 1400 cycles on the chain).
                 named_bar_sync(2, kRnnEpiThreads);
-                if (etid == 0) {
+                if (hl == 0) {
                     ASRB_TRACE(8, s);
-                    red_release_add_u32(counter, 1u);   // release: orders the CTA's stores (observed through the barrier)
+                    red_release_add_u32(counter, 1u);
                     ASRB_TRACE(10, s);
                 }
-                if (rowok) {
+                // hold the bulk stores back until the release has been issued: a MEMBAR waits for every store in flight
+                named_bar_sync(4, kRnnEpiThreads);
+                if (rowok && !(p.dbg & 1)) {
                     // saved gates, slice-major [dir][t][slice][gate][group][b][4]: consecutive batch rows (= lanes) are
                     // 16 bytes apart, so a warp store covers 2 lines instead of 16
                     float* svp = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) + (size_t)b * 4;
+                    if constexpr (BF16) st4(p.hseq + o, hn);
+                    if constexpr (CELL == ASRB_RNN_LSTM) st4(p.cseq + o, cn);
 #pragma unroll
-                    for (int v = 0; v < NVH; ++v)
-                        if (gvalid[v]) {
-                            if constexpr (BF16) st4(p.hseq + o + 4 * v, &hn[4 * v]);
-                            if constexpr (CELL == ASRB_RNN_LSTM) st4(p.cseq + o + 4 * v, &cn[4 * v]);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                st4(svp + ((size_t)q * NV + half * NVH + v) * (size_t)(B * 4), &sv[q][4 * v]);
-                        }
+                    for (int q = 0; q < 4; ++q) st4(svp + ((size_t)q * NV + ug) * (size_t)(B * 4), sv[q]);
                 }
             } else {
-                float dg[4][NJH], eg2[NJH];
+                float dg[4][4], eg2[4];
 #pragma unroll
-                for (int jj = 0; jj < NJH; ++jj) {
+                for (int jj = 0; jj < 4; ++jj) {
                     const float carry = acc[0][jj] + state_h[jj];
                     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, e2 = 0.f;
                     if (active) {
@@ -510,7 +498,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                             state_h[jj] = dh * z;
                         } else {
                             const float gi_ = in[0][jj], gf = in[1][jj], gg = in[2][jj], go = in[3][jj], cp = in[5][jj];
-                            const float tcv = ftanh(ct[(BWD && CELL == ASRB_RNN_LSTM) ? jj : 0]);
+                            const float tcv = ftanh(ct[jj]);
                             const float dc = state_c[jj] + dh * go * (1.f - tcv * tcv);
                             d0 = dc * gg * gi_ * (1.f - gi_);
                             d1 = dc * cp * gf * (1.f - gf);
@@ -528,44 +516,36 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 const size_t oh = (((size_t)dir * T + t) * B + b) * G + j0 + u0;
                 if (rowok) {   // (1) next step's MMA operand first
 #pragma unroll
-                    for (int v = 0; v < NVH; ++v)
-                        if (gvalid[v]) {
-#pragma unroll
-                            for (int q = 0; q < kGates; ++q) {
-                                const float* hv = (q == 2) ? &eg2[4 * v] : &dg[q][4 * v];
-                                if constexpr (BF16) st4_bf16(p.dghbf + oh + (size_t)q * H + 4 * v, hv);
-                                if (p.dgh) st4(p.dgh + oh + (size_t)q * H + 4 * v, hv);
-                            }
-                        }
+                    for (int q = 0; q < kGates; ++q) {
+                        const float* hv = (q == 2) ? eg2 : dg[q];
+                        if constexpr (BF16) st4_bf16(p.dghbf + (((size_t)dir * T + t) * B + b) * p.Gp + j0 + u0 + (size_t)q * H, hv);
+                        if (p.dgh) st4(p.dgh + oh + (size_t)q * H, hv);
+                    }
                 }
-                if (etid == 0) ASRB_TRACE(7, s);
-                if (tc) fence_proxy_async();
-                named_bar_sync(2, kRnnEpiThreads);
-                if (etid == 0) {
+                if (hl == 0) ASRB_TRACE(7, s);
+                named_bar_sync(2, kRnnEpiThreads);      // see the forward branch
+                if (hl == 0) {
                     ASRB_TRACE(8, s);
                     red_release_add_u32(counter, 1u);
                     ASRB_TRACE(10, s);
                 }
-                if (rowok) {   // (2) outputs only later kernels read
+                named_bar_sync(4, kRnnEpiThreads);
+                if (rowok && !(p.dbg & 1)) {   // (2) outputs only later kernels read
                     float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0 + u0;
                     // transposed copies for the weight-gradient GEMMs: lanes (batch rows) are contiguous -> coalesced
                     float* gT = p.dgiT + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b;
                     float* hT = p.dghT ? p.dghT + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b : nullptr;
 #pragma unroll
-                    for (int v = 0; v < NVH; ++v)
-                        if (gvalid[v]) {
+                    for (int q = 0; q < kGates; ++q) {
+                        const float* hv = (q == 2) ? eg2 : dg[q];
+                        st4(dgi + (size_t)q * H, dg[q]);
 #pragma unroll
-                            for (int q = 0; q < kGates; ++q) {
-                                const float* hv = (q == 2) ? &eg2[4 * v] : &dg[q][4 * v];
-                                st4(dgi + (size_t)q * H + 4 * v, &dg[q][4 * v]);
+                        for (int e = 0; e < 4; ++e) gT[((size_t)q * H + e) * p.ldT] = dg[q][e];
+                        if (hT) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) gT[((size_t)q * H + 4 * v + e) * p.ldT] = dg[q][4 * v + e];
-                                if (hT) {
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) hT[((size_t)q * H + 4 * v + e) * p.ldT] = hv[e];
-                                }
-                            }
+                            for (int e = 0; e < 4; ++e) hT[((size_t)q * H + e) * p.ldT] = hv[e];
                         }
+                    }
                 }
             }
         }
@@ -617,8 +597,8 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
         // K blocks that fit next to the resident weights; up to 4 blocks share one barrier / pipeline stage
         const int bf = (int)((kRnnMaxSmem - fixed - wf) / stage), bb = (int)((kRnnMaxSmem - fixed - wb) / stage);
         const int nkb_f = r.kpad_f / kbe, nkb_b = r.kpad_b / kbe;
-        r.chunk_f = bf >= 8 ? 4 : (bf >= 4 ? 2 : 1);
-        r.chunk_b = bb >= 8 ? 4 : (bb >= 4 ? 2 : 1);
+        r.chunk_f = g_rnn_chunk > 0 ? g_rnn_chunk : (bf >= 8 ? 4 : (bf >= 4 ? 2 : 1));
+        r.chunk_b = g_rnn_chunk > 0 ? g_rnn_chunk : (bb >= 8 ? 4 : (bb >= 4 ? 2 : 1));
         r.stages_f = bf / r.chunk_f; r.stages_b = bb / r.chunk_b;
         const int cf = ceil_div(nkb_f, r.chunk_f), cb = ceil_div(nkb_b, r.chunk_b);
         if (r.stages_f > cf) r.stages_f = cf;
@@ -656,16 +636,27 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
         const int K = BWD ? prm.G : prm.H;
         const int slabs = BWD ? 2 * prm.T : 2 * (prm.T + 2);
         uint64_t d[3] = {(uint64_t)K, (uint64_t)prm.B, (uint64_t)slabs};
-        uint64_t s[2] = {(uint64_t)K * ES, (uint64_t)prm.B * K * ES};
+        const uint64_t pitch = BF16 ? (uint64_t)round_up(K, 64) : (uint64_t)K;   // columns >= K: TMA zero fill
+        uint64_t s[2] = {pitch * ES, (uint64_t)prm.B * pitch * ES};
         uint32_t bx[3] = {KBE, (uint32_t)MROWS, 1};
         int rc = BF16 ? make_tmap_bf16(&tmA, a_base, 3, d, s, bx) : make_tmap_f32(&tmA, a_base, 3, d, s, bx);
         if (rc) return rc;
     }
     auto kern = rnn_rec_kernel<CELL, NJ, BWD, BF16, MROWS>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * sizeof(uint32_t), stream));
-    void* args[] = {(void*)&tmW, (void*)&tmA, (void*)&prm};
-    ASRB_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(2 * pl.P), dim3(kRnnThreads), args, smem, stream));
+    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * kRnnCounterStride * sizeof(uint32_t), stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pl.P);
+    cfg.blockDim = dim3(kRnnThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the step barrier spins
+    attrs[0].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    prm.dbg = g_rnn_dbg;
+    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, prm));
     return 0;
 }
 
@@ -751,6 +742,7 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
     prm.lengths = lengths; prm.counters = counters;
     prm.gi = gi; prm.b_hh = b_hh; prm.hseq = hseq; prm.cseq = cseq; prm.saved = saved;
     prm.hbf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16);
+    prm.Hp = round_up(H, 64);
     prm.trace = g_rnn_trace;
     return rnn_dispatch<false>(cell, pl, prm, wpack_fwd, pl.bf16 ? (const void*)hseq_bf16 : (const void*)hseq, stream);
 }
@@ -774,8 +766,17 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
     prm.hseq = const_cast<float*>(hseq); prm.cseq = const_cast<float*>(cseq); prm.saved = const_cast<float*>(saved);
     prm.dout = dout; prm.dgi = dgi; prm.dgh = dgh; prm.dgiT = dgiT; prm.dghT = (cell == ASRB_RNN_GRU) ? dghT : nullptr; prm.ldT = ldT;
     prm.dghbf = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
+    prm.Gp = round_up(prm.G, 64);
     prm.trace = g_rnn_trace;
     return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, pl.bf16 ? (const void*)dgh_bf16 : (const void*)dgh, stream);
+}
+
+/* DEBUG / timing experiments: K blocks per pipeline barrier (0 = automatic) */
+int asrb_debug_rnn_dbg(int bits) { g_rnn_dbg = bits; return 0; }
+int asrb_debug_rnn_chunk(int blocks) {
+    ASRB_REQUIRE(blocks >= 0 && blocks <= 8, ASRB_ERR_BAD_ARG);
+    g_rnn_chunk = blocks;
+    return 0;
 }
 
 /* DEBUG: per-step SM-clock stamps of the next asrb_rnn_fwd / asrb_rnn_bwd launches into trace[grid][T][12] (NULL = off) */

@@ -423,10 +423,10 @@ def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
     dev = gi.device
     bf16 = rnn_use_bf16(H)
     hseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32)
-    hbf = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.bfloat16) if bf16 else None
+    hbf = torch.empty(2, T + 2, B, (H + 63) // 64 * 64, device=dev, dtype=torch.bfloat16) if bf16 else None
     cseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32) if cell == LSTM else None
     saved = torch.empty(_lib.query("asrb_rnn_saved_floats", cell, H, B, int(bf16), T), device=dev, dtype=torch.float32)
-    counters = torch.empty(2, device=dev, dtype=torch.int32)
+    counters = torch.empty(128, device=dev, dtype=torch.int32)
     _call("asrb_rnn_fwd", cell, int(bf16), _p(gi), _p(b_hh), _p(wpack_fwd), _p(lengths), _p(hseq), _p(hbf), _p(cseq),
           _p(saved), _p(counters), T, B, H)
     return hseq, cseq, saved
@@ -443,10 +443,10 @@ def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
     R4 = (T * B + 3) // 4 * 4
     dgi = torch.empty(T, B, 2, G, device=dev, dtype=torch.float32)
     dgh = None if bf16 else torch.empty(2, T, B, G, device=dev, dtype=torch.float32)
-    dghbf = torch.empty(2, T, B, G, device=dev, dtype=torch.bfloat16) if bf16 else None
+    dghbf = torch.empty(2, T, B, (G + 63) // 64 * 64, device=dev, dtype=torch.bfloat16) if bf16 else None
     dgiT = torch.empty(2 * G, R4, device=dev, dtype=torch.float32)
     dghT = torch.empty(2 * G, R4, device=dev, dtype=torch.float32) if cell == GRU else None
-    counters = torch.empty(2, device=dev, dtype=torch.int32)
+    counters = torch.empty(128, device=dev, dtype=torch.int32)
     _call("asrb_rnn_bwd", cell, int(bf16), _p(dout), _p(wpack_bwd), _p(lengths), _p(hseq), _p(cseq), _p(saved), _p(dgi),
           _p(dgh), _p(dghbf), _p(dgiT), _p(dghT), R4, _p(counters), T, B, H)
     return dgi, dgiT, dghT

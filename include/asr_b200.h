@@ -79,9 +79,9 @@ int asrb_rnn_plan(int cell, int H, int B, int bf16, int* nj, int* P, size_t* wpa
 int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fwd, const float* w_hh_rev,
                           void* wpack_fwd, void* wpack_bwd, asrb_stream_t stream);
 /* gi [T,B,2,G] = x W_ih^T + b_ih for both directions; b_hh [2,G]; lengths int32[B];
- * out: hseq [2,T+2,B,H] (slot t+1 = step t; slots 0,T+1 zero), hseq_bf16 same shape in bf16 (bf16 mode, else NULL),
+ * out: hseq [2,T+2,B,H] (slot t+1 = step t; slots 0,T+1 zero), hseq_bf16 [2,T+2,B,Hp] bf16 with Hp = H rounded up to 64 (bf16 mode, else NULL),
  * cseq like hseq (LSTM only, else NULL), saved: asrb_rnn_saved_floats floats (GRU: r,z,n,W_hn h+b_hn ; LSTM: i,f,g,o);
- * counters: uint32[2] scratch. */
+ * counters: uint32[64] scratch (one step counter per direction, 128 bytes apart). */
 int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
                  float* hseq, void* hseq_bf16, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream);
@@ -90,7 +90,7 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
  * GRU, dghT [2G, ldT] = the transposed hidden-side gate gradients (they differ from dgiT in the n gate; LSTM: NULL)
  * -- the K-major operands of the weight-gradient GEMMs, written directly so no transpose pass is needed; the
  * recurrent operand of the next step is
- * dgh_bf16 [2,T,B,G] (bf16 mode, dgh may be NULL) or dgh [2,T,B,G] fp32 (tf32 mode, dgh_bf16 may be NULL). */
+ * dgh_bf16 [2,T,B,Gp] with Gp = G rounded up to 64 (bf16 mode, dgh may be NULL) or dgh [2,T,B,G] fp32 (tf32 mode, dgh_bf16 may be NULL). */
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
                  const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
                  float* dgiT, float* dghT, long long ldT, uint32_t* counters, int T, int B, int H,
@@ -98,6 +98,8 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
 /* floats in the saved-gates buffer (slice-major layout private to asrb_rnn_fwd / asrb_rnn_bwd) */
 size_t asrb_rnn_saved_floats(int cell, int H, int B, int bf16, int T);
 int asrb_debug_rnn_trace(long long* trace);
+int asrb_debug_rnn_chunk(int blocks);
+int asrb_debug_rnn_dbg(int bits);
 /* out[T,B,H] = hseq[0][1..T] + hseq[1][1..T] */
 int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream);
 

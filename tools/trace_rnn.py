@@ -13,7 +13,7 @@ lens = torch.full((B,), T, dtype=torch.int32, device=dev)
 pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
 nj, P, _, _ = ops.rnn_plan(cell, H, B, ops.rnn_use_bf16(H))
 grid = 2 * P
-names = ["P:counter ok", "P:loads issued", "M:first full", "M:commit", "E:step top", "E:tfull", "E:ld done", "E:math+stores", "E:bar done", "E:membar", "E:red"]
+names = ["P:counter ok", "P:loads issued", "M:first full", "M:commit", "E:step top", "E:tfull", "E:ld done", "E:math+stores", "E:bar done", "P:fence done", "E:red", "P:prearmed fired"]
 def timed(fn, n=3):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -21,14 +21,14 @@ def timed(fn, n=3):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for flags in (0, 16):
-    ops.set_debug_flags(flags)
+for flags in (0,):
+    _lib.query("asrb_debug_rnn_dbg", flags)
     hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
     dout = torch.randn(T, B, H, device=dev)
     tf = timed(lambda: ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H))
     tb = timed(lambda: ops.rnn_bwd(cell, dout, pb, lens, hseq, cseq, saved, T, B, H))
-    print(f"flags={flags} (no trace): fwd {tf:.3f} ms ({tf*1e3/T:.2f} us/step)  bwd {tb:.3f} ms ({tb*1e3/T:.2f} us/step)")
-ops.set_debug_flags(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    print(f"dbg={flags} (no trace): fwd {tf:.3f} ms ({tf*1e3/T:.2f} us/step)  bwd {tb:.3f} ms ({tb*1e3/T:.2f} us/step)")
+_lib.query("asrb_debug_rnn_dbg", int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 for which in ("fwd", "bwd"):
     for _ in range(2):
         hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
@@ -51,5 +51,5 @@ for which in ("fwd", "bwd"):
         x = tr[cta, s0:s1]
         top = x[:, 4]
         step_cycles = (top[1:] - top[:-1]).mean().item()
-        rel = [(x[:, k] - top).mean().item() for k in range(11)]
+        rel = [(x[:, k] - top).mean().item() for k in range(12)]
         print(f" cta {cta}: cycles/step {step_cycles:.0f}; " + "; ".join(f"{n}={r:.0f}" for n, r in zip(names, rel)))
