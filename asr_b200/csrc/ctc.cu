@@ -206,12 +206,13 @@ struct CtcBwdParams {
     int T, N, C, Smax, RS, kpl, blank, n_dp, nparts;
 };
 
-constexpr int kCtcXRing = 8;           // rows of alpha+beta in flight between the recurrence warp and the posterior warp
+constexpr int kCtcXRing = 4;           // rows of alpha+beta in flight between the recurrence warp and the posterior warp
+constexpr int kCtcBetaRing = 4;        // prefetch depth of the beta warp (contiguous rows: three steps ahead is plenty)
 
 // shared memory of a DP block (floats): cp.async rings of lp and alpha, the hand-over ring, two scratch rows, labels
 template <int KPL>
 __host__ __device__ constexpr size_t ctc_dp_smem_bytes() {
-    return (size_t)(2 * CtcRing<KPL>::R + 2 * kCtcXRing + 3) * KPL * 32 * 4 + 2 * kCtcXRing * 8 + 64;
+    return (size_t)(2 * kCtcBetaRing + 2 * kCtcXRing + 3) * KPL * 32 * 4 + 2 * kCtcXRing * 8 + 64;
 }
 
 // Backward DP of utterance n by TWO warps of a DP block:
@@ -222,9 +223,13 @@ __host__ __device__ constexpr size_t ctc_dp_smem_bytes() {
 //          (they sum to 1 over the whole row), so the class sums are taken in the linear domain, in a fixed order:
 //          the blank class by a warp reduction, the label classes as differences of ONE prefix sum over the label
 //          positions sorted by class (no pointer chasing along per-class chains, no atomics).
+__device__ __forceinline__ void named_bar_sync_ctc(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <int KPL>
 __device__ void ctc_beta_warp_role(const CtcBwdParams& p, int n, int* smi) {
-    constexpr int R = CtcRing<KPL>::R, RS = KPL * 32, XR = kCtcXRing;
+    constexpr int R = kCtcBetaRing, RS = KPL * 32, XR = kCtcXRing;
     constexpr int KP2 = (KPL + 1) / 2;                  // sorted label slots per lane (32*KP2 >= U)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.N, C = p.C, T = p.T, blank = p.blank;
@@ -246,8 +251,7 @@ __device__ void ctc_beta_warp_role(const CtcBwdParams& p, int n, int* smi) {
         }
         mbar_fence_init();
     }
-    __syncthreads();
-    if (warp > 1) return;
+    named_bar_sync_ctc(1, 64);                           // the two DP warps only
     if (Tn <= 0) return;
     const float* al = p.alpha + (size_t)n * T * RS;
     const float* gw = p.gathered + (size_t)n * T * RS;
@@ -601,49 +605,35 @@ __device__ void ctc_beta_role(const CtcBwdParams& p, int n, int* smi) {
 }
 
 // Dense gradient stream: grad[t,n,c] = g*exp(lp[t,n,c]) for every class c that does NOT occur in utterance n's labels
-// (those and the blank are written by the DP), zero rows for t >= input length.  Streaming block j works for ONE
-// utterance n = j % N (class mask built once); its 8 warps and the other blocks of the utterance deal the rows out
-// warp by warp -- no barrier, no flag, every warp keeps several 16-byte loads in flight.
-__device__ void ctc_dense_role(const CtcBwdParams& p, int j, int* smi) {
-    const int N = p.N, C = p.C, T = p.T, blank = p.blank;
-    uint32_t* mask = reinterpret_cast<uint32_t*>(smi);   // [(C+31)/32] bit c set: class c belongs to the DP
-    const int n = j % N, part = j / N;
+// (those and the blank are written by the DP), zero rows for t >= input length.  Every block works for ONE utterance
+// n = block % N (class mask built once).  The utterance's streaming warps -- warps 2..7 of its DP block plus all 8 warps
+// of its nparts-1 further blocks -- deal the rows out warp by warp: no barrier, no flag, eight 16-byte loads in flight
+// per lane.
+__device__ void ctc_dense_role(const CtcBwdParams& p, int n, int wi, int nw, uint32_t* mask) {
+    const int N = p.N, C = p.C, T = p.T;
     const int Tn = min(p.in_len[n], T);
-    const int U = p.tgt_len[n], off = p.tgt_off[n];
-    const int words = (C + 31) / 32;
-    for (int w = threadIdx.x; w < words; w += kCtcThreads) mask[w] = 0u;
-    __syncthreads();
-    if (Tn > 0) {
-        for (int i = threadIdx.x; i < U; i += kCtcThreads) {
-            const int l = p.targets[off + i];
-            atomicOr(&mask[l >> 5], 1u << (l & 31));
-        }
-        if (threadIdx.x == 0) atomicOr(&mask[blank >> 5], 1u << (blank & 31));
-    }
-    __syncthreads();
     const float g = p.gscale ? p.gscale[0] : 1.f;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nw = (kCtcThreads / 32) * p.nparts;
+    const int lane = threadIdx.x & 31;
     if (C % 4 == 0) {
         const int C4 = C / 4;
-        for (int t = part * (kCtcThreads / 32) + warp; t < T; t += nw) {
+        for (int t = wi; t < T; t += nw) {
             const float4* row4 = reinterpret_cast<const float4*>(p.lp + ((size_t)t * N + n) * C);
             float4* gr4 = reinterpret_cast<float4*>(p.grad + ((size_t)t * N + n) * C);
             if (t >= Tn) {
                 for (int c = lane; c < C4; c += 32) __stcs(gr4 + c, make_float4(0.f, 0.f, 0.f, 0.f));
                 continue;
             }
-            for (int c0 = lane; c0 < C4; c0 += 128) {     // four independent 16-byte loads in flight per lane
-                float4 x[4];
+            for (int c0 = lane; c0 < C4; c0 += 256) {
+                float4 x[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 8; ++u)
                     if (c0 + 32 * u < C4) x[u] = __ldcs(row4 + c0 + 32 * u);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const int c = c0 + 32 * u;
                     if (c < C4) {
                         float4 o;
-                        o.x = g * __expf(x[u].x); o.y = g * __expf(x[u].y); o.z = g * __expf(x[u].z); o.w = g * __expf(x[u].w);
+                        o.x = g * exp_ftz(x[u].x); o.y = g * exp_ftz(x[u].y); o.z = g * exp_ftz(x[u].z); o.w = g * exp_ftz(x[u].w);
                         const uint32_t bits = (mask[(4 * c) >> 5] >> ((4 * c) & 31)) & 0xFu;
                         if (bits == 0u) {
                             __stcs(gr4 + c, o);
@@ -659,7 +649,7 @@ __device__ void ctc_dense_role(const CtcBwdParams& p, int j, int* smi) {
             }
         }
     } else {
-        for (int t = part * (kCtcThreads / 32) + warp; t < T; t += nw) {
+        for (int t = wi; t < T; t += nw) {
             const float* row = p.lp + ((size_t)t * N + n) * C;
             float* gr = p.grad + ((size_t)t * N + n) * C;
             if (t >= Tn) {
@@ -667,24 +657,56 @@ __device__ void ctc_dense_role(const CtcBwdParams& p, int j, int* smi) {
                 continue;
             }
             for (int c = lane; c < C; c += 32)
-                if (!((mask[c >> 5] >> (c & 31)) & 1u)) gr[c] = g * __expf(__ldg(row + c));
+                if (!((mask[c >> 5] >> (c & 31)) & 1u)) gr[c] = g * exp_ftz(__ldg(row + c));
         }
     }
 }
 
-// KPL > 0: the DP blocks run the warp DP (first warp only) ; KPL == 0: block-wide DP (long label sequences)
+// bit c set: class c occurs in utterance n's labels (or is the blank) and its gradient is written by the DP
+__device__ void ctc_build_mask(const CtcBwdParams& p, int n, uint32_t* mask) {
+    const int words = (p.C + 31) / 32;
+    for (int w = threadIdx.x; w < words; w += kCtcThreads) mask[w] = 0u;
+    __syncthreads();
+    if (min(p.in_len[n], p.T) > 0) {
+        const int U = p.tgt_len[n], off = p.tgt_off[n];
+        for (int i = threadIdx.x; i < U; i += kCtcThreads) {
+            const int l = p.targets[off + i];
+            atomicOr(&mask[l >> 5], 1u << (l & 31));
+        }
+        if (threadIdx.x == 0) atomicOr(&mask[p.blank >> 5], 1u << (p.blank & 31));
+    }
+    __syncthreads();
+}
+
+// KPL > 0: warp DP -- block (n, part 0) runs the DP on warps 0,1 and streams on warps 2..7, blocks (n, part >= 1) only
+// stream.  KPL == 0 (long label sequences): block-wide DP blocks first, then streaming blocks.
 template <int KPL>
 __global__ void __launch_bounds__(kCtcThreads)
 ctc_bwd_kernel(const CtcBwdParams p) {
     extern __shared__ int smi[];
-    if ((int)blockIdx.x < p.n_dp) {
-        if constexpr (KPL > 0) {
-            ctc_beta_warp_role<KPL>(p, blockIdx.x, smi);   // whole block enters (barrier init), two warps stay
+    const int warp = threadIdx.x >> 5;
+    if constexpr (KPL > 0) {
+        const int n = blockIdx.x % p.N, part = blockIdx.x / p.N;
+        uint32_t* mask = reinterpret_cast<uint32_t*>(smi);
+        int* dp_smem = smi + (p.C + 31) / 32;
+        dp_smem += (32 - ((p.C + 31) / 32) % 32) % 32;           // keep the DP rows 128-byte aligned
+        ctc_build_mask(p, n, mask);
+        const int nw = 8 * p.nparts - 2;
+        if (part == 0) {
+            if (warp < 2) ctc_beta_warp_role<KPL>(p, n, dp_smem);
+            else          ctc_dense_role(p, n, warp - 2, nw, mask);
         } else {
-            ctc_beta_role(p, blockIdx.x, smi);
+            ctc_dense_role(p, n, 6 + 8 * (part - 1) + warp, nw, mask);
         }
     } else {
-        ctc_dense_role(p, blockIdx.x - p.n_dp, smi);
+        if ((int)blockIdx.x < p.N) {
+            ctc_beta_role(p, blockIdx.x, smi);
+        } else {
+            const int j = blockIdx.x - p.N, n = j % p.N, part = j / p.N;
+            uint32_t* mask = reinterpret_cast<uint32_t*>(smi);
+            ctc_build_mask(p, n, mask);
+            ctc_dense_role(p, n, 8 * part + warp, 8 * p.nparts, mask);
+        }
     }
 }
 
@@ -721,19 +743,24 @@ static size_t ctc_alpha_floats(int T, int N, int max_target_len) {
 
 template <int KPL>
 static int ctc_launch_bwd(CtcBwdParams& p, size_t smem_dp, asrb_stream_t stream) {
-    const size_t smem_dense = (size_t)((p.C + 31) / 32) * 4;
-    const size_t smem = smem_dp > smem_dense ? smem_dp : smem_dense;
+    const size_t smem_mask = (size_t)(((p.C + 31) / 32 + 31) / 32 * 32) * 4;
+    const size_t smem = KPL > 0 ? smem_mask + smem_dp : (smem_dp > smem_mask ? smem_dp : smem_mask);
     ASRB_REQUIRE(smem <= 160 * 1024, ASRB_ERR_UNSUPPORTED);
     auto kern = ctc_bwd_kernel<KPL>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // One launch: the N DP blocks first (they are the long pole), then the streaming blocks -- about four per SM in
-    // total.  Nothing waits on anything, so it does not matter how many of them are resident at a time.
+    // One launch, about five blocks per SM.  Nothing waits on anything, so residency does not matter; the blocks that
+    // carry a DP have the lowest indices and start first (the DP is the long pole).
     const int N = p.N;
-    int nparts = (kNumSMs * 4 + N - 1) / N;
-    if (nparts < 1) nparts = 1;
-    p.nparts = nparts;
-    p.n_dp = N;
-    kern<<<N + N * nparts, kCtcThreads, smem, stream>>>(p);
+    int nparts = (kNumSMs * 5 + N - 1) / N;
+    if (KPL > 0) {
+        if (nparts < 1) nparts = 1;
+        p.nparts = nparts;
+        kern<<<N * nparts, kCtcThreads, smem, stream>>>(p);
+    } else {
+        if (nparts < 2) nparts = 2;
+        p.nparts = nparts - 1;
+        kern<<<N + N * (nparts - 1), kCtcThreads, smem, stream>>>(p);
+    }
     ASRB_LAUNCH_OK();
     return 0;
 }
