@@ -247,21 +247,23 @@ __device__ __forceinline__ float bn_hat(const BnAct& p, int c, float y, float* x
 template <int MODE>
 __global__ void __launch_bounds__(256)
 nchw_reduce_kernel(const float* __restrict__ a, const float* __restrict__ yraw, const int* __restrict__ lengths,
-                   BnAct p, double* __restrict__ partial, int B, int C, int HW, int W, int nsplit) {
+                   BnAct p, double* __restrict__ partial, int B, int C, int HW, int W, int nsplit, unsigned wmagic) {
     const int c = blockIdx.x, b = blockIdx.y / nsplit, sp = blockIdx.y % nsplit;
     const int len = lengths ? lengths[b] : W;
     const size_t base = ((size_t)b * C + c) * HW;
     const int chunk = ceil_div(HW, nsplit);
     const int i0 = sp * chunk, i1 = min(HW, i0 + chunk);
     float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
     for (int i = i0 + threadIdx.x; i < i1; i += 256) {
         const float v = a[base + i];
+        const int w = i - (int)__umulhi((unsigned)i, wmagic) * W;
         if (MODE == 0) { s0 += v; s1 += v * v; }
-        else if (MODE == 2) { if (i % W < len) s0 += v; }
+        else if (MODE == 2) { if (w < len) s0 += v; }
         else {
             float xh;
             const float yh = bn_hat(p, c, yraw[base + i], &xh);
-            const bool pass = (i % W < len) && (!p.has_act || (yh > p.lo && yh < p.hi));
+            const bool pass = (w < len) && (!p.has_act || (yh > p.lo && yh < p.hi));
             if (pass) { s0 += v; s1 += v * xh; }
         }
     }
@@ -284,6 +286,7 @@ __global__ void reduce_finalize_kernel(const double* __restrict__ partial, int n
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s0 = 0, s1 = 0;
+#pragma unroll 8
     for (int i = 0; i < nparts; ++i) { s0 += partial[((size_t)c * nparts + i) * 2]; s1 += partial[((size_t)c * nparts + i) * 2 + 1]; }
     if (kind == 0) {
         const double mean = s0 / count;
@@ -308,66 +311,124 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* 
     if (c < C) { mean[c] = rm[c]; invstd[c] = rsqrtf(rv[c] + eps); }
 }
 
+// Elementwise NCHW kernels: blockIdx.y = (b, c) plane, blockIdx.x = chunk of the plane, kEwPerThread coalesced
+// elements per thread.  The time index of element i of a plane is i - W * floor(i / W) with the quotient taken as
+// __umulhi(i, ceil(2^32 / W)) (exact for i * W < 2^32, checked on the host) -- the former per-element 64-bit
+// division was the whole cost of these HBM-bound kernels.
+constexpr int kEwPerThread = 8;
+
 // z = mask(act(mask(bn(y))))
-__global__ void bn_act_mask_fwd_kernel(const float* __restrict__ y, const int* __restrict__ lengths, BnAct p,
-                                       float* __restrict__ z, int C, int HW, int W, long long total) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(i % W);
-        const long long bc = i / HW;
-        const int c = (int)(bc % C), b = (int)(bc / C);
-        const int len = lengths ? lengths[b] : W;
-        float v = 0.f;
-        if (w < len) {
-            float xh;
-            v = bn_hat(p, c, y[i], &xh);
-            if (p.has_act) v = fminf(fmaxf(v, p.lo), p.hi);
+__global__ void __launch_bounds__(256)
+bn_act_mask_fwd_kernel(const float* __restrict__ y, const int* __restrict__ lengths, BnAct p, float* __restrict__ z, int C,
+                       int HW, int W, unsigned wmagic) {
+    const int plane = blockIdx.y, c = plane % C, b = plane / C;
+    const int len = lengths ? lengths[b] : W;
+    const size_t base = (size_t)plane * HW;
+    float mu = 0.f, is = 1.f, ga = 1.f, sh = 0.f;
+    if (p.has_bn) { mu = p.mean[c]; is = p.invstd[c]; ga = p.gamma[c]; sh = p.beta[c]; }
+    const int i0 = blockIdx.x * (256 * kEwPerThread) + threadIdx.x;
+    float v[kEwPerThread];
+#pragma unroll
+    for (int u = 0; u < kEwPerThread; ++u) {
+        const int i = i0 + u * 256;
+        v[u] = i < HW ? __ldcs(y + base + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kEwPerThread; ++u) {
+        const int i = i0 + u * 256;
+        if (i < HW) {
+            const int w = i - (int)__umulhi((unsigned)i, wmagic) * W;
+            float o = 0.f;
+            if (w < len) {
+                o = p.has_bn ? ((v[u] - mu) * is) * ga + sh : v[u];   // same operation order as bn_hat
+                if (p.has_act) o = fminf(fmaxf(o, p.lo), p.hi);
+            }
+            z[base + i] = o;
         }
-        z[i] = v;
     }
 }
 
 // dy = mask * gamma*invstd*(g - s0/R - xhat*s1/R)   (training)  |  mask * gamma*invstd*g  (eval / no stats)
-__global__ void bn_act_mask_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ y,
-                                       const int* __restrict__ lengths, BnAct p, const float* __restrict__ s0,
-                                       const float* __restrict__ s1, float inv_count, int training,
-                                       float* __restrict__ dy, int C, int HW, int W, long long total) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(i % W);
-        const long long bc = i / HW;
-        const int c = (int)(bc % C), b = (int)(bc / C);
-        const int len = lengths ? lengths[b] : W;
-        float out = 0.f;
-        if (w < len) {
-            float xh;
-            const float yh = bn_hat(p, c, y[i], &xh);
-            float g = dz[i];
-            if (p.has_act && !(yh > p.lo && yh < p.hi)) g = 0.f;
-            if (p.has_bn) {
-                if (training) g = g - s0[c] * inv_count - xh * s1[c] * inv_count;
-                out = g * p.gamma[c] * p.invstd[c];
-            } else {
-                out = g;
+__global__ void __launch_bounds__(256)
+bn_act_mask_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ y, const int* __restrict__ lengths, BnAct p,
+                       const float* __restrict__ s0, const float* __restrict__ s1, float inv_count, int training,
+                       float* __restrict__ dy, int C, int HW, int W, unsigned wmagic) {
+    const int plane = blockIdx.y, c = plane % C, b = plane / C;
+    const int len = lengths ? lengths[b] : W;
+    const size_t base = (size_t)plane * HW;
+    float a0 = 0.f, a1 = 0.f, gi = 1.f;
+    if (p.has_bn) {
+        gi = p.gamma[c] * p.invstd[c];
+        if (training) { a0 = s0[c] * inv_count; a1 = s1[c] * inv_count; }
+    }
+    const int i0 = blockIdx.x * (256 * kEwPerThread) + threadIdx.x;
+    float g[kEwPerThread], yv[kEwPerThread];
+#pragma unroll
+    for (int u = 0; u < kEwPerThread; ++u) {
+        const int i = i0 + u * 256;
+        g[u] = i < HW ? __ldcs(dz + base + i) : 0.f;
+        yv[u] = i < HW ? __ldcs(y + base + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kEwPerThread; ++u) {
+        const int i = i0 + u * 256;
+        if (i < HW) {
+            const int w = i - (int)__umulhi((unsigned)i, wmagic) * W;
+            float out = 0.f;
+            if (w < len) {
+                float xh;
+                const float yh = bn_hat(p, c, yv[u], &xh);
+                float gg = g[u];
+                if (p.has_act && !(yh > p.lo && yh < p.hi)) gg = 0.f;
+                if (p.has_bn) {
+                    if (training) gg = gg - a0 - xh * a1;
+                    out = gg * gi;
+                } else {
+                    out = gg;
+                }
             }
+            dy[base + i] = out;
         }
-        dy[i] = out;
     }
 }
 
-// batched tiled transpose: out[n][c][r] = in[n][r][c]
-__global__ void transpose_batched_kernel(const float* __restrict__ in, int rows, int cols, long long ld_in,
-                                         long long bs_in, float* __restrict__ out, long long ld_out, long long bs_out) {
-    __shared__ float tile[32][33];
+// batched tiled transpose: out[n][c][r] = in[n][r][c] ; 64 x 64 tiles, 16-byte accesses where the strides allow
+template <bool VEC_IN, bool VEC_OUT>
+__global__ void __launch_bounds__(256)
+transpose_batched_kernel(const float* __restrict__ in, int rows, int cols, long long ld_in, long long bs_in,
+                         float* __restrict__ out, long long ld_out, long long bs_out) {
+    __shared__ float tile[64][65];
     in += (size_t)blockIdx.z * bs_in;
     out += (size_t)blockIdx.z * bs_out;
-    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : 0.f;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k, r = idx >> 4, c = (idx & 15) * 4;
+        if (r0 + r < rows) {
+            const float* src = in + (size_t)(r0 + r) * ld_in + c0 + c;
+            if (VEC_IN && c0 + c + 3 < cols) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(src));
+                tile[r][c] = v.x; tile[r][c + 1] = v.y; tile[r][c + 2] = v.z; tile[r][c + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) tile[r][c + e] = (c0 + c + e < cols) ? src[e] : 0.f;
+            }
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < cols && r < rows) out[(size_t)c * ld_out + r] = tile[threadIdx.x][i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k, c = idx >> 4, r = (idx & 15) * 4;
+        if (c0 + c < cols) {
+            float* dst = out + (size_t)(c0 + c) * ld_out + r0 + r;
+            if (VEC_OUT && r0 + r + 3 < rows) {
+                *reinterpret_cast<float4*>(dst) = make_float4(tile[r][c], tile[r + 1][c], tile[r + 2][c], tile[r + 3][c]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (r0 + r + e < rows) dst[e] = tile[r + e][c];
+            }
+        }
     }
 }
 
@@ -449,7 +510,7 @@ int asrb_conv2d_mask_bwd_weight(const float* dy, const float* x, const int32_t* 
         const int nsplit = HW >= 4096 ? 4 : 1;
         ASRB_REQUIRE(ws && ws_bytes >= (size_t)Cout * B * nsplit * 2 * sizeof(double), ASRB_ERR_WORKSPACE);
         BnAct p = {};
-        nchw_reduce_kernel<2><<<dim3(Cout, B * nsplit), 256, 0, stream>>>(dy, nullptr, lengths, p, ws, B, Cout, HW, Wout, nsplit);
+        nchw_reduce_kernel<2><<<dim3(Cout, B * nsplit), 256, 0, stream>>>(dy, nullptr, lengths, p, ws, B, Cout, HW, Wout, nsplit, (unsigned)(((1ULL << 32) + Wout - 1) / Wout));
         ASRB_LAUNCH_OK();
         reduce_finalize_kernel<<<ceil_div(Cout, 128), 128, 0, stream>>>(ws, B * nsplit, Cout, 1.0, 1, 0.f, 0.f, dbias, nullptr, nullptr, nullptr);
         ASRB_LAUNCH_OK();
@@ -472,7 +533,7 @@ int asrb_nchw_channel_sums(const float* a, const int32_t* lengths, float* out, d
     const int HW = H * W, nsplit = HW >= 4096 ? 4 : 1;
     ASRB_REQUIRE(ws_bytes >= (size_t)C * B * nsplit * 2 * sizeof(double), ASRB_ERR_WORKSPACE);
     BnAct p = {};
-    nchw_reduce_kernel<2><<<dim3(C, B * nsplit), 256, 0, stream>>>(a, nullptr, lengths, p, ws, B, C, HW, W, nsplit);
+    nchw_reduce_kernel<2><<<dim3(C, B * nsplit), 256, 0, stream>>>(a, nullptr, lengths, p, ws, B, C, HW, W, nsplit, (unsigned)(((1ULL << 32) + W - 1) / W));
     ASRB_LAUNCH_OK();
     reduce_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(ws, B * nsplit, C, 1.0, 1, 0.f, 0.f, out, nullptr, nullptr, nullptr);
     ASRB_LAUNCH_OK();
@@ -492,7 +553,7 @@ int asrb_bn2d_stats(const float* y, float* mean, float* invstd, float* running_m
     const int HW = H * W, nsplit = HW >= 4096 ? 4 : 1;
     ASRB_REQUIRE(ws_bytes >= (size_t)C * B * nsplit * 2 * sizeof(double), ASRB_ERR_WORKSPACE);
     BnAct p = {};
-    nchw_reduce_kernel<0><<<dim3(C, B * nsplit), 256, 0, stream>>>(y, nullptr, nullptr, p, ws, B, C, HW, W, nsplit);
+    nchw_reduce_kernel<0><<<dim3(C, B * nsplit), 256, 0, stream>>>(y, nullptr, nullptr, p, ws, B, C, HW, W, nsplit, (unsigned)(((1ULL << 32) + W - 1) / W));
     ASRB_LAUNCH_OK();
     reduce_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(ws, B * nsplit, C, (double)B * HW, 0, eps, momentum, mean, invstd, running_mean, running_var);
     ASRB_LAUNCH_OK();
@@ -514,7 +575,10 @@ int asrb_bn_act_mask_fwd(const float* y, const int32_t* lengths, const float* me
     ASRB_REQUIRE(!has_bn || (mean && invstd && gamma && beta), ASRB_ERR_BAD_ARG);
     BnAct p = {mean, invstd, gamma, beta, lo, hi, has_bn, has_act};
     const long long total = (long long)B * C * H * W;
-    bn_act_mask_fwd_kernel<<<ew_grid(total), 256, 0, stream>>>(y, lengths, p, z, C, H * W, W, total);
+    (void)total;
+    ASRB_REQUIRE((long long)H * W * W < (1LL << 32) && (long long)B * C <= 65535, ASRB_ERR_UNSUPPORTED);
+    const unsigned wmagic = (unsigned)(((1ULL << 32) + W - 1) / W);
+    bn_act_mask_fwd_kernel<<<dim3(ceil_div(H * W, 256 * kEwPerThread), B * C), 256, 0, stream>>>(y, lengths, p, z, C, H * W, W, wmagic);
     ASRB_LAUNCH_OK();
     return 0;
 }
@@ -530,13 +594,16 @@ int asrb_bn_act_mask_bwd(const float* dz, const float* y, const int32_t* lengths
     const int HW = H * W, nsplit = HW >= 4096 ? 4 : 1;
     if (has_bn) {
         ASRB_REQUIRE(ws_bytes >= (size_t)C * B * nsplit * 2 * sizeof(double), ASRB_ERR_WORKSPACE);
-        nchw_reduce_kernel<1><<<dim3(C, B * nsplit), 256, 0, stream>>>(dz, y, lengths, p, ws, B, C, HW, W, nsplit);
+        nchw_reduce_kernel<1><<<dim3(C, B * nsplit), 256, 0, stream>>>(dz, y, lengths, p, ws, B, C, HW, W, nsplit, (unsigned)(((1ULL << 32) + W - 1) / W));
         ASRB_LAUNCH_OK();
         reduce_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(ws, B * nsplit, C, 1.0, 1, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr);
         ASRB_LAUNCH_OK();
     }
     const long long total = (long long)B * C * HW;
-    bn_act_mask_bwd_kernel<<<ew_grid(total), 256, 0, stream>>>(dz, y, lengths, p, dbeta, dgamma, 1.0f / ((float)B * HW), training, dy, C, HW, W, total);
+    (void)total;
+    ASRB_REQUIRE((long long)HW * W < (1LL << 32) && (long long)B * C <= 65535, ASRB_ERR_UNSUPPORTED);
+    const unsigned wmagic = (unsigned)(((1ULL << 32) + W - 1) / W);
+    bn_act_mask_bwd_kernel<<<dim3(ceil_div(HW, 256 * kEwPerThread), B * C), 256, 0, stream>>>(dz, y, lengths, p, dbeta, dgamma, 1.0f / ((float)B * HW), training, dy, C, HW, W, wmagic);
     ASRB_LAUNCH_OK();
     return 0;
 }
@@ -544,9 +611,14 @@ int asrb_bn_act_mask_bwd(const float* dz, const float* y, const int32_t* lengths
 int asrb_transpose_batched(const float* in, int rows, int cols, long long ld_in, long long batch_stride_in, float* out,
                            long long ld_out, long long batch_stride_out, int nbatch, asrb_stream_t stream) {
     ASRB_REQUIRE(in && out && rows > 0 && cols > 0 && nbatch > 0 && nbatch <= 65535, ASRB_ERR_BAD_ARG);
-    dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), nbatch);
+    dim3 grid(ceil_div(cols, 64), ceil_div(rows, 64), nbatch);
     ASRB_REQUIRE(grid.y <= 65535, ASRB_ERR_UNSUPPORTED);
-    transpose_batched_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, ld_in, batch_stride_in, out, ld_out, batch_stride_out);
+    const bool vin = ld_in % 4 == 0 && batch_stride_in % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    const bool vout = ld_out % 4 == 0 && batch_stride_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (vin && vout)  transpose_batched_kernel<true, true><<<grid, 256, 0, stream>>>(in, rows, cols, ld_in, batch_stride_in, out, ld_out, batch_stride_out);
+    else if (vin)     transpose_batched_kernel<true, false><<<grid, 256, 0, stream>>>(in, rows, cols, ld_in, batch_stride_in, out, ld_out, batch_stride_out);
+    else if (vout)    transpose_batched_kernel<false, true><<<grid, 256, 0, stream>>>(in, rows, cols, ld_in, batch_stride_in, out, ld_out, batch_stride_out);
+    else              transpose_batched_kernel<false, false><<<grid, 256, 0, stream>>>(in, rows, cols, ld_in, batch_stride_in, out, ld_out, batch_stride_out);
     ASRB_LAUNCH_OK();
     return 0;
 }

@@ -303,21 +303,43 @@ gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const float* __restric
 // ------------------------------------------------------------------------------------------------
 // device: tiled transpose  out[c, r] = in[r, c]
 // ------------------------------------------------------------------------------------------------
-__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, int ld_in, float* __restrict__ out,
-                                 int ld_out) {
-    __shared__ float tile[32][33];
-    const long long r0 = (long long)blockIdx.x * 32;   // rows on grid.x (up to 2^31 blocks)
-    const int c0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        long long r = r0 + i;
-        int c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.f;
+// 64 x 64 tiles, 256 threads, 16-byte loads along the input rows and 16-byte stores along the output rows when the
+// strides and base pointers allow (VEC); tile edges fall back to scalars.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, int rows, int cols, long long ld_in, float* __restrict__ out,
+                 long long ld_out) {
+    __shared__ float tile[64][65];
+    const long long r0 = (long long)blockIdx.x * 64;   // rows on grid.x (up to 2^31 blocks)
+    const int c0 = blockIdx.y * 64;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k, r = idx >> 4, c = (idx & 15) * 4;
+        if (r0 + r < rows) {
+            const float* src = in + (r0 + r) * ld_in + c0 + c;
+            if (VEC && c0 + c + 3 < cols) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(src));
+                tile[r][c] = v.x; tile[r][c + 1] = v.y; tile[r][c + 2] = v.z; tile[r][c + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) tile[r][c + e] = (c0 + c + e < cols) ? src[e] : 0.f;
+            }
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        int c = c0 + i;
-        long long r = r0 + threadIdx.x;
-        if (c < cols && r < rows) out[(size_t)c * ld_out + r] = tile[threadIdx.x][i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int idx = threadIdx.x + 256 * k, c = idx >> 4, r = (idx & 15) * 4;
+        if (c0 + c < cols) {
+            float* dst = out + (size_t)(c0 + c) * ld_out + r0 + r;
+            if (VEC && r0 + r + 3 < rows) {
+                *reinterpret_cast<float4*>(dst) = make_float4(tile[r][c], tile[r + 1][c], tile[r + 2][c], tile[r + 3][c]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (r0 + r + e < rows) dst[e] = tile[r + e][c];
+            }
+        }
     }
 }
 
@@ -386,9 +408,12 @@ int asrb_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int
 
 int asrb_transpose(const float* in, long long rows, int cols, int ld_in, float* out, int ld_out, asrb_stream_t stream) {
     ASRB_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, ASRB_ERR_BAD_ARG);
-    dim3 grid((unsigned)ceil_div64(rows, 32), ceil_div(cols, 32));
+    dim3 grid((unsigned)ceil_div64(rows, 64), ceil_div(cols, 64));
     ASRB_REQUIRE(grid.y <= 65535u && rows < (1LL << 31), ASRB_ERR_UNSUPPORTED);
-    transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, (int)rows, cols, ld_in, out, ld_out);
+    const bool vec = ld_in % 4 == 0 && ld_out % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec) transpose_kernel<true><<<grid, 256, 0, stream>>>(in, (int)rows, cols, ld_in, out, ld_out);
+    else     transpose_kernel<false><<<grid, 256, 0, stream>>>(in, (int)rows, cols, ld_in, out, ld_out);
     ASRB_LAUNCH_OK();
     return 0;
 }

@@ -50,6 +50,7 @@ __global__ void rows_finalize_kernel(const float* __restrict__ partial, int nchu
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     double s0 = 0, s1 = 0;
+#pragma unroll 8
     for (int i = 0; i < nchunks; ++i) {
         s0 += partial[((size_t)i * 2 + 0) * cols + c];
         s1 += partial[((size_t)i * 2 + 1) * cols + c];
@@ -71,25 +72,68 @@ __global__ void rows_finalize_kernel(const float* __restrict__ partial, int nchu
     }
 }
 
-__global__ void bn_rows_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, float* __restrict__ y, long long total, int cols) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cols);
-        y[i] = (x[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+// Row-matrix elementwise kernels: blockIdx.y = chunk of rows, threads stride over the columns in 16-byte vectors
+// (cols % 4 == 0) or scalars; per-column constants are loaded once per thread and reused for every row of the chunk.
+constexpr int kRowsPerEwBlock = 32;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+bn_rows_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, long long R, int cols) {
+    constexpr int V = VEC ? 4 : 1;
+    const int c = (blockIdx.x * 256 + threadIdx.x) * V;
+    if (c >= cols) return;
+    float mu[V], is[V], ga[V], be[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { mu[e] = mean[c + e]; is[e] = invstd[c + e]; ga[e] = gamma[c + e]; be[e] = beta[c + e]; }
+    const long long r0 = (long long)blockIdx.y * kRowsPerEwBlock;
+    const long long r1 = r0 + kRowsPerEwBlock < R ? r0 + kRowsPerEwBlock : R;
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+        if constexpr (VEC) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(x + r * cols + c));
+            float4 o;
+            o.x = (v.x - mu[0]) * is[0] * ga[0] + be[0]; o.y = (v.y - mu[1]) * is[1] * ga[1] + be[1];
+            o.z = (v.z - mu[2]) * is[2] * ga[2] + be[2]; o.w = (v.w - mu[3]) * is[3] * ga[3] + be[3];
+            *reinterpret_cast<float4*>(y + r * cols + c) = o;
+        } else {
+            y[r * cols + c] = (x[r * cols + c] - mu[0]) * is[0] * ga[0] + be[0];
+        }
     }
 }
 
-__global__ void bn_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                   const float* __restrict__ mean, const float* __restrict__ invstd,
-                                   const float* __restrict__ gamma, const float* __restrict__ s0,
-                                   const float* __restrict__ s1, float inv_count, int training, float* __restrict__ dx,
-                                   long long total, int cols) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cols);
-        float g = dy[i];
-        if (training) g = g - s0[c] * inv_count - (x[i] - mean[c]) * invstd[c] * s1[c] * inv_count;
-        dx[i] = g * gamma[c] * invstd[c];
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+bn_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ s0,
+                   const float* __restrict__ s1, float inv_count, int training, float* __restrict__ dx, long long R, int cols) {
+    constexpr int V = VEC ? 4 : 1;
+    const int c = (blockIdx.x * 256 + threadIdx.x) * V;
+    if (c >= cols) return;
+    float mu[V], is[V], gi[V], a0[V], a1[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        mu[e] = mean[c + e]; is[e] = invstd[c + e]; gi[e] = gamma[c + e] * invstd[c + e];
+        a0[e] = training ? s0[c + e] * inv_count : 0.f;
+        a1[e] = training ? s1[c + e] * inv_count : 0.f;
+    }
+    const long long r0 = (long long)blockIdx.y * kRowsPerEwBlock;
+    const long long r1 = r0 + kRowsPerEwBlock < R ? r0 + kRowsPerEwBlock : R;
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+        if constexpr (VEC) {
+            const float4 g = __ldcs(reinterpret_cast<const float4*>(dy + r * cols + c));
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(x + r * cols + c));
+            float4 o;
+            o.x = (training ? g.x - a0[0] - (v.x - mu[0]) * is[0] * a1[0] : g.x) * gi[0];
+            o.y = (training ? g.y - a0[1] - (v.y - mu[1]) * is[1] * a1[1] : g.y) * gi[1];
+            o.z = (training ? g.z - a0[2] - (v.z - mu[2]) * is[2] * a1[2] : g.z) * gi[2];
+            o.w = (training ? g.w - a0[3] - (v.w - mu[3]) * is[3] * a1[3] : g.w) * gi[3];
+            *reinterpret_cast<float4*>(dx + r * cols + c) = o;
+        } else {
+            const float g = dy[r * cols + c];
+            dx[r * cols + c] = (training ? g - a0[0] - (x[r * cols + c] - mu[0]) * is[0] * a1[0] : g) * gi[0];
+        }
     }
 }
 
@@ -158,10 +202,6 @@ log_softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp
     for (int c = lane; c < C; c += 32) dlogits[row * ld + c] = g[row * C + c] - expf(lp[row * C + c]) * s;
 }
 
-static inline int ew_grid(long long n) {
-    long long g = (n + 255) / 256;
-    return (int)(g < kNumSMs * 8 ? (g > 0 ? g : 1) : kNumSMs * 8);
-}
 
 template <int MODE>
 static int rows_reduce(const float* a, int lda, const float* x, int ldx, const float* mean, const float* invstd,
@@ -203,7 +243,13 @@ int asrb_bn_rows_fwd(const float* x, const float* gamma, const float* beta, floa
         if (rc) return rc;
     }
     const long long total = R * cols;
-    bn_rows_apply_kernel<<<ew_grid(total), 256, 0, stream>>>(x, mean, invstd, gamma, beta, y, total, cols);
+    (void)total;
+    {
+        const bool vec = cols % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+        const dim3 grid(ceil_div(vec ? cols / 4 : cols, 256), (unsigned)ceil_div64(R, kRowsPerEwBlock));
+        if (vec) bn_rows_apply_kernel<true><<<grid, 256, 0, stream>>>(x, mean, invstd, gamma, beta, y, R, cols);
+        else     bn_rows_apply_kernel<false><<<grid, 256, 0, stream>>>(x, mean, invstd, gamma, beta, y, R, cols);
+    }
     ASRB_LAUNCH_OK();
     return 0;
 }
@@ -219,7 +265,14 @@ int asrb_bn_rows_bwd(const float* dy, const float* x, const float* mean, const f
     rows_finalize_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(ws, nchunks, cols, 1.0, 1, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr);
     ASRB_LAUNCH_OK();
     const long long total = R * cols;
-    bn_rows_bwd_kernel<<<ew_grid(total), 256, 0, stream>>>(dy, x, mean, invstd, gamma, dbeta, dgamma, 1.0f / (float)R, training, dx, total, cols);
+    (void)total;
+    {
+        const bool vec = cols % 4 == 0 &&
+                         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+        const dim3 grid(ceil_div(vec ? cols / 4 : cols, 256), (unsigned)ceil_div64(R, kRowsPerEwBlock));
+        if (vec) bn_rows_bwd_kernel<true><<<grid, 256, 0, stream>>>(dy, x, mean, invstd, gamma, dbeta, dgamma, 1.0f / (float)R, training, dx, R, cols);
+        else     bn_rows_bwd_kernel<false><<<grid, 256, 0, stream>>>(dy, x, mean, invstd, gamma, dbeta, dgamma, 1.0f / (float)R, training, dx, R, cols);
+    }
     ASRB_LAUNCH_OK();
     return 0;
 }
