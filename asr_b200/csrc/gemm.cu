@@ -18,6 +18,7 @@
 namespace asrb {
 
 unsigned g_debug_flags = 0;
+int g_gemm_force_bn = 0, g_gemm_bn256_gain = 118;
 
 // ------------------------------------------------------------------------------------------------
 // host: tensor map encoding
@@ -403,7 +404,27 @@ int asrb_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int
     }
     ASRB_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, ASRB_ERR_ALIGNMENT);
     if (N <= 64) return launch_gemm_tc<64>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
+    // 128 x 256 tiles read 1.5x fewer operand bytes from shared memory per FLOP than 128 x 128 (with tf32 operands the
+    // SMEM port, not the tensor pipe, is the limit: 8 KB per 64-cycle MMA at N=128), but they quantise worse; pick the
+    // tile with the smaller estimated time = waves x tile width / efficiency.
+    int bn = 128;
+    if (N > 128) {
+        const long long w128 = ceil_div64((long long)ceil_div(M, kBM) * ceil_div(N, 128), kNumSMs);
+        const long long w256 = ceil_div64((long long)ceil_div(M, kBM) * ceil_div(N, 256), kNumSMs);
+        if (w256 * 256 * 100 < w128 * 128 * g_gemm_bn256_gain) bn = 256;
+    }
+    if (g_gemm_force_bn) bn = g_gemm_force_bn;
+    if (bn == 256) return launch_gemm_tc<256>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
     return launch_gemm_tc<128>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
+}
+
+/* DEBUG / tuning: force the N tile (0 = automatic, 128, 256); gain = assumed speed of the 256-wide tile relative to
+ * the 128-wide one in percent (default 118: measured 1.10-1.18 on the configs[1] shapes) */
+int asrb_debug_gemm_tile(int force_bn, int gain_pct) {
+    ASRB_REQUIRE(force_bn == 0 || force_bn == 128 || force_bn == 256, ASRB_ERR_BAD_ARG);
+    g_gemm_force_bn = force_bn;
+    if (gain_pct > 0) g_gemm_bn256_gain = gain_pct;
+    return 0;
 }
 
 int asrb_transpose(const float* in, long long rows, int cols, int ld_in, float* out, int ld_out, asrb_stream_t stream) {

@@ -57,6 +57,7 @@ typedef struct CUstream_st* asrb_stream_t; /* == cudaStream_t */
 int asrb_version(void);
 const char* asrb_strerror(int code);
 int asrb_set_debug_flags(unsigned flags);
+int asrb_debug_gemm_tile(int force_bn, int gain_pct);
 
 /* ---------------------------------------------------------------- GEMM (tcgen05, TF32 operands, fp32 accumulate)
  * C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N]).  lda/ldb/ldc are row strides in elements; lda, ldb multiples of 4. */
