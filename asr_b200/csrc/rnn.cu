@@ -117,11 +117,32 @@ __global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float
     }
 }
 
+// backward, K split over a CTA pair: CTA p = 2*pair + r holds, for the 2*nj units of the pair (row c = unit pair*2nj + c),
+// the r-th half of the gate index: element kk <-> gate row k = r*kpad + kk
+template <typename OutT>
+__global__ void rnn_pack_bwd_split_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, OutT* __restrict__ out,
+                                          int H, int G, int nj, int P, int kpad) {
+    const int npad = 2 * nj;
+    const long long total = 2LL * P * npad * kpad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % kpad);
+        long long r = i / kpad;
+        const int c = (int)(r % npad);
+        r /= npad;
+        const int p = (int)(r % P), dir = (int)(r / P);
+        const int j = (p / 2) * npad + c, k = (p % 2) * kpad + kk;
+        float v = 0.f;
+        if (j < H && k < G) v = (dir ? w_hh1 : w_hh0)[(size_t)k * H + j];
+        pack_store(out + i, v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the recurrence
 // ------------------------------------------------------------------------------------------------
 long long* g_rnn_trace = nullptr;
 int g_rnn_dbg = 0;
+int g_rnn_ksplit = 1;   // backward K split over CTA pairs (asrb_debug_rnn_ksplit)
 int g_rnn_chunk = 0;   // DEBUG: K blocks per pipeline barrier (0 = automatic)
 
 // fast gate non-linearities (ex2.approx + approximate division): ~1e-6 absolute error
@@ -156,12 +177,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int CELL, int NJ, bool BWD, bool BF16, int MROWS>
+// KSPLIT (backward only): a cluster of two CTAs shares 2*NJ hidden units.  Each CTA holds the weights of all 2*NJ units
+// for HALF of the gate index K, streams only that half of the operand through its shared memory (the bandwidth that
+// bounds the backward step: 382 KB instead of 686 KB per CTA and step at H=800), and the two partial products are
+// exchanged through distributed shared memory: every CTA sends the peer the 64 x NJ partial sums of the peer's units
+// and finishes its own NJ units.
+template <int CELL, int NJ, bool BWD, bool BF16, int MROWS, bool KSPLIT>
 __global__ void __launch_bounds__(kRnnThreads, 1)
 rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const RnnParams p) {
+    static_assert(!KSPLIT || BWD, "the K split exists for the backward recurrence only");
     using S = RnnShape<CELL, NJ>;
     constexpr int kGates = S::kGates;
-    constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
+    constexpr int NPAD = BWD ? (KSPLIT ? 2 * NJ : S::kNpadB) : S::kNpadF;
     constexpr int kTmemCols = 64;
     constexpr int KBE = BF16 ? 64 : 32;          // elements per 128-byte K block
     constexpr int kStageBytes = MROWS * 128;     // one K block of the A tile: MROWS rows x 128 B
@@ -183,6 +210,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint64_t* tfull_bar = w_bar + 1;
     uint64_t* tempty_bar = w_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 3);
+    uint64_t* x_bar = w_bar + 4;                  // [2] KSPLIT: the peer's partial sums of parity 0 / 1 have arrived
+    float* xbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kRnnBarBytes);   // [2][MROWS][NJ] (KSPLIT)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, B = p.B, H = p.H, G = p.G, P = p.P;
@@ -190,6 +219,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const int j0 = pidx * NJ;
     const bool tc = !p.use_simt;
     uint32_t* counter = p.counters + dir * kRnnCounterStride;
+    const uint32_t crank = KSPLIT ? cluster_ctarank() : 0u;      // = pidx % 2: which half of K this CTA multiplies
+    const int kb_off = KSPLIT ? (int)crank * nkb : 0;            // first K block (of the global operand) of this CTA
     // time index processed at sequential step s
     auto t_of = [&](int s) { return (BWD ? (dir == 0) : (dir == 1)) ? (T - 1 - s) : s; };
 
@@ -203,12 +234,17 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         mbar_init(w_bar, 1);
         mbar_init(tfull_bar, 1);
         mbar_init(tempty_bar, kRnnEpiWarps);
+        if (KSPLIT) {
+            mbar_init(&x_bar[0], 1);   // armed by one local thread with the byte count the peer will send
+            mbar_init(&x_bar[1], 1);
+        }
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    if constexpr (KSPLIT) cluster_sync_all();   // the peer's exchange barriers exist before anybody arrives on them
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -242,7 +278,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nblk * kStageBytes));
                         for (int i = 0; i < nblk; ++i)
-                            tma_load_3d(st + (size_t)i * kStageBytes, &tmA, &full_bar[stage], (kb0 + i) * KBE, 0, slab);
+                            tma_load_3d(st + (size_t)i * kStageBytes, &tmA, &full_bar[stage], (kb_off + kb0 + i) * KBE, 0, slab);
                     }
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -308,6 +344,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const size_t slotHB = (size_t)B * H;
         const int u0 = 4 * ug;                   // first unit (within the slice) owned by this thread
 
+        float xsend[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t xphase[2] = {0u, 0u};
         float state_h[4];   // fwd: h_prev of our units ; bwd: direct dh carry
         float state_c[4];   // fwd LSTM: c_prev ; bwd LSTM: dc carry
 #pragma unroll
@@ -340,6 +378,12 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const int t = t_of(s);
             const bool active = rowok && (t < len);
             if (hl == 0) ASRB_TRACE(4, s);
+            if constexpr (KSPLIT) {
+                if (hl == 0 && s > 0) {   // the peer sends one 16-byte vector per (row of the tile quarters in use, unit group)
+                    const int quads = min(4, ceil_div(B, kRowsPerWarp));
+                    mbar_arrive_expect_tx(&x_bar[s & 1], (uint32_t)(quads * kRowsPerWarp * NV * 16));
+                }
+            }
             constexpr int kAccG = BWD ? 1 : kGates;      // accumulator column groups we read: gates (fwd) / units (bwd)
             float acc[kAccG][4];
 #pragma unroll
@@ -383,14 +427,37 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     tc_fence_after_sync();
                     if (warp_ld) {
                         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + u0;
+                        if constexpr (KSPLIT) {
+                            tmem_ld_32x4(taddr + crank * NJ, acc[0]);          // partial sums of our own units
+                            tmem_ld_32x4(taddr + (crank ^ 1u) * NJ, xsend);    // ... and of the peer's units
+                        } else {
 #pragma unroll
-                        for (int g = 0; g < kAccG; ++g) tmem_ld_32x4(taddr + (BWD ? 0 : g * NJ), acc[g]);
+                            for (int g = 0; g < kAccG; ++g) tmem_ld_32x4(taddr + (BWD ? 0 : g * NJ), acc[g]);
+                        }
                         tmem_ld_wait();
                     }
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar);
                     if (hl == 0) ASRB_TRACE(6, s);
+                    if constexpr (KSPLIT) {
+                        // exchange through distributed shared memory with st.async (every 16-byte store completes its
+                        // bytes on the peer's mbarrier: no fence), double-buffered by step parity: the peer can only
+                        // write parity q again after it has received our data of the step in between
+                        const int par = s & 1;
+                        float* slot = xbuf + ((size_t)par * MROWS + b) * NJ + u0;
+                        if (warp_ld && lane < kRowsPerWarp)
+                            st_async_f32x4(map_to_cta(slot, crank ^ 1u), xsend, map_to_cta(&x_bar[par], crank ^ 1u));
+                        mbar_wait_cluster(&x_bar[par], xphase[par]);
+                        xphase[par] ^= 1u;
+                        if (warp_ld && lane < kRowsPerWarp) {
+                            float xr[4];
+                            ld4(xr, slot);
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) acc[0][jj] += xr[jj];
+                        }
+                        if (hl == 0) ASRB_TRACE(11, s);
+                    }
                 } else {
                     // DEBUG path (asrb_set_debug_flags bit 1): same algorithm, plain fp32 dot products
                     if (hl == 0) {
@@ -556,6 +623,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         tc_fence_after_sync();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
+    if constexpr (KSPLIT) cluster_sync_all();   // nobody leaves while the peer may still write into its exchange buffer
 }
 
 // out[t,b,:] = hseq[0][t+1][b][:] + hseq[1][t+1][b][:]     (blocks.py:92 "sum(2)")
@@ -568,7 +636,7 @@ __global__ void rnn_sum_dirs_kernel(const float* __restrict__ hseq, float* __res
 }
 
 struct RnnPlan {
-    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, chunk_f, chunk_b, mrows, bf16;
+    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, chunk_f, chunk_b, mrows, bf16, ksplit;
     size_t smem_f, smem_b;
 };
 
@@ -588,14 +656,17 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
         if (2 * P > kNumSMs) continue;
         RnnPlan r;
         r.nj = nj; r.P = P; r.mrows = mrows; r.bf16 = bf16;
-        r.npad_f = round_up(gates * nj, 16); r.npad_b = 16;
-        r.kpad_f = round_up(H, kbe); r.kpad_b = round_up(G, kbe);
+        // backward: K split over CTA pairs when the geometry allows (see rnn_rec_kernel)
+        r.ksplit = (bf16 && nj == 16 && P % 2 == 0 && g_rnn_ksplit) ? 1 : 0;
+        r.npad_f = round_up(gates * nj, 16); r.npad_b = r.ksplit ? 2 * nj : 16;
+        r.kpad_f = round_up(H, kbe); r.kpad_b = r.ksplit ? ceil_div(ceil_div(G, kbe), 2) * kbe : round_up(G, kbe);
         const size_t wf = (size_t)r.npad_f * r.kpad_f * esize, wb = (size_t)r.npad_b * r.kpad_b * esize;
         const size_t fixed = 1024 + kRnnBarBytes;
-        if (wf + fixed + stage > (size_t)kRnnMaxSmem || wb + fixed + stage > (size_t)kRnnMaxSmem) continue;
+        const size_t xb = r.ksplit ? (size_t)2 * mrows * nj * 4 : 0;   // exchange buffers of the K split
+        if (wf + fixed + stage > (size_t)kRnnMaxSmem || wb + fixed + xb + stage > (size_t)kRnnMaxSmem) continue;
         // as many K blocks in flight as fit (the whole previous state when possible): the step is latency-bound
         // K blocks that fit next to the resident weights; up to 4 blocks share one barrier / pipeline stage
-        const int bf = (int)((kRnnMaxSmem - fixed - wf) / stage), bb = (int)((kRnnMaxSmem - fixed - wb) / stage);
+        const int bf = (int)((kRnnMaxSmem - fixed - wf) / stage), bb = (int)((kRnnMaxSmem - fixed - xb - wb) / stage);
         const int nkb_f = r.kpad_f / kbe, nkb_b = r.kpad_b / kbe;
         r.chunk_f = g_rnn_chunk > 0 ? g_rnn_chunk : (bf >= 8 ? 4 : (bf >= 4 ? 2 : 1));
         r.chunk_b = g_rnn_chunk > 0 ? g_rnn_chunk : (bb >= 8 ? 4 : (bb >= 4 ? 2 : 1));
@@ -606,17 +677,17 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
         if (r.stages_f > kRnnMaxStages) r.stages_f = kRnnMaxStages;
         if (r.stages_b > kRnnMaxStages) r.stages_b = kRnnMaxStages;
         r.smem_f = wf + fixed + (size_t)r.stages_f * r.chunk_f * stage;
-        r.smem_b = wb + fixed + (size_t)r.stages_b * r.chunk_b * stage;
+        r.smem_b = wb + fixed + xb + (size_t)r.stages_b * r.chunk_b * stage;
         *pl = r;
         return 0;
     }
     return ASRB_ERR_UNSUPPORTED;
 }
 
-template <int CELL, int NJ, bool BWD, bool BF16, int MROWS>
+template <int CELL, int NJ, bool BWD, bool BF16, int MROWS, bool KSPLIT = false>
 static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, const void* a_base, asrb_stream_t stream) {
     using S = RnnShape<CELL, NJ>;
-    constexpr int NPAD = BWD ? S::kNpadB : S::kNpadF;
+    constexpr int NPAD = BWD ? (KSPLIT ? 2 * NJ : S::kNpadB) : S::kNpadF;
     constexpr int KBE = BF16 ? 64 : 32;
     constexpr int ES = BF16 ? 2 : 4;
     const int kpad = BWD ? pl.kpad_b : pl.kpad_f;
@@ -642,7 +713,7 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
         int rc = BF16 ? make_tmap_bf16(&tmA, a_base, 3, d, s, bx) : make_tmap_f32(&tmA, a_base, 3, d, s, bx);
         if (rc) return rc;
     }
-    auto kern = rnn_rec_kernel<CELL, NJ, BWD, BF16, MROWS>;
+    auto kern = rnn_rec_kernel<CELL, NJ, BWD, BF16, MROWS, KSPLIT>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * kRnnCounterStride * sizeof(uint32_t), stream));
     cudaLaunchConfig_t cfg = {};
@@ -650,11 +721,13 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
     cfg.blockDim = dim3(kRnnThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attrs[1];
+    cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the step barrier spins
     attrs[0].val.cooperative = 1;
+    attrs[1].id = cudaLaunchAttributeClusterDimension;
+    attrs[1].val.clusterDim.x = 2; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = KSPLIT ? 2 : 1;
     prm.dbg = g_rnn_dbg;
     ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, prm));
     return 0;
@@ -665,6 +738,12 @@ static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void*
                         asrb_stream_t stream) {
 #define ASRB_RNN_CASE(C, N)                                                                              \
     if (cell == C && pl.nj == N) {                                                                       \
+        if constexpr (BWD && N == 16) {                                                                  \
+            if (pl.ksplit) {                                                                             \
+                if (pl.mrows == 64) return rnn_launch<C, N, true, true, 64, true>(pl, prm, wpack, a_base, stream);  \
+                return rnn_launch<C, N, true, true, 128, true>(pl, prm, wpack, a_base, stream);          \
+            }                                                                                            \
+        }                                                                                                \
         if (pl.bf16) {                                                                                   \
             if (pl.mrows == 64) return rnn_launch<C, N, BWD, true, 64>(pl, prm, wpack, a_base, stream);  \
             return rnn_launch<C, N, BWD, true, 128>(pl, prm, wpack, a_base, stream);                     \
@@ -720,7 +799,8 @@ int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fw
         ASRB_LAUNCH_OK();
     }
     if (wpack_bwd) {
-        if (pl.bf16) rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
+        if (pl.ksplit)    rnn_pack_bwd_split_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.kpad_b);
+        else if (pl.bf16) rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
         else         rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (float*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
         ASRB_LAUNCH_OK();
     }
@@ -770,6 +850,10 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
     prm.trace = g_rnn_trace;
     return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, pl.bf16 ? (const void*)dgh_bf16 : (const void*)dgh, stream);
 }
+
+/* DEBUG / timing experiments: backward K split over CTA pairs on (1, default) / off (0).  Changes the packed-weight
+ * layout: call before asrb_rnn_plan / asrb_rnn_pack_weights. */
+int asrb_debug_rnn_ksplit(int on) { g_rnn_ksplit = on ? 1 : 0; return 0; }
 
 /* DEBUG / timing experiments: K blocks per pipeline barrier (0 = automatic) */
 int asrb_debug_rnn_dbg(int bits) { g_rnn_dbg = bits; return 0; }

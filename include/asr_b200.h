@@ -100,6 +100,7 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
 size_t asrb_rnn_saved_floats(int cell, int H, int B, int bf16, int T);
 int asrb_debug_rnn_trace(long long* trace);
 int asrb_debug_rnn_chunk(int blocks);
+int asrb_debug_rnn_ksplit(int on);
 int asrb_debug_rnn_dbg(int bits);
 /* out[T,B,H] = hseq[0][1..T] + hseq[1][1..T] */
 int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream);

@@ -13,7 +13,7 @@ lens = torch.full((B,), T, dtype=torch.int32, device=dev)
 pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
 nj, P, _, _ = ops.rnn_plan(cell, H, B, ops.rnn_use_bf16(H))
 grid = 2 * P
-names = ["P:counter ok", "P:loads issued", "M:first full", "M:commit", "E:step top", "E:tfull", "E:ld done", "E:math+stores", "E:bar done", "P:fence done", "E:red", "P:prearmed fired"]
+names = ["P:counter ok", "P:loads issued", "M:first full", "M:commit", "E:step top", "E:tfull", "E:ld done", "E:math+stores", "E:bar done", "P:fence done", "E:red", "E:exchange done"]
 def timed(fn, n=3):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -21,14 +21,16 @@ def timed(fn, n=3):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for flags in (0,):
-    _lib.query("asrb_debug_rnn_dbg", flags)
+for flags in (0, 1):
+    _lib.query("asrb_debug_rnn_ksplit", flags)
+    pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
     hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
     dout = torch.randn(T, B, H, device=dev)
     tf = timed(lambda: ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H))
     tb = timed(lambda: ops.rnn_bwd(cell, dout, pb, lens, hseq, cseq, saved, T, B, H))
-    print(f"dbg={flags} (no trace): fwd {tf:.3f} ms ({tf*1e3/T:.2f} us/step)  bwd {tb:.3f} ms ({tb*1e3/T:.2f} us/step)")
-_lib.query("asrb_debug_rnn_dbg", int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    print(f"ksplit={flags} (no trace): fwd {tf:.3f} ms ({tf*1e3/T:.2f} us/step)  bwd {tb:.3f} ms ({tb*1e3/T:.2f} us/step)")
+_lib.query("asrb_debug_rnn_ksplit", int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
 for which in ("fwd", "bwd"):
     for _ in range(2):
         hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
