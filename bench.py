@@ -226,29 +226,53 @@ def main():
     per_op = {k: (sum(s.elapsed_time(e) for s, e in v) / args.steps, len(v) // args.steps) for k, v in prof.items()}
     Tp = (cfg["T"] - 1) // 2 + 1
     fl = flops_per_step(cfg["B"], Tp, cfg["hidden"], cfg["layers"], cfg["C"])
-    top = max(per_op, key=lambda k: per_op[k][0])
-    if top in ("asrb_rnn_fwd", "asrb_rnn_bwd"):
-        launch_flops = fl["rec"] / cfg["layers"] * (1 if top == "asrb_rnn_fwd" else 1)   # one layer per launch
-        what = f"{top}: 2*T'*B*H*G*2dirs FLOP per launch (one layer, both directions)"
-    elif top == "asrb_gemm_tn":
-        launch_flops = (3 * fl["inproj"] + 2 * fl["rec"] + 3 * fl["fc"]) / per_op[top][1]
-        what = f"{top}: mean over the {per_op[top][1]} GEMM launches of a step (in-proj fwd/dgrad/wgrad, dW_hh, FC)"
-    else:
-        launch_flops = {"asrb_conv2d_mask_fwd": (fl["conv1"] + fl["conv2"]) / 2, "asrb_conv2d_mask_bwd_data": fl["conv2"],
-                        "asrb_conv2d_mask_bwd_weight": (fl["conv1"] + fl["conv2"]) / 2}.get(top, 0.0)
-        what = f"{top}: mean conv FLOP per launch"
+    # every kernel group against its roofline: achieved = ALGORITHMIC work per launch / mean launch duration
+    B_, C_ = cfg["B"], cfg["C"]
+    groups = {   # entry point -> (bound, algorithmic work per STEP [FLOP or bytes], note)
+        "asrb_rnn_fwd": ("tensor", fl["rec"], "2*T'*B*H*G*2dirs FLOP per layer-launch; latency chain, see DESIGN.md 6"),
+        "asrb_rnn_bwd": ("tensor", fl["rec"], "2*T'*B*H*G*2dirs FLOP per layer-launch (dh = dgates W_hh)"),
+        "asrb_gemm_tn": ("tensor", 3 * fl["inproj"] + fl["rec"] + 3 * fl["fc"],
+                         "all GEMM launches of a step: in-proj fwd + dgrad + wgrad, dW_hh, FC fwd + dgrad + wgrad (tf32)"),
+        "asrb_conv32_fwd": ("tensor", fl["conv2"], "conv2 forward"),
+        "asrb_conv32_bwd_data": ("tensor", fl["conv2"], "conv2 input gradient"),
+        "asrb_conv32_bwd_weight": ("tensor", fl["conv2"], "conv2 weight gradient"),
+        "asrb_conv1_fwd": ("tensor", fl["conv1"], "conv1 forward"),
+        "asrb_conv1_bwd_weight": ("tensor", fl["conv1"], "conv1 weight gradient"),
+        "asrb_ctc_fwd": ("hbm", Tp * B_ * C_ * 4.0, "read log_probs once (alpha); launch-latency regime at C=29"),
+        "asrb_ctc_bwd": ("hbm", 2.0 * Tp * B_ * C_ * 4.0, "read log_probs + write the dense gradient"),
+    }
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the ncu --set full captures
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+    rooflines = {}
+    for k, (bound, work, note) in groups.items():
+        if k not in per_op or per_op[k][0] <= 0:
+            continue
+        ms_step, n_launch = per_op[k]
+        if bound == "tensor":
+            ach, peak, unit = work / (ms_step * 1e-3) / 1e12, tf_peak, "TFLOP/s"
+        else:
+            ach, peak, unit = work / (ms_step * 1e-3) / 1e9, hbm_peak, "GB/s"
+        rooflines[k] = {"bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
+                        "launches": n_launch, "avg_launch_ms": round(ms_step / n_launch, 4),
+                        "traffic": traffic.get(k), "algorithmic": note}
+    top = max((k for k in per_op if k in rooflines), key=lambda k: per_op[k][0])
+    what = f"{top}: {groups[top][2]}"
     avg_ms = per_op[top][0] / per_op[top][1]
-    achieved = launch_flops / (avg_ms * 1e-3) / 1e12
+    achieved = rooflines[top]["achieved"]
     line = dict(base, value=total_sec / (ms_dev * 1e-3), ms_per_step=ms_dev, dtype="tf32 operands, f32 accumulate/storage",
                 loss=loss_value, gpu_launches=launches,
                 e2e={"value": total_sec / (ms_e2e * 1e-3), "unit": "utterance-sec/s", "ms_per_step": ms_e2e,
                      "h2d_bytes_per_step": pinned.numel() * 4 + host[1].numel() * 4 + 2 * cfg["B"] * 4 + 3 * cfg["B"] * 4,
                      "d2h_bytes_per_step": 4},
                 clocks=clocks,
-                roofline={"bound": "tensor", "kernel": top, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                          "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src, "algorithmic": what,
-                          "avg_launch_ms": avg_ms,
-                          "note": "peak is the measured bf16 rate; tf32 operands run at half of it"},
+                roofline={"bound": rooflines[top]["bound"], "kernel": top, "achieved": achieved, "peak": rooflines[top]["peak"],
+                          "unit": rooflines[top]["unit"], "frac": rooflines[top]["frac"], "traffic": traffic.get(top),
+                          "peak_source": peak_src, "algorithmic": what, "avg_launch_ms": avg_ms,
+                          "note": "tensor peak is the measured bf16 rate (tf32 operands run at half of it); the "
+                                  "recurrence is a latency chain of T' grid-wide steps, see DESIGN.md section 6"},
+                rooflines=rooflines,
                 kernel_ms_per_step={k: round(v[0], 3) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1][0])})
     if not args.no_cpu_baseline and world == 1:
         v, dt, cores, sample = run_cpu_port(1, 0)
