@@ -26,6 +26,8 @@
 namespace asrb {
 
 constexpr int kCtcThreads = 256;
+int g_ctc_dbg = 0;   // DEBUG timing: 1 = no dense stream, 2 = no DP (progress pre-set to 0)
+int g_ctc_min_smem = 0, g_ctc_blocks_per_sm = 5;   // tuning (asrb_debug_ctc_tuning)
 constexpr int kCtcRing = 8;              // prefetch ring depth (time steps)
 
 // branch-free (a divergent early-out per state keeps the compiler from interleaving the independent states of a lane):
@@ -43,6 +45,15 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // blank-extended label sequence of utterance n into ext[0..S) ; returns S = 2U+1
 __device__ __forceinline__ int ctc_setup_labels(const int* __restrict__ targets, const int* __restrict__ tgt_off,
@@ -201,25 +212,29 @@ ctc_alpha_warp_kernel(const float* __restrict__ lp, const int* __restrict__ targ
 struct CtcBwdParams {
     const float* lp; const int* targets; const int* tgt_off; const int* in_len; const int* tgt_len;
     const float* alpha;      // [N, T, RS] alpha rows of the forward
-    const float* gathered;   // [N, T, RS] lp[t, n, l'_s] rows of the forward (warp DP only)
+    float* gathered;         // [N, T, RS] lp[t, n, l'_s] rows of the forward (warp DP only); the backward overwrites
+                             // a consumed row with the row's class posteriors (at the column of each class's first state)
+    int* progress;           // [N] lowest time step whose posterior row is published (starts at T)
     const float* nll; const float* gscale; float* grad;
-    int T, N, C, Smax, RS, kpl, blank, n_dp, nparts;
+    int T, N, C, Smax, RS, kpl, blank, n_dp, nparts, dbg;
 };
 
+constexpr int kDenseDepth = 8;         // 16-byte loads in flight per lane of a streaming warp (16 would cost a block per SM in registers)
+constexpr int kCtcPublishEvery = 16;   // rows between two progress publications (each is a MEMBAR.GPU)
 constexpr int kCtcXRing = 4;           // rows of alpha+beta in flight between the recurrence warp and the posterior warp
 constexpr int kCtcBetaRing = 4;        // prefetch depth of the beta warp (contiguous rows: three steps ahead is plenty)
 
 // shared memory of a DP block (floats): cp.async rings of lp and alpha, the hand-over ring, two scratch rows, labels
 template <int KPL>
 __host__ __device__ constexpr size_t ctc_dp_smem_bytes() {
-    return (size_t)(2 * kCtcBetaRing + 2 * kCtcXRing + 3) * KPL * 32 * 4 + 2 * kCtcXRing * 8 + 64;
+    return (size_t)(2 * kCtcBetaRing + kCtcXRing + 3) * KPL * 32 * 4 + 2 * kCtcXRing * 8 + 64;
 }
 
 // Backward DP of utterance n by TWO warps of a DP block:
 //   warp 0 runs the beta recurrence (the only sequential chain) and hands row after row of
-//          x[s] = alpha_t(s) + beta_t(s) - lp_t(l'_s) + nll  (and lp_t(l'_s)) to warp 1 through a shared-memory ring;
-//   warp 1 turns a row into class posteriors, post(c) = sum_{s: l'_s = c} exp(x[s]), and writes the gradient
-//          g*(exp(lp) - post) of the label classes (the streaming blocks write every other class).  These terms are probabilities
+//          x[s] = alpha_t(s) + beta_t(s) - lp_t(l'_s) + nll  to warp 1 through a shared-memory ring;
+//   warp 1 turns a row into class posteriors, post(c) = sum_{s: l'_s = c} exp(x[s]), publishes them as a compact row
+//          and every 16 rows bumps the utterance's progress word, which the streaming warps follow.  These terms are probabilities
 //          (they sum to 1 over the whole row), so the class sums are taken in the linear domain, in a fixed order:
 //          the blank class by a warp reduction, the label classes as differences of ONE prefix sum over the label
 //          positions sorted by class (no pointer chasing along per-class chains, no atomics).
@@ -232,12 +247,11 @@ __device__ void ctc_beta_warp_role(const CtcBwdParams& p, int n, int* smi) {
     constexpr int R = kCtcBetaRing, RS = KPL * 32, XR = kCtcXRing;
     constexpr int KP2 = (KPL + 1) / 2;                  // sorted label slots per lane (32*KP2 >= U)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int N = p.N, C = p.C, T = p.T, blank = p.blank;
+    const int T = p.T, blank = p.blank;
     float* ring_lp = reinterpret_cast<float*>(smi);     // [R][RS]
     float* ring_al = ring_lp + R * RS;                  // [R][RS]
     float* xr = ring_al + R * RS;                       // [XR][RS] alpha+beta-lp+nll
-    float* gr = xr + XR * RS;                           // [XR][RS] lp of the states
-    float* se = gr + XR * RS;                           // [RS] exp(x) by column
+    float* se = xr + XR * RS;                           // [RS] exp(x) by column
     float* sP = se + RS;                                // [RS] prefix sums over the sorted label slots
     int* sext = reinterpret_cast<int*>(sP + RS);        // [RS] labels by column (setup only)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(sext + RS);   // [XR]
@@ -254,7 +268,7 @@ __device__ void ctc_beta_warp_role(const CtcBwdParams& p, int n, int* smi) {
     named_bar_sync_ctc(1, 64);                           // the two DP warps only
     if (Tn <= 0) return;
     const float* al = p.alpha + (size_t)n * T * RS;
-    const float* gw = p.gathered + (size_t)n * T * RS;
+    const float* gw = p.gathered + (size_t)n * T * RS;   // read 3 steps ahead of the row being handed over
     int ext[KPL];
 #pragma unroll
     for (int k = 0; k < KPL; ++k) {
@@ -330,7 +344,6 @@ __device__ void ctc_beta_warp_role(const CtcBwdParams& p, int n, int* smi) {
 #pragma unroll
             for (int k = 0; k < KPL; ++k) {
                 xr[slot * RS + k * 32 + lane] = (a[k] + cur[k]) - g[k] + nl;
-                gr[slot * RS + k * 32 + lane] = g[k];
                 prev[k] = cur[k];
             }
             __syncwarp();
@@ -339,7 +352,6 @@ __device__ void ctc_beta_warp_role(const CtcBwdParams& p, int n, int* smi) {
         }
     } else {
         // ============================== class posteriors ==============================
-        const float gs = p.gscale ? p.gscale[0] : 1.f;
         bool isblank[KPL], lead[KPL];
         int seg_a[KPL], seg_b[KPL];                      // sorted-slot range of the class a lead position stands for
 #pragma unroll
@@ -386,13 +398,9 @@ __device__ void ctc_beta_warp_role(const CtcBwdParams& p, int n, int* smi) {
             const int t = Tn - 1 - i;
             const int slot = i % XR;
             mbar_wait(&full_bar[slot], (uint32_t)(i / XR) & 1u);
-            float e[KPL], g[KPL];
+            float e[KPL];
 #pragma unroll
-            for (int k = 0; k < KPL; ++k) {
-                const bool ok = lane * KPL + k < S;
-                e[k] = ok ? exp_ftz(xr[slot * RS + k * 32 + lane]) : 0.f;
-                g[k] = ok ? gr[slot * RS + k * 32 + lane] : 0.f;
-            }
+            for (int k = 0; k < KPL; ++k) e[k] = (lane * KPL + k < S) ? exp_ftz(xr[slot * RS + k * 32 + lane]) : 0.f;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[slot]);
             float be = 0.f;
@@ -419,12 +427,20 @@ __device__ void ctc_beta_warp_role(const CtcBwdParams& p, int n, int* smi) {
 #pragma unroll
             for (int q = 0; q < KP2; ++q) sP[lane * KP2 + q] = v[q] + excl;
             __syncwarp();
-            float* grow = p.grad + ((size_t)t * N + n) * C;
+            // posterior row, by state column: the class's first state carries the class posterior, state 0 the blank's.
+            // It replaces the gathered row t, which the recurrence warp has already consumed.
+            float* out = p.gathered + ((size_t)n * T + t) * RS + lane;
 #pragma unroll
             for (int k = 0; k < KPL; ++k) {
                 const int s = lane * KPL + k;
-                if (lead[k]) grow[ext[k]] = gs * (__expf(g[k]) - (sP[seg_b[k]] - (seg_a[k] > 0 ? sP[seg_a[k] - 1] : 0.f)));
-                if (s == 0) grow[blank] = gs * (__expf(g[k]) - be);
+                float post = 0.f;
+                if (lead[k]) post = sP[seg_b[k]] - (seg_a[k] > 0 ? sP[seg_a[k] - 1] : 0.f);
+                if (s == 0) post = be;
+                out[k * 32] = post;
+            }
+            if ((i % kCtcPublishEvery) == kCtcPublishEvery - 1 || i == Tn - 1) {
+                __syncwarp();
+                if (lane == 0) st_release_s32(p.progress + n, i == Tn - 1 ? 0 : t);   // rows >= t are complete
             }
         }
     }
@@ -604,78 +620,123 @@ __device__ void ctc_beta_role(const CtcBwdParams& p, int n, int* smi) {
     }
 }
 
-// Dense gradient stream: grad[t,n,c] = g*exp(lp[t,n,c]) for every class c that does NOT occur in utterance n's labels
-// (those and the blank are written by the DP), zero rows for t >= input length.  Every block works for ONE utterance
-// n = block % N (class mask built once).  The utterance's streaming warps -- warps 2..7 of its DP block plus all 8 warps
-// of its nparts-1 further blocks -- deal the rows out warp by warp: no barrier, no flag, eight 16-byte loads in flight
-// per lane.
-__device__ void ctc_dense_role(const CtcBwdParams& p, int n, int wi, int nw, uint32_t* mask) {
-    const int N = p.N, C = p.C, T = p.T;
+// Dense gradient stream.  Every block works for ONE utterance n = block % N; the utterance's streaming warps -- warps
+// 2..7 of its DP block plus all 8 warps of its nparts-1 further blocks -- deal the rows out warp by warp, latest time
+// step first (the order in which the DP publishes posteriors): no block barrier, eight 16-byte loads in flight per lane.
+//   POST = true  (warp DP): full rows grad = g*(exp(lp) - post).  Only the <= U+1 classes of the utterance's labels have a
+//           posterior: a C-bit mask marks them, first_state[c] says where in the DP's compact posterior row the value is,
+//           and the warp stages that row (RS floats) in shared memory once it is published.  Every store is a whole
+//           16-byte vector: no partial-sector read-modify-write in DRAM (the version in which the DP scattered the label
+//           classes' gradients itself moved 30.7 GB instead of 22 GB at the isolation shape).
+//   POST = false (block-wide DP, long label sequences): the DP writes the label classes itself, the stream skips them.
+template <bool POST>
+__device__ void ctc_dense_role(const CtcBwdParams& p, int n, int wi, int nw, const uint32_t* mask, const int* first_state,
+                               float* wpost) {
+    const int N = p.N, C = p.C, T = p.T, RS = p.RS;
     const int Tn = min(p.in_len[n], T);
     const float g = p.gscale ? p.gscale[0] : 1.f;
     const int lane = threadIdx.x & 31;
-    if (C % 4 == 0) {
-        const int C4 = C / 4;
-        for (int t = wi; t < T; t += nw) {
-            const float4* row4 = reinterpret_cast<const float4*>(p.lp + ((size_t)t * N + n) * C);
-            float4* gr4 = reinterpret_cast<float4*>(p.grad + ((size_t)t * N + n) * C);
-            if (t >= Tn) {
-                for (int c = lane; c < C4; c += 32) __stcs(gr4 + c, make_float4(0.f, 0.f, 0.f, 0.f));
-                continue;
+    const bool vec = C % 4 == 0;
+    const int C4 = C / 4;
+    // rows beyond the utterance: zeros
+    for (int t = Tn + wi; t < T; t += nw) {
+        float* gr = p.grad + ((size_t)t * N + n) * C;
+        if (vec) for (int c = lane; c < C4; c += 32) __stcs(reinterpret_cast<float4*>(gr) + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        else     for (int c = lane; c < C; c += 32) gr[c] = 0.f;
+    }
+    int seen = T;                                        // last progress value this warp has observed
+    for (int t = Tn - 1 - wi; t >= 0; t -= nw) {
+        if constexpr (POST) {
+            if (seen > t) {
+                if (lane == 0) {
+                    do { seen = ld_acquire_s32(p.progress + n); } while (seen > t);
+                }
+                seen = __shfl_sync(0xffffffffu, seen, 0);
             }
-            for (int c0 = lane; c0 < C4; c0 += 256) {
-                float4 x[8];
+            const float* post = p.gathered + ((size_t)n * T + t) * RS;
+            __syncwarp();                                // the previous row's readers are done with wpost
+            for (int i = lane; i < RS; i += 32) wpost[i] = __ldcg(post + i);   // written during this launch: bypass L1
+            __syncwarp();
+        }
+        const float* row = p.lp + ((size_t)t * N + n) * C;
+        float* gr = p.grad + ((size_t)t * N + n) * C;
+        if (vec) {
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            float4* gr4 = reinterpret_cast<float4*>(gr);
+            // kDenseDepth 16-byte loads in flight per lane: the kernel's register count (set by the DP warps) allows
+            // only two blocks per SM, so each streaming warp has to cover >= 8 KB of the HBM latency by itself
+            for (int c0 = lane; c0 < C4; c0 += 32 * kDenseDepth) {
+                float4 x[kDenseDepth];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int u = 0; u < kDenseDepth; ++u)
                     if (c0 + 32 * u < C4) x[u] = __ldcs(row4 + c0 + 32 * u);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < kDenseDepth; ++u) {
                     const int c = c0 + 32 * u;
                     if (c < C4) {
-                        float4 o;
-                        o.x = g * exp_ftz(x[u].x); o.y = g * exp_ftz(x[u].y); o.z = g * exp_ftz(x[u].z); o.w = g * exp_ftz(x[u].w);
+                        float o[4] = {exp_ftz(x[u].x), exp_ftz(x[u].y), exp_ftz(x[u].z), exp_ftz(x[u].w)};
                         const uint32_t bits = (mask[(4 * c) >> 5] >> ((4 * c) & 31)) & 0xFu;
                         if (bits == 0u) {
-                            __stcs(gr4 + c, o);
+                            __stcs(gr4 + c, make_float4(g * o[0], g * o[1], g * o[2], g * o[3]));
+                        } else if constexpr (POST) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (bits & (1u << e)) o[e] -= wpost[first_state[4 * c + e]];   // two LDS: the slow path is divergent
+                            __stcs(gr4 + c, make_float4(g * o[0], g * o[1], g * o[2], g * o[3]));
                         } else {
-                            float* gr = reinterpret_cast<float*>(gr4 + c);
-                            if (!(bits & 1u)) gr[0] = o.x;
-                            if (!(bits & 2u)) gr[1] = o.y;
-                            if (!(bits & 4u)) gr[2] = o.z;
-                            if (!(bits & 8u)) gr[3] = o.w;
+                            float* gs = reinterpret_cast<float*>(gr4 + c);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (!(bits & (1u << e))) gs[e] = g * o[e];
                         }
                     }
                 }
             }
-        }
-    } else {
-        for (int t = wi; t < T; t += nw) {
-            const float* row = p.lp + ((size_t)t * N + n) * C;
-            float* gr = p.grad + ((size_t)t * N + n) * C;
-            if (t >= Tn) {
-                for (int c = lane; c < C; c += 32) gr[c] = 0.f;
-                continue;
+        } else {
+            for (int c = lane; c < C; c += 32) {
+                const bool m = (mask[c >> 5] >> (c & 31)) & 1u;
+                if (!m) gr[c] = g * exp_ftz(__ldg(row + c));
+                else if constexpr (POST) gr[c] = g * (exp_ftz(__ldg(row + c)) - wpost[first_state[c]]);
             }
-            for (int c = lane; c < C; c += 32)
-                if (!((mask[c >> 5] >> (c & 31)) & 1u)) gr[c] = g * exp_ftz(__ldg(row + c));
         }
     }
 }
 
-// bit c set: class c occurs in utterance n's labels (or is the blank) and its gradient is written by the DP
-__device__ void ctc_build_mask(const CtcBwdParams& p, int n, uint32_t* mask) {
+// bit c of mask set: class c occurs in utterance n's labels (or is the blank); first_state[c] (POST only) = column, in
+// the DP's posterior row, of the first state of the extended label sequence that carries class c (0 for the blank)
+__device__ void ctc_build_mask(const CtcBwdParams& p, int n, uint32_t* mask, int* first_state) {
     const int words = (p.C + 31) / 32;
     for (int w = threadIdx.x; w < words; w += kCtcThreads) mask[w] = 0u;
+    const bool live = min(p.in_len[n], p.T) > 0;
+    const int U = p.tgt_len[n], off = p.tgt_off[n];
+    if (first_state && live)
+        for (int i = threadIdx.x; i < U; i += kCtcThreads) first_state[p.targets[off + i]] = 0x7fffffff;
     __syncthreads();
-    if (min(p.in_len[n], p.T) > 0) {
-        const int U = p.tgt_len[n], off = p.tgt_off[n];
+    if (live) {
         for (int i = threadIdx.x; i < U; i += kCtcThreads) {
             const int l = p.targets[off + i];
             atomicOr(&mask[l >> 5], 1u << (l & 31));
+            if (first_state) atomicMin(&first_state[l], 2 * i + 1);
         }
         if (threadIdx.x == 0) atomicOr(&mask[p.blank >> 5], 1u << (p.blank & 31));
     }
     __syncthreads();
+    // state index -> column of the DP's posterior row (done once here: the lookup sits on the streaming warps' divergent
+    // path, where an integer division per element cost 8x the whole loop body)
+    if (first_state && live) {
+        for (int i = threadIdx.x; i < U; i += kCtcThreads) {
+            const int l = p.targets[off + i];
+            if (first_state[l] == 2 * i + 1) first_state[l] = ctc_col(2 * i + 1, p.kpl);
+        }
+    }
+    __syncthreads();
+    if (first_state && live && threadIdx.x == 0) first_state[p.blank] = 0;   // column of state 0
+    __syncthreads();
+}
+
+__global__ void ctc_reset_progress_kernel(int* progress, int N, int T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) progress[i] = T;
 }
 
 // KPL > 0: warp DP -- block (n, part 0) runs the DP on warps 0,1 and streams on warps 2..7, blocks (n, part >= 1) only
@@ -685,27 +746,29 @@ __global__ void __launch_bounds__(kCtcThreads)
 ctc_bwd_kernel(const CtcBwdParams p) {
     extern __shared__ int smi[];
     const int warp = threadIdx.x >> 5;
+    const int mask_words = ((p.C + 31) / 32 + 31) / 32 * 32;     // keep what follows 128-byte aligned
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smi);
     if constexpr (KPL > 0) {
         const int n = blockIdx.x % p.N, part = blockIdx.x / p.N;
-        uint32_t* mask = reinterpret_cast<uint32_t*>(smi);
-        int* dp_smem = smi + (p.C + 31) / 32;
-        dp_smem += (32 - ((p.C + 31) / 32) % 32) % 32;           // keep the DP rows 128-byte aligned
-        ctc_build_mask(p, n, mask);
-        const int nw = 8 * p.nparts - 2;
+        int* first_state = smi + mask_words;                      // [C]
+        float* wpost = reinterpret_cast<float*>(first_state + (p.C + 31) / 32 * 32);   // [8][RS]
+        int* dp_smem = reinterpret_cast<int*>(wpost + 8 * p.RS);
+        ctc_build_mask(p, n, mask, first_state);
+        const int own = (p.dbg & 4) ? 0 : 6;                      // streaming warps inside the DP block
+        const int nw = 8 * (p.nparts - 1) + own;
         if (part == 0) {
-            if (warp < 2) ctc_beta_warp_role<KPL>(p, n, dp_smem);
-            else          ctc_dense_role(p, n, warp - 2, nw, mask);
-        } else {
-            ctc_dense_role(p, n, 6 + 8 * (part - 1) + warp, nw, mask);
+            if (warp < 2) { if (!(p.dbg & 2)) ctc_beta_warp_role<KPL>(p, n, dp_smem); }
+            else if (!(p.dbg & 1) && own) ctc_dense_role<true>(p, n, warp - 2, nw, mask, first_state, wpost + warp * p.RS);
+        } else if (!(p.dbg & 1)) {
+            ctc_dense_role<true>(p, n, own + 8 * (part - 1) + warp, nw, mask, first_state, wpost + warp * p.RS);
         }
     } else {
         if ((int)blockIdx.x < p.N) {
             ctc_beta_role(p, blockIdx.x, smi);
         } else {
             const int j = blockIdx.x - p.N, n = j % p.N, part = j / p.N;
-            uint32_t* mask = reinterpret_cast<uint32_t*>(smi);
-            ctc_build_mask(p, n, mask);
-            ctc_dense_role(p, n, 8 * part + warp, 8 * p.nparts, mask);
+            ctc_build_mask(p, n, mask, nullptr);
+            ctc_dense_role<false>(p, n, 8 * part + warp, 8 * p.nparts, mask, nullptr, nullptr);
         }
     }
 }
@@ -744,17 +807,24 @@ static size_t ctc_alpha_floats(int T, int N, int max_target_len) {
 template <int KPL>
 static int ctc_launch_bwd(CtcBwdParams& p, size_t smem_dp, asrb_stream_t stream) {
     const size_t smem_mask = (size_t)(((p.C + 31) / 32 + 31) / 32 * 32) * 4;
-    const size_t smem = KPL > 0 ? smem_mask + smem_dp : (smem_dp > smem_mask ? smem_dp : smem_mask);
-    ASRB_REQUIRE(smem <= 160 * 1024, ASRB_ERR_UNSUPPORTED);
+    const size_t smem_post = (size_t)((p.C + 31) / 32 * 32) * 4 + (size_t)8 * p.RS * 4;   // first_state[C] + 8 posterior rows
+    size_t smem = KPL > 0 ? smem_mask + smem_post + smem_dp : (smem_dp > smem_mask ? smem_dp : smem_mask);
+    // The DP warps are latency chains that share their SM with streaming warps: fewer resident blocks per SM (a larger
+    // shared-memory request) leave them more issue slots while 2-3 x 8 streaming warps still saturate HBM.
+    if (KPL > 0 && g_ctc_min_smem > 0 && smem < (size_t)g_ctc_min_smem) smem = (size_t)g_ctc_min_smem;
+    ASRB_REQUIRE(smem <= 200 * 1024, ASRB_ERR_UNSUPPORTED);
     auto kern = ctc_bwd_kernel<KPL>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // One launch, about five blocks per SM.  Nothing waits on anything, so residency does not matter; the blocks that
     // carry a DP have the lowest indices and start first (the DP is the long pole).
     const int N = p.N;
-    int nparts = (kNumSMs * 5 + N - 1) / N;
+    int nparts = (kNumSMs * g_ctc_blocks_per_sm + N - 1) / N;
     if (KPL > 0) {
         if (nparts < 1) nparts = 1;
         p.nparts = nparts;
+        p.dbg = g_ctc_dbg;
+        ctc_reset_progress_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(p.progress, N, (g_ctc_dbg & 2) ? 0 : p.T);
+        ASRB_LAUNCH_OK();
         kern<<<N * nparts, kCtcThreads, smem, stream>>>(p);
     } else {
         if (nparts < 2) nparts = 2;
@@ -771,9 +841,18 @@ using namespace asrb;
 
 extern "C" {
 
-/* alpha rows [N, T, row stride], the gathered log-prob rows (same shape), target offsets[N] */
+/* DEBUG / tuning: minimum dynamic shared memory of the backward blocks (limits blocks per SM), target blocks per SM */
+int asrb_debug_ctc_dbg(int bits) { g_ctc_dbg = bits; return 0; }
+int asrb_debug_ctc_tuning(int min_smem_bytes, int blocks_per_sm) {
+    ASRB_REQUIRE(min_smem_bytes >= 0 && blocks_per_sm >= 1 && blocks_per_sm <= 16, ASRB_ERR_BAD_ARG);
+    g_ctc_min_smem = min_smem_bytes;
+    g_ctc_blocks_per_sm = blocks_per_sm;
+    return 0;
+}
+
+/* alpha rows [N, T, row stride], the gathered log-prob rows (same shape), target offsets[N], progress[N] */
 size_t asrb_ctc_workspace_bytes(int T, int N, int max_target_len) {
-    return 2 * ctc_alpha_floats(T, N, max_target_len) * sizeof(float) + (size_t)N * sizeof(int) + 64;
+    return 2 * ctc_alpha_floats(T, N, max_target_len) * sizeof(float) + (size_t)2 * N * sizeof(int) + 64;
 }
 
 /* Forward: nll[N] per utterance and loss[1] = sum_n nll[n]; ws keeps alpha (and the gathered log-probs) for the backward. */
@@ -811,7 +890,8 @@ int asrb_ctc_fwd(const float* log_probs, const int32_t* targets, const int32_t* 
 }
 
 /* Backward: grad[T,N,C] = grad_scale[0] * d(sum nll)/d(logits); grad_scale is a DEVICE scalar (NULL = 1).
- * alpha_ws is the workspace asrb_ctc_fwd filled (read only). */
+ * alpha_ws is the workspace asrb_ctc_fwd filled; its gathered-log-prob rows are consumed (a second backward needs a
+ * new forward), alpha stays intact. */
 int asrb_ctc_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lengths,
                  const int32_t* target_lengths, float* alpha_ws, const float* nll, const float* grad_scale,
                  float* grad, int T, int N, int C, int max_target_len, int blank, asrb_stream_t stream) {
@@ -819,10 +899,10 @@ int asrb_ctc_bwd(const float* log_probs, const int32_t* targets, const int32_t* 
     ASRB_REQUIRE(T > 0 && N > 0 && C > 0 && max_target_len >= 0 && blank >= 0 && blank < C, ASRB_ERR_BAD_ARG);
     const int Smax = 2 * max_target_len + 1;
     const size_t rows = ctc_alpha_floats(T, N, max_target_len);
-    const int* tgt_off = reinterpret_cast<const int*>(alpha_ws + 2 * rows);   // filled by asrb_ctc_fwd
+    int* tgt_off = reinterpret_cast<int*>(alpha_ws + 2 * rows);   // filled by asrb_ctc_fwd
     const int kpl = ctc_pick_kpl(Smax);
-    CtcBwdParams p = {log_probs, targets, tgt_off, input_lengths, target_lengths, alpha_ws, alpha_ws + rows, nll, grad_scale, grad,
-                      T, N, C, Smax, ctc_row_stride(Smax), kpl, blank, N, 1};
+    CtcBwdParams p = {log_probs, targets, tgt_off, input_lengths, target_lengths, alpha_ws, alpha_ws + rows, tgt_off + N, nll,
+                      grad_scale, grad, T, N, C, Smax, ctc_row_stride(Smax), kpl, blank, N, 1};
     if (kpl) {
 #define ASRB_CTC_CASE(K)                                                                                   \
     case K:                                                                                                \

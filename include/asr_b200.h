@@ -185,6 +185,8 @@ int asrb_log_softmax_bwd(const float* g, const float* log_probs, float* dlogits,
 
 /* ---------------------------------------------------------------- CTC (blank-extended alpha/beta, reduction = sum) */
 size_t asrb_ctc_workspace_bytes(int T, int N, int max_target_len);
+int asrb_debug_ctc_tuning(int min_smem_bytes, int blocks_per_sm);
+int asrb_debug_ctc_dbg(int bits);
 int asrb_ctc_fwd(const float* log_probs, const int32_t* targets, const int32_t* input_lengths,
                  const int32_t* target_lengths, float* alpha_ws, size_t ws_bytes, float* nll, float* loss, int T, int N,
                  int C, int max_target_len, int blank, asrb_stream_t stream);

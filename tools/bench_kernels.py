@@ -85,6 +85,13 @@ def stft(B=64, S=160000):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ctc", "stft"]
+    if "ctctune" in which:
+        from asr_b200 import _lib
+        for bits in (0, 4):
+            _lib.query("asrb_debug_ctc_dbg", bits)
+            print("tuning", bits, 0, end=" ")
+            ctc()
+        _lib.query("asrb_debug_ctc_dbg", 0)
     if "ctc" in which:
         ctc()
     if "stft" in which:
