@@ -13,6 +13,8 @@
 //                next tile's main loop through the tmem_full/tmem_empty barriers
 // Out-of-range rows/columns/K are zero-filled by TMA and masked in the epilogue, so any M, N and
 // any K (row strides must be multiples of 16 bytes) are accepted.
+#include <cuda_bf16.h>
+
 #include "ptx.cuh"
 
 namespace asrb {
@@ -88,7 +90,9 @@ struct GemmCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// BF16 = false: fp32 operands in HBM, tf32 MMA (TMA rounds fp32 -> tf32 on the way into shared memory);
+// BF16 = true : bf16 operands (64 elements per 128-byte stage row), kind::f16 MMA.  Accumulation and C are fp32.
+template <int BN, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     float* __restrict__ C, int ldc, const float* __restrict__ bias, int M, int N, int K,
@@ -109,7 +113,8 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int lane = threadIdx.x & 31;
     const int num_m = ceil_div(M, kBM), num_n = ceil_div(N, BN);
     const int num_tiles = num_m * num_n;
-    const int num_kb = ceil_div(K, kBK);
+    constexpr int kKE = BF16 ? 2 * kBK : kBK;      // operand elements per 128-byte stage row
+    const int num_kb = ceil_div(K, kKE);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -142,8 +147,8 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kBK, m0);
-                    tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], kb * kBK, n0);
+                    tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmA, &full_bar[stage], kb * kKE, m0);
+                    tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmB, &full_bar[stage], kb * kKE, n0);
                 }
                 __syncwarp();
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -151,7 +156,7 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        constexpr uint32_t idesc = umma_idesc(kFmtTF32, kBM, BN);
+        constexpr uint32_t idesc = umma_idesc(BF16 ? kFmtBF16 : kFmtTF32, kBM, BN);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -167,8 +172,10 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
 #pragma unroll
-                    for (int k = 0; k < kBK / 8; ++k)  // UMMA_K = 8 for tf32: advance 32 B inside the swizzle row
-                        umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < kBK / 8; ++k) {  // UMMA_K = 8 tf32 / 16 bf16: advance 32 B inside the swizzle row
+                        if constexpr (BF16) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else                umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty_bar[stage]);
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
                 }
@@ -234,27 +241,28 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-template <int BN>
-static int launch_gemm_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias,
+template <int BN, bool BF16>
+static int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float* C, int ldc, const float* bias,
                           int M, int N, int K, int flags, asrb_stream_t stream) {
     using Cfg = GemmCfg<BN>;
+    constexpr int ES = BF16 ? 2 : 4;
     CUtensorMap tmA, tmB;
-    uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 4};
-    uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldb * 4};
-    uint32_t bA[2] = {kBK, kBM}, bB[2] = {kBK, (uint32_t)BN};
-    int rc = make_tmap_f32(&tmA, A, 2, dA, sA, bA);
+    uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * ES};
+    uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldb * ES};
+    uint32_t bA[2] = {128 / ES, kBM}, bB[2] = {128 / ES, (uint32_t)BN};
+    int rc = BF16 ? make_tmap_bf16(&tmA, A, 2, dA, sA, bA) : make_tmap_f32(&tmA, A, 2, dA, sA, bA);
     if (rc) return rc;
-    rc = make_tmap_f32(&tmB, B, 2, dB, sB, bB);
+    rc = BF16 ? make_tmap_bf16(&tmB, B, 2, dB, sB, bB) : make_tmap_f32(&tmB, B, 2, dB, sB, bB);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        ASRB_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ASRB_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tf32_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::kSmemBytes));
         attr_set = true;
     }
     const int tiles = ceil_div(M, kBM) * ceil_div(N, BN);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_tn_tf32_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, C, ldc, bias, M, N, K, flags);
+    gemm_tn_tf32_kernel<BN, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, C, ldc, bias, M, N, K, flags);
     ASRB_LAUNCH_OK();
     return 0;
 }
@@ -306,9 +314,22 @@ gemm_tn_simt_kernel(const float* __restrict__ A, int lda, const float* __restric
 // ------------------------------------------------------------------------------------------------
 // 64 x 64 tiles, 256 threads, 16-byte loads along the input rows and 16-byte stores along the output rows when the
 // strides and base pointers allow (VEC); tile edges fall back to scalars.
-template <bool VEC>
+__device__ __forceinline__ void store4(float* dst, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* dst, float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&lo);
+    u.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst) = u;
+}
+__device__ __forceinline__ void store1(float* dst, float a) { *dst = a; }
+__device__ __forceinline__ void store1(__nv_bfloat16* dst, float a) { *dst = __float2bfloat16_rn(a); }
+
+template <bool VEC, typename OutT>
 __global__ void __launch_bounds__(256)
-transpose_kernel(const float* __restrict__ in, int rows, int cols, long long ld_in, float* __restrict__ out,
+transpose_kernel(const float* __restrict__ in, int rows, int cols, long long ld_in, OutT* __restrict__ out,
                  long long ld_out) {
     __shared__ float tile[64][65];
     const long long r0 = (long long)blockIdx.x * 64;   // rows on grid.x (up to 2^31 blocks)
@@ -332,13 +353,13 @@ transpose_kernel(const float* __restrict__ in, int rows, int cols, long long ld_
     for (int k = 0; k < 4; ++k) {
         const int idx = threadIdx.x + 256 * k, c = idx >> 4, r = (idx & 15) * 4;
         if (c0 + c < cols) {
-            float* dst = out + (size_t)(c0 + c) * ld_out + r0 + r;
+            OutT* dst = out + (size_t)(c0 + c) * ld_out + r0 + r;
             if (VEC && r0 + r + 3 < rows) {
-                *reinterpret_cast<float4*>(dst) = make_float4(tile[r][c], tile[r + 1][c], tile[r + 2][c], tile[r + 3][c]);
+                store4(dst, tile[r][c], tile[r + 1][c], tile[r + 2][c], tile[r + 3][c]);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (r0 + r + e < rows) dst[e] = tile[r + e][c];
+                    if (r0 + r + e < rows) store1(dst + e, tile[r + e][c]);
             }
         }
     }
@@ -392,6 +413,23 @@ const char* asrb_strerror(int code) {
     return "asr_b200: unknown error";
 }
 
+namespace asrb {
+// 128 x 256 tiles read 1.5x fewer operand bytes from shared memory per FLOP than 128 x 128 (the SMEM port, not the tensor
+// pipe, is the limit: 8 KB per 64-cycle MMA at N=128), but they quantise worse; pick the tile with the smaller estimated
+// time = waves x tile width / efficiency.
+static int gemm_pick_bn(int M, int N) {
+    if (N <= 64) return 64;
+    int bn = 128;
+    if (N > 128) {
+        const long long w128 = ceil_div64((long long)ceil_div(M, kBM) * ceil_div(N, 128), kNumSMs);
+        const long long w256 = ceil_div64((long long)ceil_div(M, kBM) * ceil_div(N, 256), kNumSMs);
+        if (w256 * 256 * 100 < w128 * 128 * g_gemm_bn256_gain) bn = 256;
+    }
+    if (g_gemm_force_bn) bn = g_gemm_force_bn;
+    return bn;
+}
+}  // namespace asrb
+
 int asrb_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, int M, int N,
                  int K, int flags, asrb_stream_t stream) {
     ASRB_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, ASRB_ERR_BAD_ARG);
@@ -403,19 +441,22 @@ int asrb_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int
         return 0;
     }
     ASRB_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, ASRB_ERR_ALIGNMENT);
-    if (N <= 64) return launch_gemm_tc<64>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
-    // 128 x 256 tiles read 1.5x fewer operand bytes from shared memory per FLOP than 128 x 128 (with tf32 operands the
-    // SMEM port, not the tensor pipe, is the limit: 8 KB per 64-cycle MMA at N=128), but they quantise worse; pick the
-    // tile with the smaller estimated time = waves x tile width / efficiency.
-    int bn = 128;
-    if (N > 128) {
-        const long long w128 = ceil_div64((long long)ceil_div(M, kBM) * ceil_div(N, 128), kNumSMs);
-        const long long w256 = ceil_div64((long long)ceil_div(M, kBM) * ceil_div(N, 256), kNumSMs);
-        if (w256 * 256 * 100 < w128 * 128 * g_gemm_bn256_gain) bn = 256;
-    }
-    if (g_gemm_force_bn) bn = g_gemm_force_bn;
-    if (bn == 256) return launch_gemm_tc<256>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
-    return launch_gemm_tc<128>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
+    const int bn = gemm_pick_bn(M, N);
+    if (bn == 64) return launch_gemm_tc<64, false>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
+    if (bn == 256) return launch_gemm_tc<256, false>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
+    return launch_gemm_tc<128, false>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
+}
+
+/* Same product with bf16 operands (A [M, lda], B [N, ldb] bf16, lda/ldb multiples of 8), fp32 accumulate and C. */
+int asrb_gemm_tn_bf16(const void* A, int lda, const void* B, int ldb, float* C, int ldc, const float* bias, int M, int N,
+                      int K, int flags, asrb_stream_t stream) {
+    ASRB_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(lda >= K && ldb >= K && ldc >= N, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, ASRB_ERR_ALIGNMENT);
+    const int bn = gemm_pick_bn(M, N);
+    if (bn == 64) return launch_gemm_tc<64, true>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
+    if (bn == 256) return launch_gemm_tc<256, true>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
+    return launch_gemm_tc<128, true>(A, lda, B, ldb, C, ldc, bias, M, N, K, flags, stream);
 }
 
 /* DEBUG / tuning: force the N tile (0 = automatic, 128, 256); gain = assumed speed of the 256-wide tile relative to
@@ -433,8 +474,22 @@ int asrb_transpose(const float* in, long long rows, int cols, int ld_in, float* 
     ASRB_REQUIRE(grid.y <= 65535u && rows < (1LL << 31), ASRB_ERR_UNSUPPORTED);
     const bool vec = ld_in % 4 == 0 && ld_out % 4 == 0 &&
                      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    if (vec) transpose_kernel<true><<<grid, 256, 0, stream>>>(in, (int)rows, cols, ld_in, out, ld_out);
-    else     transpose_kernel<false><<<grid, 256, 0, stream>>>(in, (int)rows, cols, ld_in, out, ld_out);
+    if (vec) transpose_kernel<true, float><<<grid, 256, 0, stream>>>(in, (int)rows, cols, ld_in, out, ld_out);
+    else     transpose_kernel<false, float><<<grid, 256, 0, stream>>>(in, (int)rows, cols, ld_in, out, ld_out);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* out[c, r] = bf16(in[r, c]) : the bf16 K-major operands of the backward GEMMs (ld_out multiple of 8) */
+int asrb_transpose_bf16(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out, asrb_stream_t stream) {
+    ASRB_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, ASRB_ERR_BAD_ARG);
+    dim3 grid((unsigned)ceil_div64(rows, 64), ceil_div(cols, 64));
+    ASRB_REQUIRE(grid.y <= 65535u && rows < (1LL << 31), ASRB_ERR_UNSUPPORTED);
+    const bool vec = ld_in % 4 == 0 && ld_out % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (vec) transpose_kernel<true, __nv_bfloat16><<<grid, 256, 0, stream>>>(in, (int)rows, cols, ld_in, o, ld_out);
+    else     transpose_kernel<false, __nv_bfloat16><<<grid, 256, 0, stream>>>(in, (int)rows, cols, ld_in, o, ld_out);
     ASRB_LAUNCH_OK();
     return 0;
 }

@@ -24,6 +24,8 @@
 // "previous step" is a pure pointer offset for both directions (used by the dW_hh GEMM as well).
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace asrb {
@@ -61,10 +63,12 @@ struct RnnParams {
     float* saved;        // [2,T,B,4,H]
     // backward
     const float* dout;   // [T,B,H]
-    float* dgi;          // [T,B,2,G]
+    // gate gradients for the dgrad / wgrad GEMMs: fp32 in tf32 mode, bf16 in bf16 mode (the backward GEMMs then run with
+    // bf16 operands: the loss only depends on the forward, and half the bytes leave the kernel)
+    void* dgi;           // [T,B,2,G]
     float* dgh;          // [2,T,B,G]  (tf32 / debug modes: MMA operand; NULL in bf16 mode)
-    float* dgiT;         // [2G, ldT]  transposed gate gradients (row = dir*G + gate*H + unit, column = t*B + b)
-    float* dghT;         // [2G, ldT]  GRU: transposed hidden-side gate gradients (n rows differ from dgiT); NULL for LSTM
+    void* dgiT;          // [2G, ldT]  transposed gate gradients (row = dir*G + gate*H + unit, column = t*B + b)
+    void* dghT;          // [2G, ldT]  GRU: transposed hidden-side gate gradients (n rows differ from dgiT); NULL for LSTM
     long long ldT;
 };
 
@@ -598,19 +602,21 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 }
                 named_bar_sync(4, kRnnEpiThreads);
                 if (rowok && !(p.dbg & 1)) {   // (2) outputs only later kernels read
-                    float* dgi = p.dgi + (((size_t)t * B + b) * 2 + dir) * G + j0 + u0;
+                    using GT = typename std::conditional<BF16, __nv_bfloat16, float>::type;
+                    GT* dgi = reinterpret_cast<GT*>(p.dgi) + (((size_t)t * B + b) * 2 + dir) * G + j0 + u0;
                     // transposed copies for the weight-gradient GEMMs: lanes (batch rows) are contiguous -> coalesced
-                    float* gT = p.dgiT + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b;
-                    float* hT = p.dghT ? p.dghT + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b : nullptr;
+                    GT* gT = reinterpret_cast<GT*>(p.dgiT) + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b;
+                    GT* hT = p.dghT ? reinterpret_cast<GT*>(p.dghT) + ((size_t)dir * G + j0 + u0) * p.ldT + (size_t)t * B + b : nullptr;
 #pragma unroll
                     for (int q = 0; q < kGates; ++q) {
                         const float* hv = (q == 2) ? eg2 : dg[q];
-                        st4(dgi + (size_t)q * H, dg[q]);
+                        if constexpr (BF16) st4_bf16(dgi + (size_t)q * H, dg[q]);
+                        else                st4(dgi + (size_t)q * H, dg[q]);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) gT[((size_t)q * H + e) * p.ldT] = dg[q][e];
+                        for (int e = 0; e < 4; ++e) pack_store(gT + ((size_t)q * H + e) * p.ldT, dg[q][e]);
                         if (hT) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) hT[((size_t)q * H + e) * p.ldT] = hv[e];
+                            for (int e = 0; e < 4; ++e) pack_store(hT + ((size_t)q * H + e) * p.ldT, hv[e]);
                         }
                     }
                 }
@@ -828,8 +834,8 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
 }
 
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
-                 const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
-                 float* dgiT, float* dghT, long long ldT, uint32_t* counters, int T, int B, int H,
+                 const float* hseq, const float* cseq, const float* saved, void* dgi, float* dgh, void* dgh_bf16,
+                 void* dgiT, void* dghT, long long ldT, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream) {
     ASRB_REQUIRE(dout && wpack_bwd && lengths && hseq && saved && dgi && dgiT && counters && T > 0, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(cell == ASRB_RNN_GRU || cseq, ASRB_ERR_BAD_ARG);

@@ -5,6 +5,8 @@
 //   * column sums (bias gradients of the recurrent layers)
 //   * log_softmax / softmax / argmax over the class dimension (trainers/deepspeech_trainer.py:110,
 //     blocks.py:62, decoders/greedy_decoder.py:61) and the log_softmax backward.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace asrb {
@@ -138,11 +140,16 @@ bn_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
 }
 
 // out[r] = sum_c a[r*ld + c]   (one block per row, fixed reduction order)
+__device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-row_sums_kernel(const float* __restrict__ a, long long ld, float* __restrict__ out, long long cols) {
-    const float* row = a + (size_t)blockIdx.x * ld;
+row_sums_kernel(const T* __restrict__ a, long long ld, float* __restrict__ out, long long cols) {
+    const T* row = a + (size_t)blockIdx.x * ld;
     float s = 0.f;
-    for (long long c = threadIdx.x; c < cols; c += 256) s += row[c];
+#pragma unroll 4
+    for (long long c = threadIdx.x; c < cols; c += 256) s += ld_as_float(row + c);
     __shared__ float red[8];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -292,7 +299,14 @@ int asrb_col_sums(const float* a, int lda, float* out, float* ws, size_t ws_byte
 /* out[r] = sum_c a[r*ld + c] */
 int asrb_row_sums(const float* a, long long ld, float* out, int rows, long long cols, asrb_stream_t stream) {
     ASRB_REQUIRE(a && out && rows > 0 && cols > 0 && ld >= cols, ASRB_ERR_BAD_ARG);
-    row_sums_kernel<<<rows, 256, 0, stream>>>(a, ld, out, cols);
+    row_sums_kernel<float><<<rows, 256, 0, stream>>>(a, ld, out, cols);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+int asrb_row_sums_bf16(const void* a, long long ld, float* out, int rows, long long cols, asrb_stream_t stream) {
+    ASRB_REQUIRE(a && out && rows > 0 && cols > 0 && ld >= cols, ASRB_ERR_BAD_ARG);
+    row_sums_kernel<__nv_bfloat16><<<rows, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), ld, out, cols);
     ASRB_LAUNCH_OK();
     return 0;
 }

@@ -254,24 +254,31 @@ class BiRnnLayer(Function):
         db_ih_cat = ops.row_sums(dgiT, R)
         db_hh_cat = db_ih_cat if dghT is dgiT else ops.row_sums(dghT, R)
         db_hh = [db_hh_cat[d * G:(d + 1) * G] for d in range(2)]
+        # In bf16 mode the recurrent kernel hands the gate gradients over in bf16 and every backward GEMM runs with bf16
+        # operands (fp32 accumulate): the loss only depends on the forward pass, which stays tf32.
+        lowp = dgi.dtype == torch.bfloat16
+        if lowp and (I % 8 != 0 or H % 8 != 0):
+            raise ValueError("bf16 recurrent mode needs input and hidden sizes that are multiples of 8")
+        gemm = ops.gemm_tn_bf16 if lowp else ops.gemm_tn
+        tr = ops.transpose_bf16 if lowp else (lambda a: _transpose_padded(a)[:, :a.shape[0]])
         # input gradient: dx = dgi_f W_ih_f + dgi_r W_ih_r
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(R, I, device=dout.device, dtype=torch.float32)
-            ops.gemm_tn(dgi2[:, :G], _transpose_padded(w_ih.contiguous())[:, :G], out=dx)
-            ops.gemm_tn(dgi2[:, G:], _transpose_padded(w_ih_r.contiguous())[:, :G], out=dx, accumulate=True)
+            gemm(dgi2[:, :G], tr(w_ih.contiguous()), out=dx)
+            gemm(dgi2[:, G:], tr(w_ih_r.contiguous()), out=dx, accumulate=True)
             dx = dx.view(T, B, I)
         # weight gradients (K = T*B): dW_ih = dgi^T x ; dW_hh = dgh^T h_prev -- the transposed gate gradients come
         # straight from the recurrent kernel, only x and h_prev are transposed here
-        xt = _transpose_padded(x2)                              # [I, R4]
-        dw_ih = ops.gemm_tn(dgiT[:G, :R], xt[:, :R])
-        dw_ih_r = ops.gemm_tn(dgiT[G:, :R], xt[:, :R])
+        xt = tr(x2)                                             # [I, R]
+        dw_ih = gemm(dgiT[:G, :R], xt)
+        dw_ih_r = gemm(dgiT[G:, :R], xt)
         dw_hh = []
         for d in range(2):
             # previous state in forward order: slots 0..T-1 for the forward direction, 2..T+1 for the reverse one
             first = 0 if d == 0 else 2
-            hpt = _transpose_padded(hseq[d, first:first + T].reshape(R, H))   # [H, R4]
-            dw_hh.append(ops.gemm_tn(dghT[d * G:(d + 1) * G, :R], hpt[:, :R]))
+            hpt = tr(hseq[d, first:first + T].reshape(R, H))    # [H, R]
+            dw_hh.append(gemm(dghT[d * G:(d + 1) * G, :R], hpt))
         return (dx, None, None, dw_ih, dw_hh[0], db_ih_cat[:G], db_hh[0], dw_ih_r, dw_hh[1], db_ih_cat[G:], db_hh[1])
 
 

@@ -103,6 +103,30 @@ def gemm_tn(A, B, out=None, bias=None, accumulate=False):
     return out
 
 
+def gemm_tn_bf16(A, B, out=None, bias=None, accumulate=False):
+    """out[M,N] fp32 (+)= A[M,K] @ B[N,K]^T with bf16 operands (row strides multiples of 8 elements)."""
+    for t in (A, B):
+        if not t.is_cuda or t.dtype != torch.bfloat16:
+            raise RuntimeError("gemm_tn_bf16 needs bf16 CUDA operands")
+    M, K = A.shape
+    N, K2 = B.shape
+    if K != K2:
+        raise ValueError(f"inner dimensions differ: {K} vs {K2}")
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    _call("asrb_gemm_tn_bf16", _p(A), _ld(A), _p(B), _ld(B), _p(out), _ld(out), _p(bias), M, N, K, 1 if accumulate else 0)
+    return out
+
+
+def transpose_bf16(x):
+    """x [R, C] fp32 -> x^T in bf16 as a [C, R] view of a [C, R8] buffer (row stride multiple of 8 elements)."""
+    R, C = x.shape
+    R8 = (R + 7) // 8 * 8
+    buf = torch.empty(C, R8, device=x.device, dtype=torch.bfloat16)
+    _call("asrb_transpose_bf16", _p(x), R, C, _ld(x), _p(buf), R8)
+    return buf[:, :R]
+
+
 def transpose(x, out=None):
     """out[C,R] = x[R,C]^T (x may be a row-strided view)."""
     R, C = x.shape
@@ -440,12 +464,13 @@ def rnn_bwd(cell, dout, wpack_bwd, lengths, hseq, cseq, saved, T, B, H):
     G = (3 if cell == GRU else 4) * H
     dev = dout.device
     bf16 = rnn_use_bf16(H)
-    R4 = (T * B + 3) // 4 * 4
-    dgi = torch.empty(T, B, 2, G, device=dev, dtype=torch.float32)
+    gdt = torch.bfloat16 if bf16 else torch.float32   # gate gradients feed the backward GEMMs in the mode's operand type
+    R4 = (T * B + 7) // 8 * 8 if bf16 else (T * B + 3) // 4 * 4
+    dgi = torch.empty(T, B, 2, G, device=dev, dtype=gdt)
     dgh = None if bf16 else torch.empty(2, T, B, G, device=dev, dtype=torch.float32)
     dghbf = torch.empty(2, T, B, (G + 63) // 64 * 64, device=dev, dtype=torch.bfloat16) if bf16 else None
-    dgiT = torch.empty(2 * G, R4, device=dev, dtype=torch.float32)
-    dghT = torch.empty(2 * G, R4, device=dev, dtype=torch.float32) if cell == GRU else None
+    dgiT = torch.empty(2 * G, R4, device=dev, dtype=gdt)
+    dghT = torch.empty(2 * G, R4, device=dev, dtype=gdt) if cell == GRU else None
     counters = torch.empty(128, device=dev, dtype=torch.int32)
     _call("asrb_rnn_bwd", cell, int(bf16), _p(dout), _p(wpack_bwd), _p(lengths), _p(hseq), _p(cseq), _p(saved), _p(dgi),
           _p(dgh), _p(dghbf), _p(dgiT), _p(dghT), R4, _p(counters), T, B, H)
@@ -457,7 +482,7 @@ def row_sums(a, cols=None):
     rows = a.shape[0]
     cols = a.shape[1] if cols is None else cols
     out = torch.empty(rows, device=a.device, dtype=torch.float32)
-    _call("asrb_row_sums", _p(a), _ld(a), _p(out), rows, cols)
+    _call("asrb_row_sums_bf16" if a.dtype == torch.bfloat16 else "asrb_row_sums", _p(a), _ld(a), _p(out), rows, cols)
     return out
 
 

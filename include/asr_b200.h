@@ -63,8 +63,13 @@ int asrb_debug_gemm_tile(int force_bn, int gain_pct);
  * C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N]).  lda/ldb/ldc are row strides in elements; lda, ldb multiples of 4. */
 int asrb_gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, int M,
                  int N, int K, int flags, asrb_stream_t stream);
+/* Same product with bf16 operands (lda, ldb in bf16 elements, multiples of 8); fp32 accumulate and C. */
+int asrb_gemm_tn_bf16(const void* A, int lda, const void* B, int ldb, float* C, int ldc, const float* bias, int M, int N,
+                      int K, int flags, asrb_stream_t stream);
 /* out[c, r] = in[r, c] */
 int asrb_transpose(const float* in, long long rows, int cols, int ld_in, float* out, int ld_out, asrb_stream_t stream);
+/* out[c, r] = bf16(in[r, c]), ld_out in bf16 elements */
+int asrb_transpose_bf16(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out, asrb_stream_t stream);
 /* 3xTF32 operand expansion: mode 0 -> [x_hi | x_lo | x_hi], mode 1 -> [x_hi | x_hi | x_lo]  (out: [rows, 3*cols]) */
 int asrb_split3(const float* in, long long rows, int cols, int ld_in, float* out, int ld_out, int mode,
                 asrb_stream_t stream);
@@ -89,12 +94,13 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
 /* dout [T,B,H] (gradient of the direction-summed output).  out: dgi [T,B,2,G] (for the input-gradient GEMM);
  * dgiT [2G, ldT] = its transpose (row = dir*G + gate*H + unit, column = t*B + b; ldT >= T*B, multiple of 4) and, for
  * GRU, dghT [2G, ldT] = the transposed hidden-side gate gradients (they differ from dgiT in the n gate; LSTM: NULL)
- * -- the K-major operands of the weight-gradient GEMMs, written directly so no transpose pass is needed; the
+ * -- the K-major operands of the weight-gradient GEMMs, written directly so no transpose pass is needed.  dgi, dgiT
+ * and dghT are fp32 in tf32 mode and BF16 in bf16 mode (ldT then a multiple of 8; consumed by asrb_gemm_tn_bf16); the
  * recurrent operand of the next step is
  * dgh_bf16 [2,T,B,Gp] with Gp = G rounded up to 64 (bf16 mode, dgh may be NULL) or dgh [2,T,B,G] fp32 (tf32 mode, dgh_bf16 may be NULL). */
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,
-                 const float* hseq, const float* cseq, const float* saved, float* dgi, float* dgh, void* dgh_bf16,
-                 float* dgiT, float* dghT, long long ldT, uint32_t* counters, int T, int B, int H,
+                 const float* hseq, const float* cseq, const float* saved, void* dgi, float* dgh, void* dgh_bf16,
+                 void* dgiT, void* dghT, long long ldT, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream);
 /* floats in the saved-gates buffer (slice-major layout private to asrb_rnn_fwd / asrb_rnn_bwd) */
 size_t asrb_rnn_saved_floats(int cell, int H, int B, int bf16, int T);
@@ -177,6 +183,7 @@ int asrb_bn_rows_bwd(const float* dy, const float* x, const float* mean, const f
 int asrb_col_sums(const float* a, int lda, float* out, float* ws, size_t ws_bytes, long long R, int cols,
                   asrb_stream_t stream);
 int asrb_row_sums(const float* a, long long ld, float* out, int rows, long long cols, asrb_stream_t stream);
+int asrb_row_sums_bf16(const void* a, long long ld, float* out, int rows, long long cols, asrb_stream_t stream);
 /* logits[R, ld] -> log_probs[R,C] / probs[R,C] / argmax int64[R] (each optional) */
 int asrb_log_softmax_fwd(const float* logits, int ld, float* log_probs, float* probs, long long* argmax, long long R,
                          int C, asrb_stream_t stream);
