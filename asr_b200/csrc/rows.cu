@@ -147,9 +147,29 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 row_sums_kernel(const T* __restrict__ a, long long ld, float* __restrict__ out, long long cols) {
     const T* row = a + (size_t)blockIdx.x * ld;
+    constexpr int V = 16 / sizeof(T);                  // elements per 16-byte load
     float s = 0.f;
+    long long c0 = 0;
+    if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+        const long long nv = cols / V;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};           // four independent accumulators per thread
 #pragma unroll 4
-    for (long long c = threadIdx.x; c < cols; c += 256) s += ld_as_float(row + c);
+        for (long long i = threadIdx.x; i < nv; i += 256) {
+            const uint4 u = __ldcs(reinterpret_cast<const uint4*>(row) + i);
+            if constexpr (sizeof(T) == 4) {
+                acc[0] += __uint_as_float(u.x); acc[1] += __uint_as_float(u.y);
+                acc[2] += __uint_as_float(u.z); acc[3] += __uint_as_float(u.w);
+            } else {   // bf16 pairs: the low half is the first element
+                acc[0] += __uint_as_float(u.x << 16) + __uint_as_float(u.x & 0xffff0000u);
+                acc[1] += __uint_as_float(u.y << 16) + __uint_as_float(u.y & 0xffff0000u);
+                acc[2] += __uint_as_float(u.z << 16) + __uint_as_float(u.z & 0xffff0000u);
+                acc[3] += __uint_as_float(u.w << 16) + __uint_as_float(u.w & 0xffff0000u);
+            }
+        }
+        s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        c0 = nv * V;
+    }
+    for (long long c = c0 + threadIdx.x; c < cols; c += 256) s += ld_as_float(row + c);
     __shared__ float red[8];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;

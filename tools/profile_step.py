@@ -18,6 +18,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
     from asr_b200.trainers import CTCLoss, fit
+    from asr_b200 import _lib
+    if os.environ.get("ASRB_RNN_KSPLIT", "1") == "0":   # ncu cannot launch the cooperative + cluster backward kernel
+        _lib.query("asrb_debug_rnn_ksplit", 0)
 
     cfg = dict(bench.CFG, B=args.batch, T=args.frames, U=min(bench.CFG["U"], args.frames // 10))
     dev = torch.device("cuda", 0)
