@@ -727,13 +727,15 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
     cfg.blockDim = dim3(kRnnThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attrs[2];
-    attrs[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the step barrier spins
-    attrs[0].val.cooperative = 1;
-    attrs[1].id = cudaLaunchAttributeClusterDimension;
-    attrs[1].val.clusterDim.x = 2; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
+    // Plain (not cooperative) launch: the step barrier needs all 2P <= 148 CTAs co-resident, which one CTA per SM on an
+    // otherwise idle device gives (kernels of the same stream have drained; nothing else runs beside the recurrence).
+    // A cooperative launch makes the same promise formally but BLOCKS the host until the kernel can start, so the CPU
+    // could not queue the next layer's kernels behind the recurrence (measured: ~0.3 ms of idle GPU after every launch).
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = KSPLIT ? 2 : 1;
+    cfg.numAttrs = KSPLIT ? 1 : 0;
     prm.dbg = g_rnn_dbg;
     ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, prm));
     return 0;
