@@ -681,7 +681,7 @@ __device__ void ctc_dense_role(const CtcBwdParams& p, int n, int wi, int nw, con
                         } else if constexpr (POST) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                if (bits & (1u << e)) o[e] -= wpost[first_state[4 * c + e]];   // two LDS: the slow path is divergent
+                                if (bits & (1u << e)) o[e] -= wpost[-first_state[4 * c + e] - 1];   // two LDS: the slow path is divergent
                             __stcs(gr4 + c, make_float4(g * o[0], g * o[1], g * o[2], g * o[3]));
                         } else {
                             float* gs = reinterpret_cast<float*>(gr4 + c);
@@ -696,7 +696,7 @@ __device__ void ctc_dense_role(const CtcBwdParams& p, int n, int wi, int nw, con
             for (int c = lane; c < C; c += 32) {
                 const bool m = (mask[c >> 5] >> (c & 31)) & 1u;
                 if (!m) gr[c] = g * exp_ftz(__ldg(row + c));
-                else if constexpr (POST) gr[c] = g * (exp_ftz(__ldg(row + c)) - wpost[first_state[c]]);
+                else if constexpr (POST) gr[c] = g * (exp_ftz(__ldg(row + c)) - wpost[-first_state[c] - 1]);
             }
         }
     }
@@ -726,11 +726,12 @@ __device__ void ctc_build_mask(const CtcBwdParams& p, int n, uint32_t* mask, int
     if (first_state && live) {
         for (int i = threadIdx.x; i < U; i += kCtcThreads) {
             const int l = p.targets[off + i];
-            if (first_state[l] == 2 * i + 1) first_state[l] = ctc_col(2 * i + 1, p.kpl);
+            // stored as -(column + 1): a converted entry must never look like the state index of a later occurrence
+            if (first_state[l] == 2 * i + 1) first_state[l] = -(ctc_col(2 * i + 1, p.kpl) + 1);
         }
     }
     __syncthreads();
-    if (first_state && live && threadIdx.x == 0) first_state[p.blank] = 0;   // column of state 0
+    if (first_state && live && threadIdx.x == 0) first_state[p.blank] = -1;   // column 0 (state 0)
     __syncthreads();
 }
 
