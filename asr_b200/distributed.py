@@ -16,14 +16,21 @@ class FlatGradBucket:
     """All parameter gradients live in one contiguous fp32 buffer (`flat`); `param.grad` are views into it,
     so autograd accumulates straight into the bucket and the all-reduce needs no packing."""
 
-    def __init__(self, params):
+    def __init__(self, params, flatten_params=False):
+        """flatten_params: also move the parameters themselves into one contiguous buffer (`flat_params`, same
+        order; `param.data` become views), so that `asr_b200.optim.FusedAdamW` updates the whole model in one launch."""
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_params = torch.empty(n, device=dev, dtype=torch.float32) if flatten_params else None
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            if flatten_params:
+                dst = self.flat_params[off:off + p.numel()].view_as(p)
+                dst.copy_(p.data)
+                p.data = dst
             off += p.numel()
 
     def zero(self):

@@ -534,6 +534,18 @@ def ctc_bwd(log_probs, targets, input_lengths, target_lengths, alpha, nll, grad_
     return grad
 
 
+# ----------------------------------------------------------------------------- optimizer
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, inv_scale=None):
+    """In-place torch.optim.AdamW step on contiguous fp32 CUDA tensors of equal size (any shape)."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("adamw_step needs contiguous fp32 CUDA tensors")
+    if not (param.numel() == grad.numel() == exp_avg.numel() == exp_avg_sq.numel()):
+        raise ValueError("adamw_step: size mismatch")
+    _call("asrb_adamw_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr), float(beta1),
+          float(beta2), float(eps), float(weight_decay), int(step), _p(inv_scale))
+
+
 # ----------------------------------------------------------------------------- spectrogram
 def dft_basis(n_fft, device):
     basis = torch.empty(2 * (n_fft // 2 + 1), 3 * n_fft, device=device, dtype=torch.float32)

@@ -1,0 +1,57 @@
+"""Fused AdamW on our kernel: drop-in for the optimizer the reference builds at
+asr_deepspeech/trainers/__main__.py:41-47 (`AdamW(lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)`) and
+steps at trainers/deepspeech_trainer.py:86-95.
+
+It is a `torch.optim.Optimizer` (so `StepLR`, `GradScaler.step(optimizer)` and `state_dict()` keep working), with
+torch.optim.AdamW's state layout (`step`, `exp_avg`, `exp_avg_sq` per parameter).  `step()` issues ONE kernel per
+parameter tensor -- or ONE kernel for the whole model when the parameters and gradients were flattened with
+`FlatGradBucket(..., flatten_params=True)`: 28 bytes per parameter, a single HBM pass.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, bucket=None):
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError("invalid AdamW hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.bucket = bucket if bucket is not None and getattr(bucket, "flat_params", None) is not None else None
+        self._flat_state = None
+
+    @torch.no_grad()
+    def step(self, closure=None, inv_scale=None):
+        """inv_scale: optional 1-element CUDA tensor multiplied into every gradient (GradScaler's unscale, fused)."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if self.bucket is not None and len(self.param_groups) == 1:
+            g = self.param_groups[0]
+            if self._flat_state is None:
+                flat = self.bucket.flat_params
+                self._flat_state = dict(step=0, exp_avg=torch.zeros_like(flat), exp_avg_sq=torch.zeros_like(flat))
+            st = self._flat_state
+            st["step"] += 1
+            ops.adamw_step(self.bucket.flat_params, self.bucket.flat, st["exp_avg"], st["exp_avg_sq"], g["lr"], g["betas"][0],
+                           g["betas"][1], g["eps"], g["weight_decay"], st["step"], inv_scale)
+            return loss
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                ops.require_cuda(p, "FusedAdamW")
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                if not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise ValueError("FusedAdamW needs contiguous parameters and gradients")
+                ops.adamw_step(p, p.grad, st["exp_avg"], st["exp_avg_sq"], g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                               g["weight_decay"], st["step"], inv_scale)
+        return loss

@@ -201,6 +201,12 @@ int asrb_ctc_bwd(const float* log_probs, const int32_t* targets, const int32_t* 
                  const int32_t* target_lengths, float* alpha_ws, const float* nll, const float* grad_scale,
                  float* grad, int T, int N, int C, int max_target_len, int blank, asrb_stream_t stream);
 
+/* ---------------------------------------------------------------- optimizer
+ * torch.optim.AdamW step of trainers/__main__.py:41-47 / deepspeech_trainer.py:86-95 on n contiguous parameters, with the
+ * GradScaler unscale folded in (inv_scale: optional device scalar).  step is the 1-based step count. */
+int asrb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, const float* inv_scale, asrb_stream_t stream);
+
 /* ---------------------------------------------------------------- spectrogram (STFT -> |.| -> log1p -> normalise) */
 size_t asrb_spectrogram_workspace_bytes(int B, int max_samples, int n_fft, int hop);
 int asrb_dft_basis(float* basis_cat /* [2*(n_fft/2+1), 3*n_fft] */, int n_fft, asrb_stream_t stream);
