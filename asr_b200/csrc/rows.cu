@@ -350,3 +350,45 @@ int asrb_log_softmax_bwd(const float* g, const float* log_probs, float* dlogits,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// greedy CTC collapse: decoders/greedy_decoder.py:27-46 `process_string` with
+// remove_repetitions=True on the frame-wise argmax -- keep frame t iff its class is not the blank and differs from the
+// class of frame t-1.  One warp per utterance, ballot/popc stream compaction in frame order.
+// ------------------------------------------------------------------------------------------------
+namespace asrb {
+__global__ void __launch_bounds__(128)
+greedy_collapse_kernel(const long long* __restrict__ idx, const int* __restrict__ sizes, int N, int T, int blank,
+                       int* __restrict__ labels, int* __restrict__ offsets, int* __restrict__ counts) {
+    const int n = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const int len = sizes ? min(max(sizes[n], 0), T) : T;
+    const long long* row = idx + (size_t)n * T;
+    int out = 0;
+    for (int t0 = 0; t0 < len; t0 += 32) {
+        const int t = t0 + lane;
+        bool keep = false;
+        int c = blank;
+        if (t < len) {
+            c = (int)row[t];
+            keep = c != blank && (t == 0 || c != (int)row[t - 1]);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = out + __popc(m & ((1u << lane) - 1u));
+            labels[(size_t)n * T + pos] = c;
+            offsets[(size_t)n * T + pos] = t;
+        }
+        out += __popc(m);
+    }
+    if (lane == 0) counts[n] = out;
+}
+}  // namespace asrb
+
+extern "C" int asrb_greedy_collapse(const long long* argmax, const int32_t* sizes, int N, int T, int blank, int32_t* labels,
+                                    int32_t* offsets, int32_t* counts, asrb_stream_t stream) {
+    ASRB_REQUIRE(argmax && labels && offsets && counts && N > 0 && T > 0, ASRB_ERR_BAD_ARG);
+    asrb::greedy_collapse_kernel<<<asrb::ceil_div(N, 4), 128, 0, stream>>>(argmax, sizes, N, T, blank, labels, offsets, counts);
+    ASRB_LAUNCH_OK();
+    return 0;
+}

@@ -65,7 +65,18 @@ class GreedyDecoder(Decoder):
         return "".join(chars), torch.tensor(offsets, dtype=torch.int)
 
     def decode(self, probs, sizes=None):
-        """probs [B,T,C] -> (strings, offsets); argmax on the device, collapse on the host."""
+        """probs [B,T,C] -> (strings, offsets); argmax AND the collapse (drop blanks and repeated frames) on the device,
+        only the kept class indices come back to the host for the int -> char join."""
         ops.require_cuda(probs, "GreedyDecoder.decode")
         idx = F_.argmax_last_dim(probs)
-        return self.convert_to_strings(idx.cpu(), sizes, remove_repetitions=True, return_offsets=True)
+        injective = len(set(self.int_to_char.values())) == len(self.int_to_char)
+        if not injective:   # the reference compares CHARACTERS of neighbouring frames: only equivalent for distinct labels
+            return self.convert_to_strings(idx.cpu(), sizes, remove_repetitions=True, return_offsets=True)
+        sz = None if sizes is None else ops.lengths_to_device(torch.as_tensor(sizes), probs.device)
+        labels, offs, counts = ops.greedy_collapse(idx.contiguous(), sz, self.blank_index)
+        labels, offs, counts = labels.cpu(), offs.cpu(), counts.cpu().tolist()
+        strings, offsets = [], []
+        for n, k in enumerate(counts):
+            strings.append(["".join(self.int_to_char[int(c)] for c in labels[n, :k].tolist())])
+            offsets.append([offs[n, :k].clone()])
+        return strings, offsets

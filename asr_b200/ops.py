@@ -534,6 +534,17 @@ def ctc_bwd(log_probs, targets, input_lengths, target_lengths, alpha, nll, grad_
     return grad
 
 
+def greedy_collapse(idx, sizes, blank=0):
+    """idx int64 [N,T] (frame-wise argmax), sizes int32 [N] on the device or None -> (labels [N,T], offsets [N,T], counts [N])"""
+    _chk(idx, dtype=torch.int64)
+    N, T = idx.shape
+    labels = torch.empty(N, T, device=idx.device, dtype=torch.int32)
+    offsets = torch.empty(N, T, device=idx.device, dtype=torch.int32)
+    counts = torch.empty(N, device=idx.device, dtype=torch.int32)
+    _call("asrb_greedy_collapse", _p(idx), _p(sizes), N, T, int(blank), _p(labels), _p(offsets), _p(counts))
+    return labels, offsets, counts
+
+
 # ----------------------------------------------------------------------------- optimizer
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, inv_scale=None):
     """In-place torch.optim.AdamW step on contiguous fp32 CUDA tensors of equal size (any shape)."""

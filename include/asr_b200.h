@@ -190,6 +190,12 @@ int asrb_log_softmax_fwd(const float* logits, int ld, float* log_probs, float* p
 int asrb_log_softmax_bwd(const float* g, const float* log_probs, float* dlogits, int ld, long long R, int C,
                          asrb_stream_t stream);
 
+/* Greedy CTC collapse of the frame-wise argmax (decoders/greedy_decoder.py:27-46, remove_repetitions=True): for each
+ * utterance n the kept classes / their frame indices are written densely to labels[n, 0..counts[n]) / offsets[n, ...)
+ * (row stride T); sizes (int32[N], may be NULL = T) bounds the frames read. */
+int asrb_greedy_collapse(const long long* argmax, const int32_t* sizes, int N, int T, int blank, int32_t* labels,
+                         int32_t* offsets, int32_t* counts, asrb_stream_t stream);
+
 /* ---------------------------------------------------------------- CTC (blank-extended alpha/beta, reduction = sum) */
 size_t asrb_ctc_workspace_bytes(int T, int N, int max_target_len);
 int asrb_debug_ctc_tuning(int min_smem_bytes, int blocks_per_sm);

@@ -350,6 +350,32 @@ def ctc_bwd(log_probs, targets, input_lengths, target_lengths, alpha, nll, grad_
     return lp.grad * (grad_scale if grad_scale is not None else 1.0)
 
 
+def greedy_collapse(idx, sizes, blank=0):
+    N, T = idx.shape
+    labels = torch.zeros(N, T, dtype=torch.int32)
+    offsets = torch.zeros(N, T, dtype=torch.int32)
+    counts = torch.zeros(N, dtype=torch.int32)
+    for n in range(N):
+        L = T if sizes is None else max(0, min(int(sizes[n]), T))
+        k = 0
+        for t in range(L):
+            c = int(idx[n, t])
+            if c != blank and (t == 0 or c != int(idx[n, t - 1])):
+                labels[n, k], offsets[n, k] = c, t
+                k += 1
+        counts[n] = k
+    return labels, offsets, counts
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, inv_scale=None):
+    g = grad * (inv_scale if inv_scale is not None else 1.0)
+    param.mul_(1 - lr * weight_decay)
+    exp_avg.lerp_(g, 1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    denom = (exp_avg_sq.sqrt() / (1 - beta2 ** step) ** 0.5).add_(eps)
+    param.addcdiv_(exp_avg, denom, value=-lr / (1 - beta1 ** step))
+
+
 def dft_basis(n_fft, device):
     Fb = n_fft // 2 + 1
     n = torch.arange(n_fft, dtype=torch.float64)

@@ -403,3 +403,26 @@ def test_spectrogram_vs_oracle(ops):
             nf = ref.shape[1]
             assert report(f"spectrogram utt{i} norm={normalize}", spec[i, 0, :, :nf], ref) <= (2e-4 if normalize else 2e-5)
             assert spec[i, 0, :, nf:].abs().max().item() == 0 if nf < 101 else True
+
+
+def test_greedy_collapse_matches_host_loop(ops):
+    """asrb_greedy_collapse against the reference's per-frame Python loop (decoders/greedy_decoder.py:27-46,
+    remove_repetitions=True): kept classes and their frame offsets, bit-exact, ragged sizes, long rows."""
+    g = torch.Generator().manual_seed(3)
+    for N, T, C in [(5, 70, 4), (3, 501, 29), (2, 1, 3), (4, 33, 2)]:
+        idx = torch.randint(0, C, (N, T), generator=g, dtype=torch.int64)
+        idx[0, : T // 2] = 1                                  # a long run of repeats
+        sizes = torch.randint(1, T + 1, (N,), generator=g, dtype=torch.int32)
+        sizes[0] = T
+        labels, offsets, counts = ops.greedy_collapse(idx.to(DEV), sizes.to(DEV), 0)
+        labels, offsets, counts = labels.cpu(), offsets.cpu(), counts.cpu()
+        for n in range(N):
+            want_l, want_o = [], []
+            for t in range(int(sizes[n])):
+                c = int(idx[n, t])
+                if c != 0 and (t == 0 or c != int(idx[n, t - 1])):
+                    want_l.append(c)
+                    want_o.append(t)
+            k = int(counts[n])
+            assert k == len(want_l)
+            assert labels[n, :k].tolist() == want_l and offsets[n, :k].tolist() == want_o

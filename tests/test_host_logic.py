@@ -140,3 +140,28 @@ def test_greedy_decoder_strings_like_reference_tests():
     assert dec.convert_to_strings([torch.tensor([1, 0, 1])]) == [["aa"]]
     assert dec.wer("a b c", "a b c") == 0 and dec.wer("a b", "a c") == 1
     assert dec.cer("abc", "abd") == 1
+
+
+def test_fused_adamw_host_logic_matches_torch(monkeypatch):
+    """FusedAdamW's bookkeeping (state, param groups, flat bucket form, StepLR) with the kernel emulated on the CPU."""
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.distributed import FlatGradBucket
+    from asr_b200.optim import FusedAdamW
+
+    hp = dict(lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(1)
+    ref_p = [torch.nn.Parameter(torch.randn(7, 5, generator=g)), torch.nn.Parameter(torch.randn(11, generator=g))]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    flat_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    bucket = FlatGradBucket(flat_p, flatten_params=True)
+    ref, ours, flat = torch.optim.AdamW(ref_p, **hp), FusedAdamW(our_p, **hp), FusedAdamW(flat_p, bucket=bucket, **hp)
+    for _ in range(4):
+        bucket.zero()
+        for a, b, c in zip(ref_p, our_p, flat_p):
+            gr = torch.randn(a.shape, generator=g)
+            a.grad, b.grad = gr.clone(), gr.clone()
+            c.grad.copy_(gr)
+        ref.step(); ours.step(); flat.step()
+    for a, b, c in zip(ref_p, our_p, flat_p):
+        assert torch.allclose(a, b, atol=1e-7) and torch.allclose(a, c, atol=1e-7)
+    assert flat_p[0].data_ptr() == bucket.flat_params.data_ptr()      # parameters really live in the flat buffer
