@@ -19,6 +19,7 @@ _CTYPES = {
     "int": ctypes.c_int,
     "unsigned": ctypes.c_uint,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
     "size_t": ctypes.c_size_t,
     "long long": ctypes.c_longlong,
     "asrb_stream_t": ctypes.c_void_p,

@@ -13,13 +13,13 @@
 namespace asrb {
 
 struct AdamWArgs {
-    float lr, b1, b2, eps, wd, step_size, bc2_sqrt;
+    float decay, b2, one_minus_b1, one_minus_b2, eps, step_size, bc2_sqrt;   // complements taken in double on the host, like torch
 };
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamWArgs& a) {
-    p *= 1.f - a.lr * a.wd;
-    m = fmaf(1.f - a.b1, g - m, m);
-    v = fmaf(1.f - a.b2, g * g, v * a.b2);
+    p *= a.decay;
+    m = fmaf(a.one_minus_b1, g - m, m);
+    v = fmaf(a.one_minus_b2, g * g, v * a.b2);
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
     p -= a.step_size * (m / denom);
 }
@@ -59,12 +59,14 @@ extern "C" {
 
 /* One AdamW step (step >= 1 is the 1-based step count) on n parameters; exp_avg / exp_avg_sq are updated in place.
  * inv_scale: optional DEVICE scalar multiplied into the gradient (GradScaler unscale), NULL = 1. */
-int asrb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, int step, const float* inv_scale, asrb_stream_t stream) {
+int asrb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
+                    double beta2, double eps, double weight_decay, int step, const float* inv_scale, asrb_stream_t stream) {
     ASRB_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, ASRB_ERR_BAD_ARG);
-    ASRB_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f, ASRB_ERR_BAD_ARG);
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    AdamWArgs a = {lr, beta1, beta2, eps, weight_decay, (float)((double)lr / bc1), (float)sqrt(bc2)};
+    ASRB_REQUIRE(beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0. && lr >= 0., ASRB_ERR_BAD_ARG);
+    // hyper-parameters arrive as doubles (what Python holds): torch forms 1 - beta in double before rounding to fp32
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    AdamWArgs a = {(float)(1.0 - lr * weight_decay), (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
+                   (float)(lr / bc1), (float)sqrt(bc2)};
     const bool vec = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                        reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0;
     long long blocks = (n / (vec ? 4 : 1) + 255) / 256;

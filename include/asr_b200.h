@@ -210,8 +210,8 @@ int asrb_ctc_bwd(const float* log_probs, const int32_t* targets, const int32_t* 
 /* ---------------------------------------------------------------- optimizer
  * torch.optim.AdamW step of trainers/__main__.py:41-47 / deepspeech_trainer.py:86-95 on n contiguous parameters, with the
  * GradScaler unscale folded in (inv_scale: optional device scalar).  step is the 1-based step count. */
-int asrb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, int step, const float* inv_scale, asrb_stream_t stream);
+int asrb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
+                    double beta2, double eps, double weight_decay, int step, const float* inv_scale, asrb_stream_t stream);
 
 /* ---------------------------------------------------------------- spectrogram (STFT -> |.| -> log1p -> normalise) */
 size_t asrb_spectrogram_workspace_bytes(int B, int max_samples, int n_fft, int hop);
