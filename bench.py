@@ -189,14 +189,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_buf = [torch.empty_like(resident), torch.empty_like(resident)]
+
     def timed(inputs, steps, profile=False):
+        """inputs on the device: the resident-input metric.  inputs in pinned host memory: the end-to-end metric -- every
+        step's spectrogram batch crosses PCIe inside the timed region (the way a DataLoader with pin_memory and a
+        prefetching copy stream feeds a trainer: the copy of step i+1 overlaps the compute of step i, the first copy
+        does not) and every step's loss is read back with .item() inside fit()."""
+        host_inputs = not inputs.is_cuda
         barrier()
         ops.PROFILE = {} if profile else None
         l0 = ops.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
-            lv = step(inputs)
+        ready = [None, None]
+        if host_inputs:
+            copy_stream.wait_stream(stream)
+            with torch.cuda.stream(copy_stream):
+                dev_buf[0].copy_(inputs, non_blocking=True)
+                ready[0] = torch.cuda.Event()
+                ready[0].record(copy_stream)
+        for i in range(steps):
+            if host_inputs:
+                stream.wait_event(ready[i % 2])
+                if i + 1 < steps:
+                    copy_stream.wait_stream(stream)          # buffer (i+1)%2 was last read by step i-1, already queued
+                    with torch.cuda.stream(copy_stream):
+                        dev_buf[(i + 1) % 2].copy_(inputs, non_blocking=True)
+                        ready[(i + 1) % 2] = torch.cuda.Event()
+                        ready[(i + 1) % 2].record(copy_stream)
+                lv = step(dev_buf[i % 2])
+            else:
+                lv = step(inputs)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
