@@ -45,6 +45,7 @@ constexpr int kRnnBiasOffset = 704;
 
 struct RnnParams {
     int T, B, H, G, P, kpad, use_simt, stages, chunk;   // chunk = K blocks per pipeline stage / barrier
+    int P_saved;          // slices of the saved-gates layout (= the forward's P; the split backward may pad its own P)
     const int* lengths;
     uint32_t* counters;   // [2 dirs] step counters, kRnnCounterStride words apart
     int dbg;              // DEBUG timing experiments: 1 = drop the non-critical stores, 2 = drop the operand prefetch
@@ -54,7 +55,7 @@ struct RnnParams {
     __nv_bfloat16* hbf;   // [2,T+2,B,Hp] bf16 copy of hseq (forward, bf16 mode): the next step's MMA operand
     __nv_bfloat16* dghbf; // [2,T,B,Gp]  bf16 copy of dgh  (backward, bf16 mode)
     int Hp, Gp;
-    long long* trace;     // DEBUG: [gridDim][T][12] SM-clock stamps per step (asrb_debug_rnn_trace), else NULL
+    long long* trace;     // DEBUG: [gridDim][T][16] SM-clock stamps per step (asrb_debug_rnn_trace), else NULL
     // forward
     const float* gi;     // [T,B,2,G]
     const float* b_hh;   // [2,G]
@@ -121,12 +122,12 @@ __global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float
     }
 }
 
-// backward, K split over a CTA pair: CTA p = 2*pair + r holds, for the 2*nj units of the pair (row c = unit pair*2nj + c),
-// the r-th half of the gate index: element kk <-> gate row k = r*kpad + kk
+// backward, K split over a cluster of ks CTAs: CTA p = ks*cl + r holds, for the ks*nj units of the cluster (row c = unit
+// cl*ks*nj + c), the r-th part of the gate index: element kk <-> gate row k = r*kpad + kk
 template <typename OutT>
 __global__ void rnn_pack_bwd_split_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, OutT* __restrict__ out,
-                                          int H, int G, int nj, int P, int kpad) {
-    const int npad = 2 * nj;
+                                          int H, int G, int nj, int P, int kpad, int ks) {
+    const int npad = ks * nj;
     const long long total = 2LL * P * npad * kpad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int kk = (int)(i % kpad);
@@ -134,7 +135,7 @@ __global__ void rnn_pack_bwd_split_kernel(const float* __restrict__ w_hh0, const
         const int c = (int)(r % npad);
         r /= npad;
         const int p = (int)(r % P), dir = (int)(r / P);
-        const int j = (p / 2) * npad + c, k = (p % 2) * kpad + kk;
+        const int j = (p / ks) * npad + c, k = (p % ks) * kpad + kk;
         float v = 0.f;
         if (j < H && k < G) v = (dir ? w_hh1 : w_hh0)[(size_t)k * H + j];
         pack_store(out + i, v);
@@ -146,7 +147,8 @@ __global__ void rnn_pack_bwd_split_kernel(const float* __restrict__ w_hh0, const
 // ------------------------------------------------------------------------------------------------
 long long* g_rnn_trace = nullptr;
 int g_rnn_dbg = 0;
-int g_rnn_ksplit = 1;   // backward K split over CTA pairs (asrb_debug_rnn_ksplit)
+int g_rnn_ksplit = 2;   // largest backward K split allowed: 0 none, 2 CTA pairs (default), 4 clusters of four -- the
+                        // 1.5 k cycles the MMA phase gains with four are lost again in the longer exchange (measured)
 int g_rnn_chunk = 0;   // DEBUG: K blocks per pipeline barrier (0 = automatic)
 
 // fast gate non-linearities (ex2.approx + approximate division): ~1e-6 absolute error
@@ -174,25 +176,26 @@ __device__ __forceinline__ void st4_bf16(__nv_bfloat16* dst, const float* v) {
 
 #define ASRB_TRACE(slot, step)                                                                   \
     do {                                                                                         \
-        if (p.trace) p.trace[((size_t)blockIdx.x * p.T + (step)) * 12 + (slot)] = clock64();     \
+        if (p.trace) p.trace[((size_t)blockIdx.x * p.T + (step)) * 16 + (slot)] = clock64();     \
     } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// KSPLIT (backward only): a cluster of two CTAs shares 2*NJ hidden units.  Each CTA holds the weights of all 2*NJ units
-// for HALF of the gate index K, streams only that half of the operand through its shared memory (the bandwidth that
-// bounds the backward step: 382 KB instead of 686 KB per CTA and step at H=800), and the two partial products are
-// exchanged through distributed shared memory: every CTA sends the peer the 64 x NJ partial sums of the peer's units
-// and finishes its own NJ units.
-template <int CELL, int NJ, bool BWD, bool BF16, int MROWS, bool KSPLIT>
+// KS > 1 (backward only): a cluster of KS = 2 or 4 CTAs shares KS*NJ hidden units.  Each CTA holds the weights of all
+// KS*NJ units for 1/KS of the gate index K and streams only that part of the operand through its shared memory (the
+// bandwidth that bounds the backward step: 686 KB per CTA and step at H=800 unsplit, 382 KB with KS=2, 230 KB with
+// KS=4); the partial products are exchanged through distributed shared memory: every CTA sends each peer the
+// 64 x NJ partial sums of that peer's units and finishes its own NJ units.
+template <int CELL, int NJ, bool BWD, bool BF16, int MROWS, int KS>
 __global__ void __launch_bounds__(kRnnThreads, 1)
 rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const RnnParams p) {
-    static_assert(!KSPLIT || BWD, "the K split exists for the backward recurrence only");
+    static_assert(KS == 1 || BWD, "the K split exists for the backward recurrence only");
+    constexpr bool KSPLIT = KS > 1;
     using S = RnnShape<CELL, NJ>;
     constexpr int kGates = S::kGates;
-    constexpr int NPAD = BWD ? (KSPLIT ? 2 * NJ : S::kNpadB) : S::kNpadF;
+    constexpr int NPAD = BWD ? (KSPLIT ? KS * NJ : S::kNpadB) : S::kNpadF;
     constexpr int kTmemCols = 64;
     constexpr int KBE = BF16 ? 64 : 32;          // elements per 128-byte K block
     constexpr int kStageBytes = MROWS * 128;     // one K block of the A tile: MROWS rows x 128 B
@@ -215,7 +218,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint64_t* tempty_bar = w_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 3);
     uint64_t* x_bar = w_bar + 4;                  // [2] KSPLIT: the peer's partial sums of parity 0 / 1 have arrived
-    float* xbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kRnnBarBytes);   // [2][MROWS][NJ] (KSPLIT)
+    float* xbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kRnnBarBytes);   // [2][KS sources][MROWS][NJ] (KSPLIT)
+    float* xstage = xbuf + 2 * KS * MROWS * NJ;   // [2][KS-1 peers][MROWS][NJ]: our partial sums of each peer's units
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.T, B = p.B, H = p.H, G = p.G, P = p.P;
@@ -223,7 +227,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const int j0 = pidx * NJ;
     const bool tc = !p.use_simt;
     uint32_t* counter = p.counters + dir * kRnnCounterStride;
-    const uint32_t crank = KSPLIT ? cluster_ctarank() : 0u;      // = pidx % 2: which half of K this CTA multiplies
+    const uint32_t crank = KSPLIT ? cluster_ctarank() : 0u;      // = pidx % KS: which part of K this CTA multiplies
     const int kb_off = KSPLIT ? (int)crank * nkb : 0;            // first K block (of the global operand) of this CTA
     // time index processed at sequential step s
     auto t_of = [&](int s) { return (BWD ? (dir == 0) : (dir == 1)) ? (T - 1 - s) : s; };
@@ -348,7 +352,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const size_t slotHB = (size_t)B * H;
         const int u0 = 4 * ug;                   // first unit (within the slice) owned by this thread
 
-        float xsend[4] = {0.f, 0.f, 0.f, 0.f};
+        float xsend[KS > 1 ? KS - 1 : 1][4] = {};
         uint32_t xphase[2] = {0u, 0u};
         float state_h[4];   // fwd: h_prev of our units ; bwd: direct dh carry
         float state_c[4];   // fwd LSTM: c_prev ; bwd LSTM: dc carry
@@ -385,7 +389,8 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if constexpr (KSPLIT) {
                 if (hl == 0 && s > 0) {   // the peer sends one 16-byte vector per (row of the tile quarters in use, unit group)
                     const int quads = min(4, ceil_div(B, kRowsPerWarp));
-                    mbar_arrive_expect_tx(&x_bar[s & 1], (uint32_t)(quads * kRowsPerWarp * NV * 16));
+                    mbar_arrive_expect_tx(&x_bar[s & 1], (uint32_t)((KS - 1) * MROWS * NJ * 4));
+                    (void)quads;
                 }
             }
             constexpr int kAccG = BWD ? 1 : kGates;      // accumulator column groups we read: gates (fwd) / units (bwd)
@@ -409,7 +414,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 #pragma unroll
                     for (int q = 0; q < kGates; ++q) ldg4(in[q], g + (size_t)q * H);
                 } else {
-                    const float* sv = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) + (size_t)b * 4;
+                    const float* sv = p.saved + ((((size_t)dir * T + t) * p.P_saved + pidx) * 4) * (size_t)(NV * B * 4) + (size_t)b * 4;
                     const float* dop = p.dout + ((size_t)t * B + b) * H + j0 + u0;
                     const int tprev_slot = (dir == 0) ? t : t + 2;  // slot of the step that preceded t in forward order
                     const float* prevp = (CELL == ASRB_RNN_GRU ? p.hseq : p.cseq) +
@@ -433,7 +438,9 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + u0;
                         if constexpr (KSPLIT) {
                             tmem_ld_32x4(taddr + crank * NJ, acc[0]);          // partial sums of our own units
-                            tmem_ld_32x4(taddr + (crank ^ 1u) * NJ, xsend);    // ... and of the peer's units
+#pragma unroll
+                            for (int q = 1; q < KS; ++q)                       // ... and of every peer's units
+                                tmem_ld_32x4(taddr + ((crank + q) % KS) * NJ, xsend[q - 1]);
                         } else {
 #pragma unroll
                             for (int g = 0; g < kAccG; ++g) tmem_ld_32x4(taddr + (BWD ? 0 : g * NJ), acc[g]);
@@ -445,20 +452,43 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     if (lane == 0) mbar_arrive(tempty_bar);
                     if (hl == 0) ASRB_TRACE(6, s);
                     if constexpr (KSPLIT) {
-                        // exchange through distributed shared memory with st.async (every 16-byte store completes its
-                        // bytes on the peer's mbarrier: no fence), double-buffered by step parity: the peer can only
-                        // write parity q again after it has received our data of the step in between
+                        // Exchange through distributed shared memory, double-buffered by step parity (a peer can only write
+                        // parity q again after it has received our data of the step in between, which also means it has
+                        // finished reading our staging buffer of parity q).  The partial sums are staged locally and go out
+                        // as ONE bulk copy per peer.  Measured alternatives (cycles from the accumulator read to the summed
+                        // result, pairs / clusters of four): per-thread st.async with complete_tx 1.2 k / 2.5 k; bulk copy
+                        // 1.2 k / 2.1 k; plain DSMEM stores + mbarrier.arrive.release.cluster 2.5 k; plain stores + the
+                        // hardware cluster barrier 3.1 k -- ordering at cluster scope is what costs, not the bytes.
                         const int par = s & 1;
-                        float* slot = xbuf + ((size_t)par * MROWS + b) * NJ + u0;
-                        if (warp_ld && lane < kRowsPerWarp)
-                            st_async_f32x4(map_to_cta(slot, crank ^ 1u), xsend, map_to_cta(&x_bar[par], crank ^ 1u));
+                        if (warp_ld && lane < kRowsPerWarp) {
+#pragma unroll
+                            for (int q = 1; q < KS; ++q)
+                                st4(xstage + (((size_t)par * (KS - 1) + (q - 1)) * MROWS + b) * NJ + u0, xsend[q - 1]);
+                        }
+                        fence_proxy_async_smem();                      // generic stores -> the bulk copy's async-proxy reads
+                        named_bar_sync(5, kRnnEpiThreads);
+                        if (hl == 0) {
+                            ASRB_TRACE(12, s);
+#pragma unroll
+                            for (int q = 1; q < KS; ++q) {
+                                const uint32_t peer = (crank + q) % KS;
+                                // lands in slot [par][source = our rank] of the peer's buffer
+                                dsmem_bulk_copy(map_to_cta(xbuf + ((size_t)par * KS + crank) * MROWS * NJ, peer),
+                                                xstage + ((size_t)par * (KS - 1) + (q - 1)) * MROWS * NJ,
+                                                (uint32_t)(MROWS * NJ * 4), map_to_cta(&x_bar[par], peer));
+                            }
+                            ASRB_TRACE(13, s);
+                        }
                         mbar_wait_cluster(&x_bar[par], xphase[par]);
                         xphase[par] ^= 1u;
                         if (warp_ld && lane < kRowsPerWarp) {
-                            float xr[4];
-                            ld4(xr, slot);
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) acc[0][jj] += xr[jj];
+                            for (int q = 1; q < KS; ++q) {
+                                float xr[4];
+                                ld4(xr, xbuf + (((size_t)par * KS + (crank + q) % KS) * MROWS + b) * NJ + u0);
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) acc[0][jj] += xr[jj];
+                            }
                         }
                         if (hl == 0) ASRB_TRACE(11, s);
                     }
@@ -642,7 +672,7 @@ __global__ void rnn_sum_dirs_kernel(const float* __restrict__ hseq, float* __res
 }
 
 struct RnnPlan {
-    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, chunk_f, chunk_b, mrows, bf16, ksplit;
+    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, chunk_f, chunk_b, mrows, bf16, ksplit, P_b;   // ksplit: 0, 2, 4
     size_t smem_f, smem_b;
 };
 
@@ -662,13 +692,26 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
         if (2 * P > kNumSMs) continue;
         RnnPlan r;
         r.nj = nj; r.P = P; r.mrows = mrows; r.bf16 = bf16;
-        // backward: K split over CTA pairs when the geometry allows (see rnn_rec_kernel)
-        r.ksplit = (bf16 && nj == 16 && P % 2 == 0 && g_rnn_ksplit) ? 1 : 0;
-        r.npad_f = round_up(gates * nj, 16); r.npad_b = r.ksplit ? 2 * nj : 16;
-        r.kpad_f = round_up(H, kbe); r.kpad_b = r.ksplit ? ceil_div(ceil_div(G, kbe), 2) * kbe : round_up(G, kbe);
-        const size_t wf = (size_t)r.npad_f * r.kpad_f * esize, wb = (size_t)r.npad_b * r.kpad_b * esize;
+        // backward: K split over clusters of 4 (the slice count padded to a multiple of 4 with empty CTAs) or 2 CTAs
+        // when the geometry allows and at least 4 ring blocks still fit beside the weights and the exchange buffers
+        r.npad_f = round_up(gates * nj, 16);
+        r.kpad_f = round_up(H, kbe);
+        const size_t wf = (size_t)r.npad_f * r.kpad_f * esize;
         const size_t fixed = 1024 + kRnnBarBytes;
-        const size_t xb = r.ksplit ? (size_t)2 * mrows * nj * 4 : 0;   // exchange buffers of the K split
+        size_t wb = 0, xb = 0;
+        const int ks_try[3] = {4, 2, 0};
+        for (int ki = 0; ki < 3; ++ki) {
+            const int ks = ks_try[ki];
+            if (ks && !(bf16 && nj == 16 && g_rnn_ksplit >= ks)) continue;
+            if (ks && 2 * round_up(P, ks) > kNumSMs) continue;
+            r.ksplit = ks;
+            r.P_b = ks ? round_up(P, ks) : P;
+            r.npad_b = ks ? ks * nj : 16;
+            r.kpad_b = ks ? ceil_div(ceil_div(G, kbe), ks) * kbe : round_up(G, kbe);
+            wb = (size_t)r.npad_b * r.kpad_b * esize;
+            xb = ks ? (size_t)2 * (2 * ks - 1) * mrows * nj * 4 : 0;   // receive + staging buffers of the K split
+            if (!ks || wb + fixed + xb + 4 * (size_t)stage <= (size_t)kRnnMaxSmem) break;
+        }
         if (wf + fixed + stage > (size_t)kRnnMaxSmem || wb + fixed + xb + stage > (size_t)kRnnMaxSmem) continue;
         // as many K blocks in flight as fit (the whole previous state when possible): the step is latency-bound
         // K blocks that fit next to the resident weights; up to 4 blocks share one barrier / pipeline stage
@@ -690,10 +733,14 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
     return ASRB_ERR_UNSUPPORTED;
 }
 
-template <int CELL, int NJ, bool BWD, bool BF16, int MROWS, bool KSPLIT = false>
+template <int CELL, int NJ, bool BWD, bool BF16, int MROWS, int KS = 1>
 static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, const void* a_base, asrb_stream_t stream) {
     using S = RnnShape<CELL, NJ>;
-    constexpr int NPAD = BWD ? (KSPLIT ? 2 * NJ : S::kNpadB) : S::kNpadF;
+    constexpr bool KSPLIT = KS > 1;
+    constexpr int NPAD = BWD ? (KSPLIT ? KS * NJ : S::kNpadB) : S::kNpadF;
+    const int Pk = (BWD && KSPLIT) ? pl.P_b : pl.P;      // CTAs per direction of THIS launch
+    prm.P_saved = pl.P;
+    prm.P = Pk;
     constexpr int KBE = BF16 ? 64 : 32;
     constexpr int ES = BF16 ? 2 : 4;
     const int kpad = BWD ? pl.kpad_b : pl.kpad_f;
@@ -704,7 +751,7 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
     prm.wpack = BF16 ? nullptr : reinterpret_cast<const float*>(wpack);
     CUtensorMap tmW, tmA;
     {
-        uint64_t d[2] = {(uint64_t)kpad, (uint64_t)2 * pl.P * NPAD}, s[1] = {(uint64_t)kpad * ES};
+        uint64_t d[2] = {(uint64_t)kpad, (uint64_t)2 * Pk * NPAD}, s[1] = {(uint64_t)kpad * ES};
         uint32_t bx[2] = {KBE, (uint32_t)NPAD};
         int rc = BF16 ? make_tmap_bf16(&tmW, wpack, 2, d, s, bx) : make_tmap_f32(&tmW, wpack, 2, d, s, bx);
         if (rc) return rc;
@@ -719,11 +766,11 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
         int rc = BF16 ? make_tmap_bf16(&tmA, a_base, 3, d, s, bx) : make_tmap_f32(&tmA, a_base, 3, d, s, bx);
         if (rc) return rc;
     }
-    auto kern = rnn_rec_kernel<CELL, NJ, BWD, BF16, MROWS, KSPLIT>;
+    auto kern = rnn_rec_kernel<CELL, NJ, BWD, BF16, MROWS, KS>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * kRnnCounterStride * sizeof(uint32_t), stream));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pl.P);
+    cfg.gridDim = dim3(2 * Pk);
     cfg.blockDim = dim3(kRnnThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -733,7 +780,7 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
     // could not queue the next layer's kernels behind the recurrence (measured: ~0.3 ms of idle GPU after every launch).
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[0].val.clusterDim.x = KS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = KSPLIT ? 1 : 0;
     prm.dbg = g_rnn_dbg;
@@ -747,9 +794,13 @@ static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void*
 #define ASRB_RNN_CASE(C, N)                                                                              \
     if (cell == C && pl.nj == N) {                                                                       \
         if constexpr (BWD && N == 16) {                                                                  \
-            if (pl.ksplit) {                                                                             \
-                if (pl.mrows == 64) return rnn_launch<C, N, true, true, 64, true>(pl, prm, wpack, a_base, stream);  \
-                return rnn_launch<C, N, true, true, 128, true>(pl, prm, wpack, a_base, stream);          \
+            if (pl.ksplit == 2) {                                                                        \
+                if (pl.mrows == 64) return rnn_launch<C, N, true, true, 64, 2>(pl, prm, wpack, a_base, stream);  \
+                return rnn_launch<C, N, true, true, 128, 2>(pl, prm, wpack, a_base, stream);             \
+            }                                                                                            \
+            if (pl.ksplit == 4) {                                                                        \
+                if (pl.mrows == 64) return rnn_launch<C, N, true, true, 64, 4>(pl, prm, wpack, a_base, stream);  \
+                return rnn_launch<C, N, true, true, 128, 4>(pl, prm, wpack, a_base, stream);             \
             }                                                                                            \
         }                                                                                                \
         if (pl.bf16) {                                                                                   \
@@ -790,7 +841,7 @@ int asrb_rnn_plan(int cell, int H, int B, int bf16, int* nj, int* P, size_t* wpa
     if (nj) *nj = pl.nj;
     if (P) *P = pl.P;
     if (wpack_fwd_bytes) *wpack_fwd_bytes = (size_t)2 * pl.P * pl.npad_f * pl.kpad_f * es;
-    if (wpack_bwd_bytes) *wpack_bwd_bytes = (size_t)2 * pl.P * pl.npad_b * pl.kpad_b * es;
+    if (wpack_bwd_bytes) *wpack_bwd_bytes = (size_t)2 * pl.P_b * pl.npad_b * pl.kpad_b * es;
     return 0;
 }
 
@@ -807,7 +858,7 @@ int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fw
         ASRB_LAUNCH_OK();
     }
     if (wpack_bwd) {
-        if (pl.ksplit)    rnn_pack_bwd_split_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.kpad_b);
+        if (pl.ksplit)    rnn_pack_bwd_split_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P_b, pl.kpad_b, pl.ksplit);
         else if (pl.bf16) rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
         else         rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (float*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
         ASRB_LAUNCH_OK();
@@ -861,7 +912,7 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
 
 /* DEBUG / timing experiments: backward K split over CTA pairs on (1, default) / off (0).  Changes the packed-weight
  * layout: call before asrb_rnn_plan / asrb_rnn_pack_weights. */
-int asrb_debug_rnn_ksplit(int on) { g_rnn_ksplit = on ? 1 : 0; return 0; }
+int asrb_debug_rnn_ksplit(int on) { g_rnn_ksplit = on == 1 ? 2 : on; return 0; }   /* 0 off, 1 or 2 pairs, 4 clusters of four */
 
 /* DEBUG / timing experiments: K blocks per pipeline barrier (0 = automatic) */
 int asrb_debug_rnn_dbg(int bits) { g_rnn_dbg = bits; return 0; }
