@@ -9,10 +9,10 @@ for w in $what; do
     tests)    tools/gpu_checks.sh gemm conv conv32 conv1 rows rnn_simt rnn_tc ctc stft model smoke ;;
     bench)    timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit=$?"; cat gpurun_out/bench.json ;;
     kernels)  timeout 600 python tools/bench_kernels.py > gpurun_out/kernels.json 2> gpurun_out/kernels.err; echo "kernels exit=$?"; cat gpurun_out/kernels.json ;;
-    launches) export ASRB_RNN_KSPLIT=0   # ncu fails to launch the cooperative + cluster (K split) backward kernel: LaunchFailed
+    launches)
               timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
                 --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/launches.log 2>&1; echo "launches exit=$?" ;;
-    full)     export ASRB_RNN_KSPLIT=0
+    full)
               # one fwd + one bwd recurrent launch, two GEMMs (tf32 in-proj, bf16 backward), the CTC kernels: full shape
               timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
                 -k regex:'rnn_rec_kernel' -s 4 -c 2 -f -o gpurun_out/prof_rnn python tools/profile_step.py > gpurun_out/full_rnn.log 2>&1; echo "full rnn exit=$?"
