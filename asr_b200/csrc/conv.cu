@@ -280,14 +280,21 @@ nchw_reduce_kernel(const float* __restrict__ a, const float* __restrict__ yraw, 
 }
 
 // combine partials -> out0[c], out1[c]; kind 0: mean / invstd (+ running stats), kind 1: raw sums
-__global__ void reduce_finalize_kernel(const double* __restrict__ partial, int nparts, int C, double count, int kind,
-                                       float eps, float momentum, float* __restrict__ out0, float* __restrict__ out1,
-                                       float* __restrict__ running_mean, float* __restrict__ running_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: the lanes stride over the parts, fixed-order shuffle tree in double
+__global__ void __launch_bounds__(128)
+reduce_finalize_kernel(const double* __restrict__ partial, int nparts, int C, double count, int kind,
+                       float eps, float momentum, float* __restrict__ out0, float* __restrict__ out1,
+                       float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     double s0 = 0, s1 = 0;
-#pragma unroll 8
-    for (int i = 0; i < nparts; ++i) { s0 += partial[((size_t)c * nparts + i) * 2]; s1 += partial[((size_t)c * nparts + i) * 2 + 1]; }
+    for (int i = lane; i < nparts; i += 32) { s0 += partial[((size_t)c * nparts + i) * 2]; s1 += partial[((size_t)c * nparts + i) * 2 + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane != 0) return;
     if (kind == 0) {
         const double mean = s0 / count;
         double var = s1 / count - mean * mean;
@@ -512,7 +519,7 @@ int asrb_conv2d_mask_bwd_weight(const float* dy, const float* x, const int32_t* 
         BnAct p = {};
         nchw_reduce_kernel<2><<<dim3(Cout, B * nsplit), 256, 0, stream>>>(dy, nullptr, lengths, p, ws, B, Cout, HW, Wout, nsplit, (unsigned)(((1ULL << 32) + Wout - 1) / Wout));
         ASRB_LAUNCH_OK();
-        reduce_finalize_kernel<<<ceil_div(Cout, 128), 128, 0, stream>>>(ws, B * nsplit, Cout, 1.0, 1, 0.f, 0.f, dbias, nullptr, nullptr, nullptr);
+        reduce_finalize_kernel<<<ceil_div(Cout, 4), 128, 0, stream>>>(ws, B * nsplit, Cout, 1.0, 1, 0.f, 0.f, dbias, nullptr, nullptr, nullptr);
         ASRB_LAUNCH_OK();
     }
     return 0;
@@ -535,7 +542,7 @@ int asrb_nchw_channel_sums(const float* a, const int32_t* lengths, float* out, d
     BnAct p = {};
     nchw_reduce_kernel<2><<<dim3(C, B * nsplit), 256, 0, stream>>>(a, nullptr, lengths, p, ws, B, C, HW, W, nsplit, (unsigned)(((1ULL << 32) + W - 1) / W));
     ASRB_LAUNCH_OK();
-    reduce_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(ws, B * nsplit, C, 1.0, 1, 0.f, 0.f, out, nullptr, nullptr, nullptr);
+    reduce_finalize_kernel<<<ceil_div(C, 4), 128, 0, stream>>>(ws, B * nsplit, C, 1.0, 1, 0.f, 0.f, out, nullptr, nullptr, nullptr);
     ASRB_LAUNCH_OK();
     return 0;
 }
@@ -555,7 +562,7 @@ int asrb_bn2d_stats(const float* y, float* mean, float* invstd, float* running_m
     BnAct p = {};
     nchw_reduce_kernel<0><<<dim3(C, B * nsplit), 256, 0, stream>>>(y, nullptr, nullptr, p, ws, B, C, HW, W, nsplit, (unsigned)(((1ULL << 32) + W - 1) / W));
     ASRB_LAUNCH_OK();
-    reduce_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(ws, B * nsplit, C, (double)B * HW, 0, eps, momentum, mean, invstd, running_mean, running_var);
+    reduce_finalize_kernel<<<ceil_div(C, 4), 128, 0, stream>>>(ws, B * nsplit, C, (double)B * HW, 0, eps, momentum, mean, invstd, running_mean, running_var);
     ASRB_LAUNCH_OK();
     return 0;
 }
@@ -596,7 +603,7 @@ int asrb_bn_act_mask_bwd(const float* dz, const float* y, const int32_t* lengths
         ASRB_REQUIRE(ws_bytes >= (size_t)C * B * nsplit * 2 * sizeof(double), ASRB_ERR_WORKSPACE);
         nchw_reduce_kernel<1><<<dim3(C, B * nsplit), 256, 0, stream>>>(dz, y, lengths, p, ws, B, C, HW, W, nsplit, (unsigned)(((1ULL << 32) + W - 1) / W));
         ASRB_LAUNCH_OK();
-        reduce_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(ws, B * nsplit, C, 1.0, 1, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr);
+        reduce_finalize_kernel<<<ceil_div(C, 4), 128, 0, stream>>>(ws, B * nsplit, C, 1.0, 1, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr);
         ASRB_LAUNCH_OK();
     }
     const long long total = (long long)B * C * HW;

@@ -46,17 +46,28 @@ rows_reduce_kernel(const float* __restrict__ a, int lda, const float* __restrict
 }
 
 // kind 0: mean/invstd (+running stats) ; kind 1: raw sums
-__global__ void rows_finalize_kernel(const float* __restrict__ partial, int nchunks, int cols, double count, int kind,
-                                     float eps, float momentum, float* __restrict__ out0, float* __restrict__ out1,
-                                     float* __restrict__ running_mean, float* __restrict__ running_var) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// block = 32 columns x 8 chunk groups: the chunk loop is 8x shorter than with one thread per column (the kernel is pure
+// latency: 296 dependent-free but serially issued iterations cost 50 us), partials combined in a fixed order
+__global__ void __launch_bounds__(256)
+rows_finalize_kernel(const float* __restrict__ partial, int nchunks, int cols, double count, int kind,
+                     float eps, float momentum, float* __restrict__ out0, float* __restrict__ out1,
+                     float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    __shared__ double sh0[8][33], sh1[8][33];
     double s0 = 0, s1 = 0;
-#pragma unroll 8
-    for (int i = 0; i < nchunks; ++i) {
-        s0 += partial[((size_t)i * 2 + 0) * cols + c];
-        s1 += partial[((size_t)i * 2 + 1) * cols + c];
+    if (c < cols) {
+#pragma unroll 4
+        for (int i = ty; i < nchunks; i += 8) {
+            s0 += partial[((size_t)i * 2 + 0) * cols + c];
+            s1 += partial[((size_t)i * 2 + 1) * cols + c];
+        }
     }
+    sh0[ty][tx] = s0; sh1[ty][tx] = s1;
+    __syncthreads();
+    if (ty != 0 || c >= cols) return;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { s0 += sh0[i][tx]; s1 += sh1[i][tx]; }
     if (kind == 0) {
         const double mean = s0 / count;
         double var = s1 / count - mean * mean;
@@ -262,7 +273,7 @@ int asrb_bn_rows_fwd(const float* x, const float* gamma, const float* beta, floa
         int nchunks = 0;
         int rc = rows_reduce<0>(x, cols, nullptr, 0, nullptr, nullptr, ws, ws_bytes, R, cols, &nchunks, stream);
         if (rc) return rc;
-        rows_finalize_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(ws, nchunks, cols, (double)R, 0, eps, momentum, mean, invstd, running_mean, running_var);
+        rows_finalize_kernel<<<ceil_div(cols, 32), 256, 0, stream>>>(ws, nchunks, cols, (double)R, 0, eps, momentum, mean, invstd, running_mean, running_var);
         ASRB_LAUNCH_OK();
     } else {
         ASRB_REQUIRE(running_mean && running_var, ASRB_ERR_BAD_ARG);
@@ -289,7 +300,7 @@ int asrb_bn_rows_bwd(const float* dy, const float* x, const float* mean, const f
     int nchunks = 0;
     int rc = rows_reduce<1>(dy, cols, x, cols, mean, invstd, ws, ws_bytes, R, cols, &nchunks, stream);
     if (rc) return rc;
-    rows_finalize_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(ws, nchunks, cols, 1.0, 1, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr);
+    rows_finalize_kernel<<<ceil_div(cols, 32), 256, 0, stream>>>(ws, nchunks, cols, 1.0, 1, 0.f, 0.f, dbeta, dgamma, nullptr, nullptr);
     ASRB_LAUNCH_OK();
     const long long total = R * cols;
     (void)total;
@@ -311,7 +322,7 @@ int asrb_col_sums(const float* a, int lda, float* out, float* ws, size_t ws_byte
     int nchunks = 0;
     int rc = rows_reduce<2>(a, lda, nullptr, 0, nullptr, nullptr, ws, ws_bytes, R, cols, &nchunks, stream);
     if (rc) return rc;
-    rows_finalize_kernel<<<ceil_div(cols, 128), 128, 0, stream>>>(ws, nchunks, cols, 1.0, 1, 0.f, 0.f, out, nullptr, nullptr, nullptr);
+    rows_finalize_kernel<<<ceil_div(cols, 32), 256, 0, stream>>>(ws, nchunks, cols, 1.0, 1, 0.f, 0.f, out, nullptr, nullptr, nullptr);
     ASRB_LAUNCH_OK();
     return 0;
 }
