@@ -151,9 +151,12 @@ int g_rnn_ksplit = 2;   // largest backward K split allowed: 0 none, 2 CTA pairs
                         // 1.5 k cycles the MMA phase gains with four are lost again in the longer exchange (measured)
 int g_rnn_chunk = 0;   // DEBUG: K blocks per pipeline barrier (0 = automatic)
 
-// fast gate non-linearities (ex2.approx + approximate division): ~1e-6 absolute error
-__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float ftanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+// fast gate non-linearities on the flush-to-zero MUFU forms (ex2.approx.ftz + rcp.approx.ftz: ~1e-6 absolute error);
+// __expf / __fdividef spend three more instructions per call on denormal scaling and range checks
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fsigmoid(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float ftanh(float x) { return fmaf(-2.f, rcp_ftz(1.f + ex2_ftz(2.8853900817779268f * x)), 1.f); }
 
 __device__ __forceinline__ void ld4(float* dst, const float* src) {
     const float4 t = *reinterpret_cast<const float4*>(src);
