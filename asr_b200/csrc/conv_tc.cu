@@ -15,6 +15,8 @@
 // NCHW rows), M = (kw, ci) (KW time-shifted TMA boxes of the same input row; TMA needs 16-byte aligned inner coordinates, so
 // the boxes come from 4 copies of x delayed by 0..3 samples), N = co; one CTA per (kh, chunk of rows),
 // partial sums combined with fp32 atomics.
+#include <cuda_bf16.h>
+
 #include "ptx.cuh"
 
 namespace asrb {
@@ -223,9 +225,15 @@ struct ConvWgradParams {
     float* dw;                                          // [32][32][KH][KW]
 };
 
+/* BF16: operands are bf16 copies (gradient-only product, like the recurrent stack's backward GEMMs): a 128-byte
+ * swizzle row then holds 64 time samples instead of 32, which halves the SMEM bytes (TMA writes + tensor-core operand
+ * reads, the resource that bounds this kernel: every x sample is loaded KW times) per sample. */
+template <bool BF16>
 __global__ void __launch_bounds__(kCtThreads, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
                      const ConvWgradParams p) {
+    constexpr int KT = BF16 ? 64 : 32;                     // time samples per stage (one 128-byte row)
+    constexpr int NQ = BF16 ? 8 : 4;                       // delayed copies: box starts must be 16-byte aligned
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = p.m_tiles * 16384;                 // m_tiles x [128 rows = 4 kernel columns x 32 ci][32 t]
@@ -243,7 +251,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int nrows = p.B * p.Hout;
     const int r0 = chunk * p.rows_per_chunk;
     const int r1 = min(nrows, r0 + p.rows_per_chunk);
-    const int n_kb = ceil_div(p.Wout, 32);
+    const int n_kb = ceil_div(p.Wout, KT);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
@@ -280,10 +288,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.m_tiles * 4 + 1) * kCtWTile);
                     for (int j = 0; j < p.m_tiles * 4; ++j) { // kernel column j (columns >= KW are never read back)
                         const int off = j - p.PW;             // time shift; copy q holds x delayed by q samples
-                        const int q = (((-off) % 4) + 4) % 4; // so that the box start kb*32 + off + q is 16-byte aligned
-                        tma_load_5d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * 32 + off + q, hi, 0, b, q);
+                        const int q = (((-off) % NQ) + NQ) % NQ; // so that the box start kb*KT + off + q is 16-byte aligned
+                        tma_load_5d(st + j * kCtWTile, &tmX, &full_bar[stage], kb * KT + off + q, hi, 0, b, q);
                     }
-                    tma_load_4d(st + a_bytes, &tmDy, &full_bar[stage], kb * 32, ho, 0, b);
+                    tma_load_4d(st + a_bytes, &tmDy, &full_bar[stage], kb * KT, ho, 0, b);
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -292,7 +300,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     } else if (warp == 1) {
         // MMA issuer: warp-uniform loop, one elected lane issues
         if (total_rows > 0) {
-            constexpr uint32_t idesc = umma_idesc(kFmtTF32, 128, kCtC);
+            constexpr uint32_t idesc = umma_idesc(BF16 ? kFmtBF16 : kFmtTF32, 128, kCtC);
             int stage = 0;
             uint32_t phase = 0;
             const int steps = total_rows * n_kb;
@@ -305,8 +313,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     for (int mt = 0; mt < p.m_tiles; ++mt) {
                         const uint64_t adesc = umma_desc_sw128(smem_u32(st + mt * 16384));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_tf32(tmem_base + mt * 32, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+                        for (int k = 0; k < 4; ++k) {
+                            if constexpr (BF16) umma_f16(tmem_base + mt * 32, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+                            else umma_tf32(tmem_base + mt * 32, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);
                     if (s == steps - 1) umma_commit(tfull_bar);
@@ -338,6 +348,31 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// bf16 forms: xs[r][row][w] = x[row][w - r], r = 0..7, row stride ldo >= W + 7 (multiple of 8)
+__global__ void conv_shift_copies_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xs, long long rows,
+                                              int W, int ldo) {
+    const long long per = rows * ldo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / ldo;
+        const int w = (int)(i - row * ldo);
+        const float* xr = x + row * W;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            xs[r * per + i] = __float2bfloat16((w - r >= 0 && w - r < W) ? xr[w - r] : 0.f);
+    }
+}
+
+// out[row][0..ldo) = bf16(in[row][0..W)), zero padded
+__global__ void conv_rows_bf16_kernel(const float* __restrict__ in, int ldi, __nv_bfloat16* __restrict__ out, long long rows,
+                                      int W, int ldo) {
+    const long long per = rows * ldo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / ldo;
+        const int w = (int)(i - row * ldo);
+        out[i] = __float2bfloat16(w < W ? in[row * ldi + w] : 0.f);
     }
 }
 
@@ -430,41 +465,68 @@ int asrb_conv32_bwd_data(const float* dy_nhwc, const float* pack_dgrad, float* d
     return conv_row_launch(dy_nhwc, pack_dgrad, p, stream);
 }
 
-size_t asrb_conv32_bwd_weight_workspace_bytes(int B, int Hin, int Win) {
-    return (size_t)4 * B * 32 * Hin * round_up(Win + 3, 4) * sizeof(float);
+static int g_conv_wgrad_bf16 = 1;
+/* debug/tuning: 1 (default) bf16 operand copies for the 32->32 weight gradient, 0 TF32 operands */
+int asrb_debug_conv_wgrad_bf16(int v) {
+    const int old = g_conv_wgrad_bf16;
+    if (v >= 0) g_conv_wgrad_bf16 = v ? 1 : 0;
+    return old;
 }
 
-/* dw[32,32,KH,KW] from x (NCHW, dense) and dy (NCHW, already masked, row stride lddy = multiple of 4: TMA needs
- * 16-byte strides; pad odd widths with asrb_copy_rows_padded).  ws: asrb_conv32_bwd_weight_workspace_bytes. */
+size_t asrb_conv32_bwd_weight_workspace_bytes(int B, int Hin, int Win, int Hout, int Wout) {
+    const size_t f32 = (size_t)4 * B * 32 * Hin * round_up(Win + 3, 4) * sizeof(float);
+    const size_t b16 = ((size_t)8 * B * 32 * Hin * round_up(Win + 7, 8) + (size_t)B * 32 * Hout * round_up(Wout, 8)) * 2;
+    return f32 > b16 ? f32 : b16;
+}
+
+/* dw[32,32,KH,KW] from x (NCHW, dense) and dy (NCHW, already masked, row stride lddy >= Wout; the TF32 form needs
+ * lddy % 4 == 0 for TMA's 16-byte strides: pad odd widths with asrb_copy_rows_padded; the bf16 form converts dy into
+ * the workspace and takes any lddy).  ws: asrb_conv32_bwd_weight_workspace_bytes. */
 int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw, float* ws, size_t ws_bytes, int B,
                            int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW,
                            asrb_stream_t stream) {
     ASRB_REQUIRE(x && dy && dw && ws && B > 0, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(asrb_conv32_supported(32, 32, KH, KW, SH, 1, PH, PW), ASRB_ERR_UNSUPPORTED);
     ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
-    ASRB_REQUIRE(lddy >= Wout && lddy % 4 == 0, ASRB_ERR_ALIGNMENT);
-    ASRB_REQUIRE(ws_bytes >= asrb_conv32_bwd_weight_workspace_bytes(B, Hin, Win), ASRB_ERR_WORKSPACE);
-    const int ldx = round_up(Win + 3, 4);
-    const long long xrows = (long long)B * 32 * Hin;
+    const bool bf16 = g_conv_wgrad_bf16 != 0;
+    ASRB_REQUIRE(lddy >= Wout && (bf16 || lddy % 4 == 0), ASRB_ERR_ALIGNMENT);
+    ASRB_REQUIRE(ws_bytes >= asrb_conv32_bwd_weight_workspace_bytes(B, Hin, Win, Hout, Wout), ASRB_ERR_WORKSPACE);
+    const int nq = bf16 ? 8 : 4, es = bf16 ? 2 : 4;
+    const int ldx = round_up(Win + nq - 1, nq);
+    const int ldy = bf16 ? round_up(Wout, 8) : lddy;
+    const long long xrows = (long long)B * 32 * Hin, yrows = (long long)B * 32 * Hout;
+    const void* dy_src = dy;
     {
         const long long n = xrows * ldx;
         const int g = (int)((n + 255) / 256 < kNumSMs * 8 ? (n + 255) / 256 : kNumSMs * 8);
-        conv_shift_copies_kernel<<<g, 256, 0, stream>>>(x, ws, xrows, Win, ldx);
-        ASRB_LAUNCH_OK();
+        if (bf16) {
+            __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ws);
+            __nv_bfloat16* dyb = xs + (size_t)8 * xrows * ldx;
+            conv_shift_copies_bf16_kernel<<<g, 256, 0, stream>>>(x, xs, xrows, Win, ldx);
+            ASRB_LAUNCH_OK();
+            const long long m = yrows * ldy;
+            const int g2 = (int)((m + 255) / 256 < kNumSMs * 8 ? (m + 255) / 256 : kNumSMs * 8);
+            conv_rows_bf16_kernel<<<g2, 256, 0, stream>>>(dy, lddy, dyb, yrows, Wout, ldy);
+            ASRB_LAUNCH_OK();
+            dy_src = dyb;
+        } else {
+            conv_shift_copies_kernel<<<g, 256, 0, stream>>>(x, ws, xrows, Win, ldx);
+            ASRB_LAUNCH_OK();
+        }
     }
     CUtensorMap tmX, tmDy;
     {
-        uint64_t d[5] = {(uint64_t)Win + 3, (uint64_t)Hin, 32, (uint64_t)B, 4};
-        uint64_t s[4] = {(uint64_t)ldx * 4, (uint64_t)Hin * ldx * 4, (uint64_t)32 * Hin * ldx * 4, (uint64_t)xrows * ldx * 4};
-        uint32_t bx[5] = {32, 1, 32, 1, 1};
-        int rc = make_tmap_f32(&tmX, ws, 5, d, s, bx);
+        uint64_t d[5] = {(uint64_t)Win + nq - 1, (uint64_t)Hin, 32, (uint64_t)B, (uint64_t)nq};
+        uint64_t s[4] = {(uint64_t)ldx * es, (uint64_t)Hin * ldx * es, (uint64_t)32 * Hin * ldx * es, (uint64_t)xrows * ldx * es};
+        uint32_t bx[5] = {bf16 ? 64u : 32u, 1, 32, 1, 1};
+        int rc = bf16 ? make_tmap_bf16(&tmX, ws, 5, d, s, bx) : make_tmap_f32(&tmX, ws, 5, d, s, bx);
         if (rc) return rc;
     }
     {
         uint64_t d[4] = {(uint64_t)Wout, (uint64_t)Hout, 32, (uint64_t)B};
-        uint64_t s[3] = {(uint64_t)lddy * 4, (uint64_t)Hout * lddy * 4, (uint64_t)32 * Hout * lddy * 4};
-        uint32_t bx[4] = {32, 1, 32, 1};
-        int rc = make_tmap_f32(&tmDy, dy, 4, d, s, bx);
+        uint64_t s[3] = {(uint64_t)ldy * es, (uint64_t)Hout * ldy * es, (uint64_t)32 * Hout * ldy * es};
+        uint32_t bx[4] = {bf16 ? 64u : 32u, 1, 32, 1};
+        int rc = bf16 ? make_tmap_bf16(&tmDy, dy_src, 4, d, s, bx) : make_tmap_f32(&tmDy, dy_src, 4, d, s, bx);
         if (rc) return rc;
     }
     ConvWgradParams p = {B, Hin, Win, Hout, Wout, KH, KW, SH, PH, PW, 0, ceil_div(KW, 4), dw};
@@ -476,8 +538,13 @@ int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw,
     chunks = ceil_div(nrows, p.rows_per_chunk);
     ASRB_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)32 * 32 * KH * KW * sizeof(float), stream));
     const size_t smem = 200 * 1024 + 1024 + 256;
-    ASRB_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_wgrad_tc_kernel<<<KH * chunks, kCtThreads, smem, stream>>>(tmX, tmDy, p);
+    if (bf16) {
+        ASRB_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_wgrad_tc_kernel<true><<<KH * chunks, kCtThreads, smem, stream>>>(tmX, tmDy, p);
+    } else {
+        ASRB_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_wgrad_tc_kernel<false><<<KH * chunks, kCtThreads, smem, stream>>>(tmX, tmDy, p);
+    }
     ASRB_LAUNCH_OK();
     return 0;
 }

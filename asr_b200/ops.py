@@ -280,9 +280,12 @@ def conv32_bwd_weight(x, dy_masked, w_shape, stride, padding):
     B, _, Hin, Win = x.shape
     _, _, Hout, Wout = dy_masked.shape
     _, _, KH, KW = w_shape
-    dyp, lddy = pad_rows4(dy_masked)
+    if _lib.query("asrb_debug_conv_wgrad_bf16", -1):
+        dyp, lddy = dy_masked, Wout                # converted to bf16 (and padded) inside the call
+    else:
+        dyp, lddy = pad_rows4(dy_masked)
     dw = torch.empty(w_shape, device=x.device, dtype=torch.float32)
-    nb = _lib.query("asrb_conv32_bwd_weight_workspace_bytes", B, Hin, Win)
+    nb = _lib.query("asrb_conv32_bwd_weight_workspace_bytes", B, Hin, Win, Hout, Wout)
     ws = torch.empty(nb // 4, device=x.device, dtype=torch.float32)
     _call("asrb_conv32_bwd_weight", _p(x), _p(dyp), lddy, _p(dw), _p(ws), nb, B, Hin, Win, Hout, Wout, KH, KW,
           stride[0], padding[0], padding[1])

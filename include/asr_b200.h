@@ -158,7 +158,9 @@ int asrb_conv32_fwd(const float* x_nhwc, const float* pack_fwd, const float* bia
                     asrb_stream_t stream);
 int asrb_conv32_bwd_data(const float* dy_nhwc, const float* pack_dgrad, float* dx, int B, int Hin, int Win, int Hout,
                          int Wout, int KH, int KW, int SH, int PH, int PW, asrb_stream_t stream);
-size_t asrb_conv32_bwd_weight_workspace_bytes(int B, int Hin, int Win);
+size_t asrb_conv32_bwd_weight_workspace_bytes(int B, int Hin, int Win, int Hout, int Wout);
+/* operands of the weight-gradient product: 1 (default) bf16 copies, 0 TF32 (then lddy % 4 == 0); v < 0 queries */
+int asrb_debug_conv_wgrad_bf16(int v);
 int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw, float* ws, size_t ws_bytes, int B,
                            int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW,
                            asrb_stream_t stream);

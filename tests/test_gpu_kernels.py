@@ -142,10 +142,17 @@ def test_conv32_tensor_core_fwd_bwd(ops, c):
     dx = ops.conv32_bwd_data(ops.nchw_to_nhwc(dy.to(DEV)), pd, tuple(x.shape), tuple(w.shape), c["s"], c["p"])
     torch.cuda.synchronize()
     assert report("conv32 dgrad", dx, x.grad) <= 2e-3 * math.sqrt(K) * 0.05
-    dw = ops.conv32_bwd_weight(xd, dy.to(DEV), tuple(w.shape), c["s"], c["p"])
-    torch.cuda.synchronize()
+    from asr_b200 import _lib
     npix = c["B"] * y_ref.shape[2] * y_ref.shape[3]
-    assert report("conv32 wgrad", dw, w.grad) <= 2e-3 * math.sqrt(npix)
+    try:
+        for bf16, tol in ((1, 1.5e-2), (0, 2e-3)):    # bf16 operand copies (default): rounding sigma 1.6e-3*sqrt(npix) per
+            # entry, worst of 2e5 entries ~5 sigma; TF32 operands: a quarter of that
+            _lib.query("asrb_debug_conv_wgrad_bf16", bf16)
+            dw = ops.conv32_bwd_weight(xd, dy.to(DEV), tuple(w.shape), c["s"], c["p"])
+            torch.cuda.synchronize()
+            assert report(f"conv32 wgrad bf16={bf16}", dw, w.grad) <= tol * math.sqrt(npix)
+    finally:
+        _lib.query("asrb_debug_conv_wgrad_bf16", 1)
     assert report("channel sums", ops.nchw_channel_sums(dy.to(DEV), ld), b.grad) <= 1e-4 * max(1.0, b.grad.abs().max().item())
 
 
