@@ -20,7 +20,7 @@
 namespace asrb {
 
 unsigned g_debug_flags = 0;
-int g_gemm_force_bn = 0, g_gemm_bn256_gain = 118;
+int g_gemm_force_bn = 0, g_gemm_bn256_gain = 118, g_gemm_tma_store = 1;
 
 // ------------------------------------------------------------------------------------------------
 // host: tensor map encoding
@@ -87,7 +87,8 @@ struct GemmCfg {
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
     static constexpr int kStages = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
     static constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kStoreBytes = 4 * 2 * 4096;  // per epilogue warp: two 32x32 fp32 staging tiles for TMA stores
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // BF16 = false: fp32 operands in HBM, tf32 MMA (TMA rounds fp32 -> tf32 on the way into shared memory);
@@ -95,14 +96,15 @@ struct GemmCfg {
 template <int BN, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    float* __restrict__ C, int ldc, const float* __restrict__ bias, int M, int N, int K,
-                    int flags) {
+                    const __grid_constant__ CUtensorMap tmC, float* __restrict__ C, int ldc,
+                    const float* __restrict__ bias, int M, int N, int K, int flags, int tma_store) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageBytesA;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint8_t* smem_c = smem + Cfg::kStages * Cfg::kStageBytes;          // 1024-aligned (stage sizes are multiples of 4 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + Cfg::kStoreBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + Cfg::kStages;
     uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
@@ -119,6 +121,7 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (tma_store) tma_prefetch_desc(&tmC);
         for (int i = 0; i < Cfg::kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -189,6 +192,56 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int quad = warp & 3;  // TMEM lane quarter this warp may access
         const bool accumulate = flags & ASRB_GEMM_ACCUMULATE;
         const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        if (tma_store) {
+            /* Each lane owns one accumulator row, so direct stores touch 32 different rows per instruction (32 half-used
+             * sectors; the LSU then bounds tiles with short K).  Instead the warp lays its 32x32 sub-tile out in shared
+             * memory in the 128-byte-swizzle pattern (16-byte chunk j of row r at chunk j ^ (r & 7): conflict-free for
+             * the row-per-lane writes) and one lane hands it to the TMA unit, which writes whole 128-byte rows, clips at
+             * M and N, and in accumulate mode adds in L2 (cp.reduce .add.f32).  Two staging tiles per warp. */
+            uint8_t* stg = smem_c + quad * 8192;
+            int cbuf = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * kBM, n0 = (tile % num_n) * BN;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after_sync();
+                const int row0 = m0 + quad * 32;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (row0 >= M || col0 >= N) break;             // warp-uniform
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, v);
+                    tmem_ld_wait();
+                    if (bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < N) v[j] += __ldg(bias + col0 + j);
+                    }
+                    if (lane == 0) bulk_wait_group_read<1>();      // the store that last read this staging tile is done
+                    __syncwarp();
+                    uint8_t* buf = stg + cbuf * 4096;
+                    const uint32_t rowaddr = smem_u32(buf) + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_f32x4(rowaddr + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (accumulate) tma_reduce_add_2d(&tmC, buf, col0, row0);
+                        else            tma_store_2d(&tmC, buf, col0, row0);
+                        bulk_commit_group();
+                    }
+                    cbuf ^= 1;
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (lane == 0) bulk_wait_group<0>();
+        } else {
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -232,6 +285,7 @@ gemm_tn_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -254,6 +308,16 @@ static int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float*
     if (rc) return rc;
     rc = BF16 ? make_tmap_bf16(&tmB, B, 2, dB, sB, bB) : make_tmap_f32(&tmB, B, 2, dB, sB, bB);
     if (rc) return rc;
+    // TMA-store epilogue when C qualifies for a tensor map (16-byte aligned base and row stride)
+    CUtensorMap tmC = tmA;
+    int tma_store = 0;
+    if (g_gemm_tma_store && ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && M >= 32 && N >= 32) {
+        uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[1] = {(uint64_t)ldc * 4};
+        uint32_t bC[2] = {32, 32};
+        rc = make_tmap_f32(&tmC, C, 2, dC, sC, bC, true, false);
+        if (rc) return rc;
+        tma_store = 1;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         ASRB_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tf32_kernel<BN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -262,7 +326,8 @@ static int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float*
     }
     const int tiles = ceil_div(M, kBM) * ceil_div(N, BN);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_tn_tf32_kernel<BN, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, C, ldc, bias, M, N, K, flags);
+    gemm_tn_tf32_kernel<BN, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, C, ldc, bias, M, N, K,
+                                                                                    flags, tma_store);
     ASRB_LAUNCH_OK();
     return 0;
 }
@@ -461,6 +526,13 @@ int asrb_gemm_tn_bf16(const void* A, int lda, const void* B, int ldb, float* C, 
 
 /* DEBUG / tuning: force the N tile (0 = automatic, 128, 256); gain = assumed speed of the 256-wide tile relative to
  * the 128-wide one in percent (default 118: measured 1.10-1.18 on the configs[1] shapes) */
+/* debug/tuning: 1 (default) epilogue through shared memory + TMA stores, 0 direct row-per-lane stores; v < 0 queries */
+int asrb_debug_gemm_tma_store(int v) {
+    const int old = g_gemm_tma_store;
+    if (v >= 0) g_gemm_tma_store = v ? 1 : 0;
+    return old;
+}
+
 int asrb_debug_gemm_tile(int force_bn, int gain_pct) {
     ASRB_REQUIRE(force_bn == 0 || force_bn == 128 || force_bn == 256, ASRB_ERR_BAD_ARG);
     g_gemm_force_bn = force_bn;

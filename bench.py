@@ -259,8 +259,11 @@ def main():
     groups = {   # entry point -> (bound, algorithmic work per STEP [FLOP or bytes], note)
         "asrb_rnn_fwd": ("tensor", fl["rec"], "2*T'*B*H*G*2dirs FLOP per layer-launch; latency chain, see DESIGN.md 6"),
         "asrb_rnn_bwd": ("tensor", fl["rec"], "2*T'*B*H*G*2dirs FLOP per layer-launch (dh = dgates W_hh)"),
-        "asrb_gemm_tn": ("tensor", 3 * fl["inproj"] + fl["rec"] + 3 * fl["fc"],
-                         "all GEMM launches of a step: in-proj fwd + dgrad + wgrad, dW_hh, FC fwd + dgrad + wgrad (tf32)"),
+        "asrb_gemm_tn": ("tensor", fl["inproj"] + 3 * fl["fc"],
+                         "the tf32 GEMM launches of a step: in-proj fwd, FC fwd + dgrad + wgrad (tf32 operands run at half "
+                         "the bf16 peak quoted)"),
+        "asrb_gemm_tn_bf16": ("tensor", 2 * fl["inproj"] + fl["rec"],
+                              "the bf16 GEMM launches of a step (gradient-only products): in-proj dgrad + wgrad, dW_hh"),
         "asrb_conv32_fwd": ("tensor", fl["conv2"], "conv2 forward"),
         "asrb_conv32_bwd_data": ("tensor", fl["conv2"], "conv2 input gradient"),
         "asrb_conv32_bwd_weight": ("tensor", fl["conv2"], "conv2 weight gradient"),

@@ -58,6 +58,9 @@ int asrb_version(void);
 const char* asrb_strerror(int code);
 int asrb_set_debug_flags(unsigned flags);
 int asrb_debug_gemm_tile(int force_bn, int gain_pct);
+/* epilogue of the tcgen05 GEMM: 1 (default) staged in shared memory and written by TMA stores (needs ldc % 4 == 0 and a
+ * 16-byte aligned C, else the direct form is used), 0 direct row-per-lane stores; v < 0 queries.  Returns the old value. */
+int asrb_debug_gemm_tma_store(int v);
 
 /* ---------------------------------------------------------------- GEMM (tcgen05, TF32 operands, fp32 accumulate)
  * C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N]).  lda/ldb/ldc are row strides in elements; lda, ldb multiples of 4. */

@@ -71,6 +71,31 @@ def test_gemm_tn_strided_views_and_3x(ops):
     assert report("gemm 3xTF32", out3, ref) <= 2e-5 * math.sqrt(K)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 200, 96), (1000, 2400, 800), (129, 36, 40)])
+def test_gemm_tma_store_epilogue_equals_direct_stores(ops, M, N, K):
+    """the two epilogues (shared-memory staging + TMA store / reduce-add, and direct row-per-lane stores) write the
+    same fp32 values: bit-equal, with bias, in accumulate mode, and clipped at ragged M and N"""
+    from asr_b200 import _lib
+
+    A, B, bias = rnd(M, K, seed=31).to(DEV), rnd(N, K, seed=32).to(DEV), rnd(N, seed=33).to(DEV)
+    C0 = rnd(M, N + 4, seed=34).to(DEV)
+    res = {}
+    try:
+        for mode in (1, 0):
+            _lib.query("asrb_debug_gemm_tma_store", mode)
+            out = ops.gemm_tn(A, B, bias=bias)
+            buf = C0.clone()
+            ops.gemm_tn(A, B, out=buf[:, :N], accumulate=True)
+            bf = ops.gemm_tn_bf16(A.bfloat16(), B.bfloat16(), out=None)
+            torch.cuda.synchronize()
+            res[mode] = (out, buf, bf)
+    finally:
+        _lib.query("asrb_debug_gemm_tma_store", 1)
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[1][1][:, N:], C0[:, N:])           # columns past N untouched
+
+
 def test_gemm_simt_debug_path_and_transpose(ops):
     M, N, K = 200, 130, 70
     A, B = rnd(M, K, seed=6), rnd(N, K, seed=7)
