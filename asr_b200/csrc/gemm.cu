@@ -20,7 +20,7 @@
 namespace asrb {
 
 unsigned g_debug_flags = 0;
-int g_gemm_force_bn = 0, g_gemm_bn256_gain = 118, g_gemm_tma_store = 1;
+int g_gemm_force_bn = 0, g_gemm_bn256_gain = 118, g_gemm_tma_store = 1, g_gemm_cta_limit = 0;
 
 // ------------------------------------------------------------------------------------------------
 // host: tensor map encoding
@@ -325,7 +325,8 @@ static int launch_gemm_tc(const void* A, int lda, const void* B, int ldb, float*
         attr_set = true;
     }
     const int tiles = ceil_div(M, kBM) * ceil_div(N, BN);
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    if (g_gemm_cta_limit > 0 && grid > g_gemm_cta_limit) grid = g_gemm_cta_limit;   // persistent tile loop: any grid works
     gemm_tn_tf32_kernel<BN, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, C, ldc, bias, M, N, K,
                                                                                     flags, tma_store);
     ASRB_LAUNCH_OK();
@@ -526,6 +527,14 @@ int asrb_gemm_tn_bf16(const void* A, int lda, const void* B, int ldb, float* C, 
 
 /* DEBUG / tuning: force the N tile (0 = automatic, 128, 256); gain = assumed speed of the 256-wide tile relative to
  * the 128-wide one in percent (default 118: measured 1.10-1.18 on the configs[1] shapes) */
+/* Caps the number of persistent CTAs of the GEMM launches that follow (0 = no cap; returns the old value): work issued
+ * on a second stream next to a kernel that needs its own SMs (the recurrent chain) must not take all of them. */
+int asrb_gemm_cta_limit(int n) {
+    const int old = g_gemm_cta_limit;
+    if (n >= 0) g_gemm_cta_limit = n;
+    return old;
+}
+
 /* debug/tuning: 1 (default) epilogue through shared memory + TMA stores, 0 direct row-per-lane stores; v < 0 queries */
 int asrb_debug_gemm_tma_store(int v) {
     const int old = g_gemm_tma_store;

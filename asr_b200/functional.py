@@ -214,6 +214,55 @@ def _transpose_padded(a):
     return buf
 
 
+# ----------------------------------------------------------------------------- weight gradients on a side stream
+# The recurrent backward kernel of layer l is a latency chain on ~100 of the 148 SMs; the weight-gradient work of layer
+# l+1 (dW_ih, dW_hh GEMMs with K = T*B, the transposes feeding them, the bias row sums) is not on the critical path,
+# so it is issued on a second stream and fills the idle SMs while the chain runs.  Its results are accumulated into
+# `param.grad` on that stream (the Function returns None for those inputs, the usual AccumulateGrad would read them on
+# the main stream without waiting) and an end-of-backward engine callback makes the main stream wait for the side one,
+# so anything that reads `.grad` after `backward()` returns is ordered behind it.  ASRB_WGRAD_OVERLAP=0 (or
+# functional.WGRAD_OVERLAP = False) restores the plain single-stream form, which is also what runs whenever a weight is
+# not a leaf nn.Parameter.
+import os as _os
+
+WGRAD_OVERLAP = _os.environ.get("ASRB_WGRAD_OVERLAP", "1") != "0"
+WGRAD_CTAS = int(_os.environ.get("ASRB_WGRAD_CTAS", "32"))   # persistent GEMM CTAs of the side stream (0 = all SMs);
+# measured ms/step at configs[1]: overlap off 48.8; on with cap 0 / 24 / 48 / 64: 47.7 / 46.7 / 47.0 / 46.9
+_side_streams = {}
+_pending = []          # tensors the side stream still reads: kept alive until the join
+_join_queued = False
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=key)
+    return _side_streams[key]
+
+
+def _join_side_streams():
+    global _join_queued
+    _join_queued = False
+    for st in _side_streams.values():
+        torch.cuda.current_stream(st.device).wait_stream(st)
+    _pending.clear()
+
+
+def _queue_join():
+    global _join_queued
+    if not _join_queued:
+        _join_queued = True
+        torch.autograd.Variable._execution_engine.queue_callback(_join_side_streams)
+
+
+def _accumulate_grad(param, g):
+    g = g.view_as(param)
+    if param.grad is None:
+        param.grad = g
+    else:
+        param.grad.add_(g)
+
+
 # ----------------------------------------------------------------------------- bidirectional recurrent layer
 class BiRnnLayer(Function):
     """pack_padded_sequence -> 1-layer bidirectional nn.GRU / nn.LSTM -> pad_packed_sequence -> sum of the two
@@ -224,6 +273,9 @@ class BiRnnLayer(Function):
     def forward(ctx, x, lengths_dev, cell, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         T, B, I = x.shape
         G, H = w_hh.shape
+        if _pending:            # a backward pass that died before its end-of-pass callback: join now
+            _join_side_streams()
+        ctx.params = (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         x2 = x.contiguous().view(T * B, I)
         gi = torch.empty(T * B, 2 * G, device=x.device, dtype=torch.float32)
         ops.gemm_tn(x2, w_ih.contiguous(), out=gi[:, :G], bias=b_ih)
@@ -250,10 +302,6 @@ class BiRnnLayer(Function):
         dgi2 = dgi.view(R, 2 * G)
         if dghT is None:      # LSTM: hidden-side gate gradients are the input-side ones
             dghT = dgiT
-        # bias gradients = row sums of the transposed gate gradients
-        db_ih_cat = ops.row_sums(dgiT, R)
-        db_hh_cat = db_ih_cat if dghT is dgiT else ops.row_sums(dghT, R)
-        db_hh = [db_hh_cat[d * G:(d + 1) * G] for d in range(2)]
         # In bf16 mode the recurrent kernel hands the gate gradients over in bf16 and every backward GEMM runs with bf16
         # operands (fp32 accumulate): the loss only depends on the forward pass, which stays tf32.
         lowp = dgi.dtype == torch.bfloat16
@@ -261,6 +309,43 @@ class BiRnnLayer(Function):
             raise ValueError("bf16 recurrent mode needs input and hidden sizes that are multiples of 8")
         gemm = ops.gemm_tn_bf16 if lowp else ops.gemm_tn
         tr = ops.transpose_bf16 if lowp else (lambda a: _transpose_padded(a)[:, :a.shape[0]])
+
+        def weight_grads():
+            # bias gradients = row sums of the transposed gate gradients
+            db_ih_cat = ops.row_sums(dgiT, R)
+            db_hh_cat = db_ih_cat if dghT is dgiT else ops.row_sums(dghT, R)
+            # weight gradients (K = T*B): dW_ih = dgi^T x ; dW_hh = dgh^T h_prev -- the transposed gate gradients come
+            # straight from the recurrent kernel, only x and h_prev are transposed here
+            xt = tr(x2)                                             # [I, R]
+            dw_ih = gemm(dgiT[:G, :R], xt)
+            dw_ih_r = gemm(dgiT[G:, :R], xt)
+            dw_hh = []
+            for d in range(2):
+                # previous state in forward order: slots 0..T-1 for the forward direction, 2..T+1 for the reverse one
+                first = 0 if d == 0 else 2
+                hpt = tr(hseq[d, first:first + T].reshape(R, H))    # [H, R]
+                dw_hh.append(gemm(dghT[d * G:(d + 1) * G, :R], hpt))
+            # in the order of ctx.params: w_ih, w_hh, b_ih, b_hh, then the reverse direction's
+            return (dw_ih, dw_hh[0], db_ih_cat[:G], db_hh_cat[:G], dw_ih_r, dw_hh[1], db_ih_cat[G:], db_hh_cat[G:])
+
+        params = ctx.params
+        overlap = (WGRAD_OVERLAP and dout.is_cuda and all(ctx.needs_input_grad[3:])
+                   and all(isinstance(q, torch.nn.Parameter) and q.is_leaf for q in params))
+        grads = None
+        if overlap:
+            main = torch.cuda.current_stream(dout.device)
+            side = _side_stream(dout.device)
+            ready = main.record_event()
+            _pending.append((dgi, dgiT, dghT, x2, hseq))
+            old_limit = ops.gemm_cta_limit(WGRAD_CTAS)
+            try:
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    for q, g in zip(params, weight_grads()):
+                        _accumulate_grad(q, g)
+            finally:
+                ops.gemm_cta_limit(old_limit)
+            _queue_join()
         # input gradient: dx = dgi_f W_ih_f + dgi_r W_ih_r
         dx = None
         if ctx.needs_input_grad[0]:
@@ -268,18 +353,10 @@ class BiRnnLayer(Function):
             gemm(dgi2[:, :G], tr(w_ih.contiguous()), out=dx)
             gemm(dgi2[:, G:], tr(w_ih_r.contiguous()), out=dx, accumulate=True)
             dx = dx.view(T, B, I)
-        # weight gradients (K = T*B): dW_ih = dgi^T x ; dW_hh = dgh^T h_prev -- the transposed gate gradients come
-        # straight from the recurrent kernel, only x and h_prev are transposed here
-        xt = tr(x2)                                             # [I, R]
-        dw_ih = gemm(dgiT[:G, :R], xt)
-        dw_ih_r = gemm(dgiT[G:, :R], xt)
-        dw_hh = []
-        for d in range(2):
-            # previous state in forward order: slots 0..T-1 for the forward direction, 2..T+1 for the reverse one
-            first = 0 if d == 0 else 2
-            hpt = tr(hseq[d, first:first + T].reshape(R, H))    # [H, R]
-            dw_hh.append(gemm(dghT[d * G:(d + 1) * G, :R], hpt))
-        return (dx, None, None, dw_ih, dw_hh[0], db_ih_cat[:G], db_hh[0], dw_ih_r, dw_hh[1], db_ih_cat[G:], db_hh[1])
+        if overlap:
+            return (dx,) + (None,) * 10
+        grads = weight_grads()
+        return (dx, None, None) + grads
 
 
 # ----------------------------------------------------------------------------- log_softmax / CTC / argmax

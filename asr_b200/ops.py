@@ -103,6 +103,11 @@ def gemm_tn(A, B, out=None, bias=None, accumulate=False):
     return out
 
 
+def gemm_cta_limit(n):
+    """cap the persistent CTAs of the GEMM launches that follow (0 = no cap); returns the previous cap"""
+    return _lib.query("asrb_gemm_cta_limit", int(n))
+
+
 def gemm_tn_bf16(A, B, out=None, bias=None, accumulate=False):
     """out[M,N] fp32 (+)= A[M,K] @ B[N,K]^T with bf16 operands (row strides multiples of 8 elements)."""
     for t in (A, B):

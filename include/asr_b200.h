@@ -58,6 +58,9 @@ int asrb_version(void);
 const char* asrb_strerror(int code);
 int asrb_set_debug_flags(unsigned flags);
 int asrb_debug_gemm_tile(int force_bn, int gain_pct);
+/* Caps the persistent CTAs of the GEMM launches that follow (0 = no cap, n < 0 queries); returns the old value.  For
+ * work issued on a second stream beside a kernel that needs its own SMs (asr_b200/functional.py, weight gradients). */
+int asrb_gemm_cta_limit(int n);
 /* epilogue of the tcgen05 GEMM: 1 (default) staged in shared memory and written by TMA stores (needs ldc % 4 == 0 and a
  * 16-byte aligned C, else the direct form is used), 0 direct row-per-lane stores; v < 0 queries.  Returns the old value. */
 int asrb_debug_gemm_tma_store(int v);

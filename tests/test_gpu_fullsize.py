@@ -147,3 +147,46 @@ def test_ctc_full_size_against_the_cuda_criterion(T, N, C, U):
     gerr = (grad - lp_ref.grad).abs().max().item()
     assert gerr <= (3e-2 if T >= 2000 else 1e-3), gerr           # two fp32 log-space DPs at |nll| ~ 1.6e4 resp. ~ 1e3
     del offs
+
+
+def test_side_stream_weight_gradients_match_single_stream():
+    """functional.WGRAD_OVERLAP: the weight-gradient work of the recurrent layers issued on a second stream (under the
+    next layer's recurrent backward kernel) gives the gradients of the single-stream form -- same kernels, same
+    inputs, so bit-equal wherever the kernels are deterministic (the conv weight gradients use fp32 atomics) -- also
+    when `.grad` already exists (accumulation into a flat bucket's views)."""
+    from asr_b200 import functional as F_
+    from asr_b200.distributed import FlatGradBucket
+
+    cfg = dict(bench.CFG, layers=3)
+    model = bench.build_model(cfg, torch.device(DEV)).train()
+    batch, _ = _ragged_batch(cfg["B"], 601, 50, cfg["C"], seed=79)
+    old = F_.WGRAD_OVERLAP
+    try:
+        F_.WGRAD_OVERLAP = False
+        l0, g0 = _step(model, batch)
+        F_.WGRAD_OVERLAP = True
+        for _ in range(3):
+            l1, g1 = _step(model, batch)
+            assert l1 == l0
+            for k, ref in g0.items():
+                if ".rnn." in k:
+                    assert torch.equal(g1[k], ref), k
+                else:
+                    assert (g1[k] - ref).norm().item() <= 1e-5 * max(ref.norm().item(), 1e-30), k
+        # existing .grad tensors (views of a flat buffer): accumulated in place on the side stream
+        for p in model.parameters():
+            p.grad = None
+        bucket = FlatGradBucket(list(model.parameters()))
+        bucket.zero()
+        from asr_b200.trainers import CTCLoss, fit
+        x = batch[0].to(DEV)
+        _, loss, _ = fit(model, CTCLoss(reduction="sum"), (x, batch[1], batch[2], batch[3]), DEV)
+        loss.backward()
+        torch.cuda.synchronize()
+        for k, p in model.named_parameters():
+            if ".rnn." in k:
+                assert torch.equal(p.grad, g0[k]), k
+    finally:
+        F_.WGRAD_OVERLAP = old
+        for p in model.parameters():
+            p.grad = None
