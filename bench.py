@@ -146,7 +146,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "data": "synthetic",
             "config": {"workload": workload, "global_batch": cfg["B"] * max(args.gpus, 1), "frames": cfg["T"],
-                       "optimizer_step": "excluded (metric is fwd-bwd)", "l2_policy": "activations (GBs) far exceed the 126 MB L2"}}
+                       "optimizer_step": "excluded (metric is fwd-bwd)", "l2_policy": "activations (GBs) far exceed the 126 MB L2",
+                       "streams": "weight gradients of the recurrent layers on a second stream (value, e2e); the "
+                                  "per-kernel rooflines are timed in a separate single-stream pass"}}
 
     if args.impl == "reference":
         if rank != 0:
@@ -241,7 +243,12 @@ def main():
     ms_e2e, _, _, _ = timed(pinned, args.steps)          # host buffers: pinned H2D + loss D2H inside the region
     # separate, untimed-for-the-metric pass with a CUDA-event pair around every C-ABI call (the event records cost ~2 ms
     # of host time per step, which would otherwise leak into `value`): per-kernel device times for the rooflines
+    # -- also with the side-stream overlap of the weight gradients switched off, so that every kernel is timed running
+    # alone (what a roofline fraction means); `value` and `e2e` above are measured with the overlap on
+    from asr_b200 import functional as F_
+    overlap, F_.WGRAD_OVERLAP = F_.WGRAD_OVERLAP, False
     _, _, _, prof = timed(resident, args.steps, profile=True)
+    F_.WGRAD_OVERLAP = overlap
     clocks = sampler.stop() if sampler else None
     if rank != 0:
         if world > 1:
