@@ -280,8 +280,14 @@ class BiRnnLayer(Function):
         ctx.params = (w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         x2 = x.contiguous().view(T * B, I)
         gi = torch.empty(T * B, 2 * G, device=x.device, dtype=torch.float32)
-        ops.gemm_tn(x2, w_ih.contiguous(), out=gi[:, :G], bias=b_ih)
-        ops.gemm_tn(x2, w_ih_r.contiguous(), out=gi[:, G:], bias=b_ih_r)
+        # both directions in ONE product (N = 2G): the weights and biases are laid side by side first (D2D memcpys)
+        w_cat = torch.empty(2 * G, I, device=x.device, dtype=torch.float32)
+        w_cat[:G].copy_(w_ih)
+        w_cat[G:].copy_(w_ih_r)
+        b_cat = torch.empty(2 * G, device=x.device, dtype=torch.float32)
+        b_cat[:G].copy_(b_ih)
+        b_cat[G:].copy_(b_ih_r)
+        ops.gemm_tn(x2, w_cat, out=gi, bias=b_cat)
         w_hh, w_hh_r = w_hh.contiguous(), w_hh_r.contiguous()
         pack_f, _ = ops.rnn_pack_weights(cell, w_hh, w_hh_r, B, fwd=True, bwd=False)
         b_hh2 = torch.empty(2, G, device=x.device, dtype=torch.float32)   # two D2D memcpys, no arithmetic
@@ -352,8 +358,14 @@ class BiRnnLayer(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(R, I, device=dout.device, dtype=torch.float32)
-            gemm(dgi2[:, :G], tr(w_ih.contiguous()), out=dx)
-            gemm(dgi2[:, G:], tr(w_ih_r.contiguous()), out=dx, accumulate=True)
+            if lowp:    # one product with K = 2G: [dgi_f | dgi_r] . [W_f ; W_r], the transposed weights side by side
+                wt = torch.empty(I, 2 * G, device=dout.device, dtype=torch.bfloat16)
+                ops.transpose_bf16(w_ih.contiguous(), out=wt[:, :G])
+                ops.transpose_bf16(w_ih_r.contiguous(), out=wt[:, G:])
+                gemm(dgi2, wt, out=dx)
+            else:
+                gemm(dgi2[:, :G], tr(w_ih.contiguous()), out=dx)
+                gemm(dgi2[:, G:], tr(w_ih_r.contiguous()), out=dx, accumulate=True)
             dx = dx.view(T, B, I)
         if overlap:
             return (dx,) + (None,) * 10

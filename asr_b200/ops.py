@@ -123,9 +123,15 @@ def gemm_tn_bf16(A, B, out=None, bias=None, accumulate=False):
     return out
 
 
-def transpose_bf16(x):
-    """x [R, C] fp32 -> x^T in bf16 as a [C, R] view of a [C, R8] buffer (row stride multiple of 8 elements)."""
+def transpose_bf16(x, out=None):
+    """x [R, C] fp32 -> x^T in bf16 as a [C, R] view of a [C, R8] buffer (row stride multiple of 8 elements), or into
+    `out` ([C, R] bf16 view whose row stride is a multiple of 8 elements)."""
     R, C = x.shape
+    if out is not None:
+        if out.dtype != torch.bfloat16 or tuple(out.shape) != (C, R) or out.stride(1) != 1 or out.stride(0) % 8:
+            raise ValueError("transpose_bf16: out must be a [C, R] bf16 view with unit inner stride and a row stride % 8 == 0")
+        _call("asrb_transpose_bf16", _p(x), R, C, _ld(x), _p(out), out.stride(0))
+        return out
     R8 = (R + 7) // 8 * 8
     buf = torch.empty(C, R8, device=x.device, dtype=torch.bfloat16)
     _call("asrb_transpose_bf16", _p(x), R, C, _ld(x), _p(buf), R8)

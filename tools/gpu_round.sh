@@ -10,7 +10,8 @@ for w in $what; do
     bench)    timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit=$?"; cat gpurun_out/bench.json ;;
     kernels)  timeout 600 python tools/bench_kernels.py > gpurun_out/kernels.json 2> gpurun_out/kernels.err; echo "kernels exit=$?"; cat gpurun_out/kernels.json ;;
     launches)
-              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+              # single-stream form (ncu serialises the launches anyway): the same pass bench.py times its rooflines in
+              ASRB_WGRAD_OVERLAP=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
                 --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/launches.log 2>&1; echo "launches exit=$?" ;;
     full)
               # one fwd + one bwd recurrent launch, two GEMMs (tf32 in-proj, bf16 backward), the CTC kernels: full shape

@@ -31,7 +31,7 @@ def launches(src, dst):
         a[1] += ms
     tot = sum(a[1] for a in agg.values())
     with open(dst, "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none: one training step (tools/profile_step.py)\n")
+        f.write(f"# ASRB_WGRAD_OVERLAP=0 ncu --metrics gpu__time_duration.sum --clock-control none: one training step, single stream (tools/profile_step.py)\n")
         f.write(f"# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write(f"# total {tot:.3f} ms over {sum(a[0] for a in agg.values())} launches\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
