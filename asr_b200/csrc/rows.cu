@@ -403,3 +403,118 @@ extern "C" int asrb_greedy_collapse(const long long* argmax, const int32_t* size
     ASRB_LAUNCH_OK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Lookahead convolution: asr_deepspeech/modules/blocks.py:96-121 -- a depthwise Conv1d over
+// time with `context` taps looking AHEAD, zero padded at the end: y[t,n,f] = sum_k w[f,k] x[t+k,n,f], on [T,N,H]
+// activations, with the Hardtanh(0,20) that follows it in the unidirectional model (deepspeech.py:94-101) fused.
+// HBM-bound: x is read once from DRAM (the `context` re-reads of a 256-column strip hit L1/L2), y written once.
+// ------------------------------------------------------------------------------------------------
+namespace asrb {
+constexpr int kLaChunk = 32;   // time steps per block
+
+__global__ void __launch_bounds__(256)
+lookahead_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int T, int NH, int H,
+                     int ctx, int has_act, float lo, float hi) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= NH) return;
+    const float* wf = w + (size_t)(c % H) * ctx;
+    const int t1 = min(T, (int)(blockIdx.y + 1) * kLaChunk);
+    for (int t = blockIdx.y * kLaChunk; t < t1; ++t) {
+        float acc = 0.f;
+        const int kmax = min(ctx, T - t);
+        for (int k = 0; k < kmax; ++k) acc = fmaf(__ldg(wf + k), __ldg(x + (size_t)(t + k) * NH + c), acc);
+        if (has_act) acc = fminf(fmaxf(acc, lo), hi);
+        y[(size_t)t * NH + c] = acc;
+    }
+}
+
+// gradient entering the convolution: dy where the clamp was inactive (hardtanh_backward: 0 where the input was <= lo or
+// >= hi, i.e. where the OUTPUT sits on a bound)
+__device__ __forceinline__ float la_gate(const float* __restrict__ dy, const float* __restrict__ y, size_t i, int has_act,
+                                         float lo, float hi) {
+    const float g = __ldg(dy + i);
+    if (!has_act) return g;
+    const float v = __ldg(y + i);
+    return (v > lo && v < hi) ? g : 0.f;
+}
+
+// dx[t,c] = sum_k w[f,k] g[t-k,c]
+__global__ void __launch_bounds__(256)
+lookahead_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ w,
+                          float* __restrict__ dx, int T, int NH, int H, int ctx, int has_act, float lo, float hi) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= NH) return;
+    const float* wf = w + (size_t)(c % H) * ctx;
+    const int t1 = min(T, (int)(blockIdx.y + 1) * kLaChunk);
+    for (int t = blockIdx.y * kLaChunk; t < t1; ++t) {
+        float acc = 0.f;
+        const int kmax = min(ctx, t + 1);
+        for (int k = 0; k < kmax; ++k) acc = fmaf(__ldg(wf + k), la_gate(dy, y, (size_t)(t - k) * NH + c, has_act, lo, hi), acc);
+        dx[(size_t)t * NH + c] = acc;
+    }
+}
+
+// dw[f,k] = sum_{t,n} g[t,n,f] x[t+k,n,f].  Block = 32 features x 8 warps striding the batch, one time chunk; the 8
+// partial sums of a (feature, tap) meet in shared memory and ONE atomic per block goes to dw.
+__global__ void __launch_bounds__(256)
+lookahead_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+                            float* __restrict__ dw, int T, int N, int H, int ctx, int has_act, float lo, float hi) {
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + lane;
+    const int t0 = blockIdx.y * kLaChunk, t1 = min(T, t0 + kLaChunk);
+    const size_t NH = (size_t)N * H;
+    for (int k = 0; k < ctx; ++k) {
+        float s = 0.f;
+        if (f < H) {
+            for (int n = warp; n < N; n += 8) {
+                const size_t col = (size_t)n * H + f;
+                for (int t = t0; t < t1 && t + k < T; ++t)
+                    s = fmaf(la_gate(dy, y, (size_t)t * NH + col, has_act, lo, hi), __ldg(x + (size_t)(t + k) * NH + col), s);
+            }
+        }
+        part[warp][lane] = s;
+        __syncthreads();
+        if (warp == 0 && f < H) {
+            float tot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += part[i][lane];
+            atomicAdd(dw + (size_t)f * ctx + k, tot);
+        }
+        __syncthreads();
+    }
+}
+}  // namespace asrb
+
+extern "C" int asrb_lookahead_fwd(const float* x, const float* w, float* y, int T, int N, int H, int context, int has_act,
+                                  float lo, float hi, asrb_stream_t stream) {
+    ASRB_REQUIRE(x && w && y && T > 0 && N > 0 && H > 0 && context > 0, ASRB_ERR_BAD_ARG);
+    const long long NH = (long long)N * H;
+    ASRB_REQUIRE(NH < (1LL << 31) && asrb::ceil_div(T, asrb::kLaChunk) <= 65535, ASRB_ERR_UNSUPPORTED);
+    dim3 grid((unsigned)asrb::ceil_div((int)NH, 256), (unsigned)asrb::ceil_div(T, asrb::kLaChunk));
+    asrb::lookahead_fwd_kernel<<<grid, 256, 0, stream>>>(x, w, y, T, (int)NH, H, context, has_act, lo, hi);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+/* y: the forward OUTPUT (only read when has_act); dx and/or dw may be NULL; dw [H, context] is overwritten */
+extern "C" int asrb_lookahead_bwd(const float* dy, const float* x, const float* y, const float* w, float* dx, float* dw, int T,
+                                  int N, int H, int context, int has_act, float lo, float hi, asrb_stream_t stream) {
+    ASRB_REQUIRE(dy && x && w && (y || !has_act) && T > 0 && N > 0 && H > 0 && context > 0, ASRB_ERR_BAD_ARG);
+    const long long NH = (long long)N * H;
+    ASRB_REQUIRE(NH < (1LL << 31) && asrb::ceil_div(T, asrb::kLaChunk) <= 65535, ASRB_ERR_UNSUPPORTED);
+    const unsigned chunks = (unsigned)asrb::ceil_div(T, asrb::kLaChunk);
+    if (dx) {
+        dim3 grid((unsigned)asrb::ceil_div((int)NH, 256), chunks);
+        asrb::lookahead_bwd_data_kernel<<<grid, 256, 0, stream>>>(dy, y, w, dx, T, (int)NH, H, context, has_act, lo, hi);
+        ASRB_LAUNCH_OK();
+    }
+    if (dw) {
+        ASRB_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)H * context * sizeof(float), stream));
+        dim3 grid((unsigned)asrb::ceil_div(H, 32), chunks);
+        asrb::lookahead_bwd_weight_kernel<<<grid, 256, 0, stream>>>(dy, y, x, dw, T, N, H, context, has_act, lo, hi);
+        ASRB_LAUNCH_OK();
+    }
+    return 0;
+}

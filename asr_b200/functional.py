@@ -373,6 +373,31 @@ class BiRnnLayer(Function):
         return (dx, None, None) + grads
 
 
+# ----------------------------------------------------------------------------- lookahead convolution
+class LookaheadConv(Function):
+    """asr_deepspeech/modules/blocks.py:96-121 on [T,N,H] (+ the Hardtanh that follows it at deepspeech.py:94-101 when
+    act=(lo,hi)); weight is conv.weight [H,1,context]."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x, weight, context, act):
+        x = x.contiguous()
+        w2 = weight.contiguous().view(weight.shape[0], context)
+        y = ops.lookahead_fwd(x, w2, context, act)
+        ctx.save_for_backward(x, y, w2)
+        ctx.meta = (context, act, weight.shape)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    @_amp_bwd
+    def backward(ctx, dy):
+        x, y, w2 = ctx.saved_tensors
+        context, act, wshape = ctx.meta
+        dx, dw = ops.lookahead_bwd(dy.contiguous(), x, y, w2, context, act, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dx, (dw.view(wshape) if dw is not None else None), None, None
+
+
 # ----------------------------------------------------------------------------- log_softmax / CTC / argmax
 class LogSoftmaxLastDim(Function):
     """x.float().log_softmax(-1) (trainers/deepspeech_trainer.py:109-110)."""

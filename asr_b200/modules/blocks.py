@@ -148,23 +148,26 @@ class BatchRNN(nn.Module):
 
     def forward(self, x, output_lengths):
         _need_cuda(x, "BatchRNN")
-        if not self._bidirectional:
-            raise NotImplementedError("asr_b200.BatchRNN: only bidirectional=True has a kernel (every BASELINE "
-                                      "configuration is bidirectional; SURVEY.md section 2)")
         if self.batch_norm is not None:
             x = self.batch_norm(x)
         ldev = _lengths_dev(output_lengths, x.device)
         r = self.rnn
-        y = F_.BiRnnLayer.apply(x, ldev, self._cell, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0,
-                                r.weight_ih_l0_reverse, r.weight_hh_l0_reverse, r.bias_ih_l0_reverse,
-                                r.bias_hh_l0_reverse)
+        if self._bidirectional:
+            rev = (r.weight_ih_l0_reverse, r.weight_hh_l0_reverse, r.bias_ih_l0_reverse, r.bias_hh_l0_reverse)
+        else:
+            # Unidirectional layer on the two-direction kernel: a reverse direction whose weights and biases are all
+            # zero keeps its state at exactly 0 (GRU: n = tanh(0) = 0, h' = z h = 0; LSTM: g = 0, c' = f c = 0,
+            # h' = o tanh(0) = 0), so the sum of the directions IS the forward direction.  The two directions run on
+            # different SMs at the same time, so this costs SMs, not time.
+            rev = tuple(torch.zeros_like(t) for t in (r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0))
+        y = F_.BiRnnLayer.apply(x, ldev, self._cell, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, *rev)
         t_max = int(torch.as_tensor(output_lengths).max())
         return y[:t_max] if t_max < y.size(0) else y   # pad_packed_sequence trims to the longest sequence
 
 
 class Lookahead(nn.Module):
-    """asr_deepspeech/modules/blocks.py:96-132 (Wang et al. 2016).  Parameter container only: the unidirectional
-    model variant is outside this round's hot path, so forward raises."""
+    """asr_deepspeech/modules/blocks.py:96-132 (Wang et al. 2016): depthwise convolution over time looking `context`
+    frames ahead, [T,N,H] -> [T,N,H].  `self.conv` keeps the reference's parameter (conv.weight [H,1,context])."""
 
     def __init__(self, n_features, context):
         super().__init__()
@@ -175,8 +178,10 @@ class Lookahead(nn.Module):
         self.conv = nn.Conv1d(self.n_features, self.n_features, kernel_size=self.context, stride=1,
                               groups=self.n_features, padding=0, bias=None)
 
-    def forward(self, x):
-        raise NotImplementedError("asr_b200.Lookahead has no sm_100a kernel yet (bidirectional=False is out of scope)")
+    def forward(self, x, act=None):
+        """act=(lo, hi): also apply the Hardtanh that follows this layer in the model (one fused pass)"""
+        _need_cuda(x, "Lookahead")
+        return F_.LookaheadConv.apply(x, self.conv.weight, self.context, act)
 
     def __repr__(self):
         return f"{self.__class__.__name__}(n_features={self.n_features}, context={self.context})"

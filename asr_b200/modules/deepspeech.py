@@ -105,7 +105,8 @@ class DeepSpeech(nn.Module):
         for rnn in self.rnns:
             x = rnn(x, output_lengths)
         if not self.bidirectional:
-            x = self.lookahead(x)
+            la, act = self.lookahead[0], self.lookahead[1]       # Lookahead + Hardtanh(0, 20): one fused pass
+            x = la(x, act=(float(act.min_val), float(act.max_val)))
         x = self.fc(x)
         x = x.transpose(0, 1)
         x = self.inference_softmax(x)

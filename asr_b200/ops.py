@@ -571,6 +571,28 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
           float(beta2), float(eps), float(weight_decay), int(step), _p(inv_scale))
 
 
+# ----------------------------------------------------------------------------- lookahead convolution
+def lookahead_fwd(x, w, context, act=None):
+    """x [T,N,H], w [H,context] -> y[t,n,f] = sum_k w[f,k] x[t+k,n,f] (zero past T), optionally clamped to act=(lo,hi)"""
+    _chk(x, w)
+    T, N, H = x.shape
+    y = torch.empty_like(x)
+    lo, hi = act if act is not None else (0.0, 0.0)
+    _call("asrb_lookahead_fwd", _p(x), _p(w), _p(y), T, N, H, context, int(act is not None), float(lo), float(hi))
+    return y
+
+
+def lookahead_bwd(dy, x, y, w, context, act=None, need_dx=True, need_dw=True):
+    _chk(dy, x, y, w)
+    T, N, H = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty(H, context, device=x.device, dtype=torch.float32) if need_dw else None
+    lo, hi = act if act is not None else (0.0, 0.0)
+    _call("asrb_lookahead_bwd", _p(dy), _p(x), _p(y), _p(w), _p(dx), _p(dw), T, N, H, context, int(act is not None),
+          float(lo), float(hi))
+    return dx, dw
+
+
 # ----------------------------------------------------------------------------- spectrogram
 def dft_basis(n_fft, device):
     basis = torch.empty(2 * (n_fft // 2 + 1), 3 * n_fft, device=device, dtype=torch.float32)

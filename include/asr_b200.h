@@ -221,6 +221,16 @@ int asrb_ctc_bwd(const float* log_probs, const int32_t* targets, const int32_t* 
 int asrb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr, double beta1,
                     double beta2, double eps, double weight_decay, int step, const float* inv_scale, asrb_stream_t stream);
 
+/* ---------------------------------------------------------------- Lookahead convolution
+ * modules/blocks.py:96-121: depthwise Conv1d over time with `context` taps looking ahead (zero padding at the end) on
+ * [T,N,H] activations: y[t,n,f] = sum_k w[f,k] x[t+k,n,f]; w is conv.weight [H,1,context].  has_act fuses the
+ * Hardtanh(lo,hi) that follows it in the unidirectional model (modules/deepspeech.py:94-101).  Backward: y is the
+ * forward output (read only when has_act); dx and/or dw may be NULL; dw [H,context] is overwritten. */
+int asrb_lookahead_fwd(const float* x, const float* w, float* y, int T, int N, int H, int context, int has_act,
+                       float lo, float hi, asrb_stream_t stream);
+int asrb_lookahead_bwd(const float* dy, const float* x, const float* y, const float* w, float* dx, float* dw, int T,
+                       int N, int H, int context, int has_act, float lo, float hi, asrb_stream_t stream);
+
 /* ---------------------------------------------------------------- spectrogram (STFT -> |.| -> log1p -> normalise) */
 size_t asrb_spectrogram_workspace_bytes(int B, int max_samples, int n_fft, int hop);
 int asrb_dft_basis(float* basis_cat /* [2*(n_fft/2+1), 3*n_fft] */, int n_fft, asrb_stream_t stream);

@@ -17,6 +17,7 @@ Reference entry points exercised (all imported unmodified, see reference_loader.
 from __future__ import annotations
 
 import os
+import sys
 import tempfile
 from types import SimpleNamespace
 
@@ -205,9 +206,52 @@ def misc_cases():
     print("misc: seq_lens sample", seq[[100, 1000, 1500, 2000]].tolist())
 
 
+def reference_checkpoint(model, optimizer, scheduler=None, epoch=3, metrics=None):
+    """the dict DeepSpeechTrainer.save() writes (trainers/deepspeech_trainer.py:176-188)"""
+    return {"epoch": epoch, "metrics": metrics if metrics is not None else {"wer": 0.5, "cer": 0.25},
+            "optimizer": optimizer.state_dict(), "scheduler": scheduler, "state_dict": model.state_dict()}
+
+
+def reference_optimizer(model):
+    """trainers/__main__.py:41-47 with config.yml:41-47"""
+    return torch.optim.AdamW(model.parameters(), lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+
+
+def fake_grads(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    for p in model.parameters():
+        p.grad = torch.randn(p.shape, generator=g) * 0.01
+
+
+def checkpoint_manifest():
+    """Structure of a checkpoint written from the unmodified reference model after two AdamW steps: parameter order,
+    state_dict keys/shapes/dtypes, optimizer state layout -- a few KB instead of the 3 MB file itself
+    (tests/test_host_logic.py regenerates the real file from /root/reference when it is present)."""
+    model = build_reference_model("gru", 8, 2, LABELS29[:26])
+    opt = reference_optimizer(model)
+    for s in (1, 2):
+        fake_grads(model, s)
+        opt.step()
+    ck = reference_checkpoint(model, opt)
+    osd = ck["optimizer"]
+    man = dict(ckpt_keys=sorted(ck.keys()),
+               param_order=[k for k, _ in model.named_parameters()],
+               state_dict=[(k, tuple(v.shape), str(v.dtype)) for k, v in ck["state_dict"].items()],
+               opt_group_keys=sorted(k for k in osd["param_groups"][0].keys()),
+               opt_group_params=list(osd["param_groups"][0]["params"]),
+               opt_state_keys=sorted(osd["state"][0].keys()),
+               opt_step_type=type(osd["state"][0]["step"]).__name__,
+               digest={k: checksum(v.float()) for k, v in ck["state_dict"].items() if v.dtype.is_floating_point})
+    torch.save(man, os.path.join(GOLDEN_DIR, "ref_checkpoint_manifest.pt"))
+    print("checkpoint manifest:", len(man["param_order"]), "parameters,", len(man["state_dict"]), "state_dict entries")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        checkpoint_manifest()
+        return
     torch.set_num_threads(os.cpu_count())
     misc_cases()
     ctc_cases()

@@ -376,6 +376,25 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
     param.addcdiv_(exp_avg, denom, value=-lr / (1 - beta1 ** step))
 
 
+def lookahead_fwd(x, w, context, act=None):
+    T = x.shape[0]
+    y = torch.zeros_like(x)
+    for k in range(min(context, T)):
+        y[:T - k] += w[:, k] * x[k:]
+    return y.clamp(act[0], act[1]) if act is not None else y
+
+
+def lookahead_bwd(dy, x, y, w, context, act=None, need_dx=True, need_dw=True):
+    T = x.shape[0]
+    g = dy if act is None else dy * ((y > act[0]) & (y < act[1])).to(dy.dtype)
+    dx = torch.zeros_like(x)
+    dw = torch.zeros_like(w)
+    for k in range(min(context, T)):
+        dx[k:] += w[:, k] * g[:T - k]
+        dw[:, k] = (g[:T - k] * x[k:]).sum((0, 1))
+    return (dx if need_dx else None), (dw if need_dw else None)
+
+
 def dft_basis(n_fft, device):
     Fb = n_fft // 2 + 1
     n = torch.arange(n_fft, dtype=torch.float64)

@@ -458,3 +458,28 @@ def test_greedy_collapse_matches_host_loop(ops):
             k = int(counts[n])
             assert k == len(want_l)
             assert labels[n, :k].tolist() == want_l and offsets[n, :k].tolist() == want_o
+
+
+# ----------------------------------------------------------------------------- lookahead convolution (8f n4)
+@pytest.mark.parametrize("T,N,H,ctx", [(9, 3, 12, 5), (70, 5, 100, 20), (33, 2, 40, 1), (4, 2, 8, 20)])
+def test_lookahead_fwd_bwd_vs_conv1d(ops, T, N, H, ctx):
+    """kernels vs the reference formulation (blocks.py:123-128: pad (0, ctx-1) + depthwise conv1d) in fp64, with and
+    without the fused Hardtanh(0, 20)"""
+    x = (rnd(T, N, H, seed=41) * 8).requires_grad_(True)
+    w = (rnd(H, 1, ctx, seed=42) * 0.5).requires_grad_(True)
+    gy = rnd(T, N, H, seed=43)
+    for act in (None, (0.0, 20.0)):
+        x.grad = w.grad = None
+        h = F.pad(x.double().transpose(0, 1).transpose(1, 2), (0, ctx - 1))
+        ref = F.conv1d(h, w.double(), groups=H).transpose(1, 2).transpose(0, 1)
+        if act is not None:
+            ref = F.hardtanh(ref, *act)
+        ref.backward(gy.double())
+        xd, wd = x.detach().to(DEV), w.detach().to(DEV).view(H, ctx).contiguous()
+        y = ops.lookahead_fwd(xd, wd, ctx, act)
+        dx, dw = ops.lookahead_bwd(gy.to(DEV), xd, y, wd, ctx, act)
+        torch.cuda.synchronize()
+        assert report(f"lookahead fwd act={act}", y, ref.detach()) <= 1e-4
+        # a clamp decision can differ from fp64 only where the pre-activation is within rounding of a bound
+        assert report(f"lookahead dx act={act}", dx, x.grad) <= (1e-4 if act is None else 1e-4)
+        assert report(f"lookahead dw act={act}", dw.view(H, 1, ctx), w.grad) <= 1e-3

@@ -199,3 +199,105 @@ def test_fused_adamw_matches_torch_adamw(tmp_path, golden):
     sched = torch.optim.lr_scheduler.StepLR(our_opt, step_size=1, gamma=0.5)
     sched.step()
     assert abs(our_opt.param_groups[0]["lr"] - 0.75e-4) < 1e-12
+
+
+def test_gpu_batch_assembler_from_waveforms(tmp_path, golden):
+    """waveforms -> (STFT kernels) -> padded batch on the device, equal to the reference's
+    parse_audio + _collate_fn (oracle restatement) and consumable by fit()."""
+    import numpy as np
+    from oracle import explicit
+    from asr_b200.data import GpuBatchAssembler
+    from asr_b200.trainers import CTCLoss, fit
+
+    rng = np.random.default_rng(5)
+    lens = [9000, 16000, 16050, 5000]
+    batch = [((rng.standard_normal(n) * 0.2).astype(np.float32), [int(t) for t in rng.integers(1, 26, size=4)]) for n in lens]
+    asm = GpuBatchAssembler(audio_conf=audio_conf(), device=DEV)
+    inputs, targets, pct, tsz = asm(batch)
+    assert inputs.is_cuda and inputs.shape == (4, 1, 161, 101)
+    order = sorted(range(4), key=lambda i: 1 + lens[i] // 160, reverse=True)
+    assert order == [1, 2, 0, 3]
+    for x, i in enumerate(order):
+        ref = explicit.spectrogram(batch[i][0], normalize=True)
+        nf = ref.shape[1]
+        assert (inputs[x, 0, :, :nf].cpu() - ref).abs().max().item() <= 2e-4
+        assert nf == 101 or inputs[x, 0, :, nf:].abs().max().item() == 0
+        assert abs(pct[x].item() - nf / 101.0) < 1e-7
+    assert targets.tolist() == [t for i in order for t in batch[i][1]] and tsz.tolist() == [4] * 4
+    g = dict(golden("gru_small"))
+    g.update(hidden=32, layers=1, C=26)
+    model, _ = build_model(tmp_path, g)
+    model.train()
+    valid, loss, loss_value = fit(model, CTCLoss(reduction="sum"), (inputs, targets, pct, tsz), DEV)
+    assert valid and loss_value > 0
+    loss.backward()
+    torch.cuda.synchronize()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("cell", ["gru", "lstm"])
+def test_unidirectional_model_with_lookahead(tmp_path, cell):
+    """bidirectional=False (the one reference model variant besides the bidirectional ones, deepspeech.py:75-101):
+    unidirectional BatchRNN stack + Lookahead + Hardtanh against plain torch modules with the same weights
+    (blocks.py:84-93 and :123-128 restated), on the fp32 debug path (tight) and the tensor-core path."""
+    import pandas as pd
+    from asr_b200 import ops
+    from asr_b200.modules import DeepSpeech
+
+    path = os.path.join(tmp_path, "labels.csv")
+    pd.DataFrame({"label": LABELS29[:26]}).to_csv(path, index=False)
+    torch.manual_seed(21)
+    model = DeepSpeech(audio_conf=audio_conf(), decoder=None, label_path=path, rnn_type=f"nn.{cell.upper()}",
+                       rnn_hidden_size=32, rnn_hidden_layers=2, bidirectional=False, context=6).to(DEV)
+    assert "lookahead.0.conv.weight" in model.state_dict() and "rnns.0.rnn.weight_ih_l0_reverse" not in model.state_dict()
+    x = torch.randn(3, 1, 161, 81)
+    lens = torch.tensor([81, 60, 33], dtype=torch.int32)
+
+    def reference(m, x, lens):                                    # deepspeech.py:130-149 with torch's own modules
+        out_len = m.get_seq_lens(lens)
+        h = x
+        for mod in m.conv.seq_module:
+            h = mod(h)
+            mask = torch.arange(h.size(3))[None, :] >= out_len[:, None]
+            h = h.masked_fill(mask[:, None, None, :], 0)
+        h = h.view(h.size(0), h.size(1) * h.size(2), h.size(3)).transpose(1, 2).transpose(0, 1).contiguous()
+        for r in m.rnns:
+            if r.batch_norm is not None:
+                t, n = h.size(0), h.size(1)
+                h = r.batch_norm.module(h.view(t * n, -1)).view(t, n, -1)
+            pk = torch.nn.utils.rnn.pack_padded_sequence(h, out_len)
+            h, _ = torch.nn.utils.rnn.pad_packed_sequence(r.rnn(pk)[0])
+        la = m.lookahead[0]
+        h = torch.nn.functional.pad(h.transpose(0, 1).transpose(1, 2), (0, la.context - 1))
+        h = torch.nn.functional.hardtanh(la.conv(h).transpose(1, 2).transpose(0, 1).contiguous(), 0, 20)
+        t, n = h.size(0), h.size(1)
+        h = m.fc[0].module(h.view(t * n, -1)).view(t, n, -1)
+        return h.transpose(0, 1), out_len
+
+    import copy
+    cpu = copy.deepcopy(model).cpu().eval()
+    with torch.no_grad():
+        ref, ref_len = reference(cpu, x, lens)
+    model.eval()
+    for flags, tol in ((7, 2e-4), (0, 3e-2)):
+        ops.set_debug_flags(flags)
+        try:
+            with torch.no_grad():
+                out, out_len = model.forward(x.to(DEV), lens)
+        finally:
+            ops.set_debug_flags(0)
+        assert out_len.tolist() == ref_len.tolist()
+        got = out.cpu()
+        refp = ref.softmax(-1)
+        for n, tn in enumerate(out_len.tolist()):
+            err = (got[n, :tn] - refp[n, :tn]).abs().max().item()
+            assert err <= tol, (flags, n, err)
+    # training step runs and reaches every parameter
+    from asr_b200.trainers import CTCLoss, fit
+    model.train()
+    tg = torch.randint(1, 26, (9,), dtype=torch.int32)
+    valid, loss, _ = fit(model, CTCLoss(reduction="sum"), (x, tg, lens.float() / 81.0, torch.tensor([3, 3, 3], dtype=torch.int32)), DEV)
+    assert valid
+    loss.backward()
+    torch.cuda.synchronize()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())

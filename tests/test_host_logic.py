@@ -165,3 +165,163 @@ def test_fused_adamw_host_logic_matches_torch(monkeypatch):
     for a, b, c in zip(ref_p, our_p, flat_p):
         assert torch.allclose(a, b, atol=1e-7) and torch.allclose(a, c, atol=1e-7)
     assert flat_p[0].data_ptr() == bucket.flat_params.data_ptr()      # parameters really live in the flat buffer
+
+
+def _expected_collate(samples):
+    """asr_deepspeech/functional.py:9-32 restated on (spectrogram [F,T], target) pairs"""
+    batch = sorted(samples, key=lambda s: s[0].size(1), reverse=True)
+    tmax = batch[0][0].size(1)
+    inputs = torch.zeros(len(batch), 1, batch[0][0].size(0), tmax)
+    pct = torch.zeros(len(batch), dtype=torch.float32)
+    tsz = torch.zeros(len(batch), dtype=torch.int32)
+    targets = []
+    for x, (spec, tgt) in enumerate(batch):
+        inputs[x, 0, :, :spec.size(1)] = spec
+        pct[x] = spec.size(1) / float(tmax)
+        tsz[x] = len(tgt)
+        targets.extend(tgt)
+    return inputs, torch.tensor(targets, dtype=torch.int32), pct, tsz
+
+
+def test_gpu_batch_assembler_host_logic_matches_collate_fn(monkeypatch):
+    """asr_b200.data.GpuBatchAssembler = SpectrogramParser.parse_audio + _collate_fn: ordering (stable on ties),
+    padding, percentages, concatenated targets -- kernels emulated, spectrograms against the oracle restatement."""
+    import numpy as np
+    from oracle import explicit
+
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.data import GpuBatchAssembler
+
+    rng = np.random.default_rng(3)
+    lens = [8000, 16000, 4321, 16050, 160, 12345]          # 16000 and 16050 tie at 101 frames: input order is kept
+    batch = [((rng.standard_normal(n) * 0.2).astype(np.float32), list(rng.integers(1, 29, size=3 + i))) for i, n in enumerate(lens)]
+    asm = GpuBatchAssembler(audio_conf=dict(sample_rate=16000, window_size=0.02, window_stride=0.01, window="hamming"),
+                            device="cpu")
+    inputs, targets, pct, tsz = asm(batch)
+    exp = _expected_collate([(explicit.spectrogram(w, normalize=True), [int(t) for t in tg]) for w, tg in batch])
+    assert inputs.shape == exp[0].shape == (6, 1, 161, 101)
+    assert torch.equal(targets, exp[1]) and targets.dtype == torch.int32
+    assert torch.equal(pct, exp[2]) and torch.equal(tsz, exp[3])
+    assert (inputs - exp[0]).abs().max().item() <= 2e-4
+    assert tsz[5] == 3 + 4 and inputs[5, 0, :, 2:].abs().max().item() == 0   # the 160-sample utterance: last, 2 frames, rest zero
+    # second call reuses the staging buffer
+    inputs2, *_ = asm(batch[:2])
+    assert inputs2.shape == (2, 1, 161, 101)
+
+
+def _fresh_pair(tmp_path, monkeypatch):
+    """our model (reference init values of the oracle) + FusedAdamW, kernels emulated"""
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.optim import FusedAdamW
+
+    model = build_model(tmp_path, dict(C=26, rnn_type="gru", hidden=8, layers=2))
+    opt = FusedAdamW(model.parameters(), lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    return model, opt
+
+
+def test_checkpoint_layout_matches_reference_manifest(golden, tmp_path, monkeypatch):
+    """a checkpoint in the reference's format (trainers/deepspeech_trainer.py:176-188) written from
+    OUR model + FusedAdamW has the structure of one written from the unmodified reference (manifest generated by
+    oracle/make_golden.py from /root/reference): same keys, parameter ORDER (optimizer state is indexed by position),
+    shapes, dtypes and optimizer state layout -- and loads back into torch.optim.AdamW, as the reference would do."""
+    from oracle.make_golden import fake_grads, reference_checkpoint, reference_optimizer
+
+    man = golden("ref_checkpoint_manifest")
+    model, opt = _fresh_pair(tmp_path, monkeypatch)
+    for s in (1, 2):
+        fake_grads(model, s)
+        opt.step()
+    ck = reference_checkpoint(model, opt)
+    path = os.path.join(tmp_path, "model.pth")
+    torch.save(ck, path)
+    ck = torch.load(path, map_location="cpu", weights_only=False)          # deepspeech_trainer.py:157
+    assert sorted(ck.keys()) == man["ckpt_keys"]
+    assert [k for k, _ in model.named_parameters()] == man["param_order"]
+    assert [(k, tuple(v.shape), str(v.dtype)) for k, v in ck["state_dict"].items()] == man["state_dict"]
+    osd = ck["optimizer"]
+    assert list(osd["param_groups"][0]["params"]) == man["opt_group_params"]
+    assert set(man["opt_state_keys"]) == set(osd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    for k in ("lr", "betas", "eps", "weight_decay"):
+        assert k in man["opt_group_keys"] and k in osd["param_groups"][0]
+    # the reference side: torch.optim.AdamW takes our optimizer state and continues identically
+    ref_model = build_model(tmp_path, dict(C=26, rnn_type="gru", hidden=8, layers=2))
+    ref_model.load_state_dict(ck["state_dict"])
+    ref_opt = reference_optimizer(ref_model)
+    ref_opt.load_state_dict(osd)
+    fake_grads(model, 3)
+    fake_grads(ref_model, 3)
+    opt.step()
+    ref_opt.step()
+    for (k, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert torch.allclose(a, b, rtol=0, atol=1e-7), k
+
+
+def test_reference_checkpoint_round_trip(tmp_path, monkeypatch):
+    """the real thing, where the reference tree is present (this container; not the GPU box): checkpoint written from
+    the UNMODIFIED reference model + torch AdamW -> our model + FusedAdamW resume -> same next step."""
+    from oracle.reference_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    load_reference()
+    from oracle.make_golden import (LABELS29 as L, build_reference_model, fake_grads, reference_checkpoint,
+                                    reference_optimizer)
+
+    ref_model = build_reference_model("gru", 8, 2, L[:26])
+    ref_opt = reference_optimizer(ref_model)
+    sched = torch.optim.lr_scheduler.StepLR(ref_opt, step_size=1, gamma=0.99)
+    for s in (1, 2):
+        fake_grads(ref_model, s)
+        ref_opt.step()
+    sched.step()
+    path = os.path.join(tmp_path, "ref.pth")
+    torch.save(reference_checkpoint(ref_model, ref_opt, scheduler=sched), path)
+
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    model, opt = _fresh_pair(tmp_path, monkeypatch)
+    model.load_state_dict(ck["state_dict"])                                  # deepspeech_trainer.py:158
+    opt.load_state_dict(ck["optimizer"])                                     # :160
+    scheduler = ck["scheduler"]                                              # :163-167: the pickled scheduler object
+    scheduler.optimizer = opt
+    assert abs(opt.param_groups[0]["lr"] - 1.5e-4 * 0.99) < 1e-12
+    assert ck["epoch"] == 3 and ck["metrics"] == {"wer": 0.5, "cer": 0.25}
+    fake_grads(model, 3)
+    fake_grads(ref_model, 3)
+    opt.step()
+    ref_opt.step()
+    scheduler.step()
+    assert abs(opt.param_groups[0]["lr"] - 1.5e-4 * 0.99 ** 2) < 1e-12
+    for (k, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert torch.allclose(a, b, rtol=0, atol=1e-7), k
+    sd = model.state_dict()
+    for k, v in ref_model.state_dict().items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+
+
+def _reference_lookahead(x, weight, context):
+    """asr_deepspeech/modules/blocks.py:123-128 + the Hardtanh(0, 20) of deepspeech.py:94-101"""
+    h = x.transpose(0, 1).transpose(1, 2)
+    h = torch.nn.functional.pad(h, pad=(0, context - 1), value=0)
+    h = torch.nn.functional.conv1d(h, weight, groups=weight.shape[0])
+    h = h.transpose(1, 2).transpose(0, 1).contiguous()
+    return torch.nn.functional.hardtanh(h, 0.0, 20.0)
+
+
+def test_lookahead_module_matches_reference_formulation(monkeypatch):
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.modules import Lookahead
+
+    torch.manual_seed(3)
+    la = Lookahead(12, context=5)
+    assert [k for k, _ in la.state_dict().items()] == ["conv.weight"] and la.conv.weight.shape == (12, 1, 5)
+    x = (torch.randn(9, 3, 12) * 8).requires_grad_(True)
+    y = la(x, act=(0.0, 20.0))
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().clone().requires_grad_(True)
+    wr = la.conv.weight.detach().clone().requires_grad_(True)
+    yr = _reference_lookahead(xr, wr, 5)
+    yr.backward(gy)
+    assert torch.allclose(y, yr, atol=1e-5)
+    assert torch.allclose(x.grad, xr.grad, atol=1e-5) and torch.allclose(la.conv.weight.grad, wr.grad, atol=1e-4)
+    assert "Lookahead(n_features=12, context=5)" == repr(la)

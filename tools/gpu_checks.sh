@@ -11,7 +11,7 @@ run() { # name, limit, args...
   timeout $limit $PYT "$@" > gpurun_out/$name.log 2>&1
   echo "exit=$? $(tail -1 gpurun_out/$name.log)" | tee -a gpurun_out/summary.txt
 }
-groups=${@:-"gemm conv rows rnn_simt rnn_tc ctc stft model"}
+groups=${@:-"gemm conv rows rnn_simt rnn_tc ctc stft lookahead model"}
 : > gpurun_out/summary.txt
 for g in $groups; do
   case $g in
@@ -23,6 +23,7 @@ for g in $groups; do
     rnn_simt) run rnn_simt 600 tests/test_gpu_kernels.py -k "rnn and simt_debug" ;;
     rnn_tc)   run rnn_tc 300 tests/test_gpu_kernels.py -k "rnn and (tf32 or bf16)" ;;
     ctc)      run ctc 300 tests/test_gpu_kernels.py -k "ctc" ;;
+    lookahead) run lookahead 300 tests/test_gpu_kernels.py -k "lookahead" ;;
     stft)     run stft 300 tests/test_gpu_kernels.py -k "spectrogram" ;;
     model)    run model 900 tests/test_gpu_model.py ;;
     smoke)    echo "=== smoke" | tee -a gpurun_out/summary.txt; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit=$? $(tail -1 gpurun_out/smoke.log)" | tee -a gpurun_out/summary.txt ;;

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 what=${@:-"tests bench kernels launches full"}
 for w in $what; do
   case $w in
-    tests)    tools/gpu_checks.sh gemm conv conv32 conv1 rows rnn_simt rnn_tc ctc stft model smoke ;;
+    tests)    tools/gpu_checks.sh gemm conv conv32 conv1 rows rnn_simt rnn_tc ctc stft lookahead model smoke ;;
     bench)    timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit=$?"; cat gpurun_out/bench.json ;;
     kernels)  timeout 600 python tools/bench_kernels.py > gpurun_out/kernels.json 2> gpurun_out/kernels.err; echo "kernels exit=$?"; cat gpurun_out/kernels.json ;;
     launches)
