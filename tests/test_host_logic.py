@@ -325,3 +325,49 @@ def test_lookahead_module_matches_reference_formulation(monkeypatch):
     assert torch.allclose(y, yr, atol=1e-5)
     assert torch.allclose(x.grad, xr.grad, atol=1e-5) and torch.allclose(la.conv.weight.grad, wr.grad, atol=1e-4)
     assert "Lookahead(n_features=12, context=5)" == repr(la)
+
+
+@pytest.mark.parametrize("cell", ["gru", "lstm"])
+def test_unidirectional_model_host_logic(tmp_path, monkeypatch, cell):
+    """bidirectional=False (deepspeech.py:75-101): the unidirectional BatchRNN is the two-direction operator with an
+    all-zero reverse direction, followed by Lookahead + Hardtanh -- against torch's own modules with the same weights
+    (kernels emulated; the real ones are checked in tests/test_gpu_model.py::test_unidirectional_model_with_lookahead)."""
+    import copy
+    import pandas as pd
+
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.modules import DeepSpeech
+
+    path = os.path.join(tmp_path, "labels.csv")
+    pd.DataFrame({"label": LABELS29[:26]}).to_csv(path, index=False)
+    torch.manual_seed(22)
+    model = DeepSpeech(audio_conf=audio_conf(), decoder=None, label_path=path, rnn_type=f"nn.{cell.upper()}",
+                       rnn_hidden_size=16, rnn_hidden_layers=2, bidirectional=False, context=4)
+    keys = list(model.state_dict().keys())
+    assert "lookahead.0.conv.weight" in keys and not any(k.endswith("_reverse") for k in keys)
+    x = torch.randn(2, 1, 161, 41)
+    lens = torch.tensor([41, 25], dtype=torch.int32)
+    ref_m = copy.deepcopy(model).eval()
+    with torch.no_grad():
+        out_len = ref_m.get_seq_lens(lens)
+        h = x
+        for mod in ref_m.conv.seq_module:                                   # blocks.py:42-56
+            h = mod(h)
+            mask = torch.arange(h.size(3))[None, :] >= out_len[:, None]
+            h = h.masked_fill(mask[:, None, None, :], 0)
+        h = h.view(h.size(0), h.size(1) * h.size(2), h.size(3)).transpose(1, 2).transpose(0, 1).contiguous()
+        for r in ref_m.rnns:                                                # blocks.py:84-93
+            if r.batch_norm is not None:
+                t, n = h.size(0), h.size(1)
+                h = r.batch_norm.module(h.view(t * n, -1)).view(t, n, -1)
+            pk = torch.nn.utils.rnn.pack_padded_sequence(h, out_len)
+            h, _ = torch.nn.utils.rnn.pad_packed_sequence(r.rnn(pk)[0])
+        la = ref_m.lookahead[0]                                             # blocks.py:123-128
+        ref = _reference_lookahead(h, la.conv.weight, la.context)
+        t, n = ref.size(0), ref.size(1)
+        ref = ref_m.fc[0].module(ref.view(t * n, -1)).view(t, n, -1).transpose(0, 1).softmax(-1)
+        model.eval()
+        out, got_len = model.forward(x, lens)
+    assert got_len.tolist() == out_len.tolist()
+    for n_, tn in enumerate(out_len.tolist()):
+        assert (out[n_, :tn] - ref[n_, :tn]).abs().max().item() <= 1e-4
