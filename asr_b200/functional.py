@@ -251,10 +251,15 @@ def _join_side_streams():
 
 
 def _queue_join():
+    """once per backward pass: have the autograd engine call _join_side_streams when the pass ends (join at once if
+    the engine hook is not available)"""
     global _join_queued
     if not _join_queued:
-        _join_queued = True
-        torch.autograd.Variable._execution_engine.queue_callback(_join_side_streams)
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(_join_side_streams)
+            _join_queued = True
+        except (AttributeError, RuntimeError):
+            _join_side_streams()
 
 
 def _accumulate_grad(param, g):

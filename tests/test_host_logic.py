@@ -371,3 +371,36 @@ def test_unidirectional_model_host_logic(tmp_path, monkeypatch, cell):
     assert got_len.tolist() == out_len.tolist()
     for n_, tn in enumerate(out_len.tolist()):
         assert (out[n_, :tn] - ref[n_, :tn]).abs().max().item() <= 1e-4
+
+
+def test_end_of_backward_join_hook(monkeypatch):
+    """asr_b200.functional queues ONE engine callback per backward pass that joins the weight-gradient side stream
+    (torch.autograd's queue_callback): it must run exactly once, after the last node, and re-arm for the next pass."""
+    from asr_b200 import functional as F_
+
+    calls = []
+    real_join = F_._join_side_streams
+
+    def join():
+        calls.append("join")
+        real_join()
+
+    monkeypatch.setattr(F_, "_join_side_streams", join)
+
+    class Probe(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x * 2
+
+        @staticmethod
+        def backward(ctx, g):
+            calls.append("node")
+            F_._queue_join()
+            return g * 2
+
+    for _ in range(2):
+        calls.clear()
+        x = torch.ones(3, requires_grad=True)
+        Probe.apply(Probe.apply(x)).sum().backward()
+        assert calls == ["node", "node", "join"]
+        assert F_._join_queued is False and not F_._pending
