@@ -424,15 +424,21 @@ class LogSoftmaxLastDim(Function):
 
 
 class CtcLossSum(Function):
-    """torch.nn.CTCLoss(blank, reduction='sum', zero_infinity=False) forward/backward (trainers/__main__.py:53)."""
+    """torch.nn.CTCLoss(blank, reduction='sum', zero_infinity) forward/backward (trainers/__main__.py:53 builds it with
+    the default zero_infinity=False; the reference's own pipeline test uses True, tests/test_pipeline_e2e.py:67).
+    zero_infinity: utterances whose targets cannot be aligned (nll = inf) contribute 0 to the loss and get a zero
+    gradient -- decided from the kernel's per-utterance nll, on N scalars."""
 
     @staticmethod
     @_amp_fwd
-    def forward(ctx, log_probs, targets_dev, input_lengths_dev, target_lengths_dev, max_target_len, blank):
+    def forward(ctx, log_probs, targets_dev, input_lengths_dev, target_lengths_dev, max_target_len, blank,
+                zero_infinity=False):
         lp = log_probs.contiguous()
         loss, nll, alpha = ops.ctc_fwd(lp, targets_dev, input_lengths_dev, target_lengths_dev, max_target_len, blank)
         ctx.save_for_backward(lp, targets_dev, input_lengths_dev, target_lengths_dev, alpha, nll)
-        ctx.conf = (max_target_len, blank)
+        ctx.conf = (max_target_len, blank, bool(zero_infinity))
+        if zero_infinity:
+            loss = torch.where(torch.isinf(nll), torch.zeros_like(nll), nll).sum()
         return loss.view(())
 
     @staticmethod
@@ -440,10 +446,12 @@ class CtcLossSum(Function):
     @_amp_bwd
     def backward(ctx, g):
         lp, targets_dev, input_lengths_dev, target_lengths_dev, alpha, nll = ctx.saved_tensors
-        max_target_len, blank = ctx.conf
+        max_target_len, blank, zero_infinity = ctx.conf
         gscale = g.contiguous().float().view(1)
         grad = ops.ctc_bwd(lp, targets_dev, input_lengths_dev, target_lengths_dev, alpha, nll, gscale, max_target_len, blank)
-        return grad, None, None, None, None, None
+        if zero_infinity:
+            grad.masked_fill_(torch.isinf(nll)[None, :, None], 0.0)
+        return grad, None, None, None, None, None, None
 
 
 def softmax_last_dim(x):

@@ -23,8 +23,6 @@ class CTCLoss(nn.Module):
         super().__init__()
         if reduction != "sum":
             raise ValueError("asr_b200.CTCLoss implements reduction='sum' (the reference's setting, trainers/__main__.py:53)")
-        if zero_infinity:
-            raise ValueError("asr_b200.CTCLoss implements zero_infinity=False (the reference's setting)")
         self.blank = blank
         self.reduction = reduction
         self.zero_infinity = zero_infinity
@@ -39,7 +37,7 @@ class CTCLoss(nn.Module):
         t_dev = ops.lengths_to_device(targets, dev)
         il_dev = ops.lengths_to_device(input_lengths, dev)
         tl_dev = ops.lengths_to_device(tl_host, dev)
-        return F_.CtcLossSum.apply(log_probs, t_dev, il_dev, tl_dev, max_u, self.blank)
+        return F_.CtcLossSum.apply(log_probs, t_dev, il_dev, tl_dev, max_u, self.blank, self.zero_infinity)
 
 
 def fit(model, criterion, data, device):

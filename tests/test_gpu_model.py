@@ -301,3 +301,22 @@ def test_unidirectional_model_with_lookahead(tmp_path, cell):
     loss.backward()
     torch.cuda.synchronize()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_criterion_zero_infinity_on_gpu(golden):
+    """CTCLoss(zero_infinity=True) (the reference's tests/test_pipeline_e2e.py:67) on the golden case whose second
+    utterance cannot be aligned: same loss and logits-gradient as torch's criterion, zero gradient for that utterance."""
+    from asr_b200.trainers import CTCLoss
+
+    c = golden("ctc_cases")[2]
+    x = c["logits"].to(DEV).requires_grad_(True)
+    loss = CTCLoss(blank=0, reduction="sum", zero_infinity=True)(x.float().log_softmax(2), c["targets"], c["input_lengths"],
+                                                                 c["target_lengths"])
+    xr = c["logits"].clone().requires_grad_(True)
+    ref = torch.nn.CTCLoss(blank=0, reduction="sum", zero_infinity=True)(xr.log_softmax(2), c["targets"],
+                                                                         c["input_lengths"], c["target_lengths"])
+    assert torch.isfinite(loss).item() and abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    loss.backward()
+    ref.backward()
+    assert torch.allclose(x.grad.cpu(), xr.grad, atol=2e-5)
+    assert x.grad[:, 1].abs().max().item() == 0

@@ -404,3 +404,28 @@ def test_end_of_backward_join_hook(monkeypatch):
         Probe.apply(Probe.apply(x)).sum().backward()
         assert calls == ["node", "node", "join"]
         assert F_._join_queued is False and not F_._pending
+
+
+def test_ctcloss_zero_infinity_like_torch(golden, monkeypatch):
+    """nn.CTCLoss(blank=0, reduction="sum", zero_infinity=True) as the reference's pipeline test builds it
+    (tests/test_pipeline_e2e.py:67): an utterance that cannot be aligned adds 0 and gets a zero gradient."""
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.trainers import CTCLoss
+
+    c = golden("ctc_cases")[2]                      # second utterance infeasible
+    assert torch.isinf(c["nll"]).tolist() == [False, True]
+    for zi in (True, False):
+        x = c["logits"].clone().requires_grad_(True)
+        loss = CTCLoss(blank=0, reduction="sum", zero_infinity=zi)(x.log_softmax(2), c["targets"], c["input_lengths"],
+                                                                   c["target_lengths"])
+        xr = c["logits"].clone().requires_grad_(True)
+        ref = torch.nn.CTCLoss(blank=0, reduction="sum", zero_infinity=zi)(xr.log_softmax(2), c["targets"],
+                                                                            c["input_lengths"], c["target_lengths"])
+        if zi:
+            assert torch.isfinite(loss) and abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+            loss.backward()
+            ref.backward()
+            assert torch.allclose(x.grad, xr.grad, atol=1e-6)
+            assert x.grad[:, 1].abs().max().item() == 0
+        else:
+            assert torch.isinf(loss) and torch.isinf(ref)
