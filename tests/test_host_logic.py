@@ -429,3 +429,16 @@ def test_ctcloss_zero_infinity_like_torch(golden, monkeypatch):
             assert x.grad[:, 1].abs().max().item() == 0
         else:
             assert torch.isinf(loss) and torch.isinf(ref)
+
+
+def test_resolve_rnn_type_like_reference_tests():
+    """reference tests/test_rnn_type.py:6-19"""
+    import torch.nn as nn
+    from asr_b200.modules.deepspeech import resolve_rnn_type
+
+    assert resolve_rnn_type("nn.LSTM") is nn.LSTM
+    assert resolve_rnn_type("gru") is nn.GRU
+    assert resolve_rnn_type("RNN") is nn.RNN
+    assert resolve_rnn_type(nn.LSTM) is nn.LSTM
+    with pytest.raises(ValueError):
+        resolve_rnn_type("nn.Transformer")
