@@ -57,27 +57,42 @@ def fit(model, criterion, data, device):
 
 class DeepSpeechStep:
     """fit -> zero_grad -> backward -> [gradient all-reduce over the data-parallel group] -> optimizer.step,
-    i.e. one iteration of DeepSpeechTrainer.train (deepspeech_trainer.py:77-97) without AMP."""
+    i.e. one iteration of DeepSpeechTrainer.train (deepspeech_trainer.py:77-97).  mixed_precision=True reproduces the
+    reference's CUDA AMP branch (:80-91: fit() under fp16 autocast, GradScaler around backward/step); our operators
+    keep computing in fp32/TF32 under autocast (asr_b200/functional.py `_amp_fwd`), so only the loss scaling is live."""
 
-    def __init__(self, model, criterion=None, optimizer=None, device="cuda", grad_sync=None):
+    def __init__(self, model, criterion=None, optimizer=None, device="cuda", grad_sync=None, mixed_precision=False):
         self.model, self.device = model, torch.device(device)
         self.criterion = criterion if criterion is not None else CTCLoss(reduction="sum")
         self.optimizer = optimizer
         self.grad_sync = grad_sync
+        self.use_amp = bool(mixed_precision) and self.device.type == "cuda"
+        self.scaler = torch.amp.GradScaler("cuda", enabled=True) if self.use_amp else None
 
     def __call__(self, data):
-        valid, loss, loss_value = fit(self.model, self.criterion, data, self.device)
+        if self.use_amp:
+            with torch.amp.autocast("cuda", enabled=True):
+                valid, loss, loss_value = fit(self.model, self.criterion, data, self.device)
+        else:
+            valid, loss, loss_value = fit(self.model, self.criterion, data, self.device)
         if valid:
             if self.optimizer is not None:
                 self.optimizer.zero_grad(set_to_none=True)
             else:
                 for prm in self.model.parameters():
                     prm.grad = None
-            loss.backward()
+            if self.use_amp:
+                self.scaler.scale(loss).backward()
+            else:
+                loss.backward()
             if self.grad_sync is not None:
                 self.grad_sync(self.model)
             if self.optimizer is not None:
-                self.optimizer.step()
+                if self.use_amp:
+                    self.scaler.step(self.optimizer)
+                    self.scaler.update()
+                else:
+                    self.optimizer.step()
         else:
             print("Loss non valid, skipped")
         return valid, loss_value

@@ -320,3 +320,23 @@ def test_criterion_zero_infinity_on_gpu(golden):
     ref.backward()
     assert torch.allclose(x.grad.cpu(), xr.grad, atol=2e-5)
     assert x.grad[:, 1].abs().max().item() == 0
+
+
+def test_amp_branch_of_the_training_loop(tmp_path, golden):
+    """deepspeech_trainer.py:80-91: fit() under fp16 autocast + GradScaler.  Our operators compute in fp32/TF32 whatever
+    the autocast state, and the 2^16 loss scale is exact in fp32/bf16, so the AMP branch follows the plain one."""
+    from asr_b200.trainers import CTCLoss, DeepSpeechStep
+
+    g = dict(golden("gru_small"))
+    batch = synth_batch(g["seed"], g["B"], g["T"], g["U"], g["C"], g["lengths"])
+    losses = {}
+    for amp in (False, True):
+        model, _ = build_model(tmp_path, g)
+        model.train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+        step = DeepSpeechStep(model, CTCLoss(reduction="sum"), opt, DEV, mixed_precision=amp)
+        losses[amp] = [step(batch)[1] for _ in range(4)]
+        assert all(v == v and v != float("inf") for v in losses[amp])
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 1e-3 * abs(a), (losses[False], losses[True])
+    assert abs(losses[True][0] - g["loss"].item()) <= 1e-4 * abs(g["loss"].item())
