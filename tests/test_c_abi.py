@@ -39,6 +39,15 @@ def test_error_contract_without_a_gpu():
         _lib.call("asrb_rnn_plan", 1, 1024, 128, 0, None, None, None, None)
     _lib.call("asrb_rnn_plan", 1, 1024, 128, 1, ctypes.byref(nj), ctypes.byref(P), None, None)
     assert 2 * P.value <= 148
+    with pytest.raises(ValueError):           # the newer entry points keep the contract: NULL / non-positive sizes
+        _lib.call("asrb_lookahead_fwd", None, None, None, 4, 2, 8, 3, 0, 0.0, 0.0, None)
+    with pytest.raises(ValueError):
+        _lib.call("asrb_lookahead_bwd", None, None, None, None, None, None, 4, 2, 8, 0, 0, 0.0, 0.0, None)
+    with pytest.raises(ValueError):
+        _lib.call("asrb_adamw_step", None, None, None, None, 16, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None, None)
+    assert _lib.query("asrb_gemm_cta_limit", -1) == 0 and _lib.query("asrb_debug_gemm_tma_store", -1) == 1
+    assert _lib.query("asrb_debug_conv_wgrad_bf16", -1) == 1
+    assert _lib.query("asrb_conv32_bwd_weight_workspace_bytes", 64, 81, 501, 41, 501) >= 8 * 64 * 32 * 81 * 504 * 2
     ws = _lib.query("asrb_ctc_workspace_bytes", 2000, 256, 200)  # alpha and gathered log-prob rows [N,T,row stride >= 2U+1] f32 + target offsets
     assert 2 * 2000 * 256 * 401 * 4 <= ws <= 2 * 2000 * 256 * 416 * 4 + 2 * 256 * 4 + 64
 
@@ -54,5 +63,5 @@ def test_sass_contains_tcgen05_and_tma():
     if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump not on PATH")
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIBRARY], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTMAREDG"):   # + TMA store / reduce (GEMM epilogue)
         assert mnemonic in sass, mnemonic
