@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, smoke, bench, isolation benchmarks, ncu launch list and full captures.
-# Usage (under gpurun): tools/gpu_round.sh [tests] [bench] [kernels] [launches] [full]
+# Usage (under gpurun): tools/gpu_round.sh [tests] [bench] [kernels] [launches] [full] [overlap] [ctc5]
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 what=${@:-"tests bench kernels launches full"}
@@ -23,6 +23,7 @@ for w in $what; do
                 -k regex:'gemm_tn_tf32_kernel' -s 30 -c 1 -f -o gpurun_out/prof_gemm_bf16 python tools/profile_step.py > gpurun_out/full_gemm2.log 2>&1; echo "full gemm bf16 exit=$?"
               timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
                 -k regex:'ctc_' -c 4 -f -o gpurun_out/prof_ctc python tools/profile_step.py > gpurun_out/full_ctc.log 2>&1; echo "full ctc exit=$?" ;;
+    overlap)  timeout 300 python tools/bench_overlap.py > gpurun_out/overlap.txt 2>&1; echo "overlap exit=$?"; cat gpurun_out/overlap.txt ;;
     ctc5)     timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ctc_alpha_warp|ctc_bwd_kernel' -s 2 -c 2 -f \
                 -o gpurun_out/prof_ctc5 python tools/bench_kernels.py ctc > gpurun_out/full_ctc5.log 2>&1; echo "ctc5 exit=$?" ;;
   esac
