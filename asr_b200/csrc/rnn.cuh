@@ -1,0 +1,117 @@
+// asr_b200 -- declarations shared by the two recurrent kernels (rnn.cu: TMA-fed ring, tf32 / debug paths;
+// rnn2.cu: the data-is-the-flag exchange of the bf16 product path).
+#pragma once
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
+#include "ptx.cuh"
+
+namespace asrb {
+
+// warp 0: TMA producer; warp 1: MMA issuer; warps 2,3: idle (keep warp % 4 == TMEM lane quarter for the rest);
+// warps 4..19: epilogue, lane quarter = warp % 4, four 4-unit groups per quarter
+constexpr int kRnnCtrlWarps = 4;
+constexpr int kRnnEpiWarps = 16;
+constexpr int kRnnThreads = (kRnnCtrlWarps + kRnnEpiWarps) * 32;
+constexpr int kRnnEpiThreads = kRnnEpiWarps * 32;
+constexpr int kRnnCounterStride = 32;                  // step counters [dir], one 128-byte line each
+constexpr int kRnnMaxRows = 128;   // batch rows per CTA (one MMA M tile; TMA zero-fills rows >= B)
+constexpr int kRnnMaxSmem = 227 * 1024;
+constexpr int kRnnMaxStages = 40;
+constexpr int kRnnBarBytes = 1024;  // 2 x kRnnMaxStages ring barriers + 3 + TMEM slot, then the bias slice
+constexpr int kRnnBiasOffset = 704;
+
+struct RnnParams {
+    int T, B, H, G, P, kpad, use_simt, stages, chunk;   // chunk = K blocks per pipeline stage / barrier
+    int P_saved;          // slices of the saved-gates layout (= the forward's P; the split backward may pad its own P)
+    const int* lengths;
+    uint32_t* counters;   // [2 dirs] step counters, kRnnCounterStride words apart
+    int dbg;              // DEBUG timing experiments: 1 = drop the non-critical stores, 2 = drop the operand prefetch
+    const float* wpack;  // packed fp32 weight slices (global copy, SIMT debug path)
+    // bf16 MMA operands; rows padded to a multiple of 64 elements (128 bytes) so that every 128-byte box row TMA
+    // fetches is ONE aligned L2 line (H=800 rows of 1600 bytes would put every odd row across two lines)
+    __nv_bfloat16* hbf;   // [2,T+2,B,Hp] bf16 copy of hseq (forward, bf16 mode): the next step's MMA operand
+    __nv_bfloat16* dghbf; // [2,T,B,Gp]  bf16 copy of dgh  (backward, bf16 mode)
+    int Hp, Gp;
+    long long* trace;     // DEBUG: [gridDim][T][16] SM-clock stamps per step (asrb_debug_rnn_trace), else NULL
+    // forward
+    const float* gi;     // [T,B,2,G]
+    const float* b_hh;   // [2,G]
+    float* hseq;         // [2,T+2,B,H]
+    float* cseq;         // [2,T+2,B,H] (LSTM)
+    float* saved;        // [2,T,B,4,H]
+    // backward
+    const float* dout;   // [T,B,H]
+    // gate gradients for the dgrad / wgrad GEMMs: fp32 in tf32 mode, bf16 in bf16 mode (the backward GEMMs then run with
+    // bf16 operands: the loss only depends on the forward, and half the bytes leave the kernel)
+    void* dgi;           // [T,B,2,G]
+    float* dgh;          // [2,T,B,G]  (tf32 / debug modes: MMA operand; NULL in bf16 mode)
+    void* dgiT;          // [2G, ldT]  transposed gate gradients (row = dir*G + gate*H + unit, column = t*B + b)
+    void* dghT;          // [2G, ldT]  GRU: transposed hidden-side gate gradients (n rows differ from dgiT); NULL for LSTM
+    long long ldT;
+};
+
+template <int CELL, int NJ>
+struct RnnShape {
+    static constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
+    static constexpr int kNpadF = ((kGates * NJ + 15) / 16) * 16;
+    static constexpr int kNpadB = 16;
+    static_assert(NJ <= 16 && kNpadF <= 64, "slice too wide");
+};
+
+// ------------------------------------------------------------------------------------------------
+// the recurrence
+// ------------------------------------------------------------------------------------------------
+extern long long* g_rnn_trace;
+extern int g_rnn_dbg;
+extern int g_rnn_ksplit;   // largest backward K split allowed: 0 none, 2 CTA pairs (default), 4 clusters of four -- the
+                        // 1.5 k cycles the MMA phase gains with four are lost again in the longer exchange (measured)
+extern int g_rnn_chunk;   // DEBUG: K blocks per pipeline barrier (0 = automatic)
+
+// fast gate non-linearities on the flush-to-zero MUFU forms (ex2.approx.ftz + rcp.approx.ftz: ~1e-6 absolute error);
+// __expf / __fdividef spend three more instructions per call on denormal scaling and range checks
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fsigmoid(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float ftanh(float x) { return fmaf(-2.f, rcp_ftz(1.f + ex2_ftz(2.8853900817779268f * x)), 1.f); }
+
+__device__ __forceinline__ void ld4(float* dst, const float* src) {
+    const float4 t = *reinterpret_cast<const float4*>(src);
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+}
+__device__ __forceinline__ void ldg4(float* dst, const float* src) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+    dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+}
+__device__ __forceinline__ void st4(float* dst, const float* v) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* dst, const float* v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst) = u;
+}
+
+#define ASRB_TRACE(slot, step)                                                                   \
+    do {                                                                                         \
+        if (p.trace) p.trace[((size_t)blockIdx.x * p.T + (step)) * 16 + (slot)] = clock64();     \
+    } while (0)
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+
+struct RnnPlan {
+    int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, chunk_f, chunk_b, mrows, bf16, ksplit, P_b;   // ksplit: 0, 2, 4
+    size_t smem_f, smem_b;
+};
+
+
+// rnn2.cu: launches the bf16 exchange-by-data kernel for (cell, plan)
+int rnn2_dispatch(bool bwd, int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream);
+
+}  // namespace asrb

@@ -137,6 +137,48 @@ def model_case(name, rnn_type, hidden, layers, C, seed, B, T, U, lengths=None):
     print(f"{name}: loss={loss.item():.6f} out={tuple(out.shape)} sizes={output_sizes.tolist()}")
 
 
+def model_case_big(name, rnn_type, hidden, layers, C, seed, B, T, U, backward=True):
+    """Full-size BASELINE.json configurations (configs[1], configs[2]) on the unmodified reference.  The tensors are too
+    large to commit, so what is stored is: loss, output sizes, digests (norm / sum / 64 samples) of logits, d loss / d
+    logits and every parameter gradient, the BN running statistics, and -- for the bit-exact index check -- the
+    eval-mode argmax of every frame (int16) with the reference's own top-2 margin per frame (float16)."""
+    labels = LABELS29[:C] if C <= 29 else [chr(0x3041 + i) for i in range(C)]
+    model = build_reference_model(rnn_type, hidden, layers, labels)
+    assert model.num_classes == C, (model.num_classes, C)
+    batch = synth_batch(seed, B, T, U, C)
+    p = torch_path.init_params(rnn_type, hidden, layers, C)
+    sd = model.state_dict()
+    for k in sd:
+        assert torch.equal(sd[k], p[k]), f"init_params != reference init at {k}"
+    import time
+    t0 = time.time()
+    model.train()
+    rec = dict(name=name, rnn_type=rnn_type, hidden=hidden, layers=layers, C=C, seed=seed, B=B, T=T, U=U,
+               input_checksum=checksum(batch[0]), targets=batch[1], input_percentages=batch[2], target_sizes=batch[3])
+    if backward:
+        loss, out, output_sizes = reference_fit(model, batch)
+        model.zero_grad()
+        loss.backward()
+        rec.update(grads={k: grad_digest(v.grad) for k, v in model.named_parameters()},
+                   dlogits_digest=grad_digest(out.grad.detach()))
+    else:
+        loss, out, output_sizes = reference_fit(model, batch)     # forward only: the graph is built but never walked
+        loss, out = loss.detach(), out.detach()
+    rec.update(loss=loss.detach(), output_sizes=output_sizes, logits_digest=grad_digest(out.detach()),
+               running_stats={k: v.clone() for k, v in model.state_dict().items() if "running_" in k})
+    print(f"{name}: train pass {time.time() - t0:.0f} s, loss={loss.item():.6f}", flush=True)
+    model.eval()
+    with torch.no_grad():
+        input_sizes = batch[2].clone().mul_(int(batch[0].size(3))).int()
+        probs, _ = model.forward(batch[0], input_sizes)
+        top2 = torch.topk(probs, 2, dim=2)
+        rec.update(eval_argmax=torch.max(probs, 2)[1].to(torch.int16),               # greedy_decoder.py:61
+                   eval_margin=(top2.values[..., 0] - top2.values[..., 1]).to(torch.float16),
+                   eval_probs_digest=grad_digest(probs))
+    torch.save(rec, os.path.join(GOLDEN_DIR, f"{name}.pt"))
+    print(f"{name}: done {time.time() - t0:.0f} s out={tuple(out.shape)}", flush=True)
+
+
 def ctc_cases():
     """torch.nn.CTCLoss(reduction='sum') exactly as constructed at trainers/__main__.py:53 and
     called at trainers/deepspeech_trainer.py:110-111 (log_softmax first)."""
@@ -251,6 +293,16 @@ def main():
     load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         checkpoint_manifest()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg2":
+        # BASELINE.json configs[1] = the benchmarked shape (bench.py CFG: seed 1234+2), fwd + bwd once (~6 min of CPU)
+        torch.set_num_threads(os.cpu_count())
+        model_case_big("cfg2_gru800x5", "gru", 800, 5, 29, seed=1236, B=64, T=1001, U=100)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
+        # BASELINE.json configs[2]: 7 x biLSTM-1024, 15 s, 90 labels; batch reduced 128 -> 16 for the CPU run (stated)
+        torch.set_num_threads(os.cpu_count())
+        model_case_big("cfg3_lstm1024x7_b16", "lstm", 1024, 7, 90, seed=1237, B=16, T=1501, U=150, backward=False)
         return
     torch.set_num_threads(os.cpu_count())
     misc_cases()
