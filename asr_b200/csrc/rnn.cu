@@ -720,6 +720,12 @@ static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void*
     return ASRB_ERR_UNSUPPORTED;
 }
 
+// the exchange-by-data kernel (rnn2.cu): bf16 product, 16-unit slices, operand columns in whole K = 16 MMA steps;
+// asrb_debug_rnn_dbg(8) selects the counter + TMA kernel of this file instead (A/B timing)
+static inline bool rnn2_eligible(const RnnPlan& pl, const RnnParams& prm) {
+    return pl.bf16 && !prm.use_simt && !(g_rnn_dbg & 8) && pl.nj == 16 && prm.H % 16 == 0;
+}
+
 // the CUDA-core debug product reads fp32 operands: it always runs the tf32-layout variant
 static inline int rnn_effective_bf16(int bf16) { return (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 0 : (bf16 ? 1 : 0); }
 
@@ -787,7 +793,7 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
     prm.hbf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16);
     prm.Hp = round_up(H, 64);
     prm.trace = g_rnn_trace;
-    if (pl.bf16 && !prm.use_simt && !(g_rnn_dbg & 8)) return rnn2_dispatch(false, cell, pl, prm, wpack_fwd, stream);
+    if (rnn2_eligible(pl, prm)) return rnn2_dispatch(false, cell, pl, prm, wpack_fwd, stream);
     return rnn_dispatch<false>(cell, pl, prm, wpack_fwd, pl.bf16 ? (const void*)hseq_bf16 : (const void*)hseq, stream);
 }
 
@@ -812,7 +818,7 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
     prm.dghbf = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
     prm.Gp = round_up(prm.G, 64);
     prm.trace = g_rnn_trace;
-    if (pl.bf16 && !prm.use_simt && !(g_rnn_dbg & 8)) return rnn2_dispatch(true, cell, pl, prm, wpack_bwd, stream);
+    if (rnn2_eligible(pl, prm)) return rnn2_dispatch(true, cell, pl, prm, wpack_bwd, stream);
     return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, pl.bf16 ? (const void*)dgh_bf16 : (const void*)dgh, stream);
 }
 

@@ -18,8 +18,8 @@ w = [(torch.rand(G, H, device=dev) * 2 - 1) * 0.035 for _ in range(2)]
 lens = torch.full((B,), T, dtype=torch.int32, device=dev)
 dout = torch.randn(T, B, H, device=dev)
 # slot names of the exchange-by-data kernel (rnn2.cu)
-names2 = {4: "E:step top", 0: "P:canaries ok", 1: "P:TMA issued", 2: "M:first K block", 10: "E:validated", 3: "M:last commit",
-          5: "E:tfull", 6: "E:ld done", 11: "E:exchange done", 7: "E:operand stored", 8: "E:other stores issued"}
+names2 = {4: "E:step top", 0: "P:canaries ok", 10: "E:go", 8: "E:deferred stores issued", 1: "P:copies issued", 2: "M:first K block",
+          3: "M:last commit", 5: "E:tfull", 6: "E:ld+verdict", 11: "E:exchange done", 7: "E:operand stored"}
 names1 = {4: "E:step top", 0: "P:counter ok", 9: "P:fence done", 2: "M:first full", 1: "P:loads issued", 3: "M:commit",
           5: "E:tfull", 6: "E:ld done", 11: "E:exchange done", 7: "E:math+stores", 8: "E:bar done", 10: "E:red"}
 
@@ -33,7 +33,19 @@ def timed(fn, n=3):
     return e0.elapsed_time(e1) / n
 
 
-for dbg, label in ((0, "exchange-by-data (rnn2.cu)"), (8, "counter + TMA (rnn.cu)")):
+# forward outputs of every variant against the counter + TMA kernel
+ref = None
+for dbg, label in ((8, "rnn.cu"), (64, "rnn2 SS"), (0, "rnn2 TS"), (32, "rnn2 TS, rows in lanes 0..63")):
+    _lib.query("asrb_debug_rnn_dbg", dbg)
+    pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
+    hs, cs, sv = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
+    torch.cuda.synchronize()
+    if ref is None:
+        ref = hs.clone()
+    else:
+        print(f"## fwd hseq {label} vs rnn.cu: max abs diff {(hs - ref).abs().max().item():.3e} (|h| max {ref.abs().max().item():.3f})", flush=True)
+
+for dbg, label in ((0, "exchange-by-data, weights in TMEM (rnn2.cu TS)"), (1, "TS, WITHOUT the deferred stores (timing experiment)"), (64, "exchange-by-data (rnn2.cu SS)"), (65, "SS, WITHOUT the deferred stores"), (8, "counter + TMA (rnn.cu)"), (9, "rnn.cu WITHOUT the non-critical stores")):
     _lib.query("asrb_debug_rnn_dbg", dbg)
     _lib.query("asrb_debug_rnn_ksplit", ks)
     pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
@@ -43,7 +55,7 @@ for dbg, label in ((0, "exchange-by-data (rnn2.cu)"), (8, "counter + TMA (rnn.cu
     tb = timed(lambda: ops.rnn_bwd(cell, dout, pb, lens, hseq, cseq, saved, T, B, H))
     print(f"## {label}: {cellname} H={H} B={B} T={T} nj={nj} P={P} ksplit={ks}: fwd {tf:.3f} ms ({tf*1e3/T:.2f} us/step)  "
           f"bwd {tb:.3f} ms ({tb*1e3/T:.2f} us/step)", flush=True)
-    names = names1 if dbg else names2
+    names = names1 if dbg & 8 else names2
     for which in ("fwd", "bwd"):
         grid = 2 * (P + 3)
         trace = torch.zeros(grid + 8, T, 16, dtype=torch.int64, device=dev)
@@ -56,12 +68,14 @@ for dbg, label in ((0, "exchange-by-data (rnn2.cu)"), (8, "counter + TMA (rnn.cu
         _lib.call("asrb_debug_rnn_trace", None)
         tr = trace.cpu().double()
         s0, s1 = min(50, T // 4), max(T - 50, T // 2)
-        for cta in (0, 1, P // 2, P):
+        tot = tr[0, T - 1, 4] - tr[0, 0, 4]
+        print(f" {which}: first to last step top {tot:.0f} cycles = {tot / 1.965e6:.3f} ms @1965 MHz", flush=True)
+        for cta in (0, P):
             x = tr[cta, s0:s1]
             top = x[:, 4]
             step_cycles = (top[1:] - top[:-1]).mean().item()
             rel = {k: (x[:, k] - top).mean().item() for k in names}
-            extra = f"; chunks re-fetched by the CTA over {T} steps: {tr[cta, T - 1, 9].item():.0f}" if not dbg else ""
+            extra = f"; steps repeated by the CTA over {T} steps: {tr[cta, T - 1, 9].item():.0f}" if not dbg & 8 else ""
             print(f" {which} cta {cta}: cycles/step {step_cycles:.0f}; " +
                   "; ".join(f"{names[k]}={rel[k]:.0f}" for k in names if abs(rel[k]) < 1e6) + extra, flush=True)
 _lib.query("asrb_debug_rnn_dbg", 0)
