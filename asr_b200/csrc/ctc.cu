@@ -860,7 +860,7 @@ size_t asrb_ctc_workspace_bytes(int T, int N, int max_target_len) {
 int asrb_ctc_fwd(const float* log_probs, const int32_t* targets, const int32_t* input_lengths,
                  const int32_t* target_lengths, float* alpha_ws, size_t ws_bytes, float* nll, float* loss, int T, int N,
                  int C, int max_target_len, int blank, asrb_stream_t stream) {
-    ASRB_REQUIRE(log_probs && targets && input_lengths && target_lengths && alpha_ws && nll && loss, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(log_probs && (targets || max_target_len == 0) && input_lengths && target_lengths && alpha_ws && nll && loss, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(T > 0 && N > 0 && C > 0 && max_target_len >= 0 && blank >= 0 && blank < C, ASRB_ERR_BAD_ARG);
     const int Smax = 2 * max_target_len + 1;
     ASRB_REQUIRE(ws_bytes >= asrb_ctc_workspace_bytes(T, N, max_target_len), ASRB_ERR_WORKSPACE);
@@ -896,7 +896,7 @@ int asrb_ctc_fwd(const float* log_probs, const int32_t* targets, const int32_t* 
 int asrb_ctc_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lengths,
                  const int32_t* target_lengths, float* alpha_ws, const float* nll, const float* grad_scale,
                  float* grad, int T, int N, int C, int max_target_len, int blank, asrb_stream_t stream) {
-    ASRB_REQUIRE(log_probs && targets && input_lengths && target_lengths && alpha_ws && nll && grad, ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(log_probs && (targets || max_target_len == 0) && input_lengths && target_lengths && alpha_ws && nll && grad, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(T > 0 && N > 0 && C > 0 && max_target_len >= 0 && blank >= 0 && blank < C, ASRB_ERR_BAD_ARG);
     const int Smax = 2 * max_target_len + 1;
     const size_t rows = ctc_alpha_floats(T, N, max_target_len);

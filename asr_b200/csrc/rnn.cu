@@ -688,6 +688,13 @@ static int rnn_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, cons
     cfg.attrs = attrs;
     cfg.numAttrs = KSPLIT ? 1 : 0;
     prm.dbg = g_rnn_dbg;
+    {   // the step barrier spins: refuse the launch when the device cannot hold the whole grid at once
+        int dev = 0, sms = 0, per_sm = 0;
+        ASRB_CUDA_OK(cudaGetDevice(&dev));
+        ASRB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        ASRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRnnThreads, smem));
+        if (2 * Pk > sms * per_sm) return ASRB_ERR_UNSUPPORTED;
+    }
     ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmW, tmA, prm));
     return 0;
 }

@@ -326,7 +326,9 @@ class BiRnnLayer(Function):
         def weight_grads():
             # bias gradients = row sums of the transposed gate gradients
             db_ih_cat = ops.row_sums(dgiT, R)
-            db_hh_cat = db_ih_cat if dghT is dgiT else ops.row_sums(dghT, R)
+            # LSTM: the hidden-side gate gradients ARE the input-side ones, but bias_ih.grad and bias_hh.grad must not
+            # share storage (an in-place op on all grads -- GradScaler.unscale_, clip_grad_norm_ -- would hit them twice)
+            db_hh_cat = db_ih_cat.clone() if dghT is dgiT else ops.row_sums(dghT, R)
             # weight gradients (K = T*B): dW_ih = dgi^T x ; dW_hh = dgh^T h_prev -- the transposed gate gradients come
             # straight from the recurrent kernel, only x and h_prev are transposed here
             xt = tr(x2)                                             # [I, R]

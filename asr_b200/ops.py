@@ -19,12 +19,20 @@ BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
 
 
+_LAST_DEV = None   # device of the tensors of the call being assembled (set by _p): the kernels go to ITS current stream
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(_LAST_DEV).cuda_stream)
 
 
 def _p(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    global _LAST_DEV
+    if t is None:
+        return None
+    if t.is_cuda:
+        _LAST_DEV = t.device
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _chk(*tensors, dtype=torch.float32):
@@ -57,13 +65,23 @@ KERNELS_PER_CALL = {
 def _call(name, *args):
     global LAUNCHES
     LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    if _LAST_DEV is not None and _LAST_DEV.index != torch.cuda.current_device():
+        # tensors on another device than the thread's current one: the library launches on cudaGetDevice() and builds
+        # its TMA descriptors in that context, so make the tensors' device current for the call
+        with torch.cuda.device(_LAST_DEV):
+            _call_here(name, *args)
+        return
+    _call_here(name, *args)
+
+
+def _call_here(name, *args):
     if PROFILE is None:
         _lib.call(name, *args, _stream())
         return
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
+    start.record(torch.cuda.current_stream(_LAST_DEV))
     _lib.call(name, *args, _stream())
-    end.record()
+    end.record(torch.cuda.current_stream(_LAST_DEV))
     PROFILE.setdefault(name, []).append((start, end))
 
 

@@ -5,7 +5,9 @@ steps at trainers/deepspeech_trainer.py:86-95.
 It is a `torch.optim.Optimizer` (so `StepLR`, `GradScaler.step(optimizer)` and `state_dict()` keep working), with
 torch.optim.AdamW's state layout (`step`, `exp_avg`, `exp_avg_sq` per parameter).  `step()` issues ONE kernel per
 parameter tensor -- or ONE kernel for the whole model when the parameters and gradients were flattened with
-`FlatGradBucket(..., flatten_params=True)`: 28 bytes per parameter, a single HBM pass.
+`FlatGradBucket(..., flatten_params=True)`: 28 bytes per parameter, a single HBM pass.  In the flat form the per-parameter
+`exp_avg` / `exp_avg_sq` of `self.state` are VIEWS into two flat moment buffers, so `state_dict()` saves them and
+`load_state_dict()` (which replaces them by copies) re-flattens: a resumed run continues with its moments and step count.
 """
 from __future__ import annotations
 
@@ -22,6 +24,32 @@ class FusedAdamW(torch.optim.Optimizer):
         self.bucket = bucket if bucket is not None and getattr(bucket, "flat_params", None) is not None else None
         self._flat_state = None
 
+    def _flatten_state(self):
+        """flat form: the moments of all parameters in two flat buffers, `self.state[p]` holding views into them; state
+        that is already there (first step after `load_state_dict`) is copied in"""
+        if self._flat_state is not None:
+            return
+        flat = self.bucket.flat_params
+        st = dict(step=0, exp_avg=torch.zeros_like(flat), exp_avg_sq=torch.zeros_like(flat))
+        off = 0
+        for p in self.bucket.params:
+            n = p.numel()
+            views = {k: st[k][off:off + n].view_as(p) for k in ("exp_avg", "exp_avg_sq")}
+            old = self.state.get(p)
+            if old:
+                for k, v in views.items():
+                    v.copy_(old[k])
+                st["step"] = max(st["step"], int(old["step"]))
+            self.state[p] = dict(step=st["step"], **views)
+            off += n
+        for p in self.bucket.params:
+            self.state[p]["step"] = st["step"]
+        self._flat_state = st
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._flat_state = None          # the loaded moments are copies: re-flatten them at the next step
+
     @torch.no_grad()
     def step(self, closure=None, inv_scale=None):
         """inv_scale: optional 1-element CUDA tensor multiplied into every gradient (GradScaler's unscale, fused)."""
@@ -31,11 +59,15 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         if self.bucket is not None and len(self.param_groups) == 1:
             g = self.param_groups[0]
-            if self._flat_state is None:
-                flat = self.bucket.flat_params
-                self._flat_state = dict(step=0, exp_avg=torch.zeros_like(flat), exp_avg_sq=torch.zeros_like(flat))
+            self._flatten_state()
+            for p, v in zip(self.bucket.params, self.bucket.views):
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    raise RuntimeError("FusedAdamW(bucket=...): a parameter's .grad is not the bucket's view any more (was "
+                                       "zero_grad(set_to_none=True) called?  use bucket.zero() to re-arm the gradients)")
             st = self._flat_state
             st["step"] += 1
+            for p in self.bucket.params:
+                self.state[p]["step"] = st["step"]
             ops.adamw_step(self.bucket.flat_params, self.bucket.flat, st["exp_avg"], st["exp_avg_sq"], g["lr"], g["betas"][0],
                            g["betas"][1], g["eps"], g["weight_decay"], st["step"], inv_scale)
             return loss

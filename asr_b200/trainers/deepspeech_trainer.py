@@ -61,10 +61,18 @@ class DeepSpeechStep:
     reference's CUDA AMP branch (:80-91: fit() under fp16 autocast, GradScaler around backward/step); our operators
     keep computing in fp32/TF32 under autocast (asr_b200/functional.py `_amp_fwd`), so only the loss scaling is live."""
 
-    def __init__(self, model, criterion=None, optimizer=None, device="cuda", grad_sync=None, mixed_precision=False):
+    def __init__(self, model, criterion=None, optimizer=None, device="cuda", grad_sync=None, mixed_precision=False,
+                 bucket=None):
+        """bucket: an asr_b200.distributed.FlatGradBucket over the model's parameters.  With a bucket the gradients must
+        stay the bucket's views: the step re-arms it with `bucket.zero()` instead of `zero_grad(set_to_none=True)` (which
+        would detach the views and leave the all-reduce and the flat FusedAdamW reading a stale buffer), and the
+        all-reduce defaults to `bucket.all_reduce_mean`."""
         self.model, self.device = model, torch.device(device)
         self.criterion = criterion if criterion is not None else CTCLoss(reduction="sum")
         self.optimizer = optimizer
+        self.bucket = bucket
+        if bucket is not None and grad_sync is None:
+            grad_sync = lambda _model: bucket.all_reduce_mean()   # noqa: E731
         self.grad_sync = grad_sync
         self.use_amp = bool(mixed_precision) and self.device.type == "cuda"
         self.scaler = torch.amp.GradScaler("cuda", enabled=True) if self.use_amp else None
@@ -76,7 +84,9 @@ class DeepSpeechStep:
         else:
             valid, loss, loss_value = fit(self.model, self.criterion, data, self.device)
         if valid:
-            if self.optimizer is not None:
+            if self.bucket is not None:
+                self.bucket.zero()
+            elif self.optimizer is not None:
                 self.optimizer.zero_grad(set_to_none=True)
             else:
                 for prm in self.model.parameters():

@@ -442,3 +442,119 @@ def test_resolve_rnn_type_like_reference_tests():
     assert resolve_rnn_type(nn.LSTM) is nn.LSTM
     with pytest.raises(ValueError):
         resolve_rnn_type("nn.Transformer")
+
+
+# ----------------------------------------------------------------------------- round-1 advisor findings
+@pytest.mark.parametrize("name", ["gru_small", "lstm_small"])
+def test_every_parameter_gradient_has_its_own_storage(golden, monkeypatch, tmp_path, name):
+    """LSTM: bias_ih.grad and bias_hh.grad are equal in value but must not alias (an in-place op over all gradients --
+    GradScaler.unscale_, clip_grad_norm_ -- would otherwise be applied twice to them)."""
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.trainers import CTCLoss, fit
+
+    g = golden(name)
+    model = build_model(tmp_path, g)
+    batch = synth_batch(g["seed"], g["B"], g["T"], g["U"], g["C"], g["lengths"])
+    model.train()
+    _, loss, _ = fit(model, CTCLoss(reduction="sum"), batch, "cpu")
+    loss.backward()
+    before = {k: p.grad.clone() for k, p in model.named_parameters()}
+    spans = sorted((p.grad.untyped_storage().data_ptr() + p.grad.storage_offset() * 4, p.grad.numel() * 4, k)
+                   for k, p in model.named_parameters())
+    for (a0, an, ka), (b0, _, kb) in zip(spans, spans[1:]):
+        assert a0 + an <= b0, f"{ka} and {kb} share gradient memory"
+    for p in model.parameters():      # what GradScaler.unscale_ / clip_grad_norm_ do
+        p.grad.mul_(0.5)
+    for k, p in model.named_parameters():
+        assert torch.allclose(p.grad, 0.5 * before[k], rtol=0, atol=0), k
+    # a second backward without zeroing accumulates g, not 2 g
+    _, loss, _ = fit(model, CTCLoss(reduction="sum"), batch, "cpu")
+    for p in model.parameters():
+        p.grad = None
+    loss.backward()
+    again = {k: p.grad.clone() for k, p in model.named_parameters()}
+    _, loss, _ = fit(model, CTCLoss(reduction="sum"), batch, "cpu")
+    loss.backward()
+    for k, p in model.named_parameters():
+        if "running" in k:
+            continue
+        assert (p.grad.norm() - 2 * again[k].norm()).abs() <= 2e-2 * again[k].norm() + 1e-7, k
+
+
+def test_training_step_with_flat_bucket_and_fused_adamw(golden, monkeypatch, tmp_path):
+    """DeepSpeechStep + FlatGradBucket + FusedAdamW(bucket) against the same steps with torch.optim.AdamW: the step must
+    re-arm the bucket (not detach its views), and a bucket whose views were detached must raise instead of stepping on a
+    stale buffer."""
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.distributed import FlatGradBucket
+    from asr_b200.optim import FusedAdamW
+    from asr_b200.trainers import CTCLoss, DeepSpeechStep
+
+    g = golden("gru_small")
+    batch = synth_batch(g["seed"], g["B"], g["T"], g["U"], g["C"], g["lengths"])
+    hp = dict(lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    ref_model, our_model = build_model(tmp_path, g), build_model(tmp_path, g)
+    ref_model.train(); our_model.train()
+    ref_step = DeepSpeechStep(ref_model, CTCLoss(reduction="sum"), torch.optim.AdamW(ref_model.parameters(), **hp), "cpu")
+    bucket = FlatGradBucket(our_model.parameters(), flatten_params=True)
+    opt = FusedAdamW(our_model.parameters(), bucket=bucket, **hp)
+    our_step = DeepSpeechStep(our_model, CTCLoss(reduction="sum"), opt, "cpu", bucket=bucket)
+    for _ in range(3):
+        (va, la), (vb, lb) = ref_step(batch), our_step(batch)
+        assert va and vb and abs(la - lb) <= 1e-5 * abs(la)
+    for (k, a), (_, b) in zip(ref_model.named_parameters(), our_model.named_parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), k
+    for p, v in zip(bucket.params, bucket.views):
+        assert p.grad.data_ptr() == v.data_ptr()
+    # detached views are detected
+    opt.zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError):
+        opt.step()
+
+
+def test_fused_adamw_flat_state_survives_a_checkpoint(monkeypatch):
+    """flat form: state_dict() carries the moments and the step count; after load_state_dict() the next step equals the
+    step of an uninterrupted run (and of torch.optim.AdamW)."""
+    kernel_emulator.install(monkeypatch)
+    from asr_b200.distributed import FlatGradBucket
+    from asr_b200.optim import FusedAdamW
+
+    hp = dict(lr=1.5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    gen = torch.Generator().manual_seed(3)
+    init = [torch.randn(6, 4, generator=gen), torch.randn(9, generator=gen)]
+    grads = [[torch.randn(t.shape, generator=gen) for t in init] for _ in range(5)]
+
+    def make():
+        ps = [torch.nn.Parameter(t.clone()) for t in init]
+        b = FlatGradBucket(ps, flatten_params=True)
+        return ps, b, FusedAdamW(ps, bucket=b, **hp)
+
+    def run(ps, b, opt, steps):
+        for gs in steps:
+            b.zero()
+            for p, gr in zip(ps, gs):
+                p.grad.copy_(gr)
+            opt.step()
+
+    ps_a, b_a, opt_a = make()
+    run(ps_a, b_a, opt_a, grads)                        # uninterrupted
+    ps_b, b_b, opt_b = make()
+    run(ps_b, b_b, opt_b, grads[:3])
+    sd = opt_b.state_dict()
+    assert len(sd["state"]) == 2 and int(sd["state"][0]["step"]) == 3
+    assert sd["state"][0]["exp_avg"].abs().sum() > 0
+    ps_c, b_c, opt_c = make()
+    with torch.no_grad():
+        for c, b in zip(ps_c, ps_b):
+            c.copy_(b)
+    opt_c.load_state_dict(sd)
+    run(ps_c, b_c, opt_c, grads[3:])
+    ref_p = [torch.nn.Parameter(t.clone()) for t in init]
+    ref = torch.optim.AdamW(ref_p, **hp)
+    for gs in grads:
+        for p, gr in zip(ref_p, gs):
+            p.grad = gr.clone()
+        ref.step()
+    for a, c, r in zip(ps_a, ps_c, ref_p):
+        assert torch.allclose(a, c, rtol=0, atol=1e-8)
+        assert torch.allclose(a, r, atol=1e-7)
