@@ -727,10 +727,15 @@ static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void*
     return ASRB_ERR_UNSUPPORTED;
 }
 
-// the exchange-by-data kernel (rnn2.cu): bf16 product, 16-unit slices, operand columns in whole K = 16 MMA steps;
-// asrb_debug_rnn_dbg(8) selects the counter + TMA kernel of this file instead (A/B timing)
+// Which kernel runs the bf16 recurrent product (asrb_debug_rnn_dbg bits, for A/B timing):
+//   forward, batch <= 64, H <= 896: rnn3.cu (weights in tensor memory, two interleaved half-batch chains) -- default;
+//   bit 8: the counter + TMA kernel of this file (the default for everything rnn3.cu does not cover);
+//   bit 256: the experimental exchange-by-data kernel (rnn2.cu), forward and backward.
 static inline bool rnn2_eligible(const RnnPlan& pl, const RnnParams& prm) {
-    return pl.bf16 && !prm.use_simt && !(g_rnn_dbg & 8) && pl.nj == 16 && prm.H % 16 == 0;
+    return pl.bf16 && !prm.use_simt && (g_rnn_dbg & 256) && pl.nj == 16 && prm.H % 16 == 0;
+}
+static inline bool rnn3_eligible(const RnnPlan& pl, const RnnParams& prm) {
+    return pl.bf16 && !prm.use_simt && !(g_rnn_dbg & (8 | 256)) && pl.nj == 16 && prm.B <= 64 && pl.kpad_f <= 896;
 }
 
 // the CUDA-core debug product reads fp32 operands: it always runs the tf32-layout variant
@@ -800,6 +805,7 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
     prm.hbf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16);
     prm.Hp = round_up(H, 64);
     prm.trace = g_rnn_trace;
+    if (rnn3_eligible(pl, prm)) return rnn3_forward(cell, pl, prm, wpack_fwd, stream);
     if (rnn2_eligible(pl, prm)) return rnn2_dispatch(false, cell, pl, prm, wpack_fwd, stream);
     return rnn_dispatch<false>(cell, pl, prm, wpack_fwd, pl.bf16 ? (const void*)hseq_bf16 : (const void*)hseq, stream);
 }

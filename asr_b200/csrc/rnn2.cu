@@ -46,41 +46,6 @@ __device__ __forceinline__ void st_relaxed_bf16(__nv_bfloat16* dst, float v) {
     const __nv_bfloat16 b = __float2bfloat16_rn(v);
     asm volatile("st.relaxed.gpu.global.b16 [%0], %1;" ::"l"(dst), "h"(*reinterpret_cast<const uint16_t*>(&b)) : "memory");
 }
-__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-    return v;
-}
-// 16 TMEM lanes x 4 columns: thread t receives column t%4 of lanes t/4 (a) and t/4 + 8 (b)  (tools/ubench/tmem_ld_layout.cu)
-__device__ __forceinline__ void tmem_ld_16x128b(uint32_t taddr, float& a, float& b) {
-    uint32_t ra, rb;
-    asm volatile("tcgen05.ld.sync.aligned.16x128b.x1.b32 {%0, %1}, [%2];" : "=r"(ra), "=r"(rb) : "r"(taddr) : "memory");
-    a = __uint_as_float(ra);
-    b = __uint_as_float(rb);
-}
-// 16 TMEM lanes x 16 columns: thread t receives, for lanes t/4 (v[0..1], v[4..5]) and t/4 + 8 (v[2..3], v[6..7]),
-// columns 2*(t%4) + {0,1} (v[0..3]) and 8 + 2*(t%4) + {0,1} (v[4..7])   (tools/ubench/tmem_ld_layout.cu)
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-}
-// registers -> TMEM: thread i of the warp writes 8 consecutive 32-bit columns of lane (base lane + i)
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (M x 16 bf16 = 8 columns) is read from tensor memory
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 // does one of the two 16-bit halves of w still hold the fill pattern 0xFFFF?  ("has a zero half" of ~w)
 __device__ __forceinline__ bool half_unwritten(uint32_t w) {
     const uint32_t x = ~w;

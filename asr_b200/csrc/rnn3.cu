@@ -1,0 +1,406 @@
+// asr_b200 -- forward GRU / LSTM recurrence: weights in tensor memory, two interleaved half-batch chains.
+//
+// Same decomposition and step barrier as rnn.cu (CTA (dir, p) owns 16 hidden units, a release/acquire counter in global
+// memory is the step barrier between the CTAs of a direction; modules/blocks.py:87-89 of the reference), restructured
+// around what the SM-clock traces and microbenchmarks of round 2 established:
+//
+//   * a step of rnn.cu is ~10 k cycles of which ~4 k are exposed hand-over latency: the all-to-all visibility of the
+//     freshly written state costs ~2.5 k cycles whatever the protocol (tools/ubench/xchg2.cu: 2-byte or 16-byte stores,
+//     counters or data-as-flag polling), because every word crosses to its L2 home and back, half of the time over the
+//     die-to-die link (tools/ubench/pingpong.cu: 450 cycles one way on the home die, 850-1000 otherwise).  It cannot be
+//     removed -- but the batch rows are independent recurrences, so it can be HIDDEN: the batch is cut into two chains
+//     of 32 rows with their own step counters, TMA / MMA / epilogue warps, shared-memory tiles and accumulators, and the
+//     warp scheduler runs one chain's copy, product and cell math in the shadow of the other chain's hand-over.
+//   * the recurrent product of rnn.cu is bound by shared-memory bandwidth (per step the state is written by TMA and read
+//     back by the tensor core together with the resident weight slice).  Here the weight slice is the A operand in
+//     TENSOR memory (M = 64 gate rows x K, written once with tcgen05.st; 416 of the 512 columns at H = 800), the chain's
+//     32 batch rows are the N dimension and come from shared memory as the B operand: the tensor core reads only the
+//     state, and N = 32 makes an MMA cost 16 cycles.
+//   * the accumulator therefore comes out transposed (TMEM lane = gate row, column = batch row); it is read with
+//     tcgen05.ld.16x256b (all 32 lanes hold data in the M = 64 layout) and handed through a small shared-memory tile to
+//     the (batch row, unit) threads of the cell math.
+//   * the load/store unit is kept free for the hand-over: the gate pre-activations arrive by TMA (64-byte-swizzle boxes,
+//     a step ahead) instead of 48 scattered wavefronts per warp.
+//
+// Used for batch <= 64 and H <= 896 (64 + kpad/2 TMEM columns); everything else runs rnn.cu.
+#include "rnn.cuh"
+
+namespace asrb {
+
+constexpr int kR3Chunk = 4;                 // K blocks per TMA barrier
+constexpr int kR3MaxChunks = 4;             // kpad <= 1024
+constexpr int kR3CounterStride = 16;        // step counters [dir][chain], 64 bytes apart (8 of them in the 512-byte block)
+
+// NCH chains of 64 / NCH batch rows.  Warp c < NCH is chain c's control warp (polls the chain's step counter, issues its TMA
+// copies, then its MMAs -- the steps of a chain are sequential anyway); warps 4 .. 19 are the epilogue warps, 16 / NCH per
+// chain, with warp % 4 = TMEM lane quarter = gate.
+template <int CELL, int NCH>
+__global__ void __launch_bounds__(kRnnThreads, 1)
+rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmGi, const RnnParams p) {
+    constexpr int kR3Chains = NCH;
+    constexpr int kR3Rows = 64 / NCH;           // batch rows of a chain = N of its MMAs
+    constexpr int kR3EpiWarps = 16 / NCH;       // per chain
+    constexpr int kR3EpiThreads = kR3EpiWarps * 32;
+    constexpr int kR3DtStride = kR3Rows + 8;    // floats per gate row of a chain's transposed accumulator tile (2-way conflicts
+                                                // on the 256-byte float2 stores = the minimum; conflict-free reads)
+    constexpr int NJ = 16;
+    constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
+    constexpr int NPAD = ((kGates * NJ + 15) / 16) * 16;      // rows of the packed forward slice
+    constexpr int kTmemCols = 512;
+    constexpr int KBE = 64;
+    constexpr uint32_t kSlotBytes = kR3Rows * 128;            // one K block of a chain's operand: 32 rows x 128 B (swizzled)
+    constexpr int kGiRegion = kR3Rows * 64;                   // one gate's [32 rows x 16 floats] box (2 KB = 4 swizzle atoms)
+    constexpr int NV = NJ / 4;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int T = p.T, B = p.B, H = p.H, G = p.G, P = p.P;
+    const int nkb = p.kpad / KBE;
+    const int nchunks = ceil_div(nkb, kR3Chunk);
+    // per chain: operand tile, gate boxes (2 step parities), transposed accumulator tile, barriers
+    const size_t a_bytes = (size_t)nkb * kSlotBytes, gi_bytes = (size_t)2 * kGates * kGiRegion;
+    const size_t dt_bytes = (size_t)64 * kR3DtStride * 4;
+    const size_t chain_bytes = (a_bytes + gi_bytes + dt_bytes + 256 + 1023) & ~size_t(1023);   // operand tiles: 1 KB aligned
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.x / P, pidx = blockIdx.x % P;
+    const int j0 = pidx * NJ;
+    const int chain = warp < kRnnCtrlWarps ? warp : (warp - kRnnCtrlWarps) / kR3EpiWarps;
+    const int row0 = chain * kR3Rows;                         // first batch row of the chain
+    const bool chain_on = chain < NCH && row0 < B;
+    uint8_t* cs = smem + (size_t)(chain < NCH ? chain : 0) * chain_bytes;
+    uint8_t* smem_a = cs;                                     // [nkb][32 rows x 128 B]
+    uint8_t* smem_gi = cs + a_bytes;                          // [2][kGates][kGiRegion]
+    float* dt = reinterpret_cast<float*>(cs + a_bytes + gi_bytes);   // [64 gate rows][kR3DtStride]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cs + a_bytes + gi_bytes + dt_bytes);
+    uint64_t* full_bar = bars;                                // [kR3MaxChunks]
+    uint64_t* tfull_bar = bars + kR3MaxChunks;
+    uint64_t* gi_bar = bars + kR3MaxChunks + 1;               // [2]
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + (size_t)kR3Chains * chain_bytes);   // weights are in tensor memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(w_bar + 2);      // [kGates][NJ]
+
+    uint32_t* counter = p.counters + (dir * kR3Chains + (chain < NCH ? chain : 0)) * kR3CounterStride;
+    auto t_of = [&](int s) { return dir == 1 ? (T - 1 - s) : s; };
+
+    if (warp < NCH && lane == 0) {
+        if (warp == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmGi);
+            mbar_init(w_bar, 1);
+        }
+        for (int i = 0; i < kR3MaxChunks; ++i) mbar_init(&full_bar[i], 1);
+        mbar_init(tfull_bar, 1);
+        mbar_init(&gi_bar[0], 1);
+        mbar_init(&gi_bar[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_d = tmem_base + chain * kR3Rows;      // the chain's accumulator: kR3Rows columns
+    const uint32_t tmem_w = tmem_base + kR3Chains * kR3Rows;  // weights: kpad/2 columns
+
+    if (warp < kRnnCtrlWarps) {
+        // ===================== control warp of the chain: TMA copies, then the MMAs =====================
+        //   D[64 gate rows, kR3Rows batch rows] = W[tensor memory] x h^T[shared memory]
+        if (chain_on) {
+            constexpr uint32_t idesc = umma_idesc(kFmtBF16, 64, kR3Rows);
+            auto load_gi = [&](int s) {   // the slice's gate pre-activations of step s, rows of this chain -> buffer s & 1
+                const int t = t_of(s);
+                mbar_arrive_expect_tx(&gi_bar[s & 1], (uint32_t)(kGates * kR3Rows * NJ * 4));
+#pragma unroll
+                for (int q = 0; q < kGates; ++q)
+                    tma_load_3d(smem_gi + (size_t)((s & 1) * kGates + q) * kGiRegion, &tmGi, &gi_bar[s & 1], dir * G + q * H + j0, row0, t);
+            };
+            if (elect_one()) {
+                load_gi(0);
+                if (T > 1) load_gi(1);
+            }
+            __syncwarp();
+            mbar_wait(w_bar, 0);           // the weight slice is in tensor memory
+            tc_fence_after_sync();
+            for (int s = 1; s < T; ++s) {
+                // step barrier of the chain: every CTA of this direction has published step s-1 of these rows
+                const uint32_t need = (uint32_t)P * (uint32_t)s;
+                while (ld_acquire_u32(counter) < need) {
+                }
+                if (lane == 0 && chain == 0) ASRB_TRACE(0, s);
+                fence_proxy_async_global();      // the others' generic-proxy stores -> our async-proxy (TMA) reads
+                const int slab = dir * (T + 2) + t_of(s - 1) + 1;
+                // (our own arrival is part of `need`: our MMAs of step s-1 have read the tile, our epilogue its gate boxes)
+                if (elect_one()) {
+                    for (int c = 0; c < nchunks; ++c) {
+                        const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
+                        mbar_arrive_expect_tx(&full_bar[c], (uint32_t)nblk * kSlotBytes);
+                        for (int i = 0; i < nblk; ++i)
+                            tma_load_3d(smem_a + (size_t)(kb0 + i) * kSlotBytes, &tmA, &full_bar[c], (kb0 + i) * KBE, row0, slab);
+                    }
+                    if (s + 1 < T) load_gi(s + 1);
+                }
+                __syncwarp();
+                if (lane == 0 && chain == 0) ASRB_TRACE(1, s);
+                const uint32_t ph = (uint32_t)((s - 1) & 1);
+                for (int c = 0; c < nchunks; ++c) {
+                    const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
+                    mbar_wait(&full_bar[c], ph);
+                    if (c == 0 && lane == 0 && chain == 0) ASRB_TRACE(2, s);
+                    tc_fence_after_sync();
+                    if (elect_one()) {
+                        for (int i = 0; i < nblk; ++i) {
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_a + (size_t)(kb0 + i) * kSlotBytes));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)   // 8 TMEM columns of weights per K = 16 step
+                                umma_f16_ts(tmem_d, tmem_w + ((kb0 + i) * 4 + k) * 8, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                        }
+                        if (c == nchunks - 1) umma_commit(tfull_bar);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0 && chain == 0) ASRB_TRACE(3, s);
+            }
+        }
+    } else {
+        // ===================== epilogue warps of the chain: 8 warps =====================
+        // accumulator role: lane quarter q = warp % 4 holds gate q of the 16 units (rows), this warp takes the chain's
+        // batch columns 16*half .. +15.  cell role: thread = unit 4*ug + lane%4 of two batch rows of the chain.
+        constexpr int kRp16 = kR3Rows / 16;                    // 16-row groups of the chain
+        const int wl = (warp - kRnnCtrlWarps) % kR3EpiWarps;
+        const int quad = warp & 3, half = wl >> 2;
+        const int ug = wl / kRp16, ul = lane & 3;
+        const int el = wl * 32 + lane;                         // 0..255 within the chain
+        const int ju = 4 * ug + ul, unit = j0 + ju;
+        const bool uvalid = unit < H;
+        int row[2], len[2];
+        bool cellok[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            row[c] = row0 + 16 * (wl % kRp16) + (lane >> 2) + 8 * c;
+            cellok[c] = uvalid && row[c] < B;
+            len[c] = cellok[c] ? p.lengths[row[c]] : 0;
+        }
+        const size_t slotHB = (size_t)B * H;
+        uint32_t gi_off[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int rl = row[c] - row0;
+            gi_off[c] = (uint32_t)(rl * 64 + ((ug ^ ((rl >> 1) & 3)) << 4) + ul * 4);
+        }
+        const uint32_t smem_gi_u32 = smem_u32(smem_gi);
+
+        // ---- once: zero boundary slots, biases, the weight slice -> tensor memory ----
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (cellok[c]) {
+                const size_t o = ((size_t)dir * (T + 2)) * slotHB + (size_t)row[c] * H + unit;
+                p.hseq[o] = 0.f;
+                p.hseq[o + (size_t)(T + 1) * slotHB] = 0.f;
+                if constexpr (CELL == ASRB_RNN_LSTM) {
+                    p.cseq[o] = 0.f;
+                    p.cseq[o + (size_t)(T + 1) * slotHB] = 0.f;
+                }
+            }
+        }
+        if (chain == 0) {
+            for (int i = el; i < kGates * NJ; i += kR3EpiThreads) {
+                const int g = i / NJ, jj = i % NJ;
+                s_bias[i] = (j0 + jj < H) ? p.b_hh[(size_t)dir * G + g * H + j0 + jj] : 0.f;
+            }
+            if (wl < 4) {
+                // gate row c = 16 * quarter + i sits in TMEM lane 32 * quarter + i (the M = 64 data path layout, like the
+                // accumulator rows); 16 bf16 = 8 columns per store
+                const int c = 16 * quad + lane;
+                const bool have = lane < 16 && c < NPAD;
+                const uint4* wrow = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.wpack) + ((size_t)(dir * P + pidx) * NPAD + (have ? c : 0)) * p.kpad);
+                for (int k16 = 0; k16 < p.kpad / 16; ++k16) {
+                    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+                    if (have) { lo = __ldg(wrow + 2 * k16); hi = __ldg(wrow + 2 * k16 + 1); }
+                    const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    tmem_st_32x8(tmem_w + (uint32_t(quad * 32) << 16) + k16 * 8, r);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before_sync();
+        }
+        named_bar_sync(3, kRnnEpiThreads);                      // all 16 epilogue warps
+        if (warp == kRnnCtrlWarps && lane == 0) mbar_arrive(w_bar);
+        float bias[kGates];
+#pragma unroll
+        for (int g = 0; g < kGates; ++g) bias[g] = s_bias[g * NJ + ju];
+
+        if (chain_on) {
+            float state_h[2] = {0.f, 0.f}, state_c[2] = {0.f, 0.f};
+            for (int s = 0; s < T; ++s) {
+                const int t = t_of(s);
+                bool active[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) active[c] = cellok[c] && (t < len[c]);
+                if (el == 0 && chain == 0) ASRB_TRACE(4, s);
+                float acc[kGates][2];
+#pragma unroll
+                for (int g = 0; g < kGates; ++g) acc[g][0] = acc[g][1] = 0.f;
+                if (s > 0) {
+                    mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
+                    if (el == 0 && chain == 0) ASRB_TRACE(5, s);
+                    tc_fence_after_sync();
+                    if (quad < kGates) {
+                        float v[8];
+                        tmem_ld_16x256b_x2(tmem_d + (uint32_t(quad * 32) << 16) + 16 * half, v);
+                        tmem_ld_wait();
+                        float* d = dt + (quad * 16 + (lane >> 2)) * kR3DtStride + 16 * half + 2 * ul;
+                        *reinterpret_cast<float2*>(d) = make_float2(v[0], v[1]);
+                        *reinterpret_cast<float2*>(d + 8 * kR3DtStride) = make_float2(v[2], v[3]);
+                        *reinterpret_cast<float2*>(d + 8) = make_float2(v[4], v[5]);
+                        *reinterpret_cast<float2*>(d + 8 * kR3DtStride + 8) = make_float2(v[6], v[7]);
+                    }
+                    tc_fence_before_sync();    // the counter arrival below orders these reads before the next step's MMAs
+                    named_bar_sync(4 + chain, kR3EpiThreads);
+#pragma unroll
+                    for (int g = 0; g < kGates; ++g)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) acc[g][c] = dt[(g * 16 + ju) * kR3DtStride + (row[c] - row0)];
+                    if (el == 0 && chain == 0) ASRB_TRACE(6, s);
+                }
+                // gate pre-activations of this step (TMA, a step ahead)
+                mbar_wait(&gi_bar[s & 1], (uint32_t)((s >> 1) & 1));
+                float in[kGates][2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int q = 0; q < kGates; ++q)
+                        in[q][c] = active[c] ? ld_shared_f32(smem_gi_u32 + (uint32_t)(((s & 1) * kGates + q) * kGiRegion) + gi_off[c]) : 0.f;
+
+                float hn[2], cn[2], sv[4][2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float h_ = 0.f, c_ = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    if (active[c]) {
+                        if constexpr (CELL == ASRB_RNN_GRU) {
+                            const float gn = acc[2][c] + bias[2];
+                            const float r = fsigmoid(in[0][c] + acc[0][c] + bias[0]);
+                            const float z = fsigmoid(in[1][c] + acc[1][c] + bias[1]);
+                            const float n = ftanh(in[2][c] + r * gn);
+                            h_ = (1.f - z) * n + z * state_h[c];
+                            s0 = r; s1 = z; s2 = n; s3 = gn;
+                        } else {
+                            const float gi_ = fsigmoid(in[0][c] + acc[0][c] + bias[0]);
+                            const float gf = fsigmoid(in[1][c] + acc[1][c] + bias[1]);
+                            const float gg = ftanh(in[2][c] + acc[2][c] + bias[2]);
+                            const float go = fsigmoid(in[3][c] + acc[kGates - 1][c] + bias[kGates - 1]);
+                            c_ = gf * state_c[c] + gi_ * gg;
+                            h_ = go * ftanh(c_);
+                            s0 = gi_; s1 = gf; s2 = gg; s3 = go;
+                        }
+                    }
+                    hn[c] = h_; cn[c] = c_;
+                    sv[0][c] = s0; sv[1][c] = s1; sv[2][c] = s2; sv[3][c] = s3;
+                    state_h[c] = h_;
+                    state_c[c] = c_;
+                }
+                // (1) the next step's MMA operand, published through the chain's step counter
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    if (cellok[c]) p.hbf[(((size_t)dir * (T + 2) + t + 1) * B + row[c]) * p.Hp + unit] = __float2bfloat16_rn(hn[c]);
+                if (el == 0 && chain == 0) ASRB_TRACE(7, s);
+                named_bar_sync(8 + chain, kR3EpiThreads);
+                if (el == 0) {
+                    if (chain == 0) ASRB_TRACE(8, s);
+                    red_release_add_u32(counter, 1u);
+                    if (chain == 0) ASRB_TRACE(10, s);
+                }
+                // hold the other stores back until the release has been issued: its MEMBAR waits for every store in flight
+                named_bar_sync(12 + chain, kR3EpiThreads);
+                // (2) the stores nobody waits for
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (cellok[c]) {
+                        const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)row[c] * H + unit;
+                        float* svp = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) +
+                                     (size_t)ug * (B * 4) + (size_t)row[c] * 4 + ul;
+                        p.hseq[o] = hn[c];
+                        if constexpr (CELL == ASRB_RNN_LSTM) p.cseq[o] = cn[c];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) svp[(size_t)q * NV * (B * 4)] = sv[q][c];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+template <int CELL, int NCH>
+static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {
+    constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
+    constexpr int kR3Chains = NCH, kR3Rows = 64 / NCH, kR3DtStride = kR3Rows + 8;
+    const int kpad = pl.kpad_f, nkb = kpad / 64;
+    const int B = prm.B;
+    if (ceil_div(nkb, kR3Chunk) > kR3MaxChunks || kR3Chains * kR3Rows + kpad / 2 > 512) return ASRB_ERR_UNSUPPORTED;
+    prm.P_saved = pl.P;
+    prm.P = pl.P;
+    prm.kpad = kpad;
+    prm.wpack = reinterpret_cast<const float*>(wpack);       // bf16 slices, read once into tensor memory
+    const size_t chain_bytes = ((size_t)nkb * kR3Rows * 128 + (size_t)2 * kGates * kR3Rows * 64 + (size_t)64 * kR3DtStride * 4 + 256 + 1023) & ~size_t(1023);
+    const size_t smem = 1024 + kR3Chains * chain_bytes + 16 + kGates * 16 * 4 + 64;
+    if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return ASRB_ERR_DRIVER;
+    CUtensorMap tmA, tmGi;
+    {   // hbf [2(T+2)][B][Hp] bf16, box = 64 columns x 32 rows (one chain), 128-byte swizzle; rows >= B, columns >= H: zero fill
+        uint64_t d[3] = {(uint64_t)prm.H, (uint64_t)B, (uint64_t)2 * (prm.T + 2)};
+        uint64_t s[2] = {(uint64_t)prm.Hp * 2, (uint64_t)B * prm.Hp * 2};
+        uint32_t bx[3] = {64, (uint32_t)kR3Rows, 1};
+        int rc = make_tmap_bf16(&tmA, prm.hbf, 3, d, s, bx);
+        if (rc) return rc;
+    }
+    {   // gi [T][B][2G] fp32, box = 16 columns x 32 rows, 64-byte swizzle (conflict-free reads by (row, unit) threads)
+        if ((reinterpret_cast<uintptr_t>(prm.gi) & 15) != 0) return ASRB_ERR_ALIGNMENT;
+        cuuint64_t gdim[3] = {(cuuint64_t)2 * prm.G, (cuuint64_t)B, (cuuint64_t)prm.T};
+        cuuint64_t gstr[2] = {(cuuint64_t)2 * prm.G * 4, (cuuint64_t)B * 2 * prm.G * 4};
+        cuuint32_t bx[3] = {16, (cuuint32_t)kR3Rows, 1}, es[3] = {1, 1, 1};
+        CUresult r = enc(&tmGi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(prm.gi), gdim, gstr, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return ASRB_ERR_TENSORMAP;
+    }
+    auto kern = rnn_rec3_kernel<CELL, NCH>;
+    ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // the step barrier spins: refuse the launch when the device cannot hold the whole grid at once
+        int dev = 0, sms = 0, per_sm = 0;
+        ASRB_CUDA_OK(cudaGetDevice(&dev));
+        ASRB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        ASRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRnnThreads, smem));
+        if (2 * pl.P > sms * per_sm) return ASRB_ERR_UNSUPPORTED;
+    }
+    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * kR3Chains * kR3CounterStride * sizeof(uint32_t), stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pl.P);
+    cfg.blockDim = dim3(kRnnThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    prm.dbg = g_rnn_dbg;
+    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmGi, prm));
+    return 0;
+}
+
+int rnn3_forward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {
+    // Two chains of 32 rows.  Four chains of 16 (asrb_debug_rnn_dbg bit 512) measure the same: what a chain waits for is
+    // shared -- the release's MEMBAR covers every store the SM has in flight, and the chains' copies share the TMA / L2
+    // bandwidth -- and starting the chains staggered (0.25 .. 6 k cycles apart) changes nothing either: they couple.
+    if (g_rnn_dbg & 512) {
+        if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 4>(pl, prm, wpack, stream);
+        return rnn3_launch<ASRB_RNN_LSTM, 4>(pl, prm, wpack, stream);
+    }
+    if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 2>(pl, prm, wpack, stream);
+    return rnn3_launch<ASRB_RNN_LSTM, 2>(pl, prm, wpack, stream);
+}
+
+}  // namespace asrb

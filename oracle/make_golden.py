@@ -133,6 +133,7 @@ def model_case(name, rnn_type, hidden, layers, C, seed, B, T, U, lengths=None):
         running_stats=stats, eval_argmax=idx, eval_probs_digest=grad_digest(probs),
         eval_strings=[s[0] for s in strings],
     )
+    rec.update(eval64_fields(model, batch))
     torch.save(rec, os.path.join(GOLDEN_DIR, f"{name}.pt"))
     print(f"{name}: loss={loss.item():.6f} out={tuple(out.shape)} sizes={output_sizes.tolist()}")
 
@@ -175,8 +176,56 @@ def model_case_big(name, rnn_type, hidden, layers, C, seed, B, T, U, backward=Tr
         rec.update(eval_argmax=torch.max(probs, 2)[1].to(torch.int16),               # greedy_decoder.py:61
                    eval_margin=(top2.values[..., 0] - top2.values[..., 1]).to(torch.float16),
                    eval_probs_digest=grad_digest(probs))
+    rec.update(eval64_fields(model, batch))
     torch.save(rec, os.path.join(GOLDEN_DIR, f"{name}.pt"))
     print(f"{name}: done {time.time() - t0:.0f} s out={tuple(out.shape)}", flush=True)
+
+
+def eval64_fields(model, batch):
+    """The eval-mode forward of the SAME unmodified reference modules in fp64 (BN on the running statistics the model
+    holds): per frame the two most probable classes and the log-probability margin between them.  tests use it to
+    settle every frame where a GPU argmax differs from the reference's fp32 argmax: either the GPU picked the fp64
+    winner (the fp32 reference is the one on the wrong side), or the fp64 margin is below the arithmetic noise."""
+    import copy
+
+    m64 = copy.deepcopy(model).double().eval()
+    with torch.no_grad():
+        input_sizes = batch[2].clone().mul_(int(batch[0].size(3))).int()
+        # eval mode has no cross-utterance arithmetic (BN on running statistics): 4 utterances at a time keeps the fp64
+        # convolution's workspace small; the time axis of a chunk is the full padded one, as in the one-batch call
+        outs = []
+        for i in range(0, batch[0].size(0), 4):
+            pr, _ = m64.forward(batch[0][i:i + 4].double(), input_sizes[i:i + 4])
+            outs.append(pr)
+        probs = torch.cat(outs, 0)
+        lp = probs.log()
+        top2 = torch.topk(lp, 2, dim=2)
+    return dict(eval64_top2=top2.indices.to(torch.int16),
+                eval64_margin=(top2.values[..., 0] - top2.values[..., 1]).float(),
+                eval64_logp_digest=grad_digest(lp.float()))
+
+
+def augment_eval64(name):
+    """add the fp64 eval fields to an existing golden file (weights = the seeded init, BN statistics = the stored ones)"""
+    path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+    rec = torch.load(path)
+    C = rec["C"]
+    labels = LABELS29[:C] if C <= 29 else [chr(0x3041 + i) for i in range(C)]
+    model = build_reference_model(rec["rnn_type"], rec["hidden"], rec["layers"], labels)
+    sd = model.state_dict()
+    for k, v in rec["running_stats"].items():
+        sd[k].copy_(v)
+    batch = synth_batch(rec["seed"], rec["B"], rec["T"], rec["U"], C, rec.get("lengths"))
+    assert torch.equal(checksum(batch[0]), rec["input_checksum"])
+    model.eval()
+    with torch.no_grad():       # the stored fp32 argmax is reproduced before anything is added
+        input_sizes = batch[2].clone().mul_(int(batch[0].size(3))).int()
+        probs, _ = model.forward(batch[0], input_sizes)
+    assert torch.equal(torch.max(probs, 2)[1].to(rec["eval_argmax"].dtype), rec["eval_argmax"]), "fp32 eval argmax not reproduced"
+    rec.update(eval64_fields(model, batch))
+    torch.save(rec, path)
+    flips = (rec["eval64_top2"][..., 0].long() != rec["eval_argmax"].long()).sum().item()
+    print(f"{name}: fp64 eval fields added; the reference's own fp32 argmax differs from fp64 in {flips} frames", flush=True)
 
 
 def ctc_cases():
@@ -294,15 +343,20 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
         checkpoint_manifest()
         return
+    if len(sys.argv) > 2 and sys.argv[1] == "eval64":
+        torch.set_num_threads(os.cpu_count())
+        for name in sys.argv[2:]:
+            augment_eval64(name)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "cfg2":
         # BASELINE.json configs[1] = the benchmarked shape (bench.py CFG: seed 1234+2), fwd + bwd once (~6 min of CPU)
         torch.set_num_threads(os.cpu_count())
         model_case_big("cfg2_gru800x5", "gru", 800, 5, 29, seed=1236, B=64, T=1001, U=100)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
-        # BASELINE.json configs[2]: 7 x biLSTM-1024, 15 s, 90 labels; batch reduced 128 -> 16 for the CPU run (stated)
+        # BASELINE.json configs[2]: 7 x biLSTM-1024, 15 s, 90 labels; batch reduced 128 -> 16 for the CPU run (stated), fwd + bwd
         torch.set_num_threads(os.cpu_count())
-        model_case_big("cfg3_lstm1024x7_b16", "lstm", 1024, 7, 90, seed=1237, B=16, T=1501, U=150, backward=False)
+        model_case_big("cfg3_lstm1024x7_b16", "lstm", 1024, 7, 90, seed=1237, B=16, T=1501, U=150, backward=True)
         return
     torch.set_num_threads(os.cpu_count())
     misc_cases()

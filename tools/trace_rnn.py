@@ -35,7 +35,7 @@ def timed(fn, n=3):
 
 # forward outputs of every variant against the counter + TMA kernel
 ref = None
-for dbg, label in ((8, "rnn.cu"), (64, "rnn2 SS"), (0, "rnn2 TS"), (32, "rnn2 TS, rows in lanes 0..63")):
+for dbg, label in ((8, "rnn.cu"), (0, "rnn3 (TMEM weights, two chains)"), (512, "rnn3, four chains"), (256, "rnn2 TS")):
     _lib.query("asrb_debug_rnn_dbg", dbg)
     pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
     hs, cs, sv = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
@@ -45,7 +45,8 @@ for dbg, label in ((8, "rnn.cu"), (64, "rnn2 SS"), (0, "rnn2 TS"), (32, "rnn2 TS
     else:
         print(f"## fwd hseq {label} vs rnn.cu: max abs diff {(hs - ref).abs().max().item():.3e} (|h| max {ref.abs().max().item():.3f})", flush=True)
 
-for dbg, label in ((0, "exchange-by-data, weights in TMEM (rnn2.cu TS)"), (1, "TS, WITHOUT the deferred stores (timing experiment)"), (64, "exchange-by-data (rnn2.cu SS)"), (65, "SS, WITHOUT the deferred stores"), (8, "counter + TMA (rnn.cu)"), (9, "rnn.cu WITHOUT the non-critical stores")):
+variants = [(0, "default: rnn3.cu forward (TMEM weights, two chains of 32 rows), rnn.cu backward"), (512, "rnn3.cu forward with four chains of 16 rows"), (8, "counter + TMA (rnn.cu)"), (256, "exchange-by-data (rnn2.cu)")]
+for dbg, label in variants:
     _lib.query("asrb_debug_rnn_dbg", dbg)
     _lib.query("asrb_debug_rnn_ksplit", ks)
     pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
@@ -55,7 +56,7 @@ for dbg, label in ((0, "exchange-by-data, weights in TMEM (rnn2.cu TS)"), (1, "T
     tb = timed(lambda: ops.rnn_bwd(cell, dout, pb, lens, hseq, cseq, saved, T, B, H))
     print(f"## {label}: {cellname} H={H} B={B} T={T} nj={nj} P={P} ksplit={ks}: fwd {tf:.3f} ms ({tf*1e3/T:.2f} us/step)  "
           f"bwd {tb:.3f} ms ({tb*1e3/T:.2f} us/step)", flush=True)
-    names = names1 if dbg & 8 else names2
+    names = names2 if dbg & 256 else names1
     for which in ("fwd", "bwd"):
         grid = 2 * (P + 3)
         trace = torch.zeros(grid + 8, T, 16, dtype=torch.int64, device=dev)
@@ -70,12 +71,14 @@ for dbg, label in ((0, "exchange-by-data, weights in TMEM (rnn2.cu TS)"), (1, "T
         s0, s1 = min(50, T // 4), max(T - 50, T // 2)
         tot = tr[0, T - 1, 4] - tr[0, 0, 4]
         print(f" {which}: first to last step top {tot:.0f} cycles = {tot / 1.965e6:.3f} ms @1965 MHz", flush=True)
+        if dbg >> 16:
+            continue
         for cta in (0, P):
             x = tr[cta, s0:s1]
             top = x[:, 4]
             step_cycles = (top[1:] - top[:-1]).mean().item()
             rel = {k: (x[:, k] - top).mean().item() for k in names}
-            extra = f"; steps repeated by the CTA over {T} steps: {tr[cta, T - 1, 9].item():.0f}" if not dbg & 8 else ""
+            extra = f"; steps repeated by the CTA over {T} steps: {tr[cta, T - 1, 9].item():.0f}" if dbg & 256 else ""
             print(f" {which} cta {cta}: cycles/step {step_cycles:.0f}; " +
                   "; ".join(f"{names[k]}={rel[k]:.0f}" for k in names if abs(rel[k]) < 1e6) + extra, flush=True)
 _lib.query("asrb_debug_rnn_dbg", 0)
