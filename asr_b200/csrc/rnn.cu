@@ -603,10 +603,18 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
         const size_t wf = (size_t)r.npad_f * r.kpad_f * esize;
         const size_t fixed = 1024 + kRnnBarBytes;
         size_t wb = 0, xb = 0;
+        // rnn3.cu backward (weights in tensor memory): clusters of 4, the K quarter has to fit 448 TMEM columns
+        r.ts_bwd = 0;
+        {
+            const int kpad4 = ceil_div(ceil_div(G, 64), 4) * 64;
+            if (bf16 && nj == 16 && B <= 64 && !(g_rnn_dbg & (8 | 256 | 1024)) && kpad4 <= 896 && 2 * round_up(P, 4) <= kNumSMs)
+                r.ts_bwd = 1;
+        }
         const int ks_try[3] = {4, 2, 0};
         for (int ki = 0; ki < 3; ++ki) {
             const int ks = ks_try[ki];
-            if (ks && !(bf16 && nj == 16 && g_rnn_ksplit >= ks)) continue;
+            if (r.ts_bwd && ks != 4) continue;
+            if (ks && !(bf16 && nj == 16 && (g_rnn_ksplit >= ks || r.ts_bwd))) continue;
             if (ks && 2 * round_up(P, ks) > kNumSMs) continue;
             r.ksplit = ks;
             r.P_b = ks ? round_up(P, ks) : P;
@@ -614,8 +622,9 @@ static int rnn_make_plan(int cell, int H, int B, int bf16, RnnPlan* pl) {
             r.kpad_b = ks ? ceil_div(ceil_div(G, kbe), ks) * kbe : round_up(G, kbe);
             wb = (size_t)r.npad_b * r.kpad_b * esize;
             xb = ks ? (size_t)2 * (2 * ks - 1) * mrows * nj * 4 : 0;   // receive + staging buffers of the K split
-            if (!ks || wb + fixed + xb + 4 * (size_t)stage <= (size_t)kRnnMaxSmem) break;
+            if (!ks || r.ts_bwd || wb + fixed + xb + 4 * (size_t)stage <= (size_t)kRnnMaxSmem) break;
         }
+        if (r.ts_bwd) wb = xb = 0;     // its shared-memory budget is its own (rnn3_bwd_launch)
         if (wf + fixed + stage > (size_t)kRnnMaxSmem || wb + fixed + xb + stage > (size_t)kRnnMaxSmem) continue;
         // as many K blocks in flight as fit (the whole previous state when possible): the step is latency-bound
         // K blocks that fit next to the resident weights; up to 4 blocks share one barrier / pipeline stage
@@ -730,6 +739,8 @@ static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void*
 // Which kernel runs the bf16 recurrent product (asrb_debug_rnn_dbg bits, for A/B timing):
 //   forward, batch <= 64, H <= 896: rnn3.cu (weights in tensor memory, two interleaved half-batch chains) -- default;
 //   bit 8: the counter + TMA kernel of this file (the default for everything rnn3.cu does not cover);
+//   backward, batch <= 64, G/4 <= 896: rnn3.cu (weights in tensor memory, clusters of 4, two chains) -- default;
+//     bit 1024: the backward of this file instead;
 //   bit 256: the experimental exchange-by-data kernel (rnn2.cu), forward and backward.
 static inline bool rnn2_eligible(const RnnPlan& pl, const RnnParams& prm) {
     return pl.bf16 && !prm.use_simt && (g_rnn_dbg & 256) && pl.nj == 16 && prm.H % 16 == 0;
@@ -831,6 +842,7 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
     prm.dghbf = reinterpret_cast<__nv_bfloat16*>(dgh_bf16);
     prm.Gp = round_up(prm.G, 64);
     prm.trace = g_rnn_trace;
+    if (pl.ts_bwd && !prm.use_simt) return rnn3_backward(cell, pl, prm, wpack_bwd, stream);
     if (rnn2_eligible(pl, prm)) return rnn2_dispatch(true, cell, pl, prm, wpack_bwd, stream);
     return rnn_dispatch<true>(cell, pl, prm, wpack_bwd, pl.bf16 ? (const void*)dgh_bf16 : (const void*)dgh, stream);
 }

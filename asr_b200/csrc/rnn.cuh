@@ -27,6 +27,7 @@ struct RnnParams {
     int P_saved;          // slices of the saved-gates layout (= the forward's P; the split backward may pad its own P)
     const int* lengths;
     uint32_t* counters;   // [2 dirs] step counters, kRnnCounterStride words apart
+    int stage_out;        // rnn3.cu backward: gate-gradient outputs through shared-memory tiles + TMA stores
     int dbg;              // DEBUG timing experiments: 1 = drop the non-critical stores, 2 = drop the operand prefetch
     const float* wpack;  // packed fp32 weight slices (global copy, SIMT debug path)
     // bf16 MMA operands; rows padded to a multiple of 64 elements (128 bytes) so that every 128-byte box row TMA
@@ -144,6 +145,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 
 struct RnnPlan {
     int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, chunk_f, chunk_b, mrows, bf16, ksplit, P_b;   // ksplit: 0, 2, 4
+    int ts_bwd;   // the backward recurrence runs rnn3.cu (weights in tensor memory, clusters of 4): packed layout of ks = 4
     size_t smem_f, smem_b;
 };
 
@@ -152,5 +154,7 @@ struct RnnPlan {
 int rnn2_dispatch(bool bwd, int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream);
 // rnn3.cu: forward recurrence, weights in tensor memory, two interleaved half-batch chains (B <= 64, H <= 896, nj == 16)
 int rnn3_forward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream);
+// rnn3.cu: backward recurrence, weights in tensor memory, K split over clusters of 4, two chains (plan.ts_bwd)
+int rnn3_backward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream);
 
 }  // namespace asrb

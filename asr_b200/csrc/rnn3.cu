@@ -391,6 +391,449 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     return 0;
 }
 
+// ================================================================================================
+// backward recurrence: dh_{t-1} = dgates_t W_hh, weights in tensor memory, K split over a cluster of four CTAs,
+// two interleaved half-batch chains
+// ================================================================================================
+// A cluster of 4 CTAs shares 64 hidden units (16 each).  CTA rank r keeps, for ALL 64 units, the r-th quarter of the gate
+// index K (the layout rnn_pack_bwd_split_kernel writes for ks = 4): A = [M = 64 units, K = kpad] in tensor memory.  Per
+// step and chain it copies only its quarter of the chain's gate-gradient rows (32 rows x kpad), multiplies, and the four
+// 16-unit quarters of the transposed accumulator D[64 units, 32 rows] go where they belong: quarter r stays, the other
+// three travel to their owners through distributed shared memory (one 2.5 KB bulk copy each, completing on the owner's
+// mbarrier); every CTA then adds the four partial sums of its own 16 units.  The exchange latency (~1.2-2 k cycles)
+// sits in the shadow of the other chain like the step hand-over does.
+constexpr int kR3XStride = 40;                              // floats per unit row of an exchanged quarter [16 units][32 rows + pad]
+constexpr int kR3XBytes = 16 * kR3XStride * 4;              // 2560
+constexpr int kR3StageBytes = 32 * 16 * 2;                  // one gate's [32 rows x 16 units] bf16 tile of a staged output
+
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int CELL>
+__global__ void __launch_bounds__(kRnnThreads, 1)
+rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmDgi,
+                    const __grid_constant__ CUtensorMap tmGT, const __grid_constant__ CUtensorMap tmHT, const RnnParams p) {
+    constexpr int NCH = 2, KS = 4;
+    constexpr int kRows = 64 / NCH;             // batch rows of a chain = N of its MMAs
+    constexpr int kEpiWarps = 16 / NCH, kEpiThreads = kEpiWarps * 32;
+    constexpr int NJ = 16, NV = NJ / 4;
+    constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
+    constexpr int kTmemCols = 512;
+    constexpr int KBE = 64;
+    constexpr uint32_t kSlotBytes = kRows * 128;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int T = p.T, B = p.B, H = p.H, G = p.G, P = p.P;
+    const int nkb = p.kpad / KBE;
+    const int nchunks = ceil_div(nkb, kR3Chunk);
+    // per chain: operand tile | own quarter [16][40] | staging [2 parities][4 peers][16][40] | receive [2][4 sources][16][40] | barriers
+    const size_t a_bytes = (size_t)nkb * kSlotBytes;
+    const size_t x_bytes = (size_t)(1 + 2 * KS + 2 * KS) * kR3XBytes;
+    const size_t st_bytes = (size_t)3 * kGates * kR3StageBytes;     // staged outputs: dgi, dgiT, dghT tiles of every gate
+    const size_t chain_bytes = (a_bytes + x_bytes + st_bytes + 256 + 1023) & ~size_t(1023);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.x / P, pidx = blockIdx.x % P;
+    const int j0 = pidx * NJ;
+    const uint32_t crank = cluster_ctarank();                  // = pidx % 4: our K quarter, and the accumulator quarter we own
+    const int chain = warp < kRnnCtrlWarps ? warp : (warp - kRnnCtrlWarps) / kEpiWarps;
+    const int row0 = chain * kRows;
+    const bool chain_on = chain < NCH && row0 < B;
+    uint8_t* cs = smem + (size_t)(chain < NCH ? chain : 0) * chain_bytes;
+    uint8_t* smem_a = cs;
+    float* dt = reinterpret_cast<float*>(cs + a_bytes);                       // our own partial sums [16 units][kR3XStride]
+    float* xs = dt + 16 * kR3XStride;                                         // [2][KS][16][kR3XStride] staging, by peer
+    float* xr = xs + 2 * KS * 16 * kR3XStride;                                // [2][KS][16][kR3XStride] received, by source
+    // staged outputs (TMA stores): [gate][32 rows][16 units] for dgi, [gate][16 units][32 rows] for the transposed copies
+    __nv_bfloat16* st_dgi = reinterpret_cast<__nv_bfloat16*>(cs + a_bytes + x_bytes);
+    __nv_bfloat16* st_gT = st_dgi + kGates * (kR3StageBytes / 2);
+    __nv_bfloat16* st_hT = st_gT + kGates * (kR3StageBytes / 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cs + a_bytes + x_bytes + st_bytes);
+    uint64_t* full_bar = bars;                                // [kR3MaxChunks]
+    uint64_t* tfull_bar = bars + kR3MaxChunks;
+    uint64_t* x_bar = bars + kR3MaxChunks + 1;                // [2] the peers' quarters of step parity 0 / 1 have arrived
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + (size_t)NCH * chain_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+    uint32_t* counter = p.counters + (dir * NCH + (chain < NCH ? chain : 0)) * kR3CounterStride;
+    const int kcol0 = (int)crank * p.kpad;                    // first gate column of our K quarter
+    auto t_of = [&](int s) { return dir == 0 ? (T - 1 - s) : s; };     // the backward pass walks each direction in reverse
+
+    if (warp < NCH && lane == 0) {
+        if (warp == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmDgi);
+            tma_prefetch_desc(&tmGT);
+            tma_prefetch_desc(&tmHT);
+            mbar_init(w_bar, 1);
+        }
+        for (int i = 0; i < kR3MaxChunks; ++i) mbar_init(&full_bar[i], 1);
+        mbar_init(tfull_bar, 1);
+        mbar_init(&x_bar[0], 1);
+        mbar_init(&x_bar[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    cluster_sync_all();                      // the peers' exchange barriers exist before anybody sends
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_d = tmem_base + chain * kRows;
+    const uint32_t tmem_w = tmem_base + NCH * kRows;
+
+    if (warp < kRnnCtrlWarps) {
+        // ===================== control warp of the chain: TMA copies, then the MMAs =====================
+        //   D[64 units of the cluster, kRows batch rows] = W_hh^T[our K quarter, tensor memory] x dgates^T[shared memory]
+        if (chain_on) {
+            constexpr uint32_t idesc = umma_idesc(kFmtBF16, 64, kRows);
+            mbar_wait(w_bar, 0);
+            tc_fence_after_sync();
+            for (int s = 1; s < T; ++s) {
+                const uint32_t need = (uint32_t)P * (uint32_t)s;
+                while (ld_acquire_u32(counter) < need) {
+                }
+                if (lane == 0 && chain == 0) ASRB_TRACE(0, s);
+                fence_proxy_async_global();
+                const int slab = dir * T + t_of(s - 1);
+                if (elect_one()) {
+                    for (int c = 0; c < nchunks; ++c) {
+                        const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
+                        mbar_arrive_expect_tx(&full_bar[c], (uint32_t)nblk * kSlotBytes);
+                        for (int i = 0; i < nblk; ++i)      // columns >= G and rows >= B: TMA zero fill
+                            tma_load_3d(smem_a + (size_t)(kb0 + i) * kSlotBytes, &tmA, &full_bar[c], kcol0 + (kb0 + i) * KBE, row0, slab);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && chain == 0) ASRB_TRACE(1, s);
+                const uint32_t ph = (uint32_t)((s - 1) & 1);
+                for (int c = 0; c < nchunks; ++c) {
+                    const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
+                    mbar_wait(&full_bar[c], ph);
+                    if (c == 0 && lane == 0 && chain == 0) ASRB_TRACE(2, s);
+                    tc_fence_after_sync();
+                    if (elect_one()) {
+                        for (int i = 0; i < nblk; ++i) {
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_a + (size_t)(kb0 + i) * kSlotBytes));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16_ts(tmem_d, tmem_w + ((kb0 + i) * 4 + k) * 8, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                        }
+                        if (c == nchunks - 1) umma_commit(tfull_bar);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0 && chain == 0) ASRB_TRACE(3, s);
+            }
+        }
+    } else {
+        // ===================== epilogue warps of the chain =====================
+        // accumulator role: lane quarter q = warp % 4 holds the 16 units of cluster rank q, this warp takes the chain's
+        // batch columns 16*half .. +15.  cell role: thread = unit 4*ug + lane%4 of two batch rows of the chain.
+        constexpr int kRp16 = kRows / 16;
+        const int wl = (warp - kRnnCtrlWarps) % kEpiWarps;
+        const int quad = warp & 3, half = wl >> 2;
+        const int ug = wl / kRp16, ul = lane & 3;
+        const int el = wl * 32 + lane;
+        const int ju = 4 * ug + ul, unit = j0 + ju;
+        const bool uvalid = unit < H;
+        int row[2], len[2];
+        bool cellok[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            row[c] = row0 + 16 * (wl % kRp16) + (lane >> 2) + 8 * c;
+            cellok[c] = uvalid && row[c] < B;
+            len[c] = cellok[c] ? p.lengths[row[c]] : 0;
+        }
+        const size_t slotHB = (size_t)B * H;
+
+        // ---- once: the weight quarter -> tensor memory ----
+        if (chain == 0) {
+            if (wl < 4) {
+                // row c of the packed slice = unit c of the cluster; TMEM lane 32 * quarter + i holds row 16 * quarter + i
+                const int c = 16 * quad + lane;
+                const bool have = lane < 16;
+                const uint4* wrow = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.wpack) + ((size_t)(dir * P + pidx) * 64 + (have ? c : 0)) * p.kpad);
+                for (int k16 = 0; k16 < p.kpad / 16; ++k16) {
+                    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+                    if (have) { lo = __ldg(wrow + 2 * k16); hi = __ldg(wrow + 2 * k16 + 1); }
+                    const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    tmem_st_32x8(tmem_w + (uint32_t(quad * 32) << 16) + k16 * 8, r);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before_sync();
+        }
+        named_bar_sync(3, kRnnEpiThreads);
+        if (warp == kRnnCtrlWarps && lane == 0) mbar_arrive(w_bar);
+
+        if (chain_on) {
+            float state_h[2] = {0.f, 0.f}, state_c[2] = {0.f, 0.f};   // direct dh / dc carries
+            uint32_t xphase[2] = {0u, 0u};
+            // The outputs only later kernels read (gate gradients row-major and transposed: 18 scattered 2-byte stores per
+            // thread and step, ~2 k cycles of LSU issue time per chain that the trace showed on the chain's critical path)
+            // go through shared-memory tiles and TMA stores when the tiles are whole: 32 batch rows, 16 valid units.
+            const bool staged = p.stage_out && j0 + NJ <= H && row0 + kRows <= B;
+            const int rl0 = 16 * (wl % kRp16) + (lane >> 2);      // first of our two rows within the chain
+            for (int s = 0; s < T; ++s) {
+                const int t = t_of(s);
+                bool active[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) active[c] = cellok[c] && (t < len[c]);
+                if (el == 0 && chain == 0) ASRB_TRACE(4, s);
+                if (el == 0 && s > 0) mbar_arrive_expect_tx(&x_bar[s & 1], (uint32_t)((KS - 1) * kR3XBytes));
+                // ---- operand prefetch (independent of the recurrent product) ----
+                float in[6][2], ct[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) in[q][c] = 0.f;
+                    ct[c] = 0.f;
+                    if (active[c]) {
+                        const float* sv = p.saved + ((((size_t)dir * T + t) * p.P_saved + pidx) * 4) * (size_t)(NV * B * 4) +
+                                          (size_t)ug * (B * 4) + (size_t)row[c] * 4 + ul;
+                        const int tprev_slot = (dir == 0) ? t : t + 2;   // slot of the step that preceded t in forward order
+                        const size_t ro = (size_t)row[c] * H + unit;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) in[q][c] = sv[(size_t)q * NV * (B * 4)];
+                        in[4][c] = __ldg(p.dout + (size_t)t * slotHB + ro);
+                        in[5][c] = (CELL == ASRB_RNN_GRU ? p.hseq : p.cseq)[((size_t)dir * (T + 2) + tprev_slot) * slotHB + ro];
+                        if constexpr (CELL == ASRB_RNN_LSTM) ct[c] = p.cseq[((size_t)dir * (T + 2) + t + 1) * slotHB + ro];
+                    }
+                }
+                float acc[2] = {0.f, 0.f};
+                if (s > 0) {
+                    const int par = s & 1;
+                    mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
+                    if (el == 0 && chain == 0) ASRB_TRACE(5, s);
+                    tc_fence_after_sync();
+                    {
+                        float v[8];
+                        tmem_ld_16x256b_x2(tmem_d + (uint32_t(quad * 32) << 16) + 16 * half, v);
+                        tmem_ld_wait();
+                        // quarter `quad` of the accumulator belongs to cluster rank `quad`: ours stays, the others are staged
+                        float* dst = ((uint32_t)quad == crank ? dt : xs + ((size_t)par * KS + quad) * 16 * kR3XStride) +
+                                     (lane >> 2) * kR3XStride + 16 * half + 2 * ul;
+                        *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+                        *reinterpret_cast<float2*>(dst + 8 * kR3XStride) = make_float2(v[2], v[3]);
+                        *reinterpret_cast<float2*>(dst + 8) = make_float2(v[4], v[5]);
+                        *reinterpret_cast<float2*>(dst + 8 * kR3XStride + 8) = make_float2(v[6], v[7]);
+                    }
+                    tc_fence_before_sync();
+                    fence_proxy_async_smem();                  // generic stores -> the bulk copies' async-proxy reads
+                    if (staged && el == 0) bulk_wait_group_read<0>();   // the previous step's TMA stores have read their tiles
+                    named_bar_sync(4 + chain, kEpiThreads);
+                    if (el == 0) {
+                        if (chain == 0) ASRB_TRACE(6, s);
+#pragma unroll
+                        for (int q = 1; q < KS; ++q) {
+                            const uint32_t peer = (crank + q) % KS;
+                            // lands in slot [par][source = our rank] of the peer's receive buffer of this chain
+                            dsmem_bulk_copy(map_to_cta(xr + ((size_t)par * KS + crank) * 16 * kR3XStride, peer),
+                                            xs + ((size_t)par * KS + peer) * 16 * kR3XStride, (uint32_t)kR3XBytes,
+                                            map_to_cta(&x_bar[par], peer));
+                        }
+                    }
+                    mbar_wait_cluster(&x_bar[par], xphase[par]);
+                    xphase[par] ^= 1u;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int o = ju * kR3XStride + (row[c] - row0);
+                        float a = dt[o];
+#pragma unroll
+                        for (int q = 1; q < KS; ++q) a += xr[((size_t)par * KS + (crank + q) % KS) * 16 * kR3XStride + o];
+                        acc[c] = a;
+                    }
+                    if (el == 0 && chain == 0) ASRB_TRACE(11, s);
+                }
+
+                // ---- cell math ----
+                float dg[4][2], eg2[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float carry = acc[c] + state_h[c];
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, e2 = 0.f;
+                    if (active[c]) {
+                        const float dh = carry + in[4][c];
+                        if constexpr (CELL == ASRB_RNN_GRU) {
+                            const float r = in[0][c], z = in[1][c], n = in[2][c], gn = in[3][c], hp = in[5][c];
+                            const float dn = dh * (1.f - z) * (1.f - n * n);
+                            d2 = dn;                          // d gi_n
+                            e2 = dn * r;                      // d gh_n
+                            d1 = dh * (hp - n) * z * (1.f - z);
+                            d0 = dn * gn * r * (1.f - r);
+                            state_h[c] = dh * z;
+                        } else {
+                            const float gi_ = in[0][c], gf = in[1][c], gg = in[2][c], go = in[3][c], cp = in[5][c];
+                            const float tcv = ftanh(ct[c]);
+                            const float dc = state_c[c] + dh * go * (1.f - tcv * tcv);
+                            d0 = dc * gg * gi_ * (1.f - gi_);
+                            d1 = dc * cp * gf * (1.f - gf);
+                            d2 = dc * gi_ * (1.f - gg * gg);
+                            d3 = dh * tcv * go * (1.f - go);
+                            e2 = d2;
+                            state_c[c] = dc * gf;
+                            state_h[c] = 0.f;
+                        }
+                    } else {
+                        state_h[c] = carry;  // gradient passes an inactive step untouched
+                    }
+                    dg[0][c] = d0; dg[1][c] = d1; dg[2][c] = d2; dg[3][c] = d3; eg2[c] = e2;
+                }
+                // (1) the next step's MMA operand (hidden-side gate gradients), published through the chain's step counter
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (cellok[c]) {
+                        __nv_bfloat16* o = p.dghbf + (((size_t)dir * T + t) * B + row[c]) * p.Gp + unit;
+#pragma unroll
+                        for (int q = 0; q < kGates; ++q) o[(size_t)q * H] = __float2bfloat16_rn((q == 2) ? eg2[c] : dg[q][c]);
+                    }
+                }
+                if (staged) {
+                    if (s == 0 && el == 0) bulk_wait_group_read<0>();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int rl = rl0 + 8 * c;
+#pragma unroll
+                        for (int q = 0; q < kGates; ++q) {
+                            const __nv_bfloat16 v = __float2bfloat16_rn(dg[q][c]);
+                            st_dgi[q * (kR3StageBytes / 2) + rl * NJ + ju] = v;
+                            st_gT[q * (kR3StageBytes / 2) + ju * kRows + rl] = v;
+                            if (p.dghT) st_hT[q * (kR3StageBytes / 2) + ju * kRows + rl] = (q == 2) ? __float2bfloat16_rn(eg2[c]) : v;
+                        }
+                    }
+                    fence_proxy_async_smem();                  // generic stores -> the TMA stores' async-proxy reads
+                }
+                if (el == 0 && chain == 0) ASRB_TRACE(7, s);
+                named_bar_sync(8 + chain, kEpiThreads);
+                if (el == 0) {
+                    if (chain == 0) ASRB_TRACE(8, s);
+                    red_release_add_u32(counter, 1u);
+                    if (chain == 0) ASRB_TRACE(10, s);
+                    if (staged) {
+#pragma unroll
+                        for (int q = 0; q < kGates; ++q) {
+                            tma_store_3d(&tmDgi, st_dgi + q * (kR3StageBytes / 2), dir * G + q * H + j0, row0, t);
+                            tma_store_2d(&tmGT, st_gT + q * (kR3StageBytes / 2), t * B + row0, dir * G + q * H + j0);
+                            if (p.dghT) tma_store_2d(&tmHT, st_hT + q * (kR3StageBytes / 2), t * B + row0, dir * G + q * H + j0);
+                        }
+                        bulk_commit_group();
+                    }
+                }
+                if (!staged) {
+                    named_bar_sync(12 + chain, kEpiThreads);      // the release's MEMBAR waits for every store in flight: rest after it
+                    // (2) outputs only later kernels read
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (cellok[c]) {
+                            __nv_bfloat16* dgi = reinterpret_cast<__nv_bfloat16*>(p.dgi) + (((size_t)t * B + row[c]) * 2 + dir) * G + unit;
+                            // transposed copies for the weight-gradient GEMMs (row = gate row, column = t*B + b)
+                            __nv_bfloat16* gT = reinterpret_cast<__nv_bfloat16*>(p.dgiT) + ((size_t)dir * G + unit) * p.ldT + (size_t)t * B + row[c];
+                            __nv_bfloat16* hT = p.dghT ? reinterpret_cast<__nv_bfloat16*>(p.dghT) + ((size_t)dir * G + unit) * p.ldT + (size_t)t * B + row[c] : nullptr;
+#pragma unroll
+                            for (int q = 0; q < kGates; ++q) {
+                                const __nv_bfloat16 v = __float2bfloat16_rn(dg[q][c]);
+                                dgi[(size_t)q * H] = v;
+                                gT[(size_t)q * H * p.ldT] = v;
+                                if (hT) hT[(size_t)q * H * p.ldT] = (q == 2) ? __float2bfloat16_rn(eg2[c]) : v;
+                            }
+                        }
+                    }
+                }
+            }
+            if (staged && el == 0) bulk_wait_group<0>();      // the last TMA stores have been written
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+    cluster_sync_all();   // nobody leaves while a peer may still write into its receive buffers
+}
+
+template <int CELL>
+static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {
+    const int kpad = pl.kpad_b, nkb = kpad / 64;
+    const int B = prm.B;
+    if (pl.ksplit != 4 || pl.npad_b != 64 || ceil_div(nkb, kR3Chunk) > kR3MaxChunks || 64 + kpad / 2 > 512) return ASRB_ERR_UNSUPPORTED;
+    prm.P_saved = pl.P;
+    prm.P = pl.P_b;
+    prm.kpad = kpad;
+    prm.wpack = reinterpret_cast<const float*>(wpack);
+    constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
+    const size_t chain_bytes = ((size_t)nkb * 32 * 128 + (size_t)(1 + 4 * 4) * kR3XBytes + (size_t)3 * kGates * kR3StageBytes + 256 + 1023) & ~size_t(1023);
+    const size_t smem = 1024 + 2 * chain_bytes + 64;
+    if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return ASRB_ERR_DRIVER;
+    CUtensorMap tmA, tmDgi, tmGT, tmHT;
+    // staged outputs: whole 32-row x 16-unit tiles only, and 16-byte aligned tile rows in the transposed copies
+    prm.stage_out = (B % 32 == 0 && prm.H % 16 == 0 && !(g_rnn_dbg & 2048)) ? 1 : 0;
+    if (prm.stage_out) {
+        auto plain = [&](CUtensorMap* m, void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* bx) {
+            cuuint32_t es[3] = {1, 1, 1};
+            if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+            return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        bool ok = true;
+        {   // dgi [T][B][2G] bf16, box = 16 columns x 32 rows
+            cuuint64_t gdim[3] = {(cuuint64_t)2 * prm.G, (cuuint64_t)B, (cuuint64_t)prm.T};
+            cuuint64_t gstr[2] = {(cuuint64_t)2 * prm.G * 2, (cuuint64_t)B * 2 * prm.G * 2};
+            cuuint32_t bx[3] = {16, 32, 1};
+            ok = ok && plain(&tmDgi, prm.dgi, 3, gdim, gstr, bx);
+        }
+        {   // dgiT / dghT [2G][ldT] bf16, box = 32 columns (batch rows of one time step) x 16 rows (units)
+            cuuint64_t gdim[2] = {(cuuint64_t)prm.ldT, (cuuint64_t)2 * prm.G};
+            cuuint64_t gstr[1] = {(cuuint64_t)prm.ldT * 2};
+            cuuint32_t bx[2] = {32, 16};
+            ok = ok && plain(&tmGT, prm.dgiT, 2, gdim, gstr, bx);
+            ok = ok && plain(&tmHT, prm.dghT ? prm.dghT : prm.dgiT, 2, gdim, gstr, bx);
+        }
+        if (!ok) prm.stage_out = 0;
+    }
+    if (!prm.stage_out) tmDgi = tmGT = tmHT = CUtensorMap{};
+    {   // dghbf [2 T][B][Gp] bf16, box = 64 columns x 32 rows (one chain), 128-byte swizzle
+        uint64_t d[3] = {(uint64_t)prm.G, (uint64_t)B, (uint64_t)2 * prm.T};
+        uint64_t s[2] = {(uint64_t)prm.Gp * 2, (uint64_t)B * prm.Gp * 2};
+        uint32_t bx[3] = {64, 32, 1};
+        int rc = make_tmap_bf16(&tmA, prm.dghbf, 3, d, s, bx);
+        if (rc) return rc;
+    }
+    auto kern = rnn_rec3_bwd_kernel<CELL>;
+    ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * 2 * kR3CounterStride * sizeof(uint32_t), stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pl.P_b);
+    cfg.blockDim = dim3(kRnnThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 4; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    {   // the step barrier spins: refuse the launch when the device cannot hold the whole grid (in clusters of 4) at once
+        int nclusters = 0;
+        ASRB_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
+        if (2 * pl.P_b > 4 * nclusters) return ASRB_ERR_UNSUPPORTED;
+    }
+    prm.dbg = g_rnn_dbg;
+    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmDgi, tmGT, tmHT, prm));
+    return 0;
+}
+
+int rnn3_backward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {
+    if (cell == ASRB_RNN_GRU) return rnn3_bwd_launch<ASRB_RNN_GRU>(pl, prm, wpack, stream);
+    return rnn3_bwd_launch<ASRB_RNN_LSTM>(pl, prm, wpack, stream);
+}
+
 int rnn3_forward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {
     // Two chains of 32 rows.  Four chains of 16 (asrb_debug_rnn_dbg bit 512) measure the same: what a chain waits for is
     // shared -- the release's MEMBAR covers every store the SM has in flight, and the chains' copies share the TMA / L2

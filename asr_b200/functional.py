@@ -226,7 +226,7 @@ def _transpose_padded(a):
 import os as _os
 
 WGRAD_OVERLAP = _os.environ.get("ASRB_WGRAD_OVERLAP", "1") != "0"
-WGRAD_CTAS = int(_os.environ.get("ASRB_WGRAD_CTAS", "48"))   # persistent GEMM CTAs of the side stream (0 = all SMs);
+WGRAD_CTAS = int(_os.environ.get("ASRB_WGRAD_CTAS", "44"))   # the backward recurrence holds 104 of the 148 SMs (13 clusters of 4 per direction)
 # measured ms/step at configs[1], same box, two runs each: overlap off 48.5; on with cap 0 / 16 / 32 / 48:
 # 47.0 / 50.3 / 47.4 / 46.9.  The chain itself slows by ~8 % under the extra L2 traffic, which is why the gain is
 # 1.6 ms and not the 5 ms of work that moved off the critical path.

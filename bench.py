@@ -180,13 +180,32 @@ def run_torch_cudnn(dev, steps, warmup, cfg=CFG):
     from oracle import torch_path
 
     p = {k: v.to(dev) for k, v in torch_path.init_params(cfg["rnn_type"], cfg["hidden"], cfg["layers"], cfg["C"]).items()}
+    names = set(torch_path.trainable(p))
+    q = {k: (v.clone().requires_grad_(True) if k in names and ".rnn." not in k else v) for k, v in p.items()}
+    # the recurrent layers as real nn.GRU modules with flattened weights, as the reference's BatchRNN holds them
+    # (modules/blocks.py:75-78,81-82): cuDNN's fast path, no per-call weight compaction
+    cls = {"gru": torch.nn.GRU, "lstm": torch.nn.LSTM}[cfg["rnn_type"]]
+    mods = []
+    for l in range(cfg["layers"]):
+        w = p[f"rnns.{l}.rnn.weight_ih_l0"]
+        m = cls(input_size=w.shape[1], hidden_size=cfg["hidden"], bidirectional=True, bias=True).to(dev)
+        m.load_state_dict({n: p[f"rnns.{l}.rnn.{n}"] for n, _ in m.named_parameters()})
+        m.flatten_parameters()
+        mods.append(m)
     host = make_batch(cfg["B"])
     x = host[0].to(dev)
     out = {}
     for name, amp in (("fp32", False), ("fp16_autocast", True)):
         def one():
+            for t in q.values():
+                if t.requires_grad:
+                    t.grad = None
+            for m in mods:
+                m.zero_grad(set_to_none=True)
             with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
-                return torch_path.loss_and_grads(p, x, host[1], host[2], host[3], rnn_type=cfg["rnn_type"])[0]
+                loss, _ = torch_path.fit_loss(q, x, host[1], host[2], host[3], cfg["rnn_type"], {}, mods)
+            loss.backward()
+            return loss.detach()
         try:
             for _ in range(max(warmup, 2)):
                 loss = one()

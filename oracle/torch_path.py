@@ -81,18 +81,23 @@ def _rnn_module(rnn_type: str, input_size: int, hidden: int, bidirectional: bool
     return cls(input_size=input_size, hidden_size=hidden, bidirectional=bidirectional, bias=True)
 
 
-def batch_rnn(p, layer, x, out_lengths, rnn_type, bidirectional=True, training=True, stats_out=None):
-    """BatchRNN.forward (blocks.py:84-93): [SequenceWise BN1d] -> pack -> 1-layer RNN -> pad -> sum dirs."""
+def batch_rnn(p, layer, x, out_lengths, rnn_type, bidirectional=True, training=True, stats_out=None, rnn_modules=None):
+    """BatchRNN.forward (blocks.py:84-93): [SequenceWise BN1d] -> pack -> 1-layer RNN -> pad -> sum dirs.
+    rnn_modules: optional list of ready nn.GRU / nn.LSTM modules holding the layer weights (as the reference's BatchRNN
+    does, blocks.py:75-78, with flatten_parameters() on CUDA): used instead of the functional call on `p`."""
     T, N, I = x.shape
     pre = f"rnns.{layer}"
     if pre + ".batch_norm.module.weight" in p:
         x = _batch_norm(x.reshape(T * N, I), p, pre + ".batch_norm.module", training, stats_out).reshape(T, N, I)
     hidden = p[pre + ".rnn.weight_hh_l0"].shape[1]
-    mod = _rnn_module(rnn_type, I, hidden, bidirectional).to(x.dtype)
-    names = [n for n, _ in mod.named_parameters()]
-    weights = {n: p[f"{pre}.rnn.{n}"] for n in names}
     packed = pack_padded_sequence(x, out_lengths.cpu())
-    y, _ = torch.func.functional_call(mod, weights, (packed,))
+    if rnn_modules is not None:
+        y, _ = rnn_modules[layer](packed)
+    else:
+        mod = _rnn_module(rnn_type, I, hidden, bidirectional).to(x.dtype)
+        names = [n for n, _ in mod.named_parameters()]
+        weights = {n: p[f"{pre}.rnn.{n}"] for n in names}
+        y, _ = torch.func.functional_call(mod, weights, (packed,))
     y, _ = pad_packed_sequence(y)
     if bidirectional:
         y = y.view(y.size(0), y.size(1), 2, -1).sum(2)
@@ -106,14 +111,14 @@ def n_rnn_layers(p) -> int:
     return n
 
 
-def forward(p, x, lengths, rnn_type="gru", bidirectional=True, training=True, stats_out=None):
+def forward(p, x, lengths, rnn_type="gru", bidirectional=True, training=True, stats_out=None, rnn_modules=None):
     """DeepSpeech.forward (deepspeech.py:130-149).  Returns (out[N,T',C], output_lengths)."""
     out_lengths = get_seq_lens(lengths)
     x = mask_conv(p, x, out_lengths, training, stats_out)
     b, c, d, t = x.shape
     x = x.view(b, c * d, t).transpose(1, 2).transpose(0, 1).contiguous()  # T x N x (C*D)
     for layer in range(n_rnn_layers(p)):
-        x = batch_rnn(p, layer, x, out_lengths, rnn_type, bidirectional, training, stats_out)
+        x = batch_rnn(p, layer, x, out_lengths, rnn_type, bidirectional, training, stats_out, rnn_modules)
     T, N, H = x.shape
     x = _batch_norm(x.reshape(T * N, H), p, "fc.0.module.0", training, stats_out)
     x = F.linear(x, p["fc.0.module.1.weight"]).view(T, N, -1)  # Linear(bias=False), deepspeech.py:105
@@ -123,11 +128,11 @@ def forward(p, x, lengths, rnn_type="gru", bidirectional=True, training=True, st
     return x, out_lengths
 
 
-def fit_loss(p, inputs, targets, input_percentages, target_sizes, rnn_type="gru", stats_out=None):
+def fit_loss(p, inputs, targets, input_percentages, target_sizes, rnn_type="gru", stats_out=None, rnn_modules=None):
     """The six arithmetic lines of DeepSpeechTrainer.fit (trainers/deepspeech_trainer.py:104-112)
     with criterion = CTCLoss(reduction='sum') (trainers/__main__.py:53).  Returns (loss/B, logits)."""
     input_sizes = (input_percentages * int(inputs.size(3))).int()
-    out, output_sizes = forward(p, inputs, input_sizes, rnn_type, True, True, stats_out)
+    out, output_sizes = forward(p, inputs, input_sizes, rnn_type, True, True, stats_out, rnn_modules)
     log_probs = out.transpose(0, 1).float().log_softmax(2)
     loss = F.ctc_loss(log_probs, targets, output_sizes, target_sizes, blank=0, reduction="sum",
                       zero_infinity=False)
@@ -145,7 +150,7 @@ def init_params(rnn_type="gru", hidden=800, layers=5, num_classes=29, seed=12345
     (seed mirrors asr_deepspeech/vars.py:13), built WITHOUT the reference package so that it
     runs on the GPU box; parameter creation order follows build_network (deepspeech.py:58-110)
     so the values are identical to instantiating the reference model after the same seed
-    (checked by tests/test_oracle_vs_reference.py)."""
+    (checked by oracle/make_golden.py at generation time and by tests/test_oracle_vs_reference.py)."""
     import math
     from collections import OrderedDict
 

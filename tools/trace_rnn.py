@@ -33,19 +33,24 @@ def timed(fn, n=3):
     return e0.elapsed_time(e1) / n
 
 
-# forward outputs of every variant against the counter + TMA kernel
+# outputs of every variant against the counter + TMA kernels of rnn.cu
 ref = None
-for dbg, label in ((8, "rnn.cu"), (0, "rnn3 (TMEM weights, two chains)"), (512, "rnn3, four chains"), (256, "rnn2 TS")):
+for dbg, label in ((8, "rnn.cu"), (0, "rnn3 forward + backward (TMEM weights, two chains)"), (1024, "rnn3 forward, rnn.cu backward"), (256, "rnn2")):
     _lib.query("asrb_debug_rnn_dbg", dbg)
     pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
     hs, cs, sv = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
+    dgi, dgiT, dghT = ops.rnn_bwd(cell, dout, pb, lens, hs, cs, sv, T, B, H)
     torch.cuda.synchronize()
     if ref is None:
-        ref = hs.clone()
+        ref = (hs.clone(), dgi.float().clone(), dgiT.float().clone(), None if dghT is None else dghT.float().clone())
     else:
-        print(f"## fwd hseq {label} vs rnn.cu: max abs diff {(hs - ref).abs().max().item():.3e} (|h| max {ref.abs().max().item():.3f})", flush=True)
+        msg = f"## {label} vs rnn.cu: hseq max abs diff {(hs - ref[0]).abs().max().item():.3e} (|h| max {ref[0].abs().max().item():.3f}); " \
+              f"dgi {(dgi.float() - ref[1]).abs().max().item():.3e} (max {ref[1].abs().max().item():.3f}); dgiT {(dgiT.float() - ref[2]).abs().max().item():.3e}"
+        if dghT is not None:
+            msg += f"; dghT {(dghT.float() - ref[3]).abs().max().item():.3e}"
+        print(msg, flush=True)
 
-variants = [(0, "default: rnn3.cu forward (TMEM weights, two chains of 32 rows), rnn.cu backward"), (512, "rnn3.cu forward with four chains of 16 rows"), (8, "counter + TMA (rnn.cu)"), (256, "exchange-by-data (rnn2.cu)")]
+variants = [(0, "default: rnn3.cu forward and backward (weights in tensor memory, two chains of 32 rows)"), (8, "counter + TMA (rnn.cu)")]
 for dbg, label in variants:
     _lib.query("asrb_debug_rnn_dbg", dbg)
     _lib.query("asrb_debug_rnn_ksplit", ks)
