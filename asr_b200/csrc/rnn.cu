@@ -38,57 +38,38 @@ int g_rnn_chunk = 0;
 __device__ __forceinline__ void pack_store(float* o, float v) { *o = v; }
 __device__ __forceinline__ void pack_store(__nv_bfloat16* o, float v) { *o = __float2bfloat16_rn(v); }
 
+// one block per output row: a row of W_hh is copied (and converted) with coalesced reads and writes
 template <typename OutT>
 __global__ void rnn_pack_fwd_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, OutT* __restrict__ out,
                                     int H, int gates, int nj, int P, int npad, int kpad) {
-    const long long total = 2LL * P * npad * kpad;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % kpad);
-        long long r = i / kpad;
-        const int c = (int)(r % npad);
-        r /= npad;
-        const int p = (int)(r % P), dir = (int)(r / P);
-        const int g = c / nj, j = p * nj + c % nj;
-        float v = 0.f;
-        if (g < gates && j < H && k < H) v = (dir ? w_hh1 : w_hh0)[(size_t)(g * H + j) * H + k];
-        pack_store(out + i, v);
-    }
+    const int row = blockIdx.x;                       // (dir, p, c)
+    const int c = row % npad, p = (row / npad) % P, dir = row / (npad * P);
+    const int g = c / nj, j = p * nj + c % nj;
+    const bool have = g < gates && j < H;
+    const float* src = (dir ? w_hh1 : w_hh0) + (size_t)(have ? g * H + j : 0) * H;
+    OutT* dst = out + (size_t)row * kpad;
+    for (int k = threadIdx.x; k < kpad; k += blockDim.x) pack_store(dst + k, (have && k < H) ? __ldg(src + k) : 0.f);
 }
-// backward: row c = unit p*nj + c  ->  W_hh[dir][0..G)[unit]   (a column of W_hh)
+// backward: out[(dir, p)][c][kk] = W_hh[dir][k0(p) + kk][j0(p) + c]: a transposed block of W_hh per CTA, moved in 32 x 32
+// tiles through shared memory (coalesced along the units on the way in, along K on the way out).
+//   unsplit: j0 = p*nj, k0 = 0, rows c < nj valid ; split over ks CTAs: j0 = (p/ks)*npad, k0 = (p%ks)*kpad
 template <typename OutT>
-__global__ void rnn_pack_bwd_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, OutT* __restrict__ out,
-                                    int H, int G, int nj, int P, int npad, int kpad) {
-    const long long total = 2LL * P * npad * kpad;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % kpad);
-        long long r = i / kpad;
-        const int c = (int)(r % npad);
-        r /= npad;
-        const int p = (int)(r % P), dir = (int)(r / P);
-        const int j = p * nj + c;
-        float v = 0.f;
-        if (c < nj && j < H && k < G) v = (dir ? w_hh1 : w_hh0)[(size_t)k * H + j];
-        pack_store(out + i, v);
+__global__ void rnn_pack_bwd_tiled_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, OutT* __restrict__ out,
+                                          int H, int G, int nj, int P, int npad, int kpad, int ks) {
+    __shared__ float tile[32][33];
+    const int dp = blockIdx.z, p = dp % P, dir = dp / P;
+    const int j0 = ks ? (p / ks) * npad : p * nj, k0 = ks ? (p % ks) * kpad : 0;
+    const int cvalid = ks ? npad : nj;
+    const float* w = dir ? w_hh1 : w_hh0;
+    const int kk0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {            // read W[k0 + kk0 + r][j0 + c0 + x]
+        const int k = k0 + kk0 + r, c = c0 + threadIdx.x, j = j0 + c;
+        tile[r][threadIdx.x] = (kk0 + r < kpad && k < G && c < cvalid && j < H) ? __ldg(w + (size_t)k * H + j) : 0.f;
     }
-}
-
-// backward, K split over a cluster of ks CTAs: CTA p = ks*cl + r holds, for the ks*nj units of the cluster (row c = unit
-// cl*ks*nj + c), the r-th part of the gate index: element kk <-> gate row k = r*kpad + kk
-template <typename OutT>
-__global__ void rnn_pack_bwd_split_kernel(const float* __restrict__ w_hh0, const float* __restrict__ w_hh1, OutT* __restrict__ out,
-                                          int H, int G, int nj, int P, int kpad, int ks) {
-    const int npad = ks * nj;
-    const long long total = 2LL * P * npad * kpad;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int kk = (int)(i % kpad);
-        long long r = i / kpad;
-        const int c = (int)(r % npad);
-        r /= npad;
-        const int p = (int)(r % P), dir = (int)(r / P);
-        const int j = (p / ks) * npad + c, k = (p % ks) * kpad + kk;
-        float v = 0.f;
-        if (j < H && k < G) v = (dir ? w_hh1 : w_hh0)[(size_t)k * H + j];
-        pack_store(out + i, v);
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {            // write out[c0 + r][kk0 + x]
+        const int c = c0 + r, kk = kk0 + threadIdx.x;
+        if (c < npad && kk < kpad) pack_store(out + ((size_t)dp * npad + c) * kpad + kk, tile[threadIdx.x][r]);
     }
 }
 
@@ -786,22 +767,26 @@ int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fw
     if (rc) return rc;
     const int gates = cell == ASRB_RNN_GRU ? 3 : 4;
     if (wpack_fwd) {
-        if (pl.bf16) rnn_pack_fwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_fwd, H, gates, pl.nj, pl.P, pl.npad_f, pl.kpad_f);
-        else         rnn_pack_fwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (float*)wpack_fwd, H, gates, pl.nj, pl.P, pl.npad_f, pl.kpad_f);
+        const int rows = 2 * pl.P * pl.npad_f;
+        if (pl.bf16) rnn_pack_fwd_kernel<<<rows, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_fwd, H, gates, pl.nj, pl.P, pl.npad_f, pl.kpad_f);
+        else         rnn_pack_fwd_kernel<<<rows, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (float*)wpack_fwd, H, gates, pl.nj, pl.P, pl.npad_f, pl.kpad_f);
         ASRB_LAUNCH_OK();
     }
     if (wpack_bwd) {
-        if (pl.ksplit)    rnn_pack_bwd_split_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P_b, pl.kpad_b, pl.ksplit);
-        else if (pl.bf16) rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
-        else         rnn_pack_bwd_kernel<<<kNumSMs * 4, 256, 0, stream>>>(w_hh_fwd, w_hh_rev, (float*)wpack_bwd, H, gates * H, pl.nj, pl.P, pl.npad_b, pl.kpad_b);
+        const int Pb = pl.ksplit ? pl.P_b : pl.P;
+        const dim3 grid(ceil_div(pl.kpad_b, 32), ceil_div(pl.npad_b, 32), 2 * Pb), block(32, 8);
+        if (pl.ksplit || pl.bf16)
+            rnn_pack_bwd_tiled_kernel<<<grid, block, 0, stream>>>(w_hh_fwd, w_hh_rev, (__nv_bfloat16*)wpack_bwd, H, gates * H, pl.nj, Pb, pl.npad_b, pl.kpad_b, pl.ksplit);
+        else
+            rnn_pack_bwd_tiled_kernel<<<grid, block, 0, stream>>>(w_hh_fwd, w_hh_rev, (float*)wpack_bwd, H, gates * H, pl.nj, Pb, pl.npad_b, pl.kpad_b, 0);
         ASRB_LAUNCH_OK();
     }
     return 0;
 }
 
-int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
-                 float* hseq, void* hseq_bf16, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
-                 asrb_stream_t stream) {
+int asrb_rnn_fwd_sum(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
+                     float* hseq, void* hseq_bf16, float* cseq, float* saved, float* out_sum, uint32_t* counters, int T, int B,
+                     int H, asrb_stream_t stream) {
     ASRB_REQUIRE(gi && b_hh && wpack_fwd && lengths && hseq && saved && counters && T > 0, ASRB_ERR_BAD_ARG);
     ASRB_REQUIRE(cell == ASRB_RNN_GRU || cseq, ASRB_ERR_BAD_ARG);
     RnnPlan pl;
@@ -816,9 +801,26 @@ int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const v
     prm.hbf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16);
     prm.Hp = round_up(H, 64);
     prm.trace = g_rnn_trace;
-    if (rnn3_eligible(pl, prm)) return rnn3_forward(cell, pl, prm, wpack_fwd, stream);
-    if (rnn2_eligible(pl, prm)) return rnn2_dispatch(false, cell, pl, prm, wpack_fwd, stream);
-    return rnn_dispatch<false>(cell, pl, prm, wpack_fwd, pl.bf16 ? (const void*)hseq_bf16 : (const void*)hseq, stream);
+    if (rnn3_eligible(pl, prm)) {
+        // DEBUG bit 4096: the kernel itself adds both directions' h tiles into out_sum with TMA reduce-adds and stores the
+        // fp32 state / saved activations through shared-memory tiles.  Measured at configs[1]: 12.45 ms per step for the
+        // five forward launches against 11.46 + 0.27 (separate sum kernel) -- the reduce-adds cost more L2 time than the
+        // streaming sum, and the 11 staging stores per thread more issue slots than the scattered global ones; off.
+        prm.out_sum = (g_rnn_dbg & 4096) ? out_sum : nullptr;
+        rc = rnn3_forward(cell, pl, prm, wpack_fwd, stream);
+        if (rc == 0 && out_sum && !prm.out_sum) rc = asrb_rnn_sum_dirs(hseq, out_sum, T, B, H, stream);
+        return rc;
+    }
+    if (rnn2_eligible(pl, prm)) rc = rnn2_dispatch(false, cell, pl, prm, wpack_fwd, stream);
+    else rc = rnn_dispatch<false>(cell, pl, prm, wpack_fwd, pl.bf16 ? (const void*)hseq_bf16 : (const void*)hseq, stream);
+    if (rc == 0 && out_sum) rc = asrb_rnn_sum_dirs(hseq, out_sum, T, B, H, stream);
+    return rc;
+}
+
+int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
+                 float* hseq, void* hseq_bf16, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
+                 asrb_stream_t stream) {
+    return asrb_rnn_fwd_sum(cell, bf16, gi, b_hh, wpack_fwd, lengths, hseq, hseq_bf16, cseq, saved, nullptr, counters, T, B, H, stream);
 }
 
 int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, const int32_t* lengths,

@@ -27,7 +27,8 @@ struct RnnParams {
     int P_saved;          // slices of the saved-gates layout (= the forward's P; the split backward may pad its own P)
     const int* lengths;
     uint32_t* counters;   // [2 dirs] step counters, kRnnCounterStride words apart
-    int stage_out;        // rnn3.cu backward: gate-gradient outputs through shared-memory tiles + TMA stores
+    float* out_sum;       // forward, optional: [T,B,H] = sum of the two directions (blocks.py:92), written by the kernel itself
+    int stage_out;        // rnn3.cu: gate-gradient outputs through shared-memory tiles + TMA stores
     int dbg;              // DEBUG timing experiments: 1 = drop the non-critical stores, 2 = drop the operand prefetch
     const float* wpack;  // packed fp32 weight slices (global copy, SIMT debug path)
     // bf16 MMA operands; rows padded to a multiple of 64 elements (128 bytes) so that every 128-byte box row TMA

@@ -27,6 +27,16 @@
 
 namespace asrb {
 
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// global += shared (fp32), 3-D tile
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 constexpr int kR3Chunk = 4;                 // K blocks per TMA barrier
 constexpr int kR3MaxChunks = 4;             // kpad <= 1024
 constexpr int kR3CounterStride = 16;        // step counters [dir][chain], 64 bytes apart (8 of them in the 512-byte block)
@@ -36,7 +46,9 @@ constexpr int kR3CounterStride = 16;        // step counters [dir][chain], 64 by
 // chain, with warp % 4 = TMEM lane quarter = gate.
 template <int CELL, int NCH>
 __global__ void __launch_bounds__(kRnnThreads, 1)
-rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmGi, const RnnParams p) {
+rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmGi,
+                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmC,
+                const __grid_constant__ CUtensorMap tmSaved, const __grid_constant__ CUtensorMap tmOut, const RnnParams p) {
     constexpr int kR3Chains = NCH;
     constexpr int kR3Rows = 64 / NCH;           // batch rows of a chain = N of its MMAs
     constexpr int kR3EpiWarps = 16 / NCH;       // per chain
@@ -60,7 +72,10 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // per chain: operand tile, gate boxes (2 step parities), transposed accumulator tile, barriers
     const size_t a_bytes = (size_t)nkb * kSlotBytes, gi_bytes = (size_t)2 * kGates * kGiRegion;
     const size_t dt_bytes = (size_t)64 * kR3DtStride * 4;
-    const size_t chain_bytes = (a_bytes + gi_bytes + dt_bytes + 256 + 1023) & ~size_t(1023);   // operand tiles: 1 KB aligned
+    // staged outputs (TMA stores): h and c tiles [rows][16 units] fp32, saved activations [4 gates x 4 unit groups][rows][4]
+    const size_t hc_bytes = (size_t)kR3Rows * NJ * 4, sv_bytes = (size_t)16 * kR3Rows * 16;
+    const size_t st_bytes = 2 * hc_bytes + sv_bytes;
+    const size_t chain_bytes = (a_bytes + gi_bytes + dt_bytes + st_bytes + 256 + 1023) & ~size_t(1023);   // operand tiles: 1 KB aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.x / P, pidx = blockIdx.x % P;
@@ -72,7 +87,10 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* smem_a = cs;                                     // [nkb][32 rows x 128 B]
     uint8_t* smem_gi = cs + a_bytes;                          // [2][kGates][kGiRegion]
     float* dt = reinterpret_cast<float*>(cs + a_bytes + gi_bytes);   // [64 gate rows][kR3DtStride]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cs + a_bytes + gi_bytes + dt_bytes);
+    float* st_h = reinterpret_cast<float*>(cs + a_bytes + gi_bytes + dt_bytes);      // [rows][16]
+    float* st_c = st_h + kR3Rows * NJ;                                               // [rows][16]
+    float* st_sv = st_c + kR3Rows * NJ;                                              // [gate * 4 + unit group][rows][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cs + a_bytes + gi_bytes + dt_bytes + st_bytes);
     uint64_t* full_bar = bars;                                // [kR3MaxChunks]
     uint64_t* tfull_bar = bars + kR3MaxChunks;
     uint64_t* gi_bar = bars + kR3MaxChunks + 1;               // [2]
@@ -87,6 +105,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (warp == 0) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmGi);
+            tma_prefetch_desc(&tmH);
+            tma_prefetch_desc(&tmSaved);
             mbar_init(w_bar, 1);
         }
         for (int i = 0; i < kR3MaxChunks; ++i) mbar_init(&full_bar[i], 1);
@@ -233,6 +253,12 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
         if (chain_on) {
             float state_h[2] = {0.f, 0.f}, state_c[2] = {0.f, 0.f};
+            // The stores nobody waits for (fp32 state, saved activations: 10 scattered 4-byte stores per thread and step)
+            // go through shared-memory tiles and TMA stores when the tiles are whole (32 / 16 batch rows, 16 valid units):
+            // no LSU issue time, and the release's MEMBAR does not wait for them.  The direction sum the next layer reads
+            // (blocks.py:92) is a TMA reduce-add of the same h tile into the zero-filled output.
+            const bool staged = p.stage_out && j0 + NJ <= H && row0 + kR3Rows <= B;
+            const int rl0 = 16 * (wl % kRp16) + (lane >> 2);
             for (int s = 0; s < T; ++s) {
                 const int t = t_of(s);
                 bool active[2];
@@ -257,6 +283,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         *reinterpret_cast<float2*>(d + 8 * kR3DtStride + 8) = make_float2(v[6], v[7]);
                     }
                     tc_fence_before_sync();    // the counter arrival below orders these reads before the next step's MMAs
+                    if (staged && el == 0) bulk_wait_group_read<0>();   // the previous step's TMA stores have read their tiles
                     named_bar_sync(4 + chain, kR3EpiThreads);
 #pragma unroll
                     for (int g = 0; g < kGates; ++g)
@@ -304,29 +331,51 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                     if (cellok[c]) p.hbf[(((size_t)dir * (T + 2) + t + 1) * B + row[c]) * p.Hp + unit] = __float2bfloat16_rn(hn[c]);
+                if (staged) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int rl = rl0 + 8 * c;
+                        st_h[rl * NJ + ju] = hn[c];
+                        if constexpr (CELL == ASRB_RNN_LSTM) st_c[rl * NJ + ju] = cn[c];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) st_sv[((q * NV + ug) * kR3Rows + rl) * 4 + ul] = sv[q][c];
+                    }
+                    fence_proxy_async_smem();                  // generic stores -> the TMA stores' async-proxy reads
+                }
                 if (el == 0 && chain == 0) ASRB_TRACE(7, s);
                 named_bar_sync(8 + chain, kR3EpiThreads);
                 if (el == 0) {
                     if (chain == 0) ASRB_TRACE(8, s);
                     red_release_add_u32(counter, 1u);
                     if (chain == 0) ASRB_TRACE(10, s);
+                    if (staged) {
+                        tma_store_3d(&tmH, st_h, j0, row0, dir * (T + 2) + t + 1);
+                        if constexpr (CELL == ASRB_RNN_LSTM) tma_store_3d(&tmC, st_c, j0, row0, dir * (T + 2) + t + 1);
+                        tma_store_3d(&tmSaved, st_sv, 0, row0, (((dir * T + t) * P + pidx) * 4) * NV);
+                        if (p.out_sum) tma_reduce_add_3d(&tmOut, st_h, j0, row0, t);
+                        bulk_commit_group();
+                    }
                 }
-                // hold the other stores back until the release has been issued: its MEMBAR waits for every store in flight
-                named_bar_sync(12 + chain, kR3EpiThreads);
-                // (2) the stores nobody waits for
+                if (!staged) {
+                    // hold the other stores back until the release has been issued: its MEMBAR waits for every store in flight
+                    named_bar_sync(12 + chain, kR3EpiThreads);
+                    // (2) the stores nobody waits for
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (cellok[c]) {
-                        const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)row[c] * H + unit;
-                        float* svp = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) +
-                                     (size_t)ug * (B * 4) + (size_t)row[c] * 4 + ul;
-                        p.hseq[o] = hn[c];
-                        if constexpr (CELL == ASRB_RNN_LSTM) p.cseq[o] = cn[c];
+                    for (int c = 0; c < 2; ++c) {
+                        if (cellok[c]) {
+                            const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)row[c] * H + unit;
+                            float* svp = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) +
+                                         (size_t)ug * (B * 4) + (size_t)row[c] * 4 + ul;
+                            p.hseq[o] = hn[c];
+                            if constexpr (CELL == ASRB_RNN_LSTM) p.cseq[o] = cn[c];
+                            if (p.out_sum) atomicAdd(p.out_sum + (size_t)t * slotHB + (size_t)row[c] * H + unit, hn[c]);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) svp[(size_t)q * NV * (B * 4)] = sv[q][c];
+                            for (int q = 0; q < 4; ++q) svp[(size_t)q * NV * (B * 4)] = sv[q][c];
+                        }
                     }
                 }
             }
+            if (staged && el == 0) bulk_wait_group<0>();      // the last TMA stores have been written
         }
     }
     tc_fence_before_sync();
@@ -348,12 +397,43 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     prm.P = pl.P;
     prm.kpad = kpad;
     prm.wpack = reinterpret_cast<const float*>(wpack);       // bf16 slices, read once into tensor memory
-    const size_t chain_bytes = ((size_t)nkb * kR3Rows * 128 + (size_t)2 * kGates * kR3Rows * 64 + (size_t)64 * kR3DtStride * 4 + 256 + 1023) & ~size_t(1023);
+    const size_t st_bytes = (size_t)2 * kR3Rows * 16 * 4 + (size_t)16 * kR3Rows * 16;
+    const size_t chain_bytes = ((size_t)nkb * kR3Rows * 128 + (size_t)2 * kGates * kR3Rows * 64 + (size_t)64 * kR3DtStride * 4 + st_bytes + 256 + 1023) & ~size_t(1023);
     const size_t smem = 1024 + kR3Chains * chain_bytes + 16 + kGates * 16 * 4 + 64;
     if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return ASRB_ERR_DRIVER;
-    CUtensorMap tmA, tmGi;
+    if (prm.out_sum)     // both directions add their h tiles into it
+        ASRB_CUDA_OK(cudaMemsetAsync(prm.out_sum, 0, (size_t)prm.T * B * prm.H * sizeof(float), stream));
+    CUtensorMap tmA, tmGi, tmH, tmC, tmSaved, tmOut;
+    // staged outputs: whole tiles only (rows of a chain, 16 valid units)
+    prm.stage_out = (B % kR3Rows == 0 && prm.H % 16 == 0 && (g_rnn_dbg & 4096)) ? 1 : 0;   // see asrb_rnn_fwd_sum: off
+    if (prm.stage_out) {
+        auto plain = [&](CUtensorMap* m, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* bx) {
+            cuuint32_t es[3] = {1, 1, 1};
+            if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+            return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        bool ok = true;
+        {   // hseq / cseq [2(T+2)][B][H] fp32 and the direction sum [T][B][H]: box = 16 units x rows of a chain
+            cuuint64_t gdim[3] = {(cuuint64_t)prm.H, (cuuint64_t)B, (cuuint64_t)2 * (prm.T + 2)};
+            cuuint64_t gstr[2] = {(cuuint64_t)prm.H * 4, (cuuint64_t)B * prm.H * 4};
+            cuuint32_t bx[3] = {16, (cuuint32_t)kR3Rows, 1};
+            ok = ok && plain(&tmH, prm.hseq, gdim, gstr, bx);
+            ok = ok && plain(&tmC, prm.cseq ? prm.cseq : prm.hseq, gdim, gstr, bx);
+            gdim[2] = (cuuint64_t)prm.T;
+            ok = ok && plain(&tmOut, prm.out_sum ? prm.out_sum : prm.hseq, gdim, gstr, bx);
+        }
+        {   // saved [2 T P 16 (gate, unit group)][B][4] fp32: box = one step's 16 (gate, group) planes x rows of a chain
+            cuuint64_t gdim[3] = {4, (cuuint64_t)B, (cuuint64_t)2 * prm.T * pl.P * 16};
+            cuuint64_t gstr[2] = {16, (cuuint64_t)B * 16};
+            cuuint32_t bx[3] = {4, (cuuint32_t)kR3Rows, 16};
+            ok = ok && plain(&tmSaved, prm.saved, gdim, gstr, bx);
+        }
+        if (!ok) prm.stage_out = 0;
+    }
+    if (!prm.stage_out) tmH = tmC = tmSaved = tmOut = CUtensorMap{};
     {   // hbf [2(T+2)][B][Hp] bf16, box = 64 columns x 32 rows (one chain), 128-byte swizzle; rows >= B, columns >= H: zero fill
         uint64_t d[3] = {(uint64_t)prm.H, (uint64_t)B, (uint64_t)2 * (prm.T + 2)};
         uint64_t s[2] = {(uint64_t)prm.Hp * 2, (uint64_t)B * prm.Hp * 2};
@@ -387,7 +467,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     prm.dbg = g_rnn_dbg;
-    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmGi, prm));
+    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmGi, tmH, tmC, tmSaved, tmOut, prm));
     return 0;
 }
 
@@ -405,11 +485,6 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
 constexpr int kR3XStride = 40;                              // floats per unit row of an exchanged quarter [16 units][32 rows + pad]
 constexpr int kR3XBytes = 16 * kR3XStride * 4;              // 2560
 constexpr int kR3StageBytes = 32 * 16 * 2;                  // one gate's [32 rows x 16 units] bf16 tile of a staged output
-
-__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 :: "l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 
 template <int CELL>
 __global__ void __launch_bounds__(kRnnThreads, 1)

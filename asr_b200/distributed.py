@@ -50,6 +50,63 @@ class FlatGradBucket:
                 self.flat.div_(dist.get_world_size(group))
 
 
+class OverlappedGradSync:
+    """The one gradient all-reduce of data-parallel training, cut in two so that it hides under the backward pass: the
+    tail of the flat bucket (recurrent layers + head: 99.7 % of the bytes) is reduced on a communication stream as soon as
+    the recurrent stack's backward is done -- while the conv backward still runs -- and the few conv gradients follow at
+    the end.  Same arithmetic as `FlatGradBucket.all_reduce_mean` (the reference's SUM-then-divide rule, functional.py:35-42).
+
+        sync = OverlappedGradSync(bucket, model)       # sets model.after_rnn_backward
+        ... bucket.zero(); loss.backward(); sync.finish()
+    """
+
+    def __init__(self, bucket, model, group=None):
+        self.bucket, self.group = bucket, group
+        conv_ids = {id(p) for p in model.conv.parameters()}
+        head = 0
+        for p in bucket.params:          # bucket order = model.parameters() order: the conv stack comes first
+            if id(p) not in conv_ids:
+                break
+            head += p.numel()
+        self.head = head
+        self.work = None
+        self.comm = torch.cuda.Stream(device=bucket.flat.device) if bucket.flat.is_cuda else None
+        model.after_rnn_backward = self.start_tail
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def start_tail(self):
+        if not self._active() or self.comm is None:
+            return
+        from . import functional as F_
+
+        dev = self.bucket.flat.device
+        self.comm.wait_stream(torch.cuda.current_stream(dev))
+        side = F_._side_streams.get(dev.index if dev.index is not None else torch.cuda.current_device())
+        if side is not None:             # the weight gradients of the recurrent layers are issued on the side stream
+            self.comm.wait_stream(side)
+        with torch.cuda.stream(self.comm):
+            self.work = dist.all_reduce(self.bucket.flat[self.head:], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+
+    def finish(self):
+        """after backward(): the rest of the bucket, and the main stream waits for the overlapped part"""
+        if not self._active():
+            return
+        flat = self.bucket.flat
+        if self.work is None:            # the hook did not fire (no gradient into the recurrent stack's input): one piece
+            self.bucket.all_reduce_mean(self.group)
+            return
+        if self.head:
+            if flat.is_cuda:
+                dist.all_reduce(flat[:self.head], op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(flat[:self.head], op=dist.ReduceOp.SUM, group=self.group)
+                flat[:self.head].div_(dist.get_world_size(self.group))
+        self.work.wait()
+        self.work = None
+
+
 def frame_balanced_shards(num_frames, world_size):
     """Assign utterances to ranks so that every rank gets the same COUNT and a nearly equal SUM of frames
     (longest-first greedy with a per-rank capacity).  Whole-bin dealing, the reference's rule, leaves a 3.3x

@@ -263,9 +263,9 @@ def _queue_join():
 
 
 def _accumulate_grad(param, g):
-    g = g.view_as(param)
+    g = g.view_as(param) if g.is_contiguous() else g.reshape(param.shape)
     if param.grad is None:
-        param.grad = g
+        param.grad = g if g.is_contiguous() else g.contiguous()
     else:
         param.grad.add_(g)
 
@@ -324,24 +324,51 @@ class BiRnnLayer(Function):
         tr = ops.transpose_bf16 if lowp else (lambda a: _transpose_padded(a)[:, :a.shape[0]])
 
         def weight_grads():
-            # bias gradients = row sums of the transposed gate gradients
-            db_ih_cat = ops.row_sums(dgiT, R)
-            # LSTM: the hidden-side gate gradients ARE the input-side ones, but bias_ih.grad and bias_hh.grad must not
-            # share storage (an in-place op on all grads -- GradScaler.unscale_, clip_grad_norm_ -- would hit them twice)
-            db_hh_cat = db_ih_cat.clone() if dghT is dgiT else ops.row_sums(dghT, R)
             # weight gradients (K = T*B): dW_ih = dgi^T x ; dW_hh = dgh^T h_prev -- the transposed gate gradients come
-            # straight from the recurrent kernel, only x and h_prev are transposed here
-            xt = tr(x2)                                             # [I, R]
-            dw_ih = gemm(dgiT[:G, :R], xt)
-            dw_ih_r = gemm(dgiT[G:, :R], xt)
-            dw_hh = []
+            # straight from the recurrent kernel, only x and h_prev are transposed here.
+            # bf16 mode: the bias gradients (row sums of the transposed gate gradients: 3 GB of re-reads per step when done as
+            # a separate pass) come out of the same products -- a row of ones appended to x^T / h_prev^T makes them column I
+            # (resp. H) of the result.
+            if not lowp:
+                db_ih_cat = ops.row_sums(dgiT, R)
+                db_hh_cat = db_ih_cat.clone() if dghT is dgiT else ops.row_sums(dghT, R)
+                xt = tr(x2)                                             # [I, R]
+                dw_ih = gemm(dgiT[:G, :R], xt)
+                dw_ih_r = gemm(dgiT[G:, :R], xt)
+                dw_hh = []
+                for d in range(2):
+                    first = 0 if d == 0 else 2
+                    hpt = tr(hseq[d, first:first + T].reshape(R, H))    # [H, R]
+                    dw_hh.append(gemm(dghT[d * G:(d + 1) * G, :R], hpt))
+                return (dw_ih, dw_hh[0], db_ih_cat[:G], db_hh_cat[:G], dw_ih_r, dw_hh[1], db_ih_cat[G:], db_hh_cat[G:])
+            R8 = (R + 7) // 8 * 8
+
+            def with_ones(src, C):                                      # [C+1, R] bf16: src^T and a row of ones
+                buf = torch.empty(C + 1, R8, device=src.device, dtype=torch.bfloat16)
+                ops.transpose_bf16(src, out=buf[:C, :R])
+                buf[C].fill_(1.0)
+                return buf[:, :R]
+
+            def product(gT, bt, C):                                     # [G, C] weight gradient and [G] bias gradient
+                out = torch.empty(G, (C + 1 + 3) // 4 * 4, device=gT.device, dtype=torch.float32)
+                gemm(gT, bt, out=out[:, :C + 1])
+                return out[:, :C], out[:, C]
+
+            xt = with_ones(x2, I)
+            dw_ih, db_ih = product(dgiT[:G, :R], xt, I)
+            dw_ih_r, db_ih_r = product(dgiT[G:, :R], xt, I)
+            dw_hh, db_hh = [], []
             for d in range(2):
                 # previous state in forward order: slots 0..T-1 for the forward direction, 2..T+1 for the reverse one
                 first = 0 if d == 0 else 2
-                hpt = tr(hseq[d, first:first + T].reshape(R, H))    # [H, R]
-                dw_hh.append(gemm(dghT[d * G:(d + 1) * G, :R], hpt))
+                hpt = with_ones(hseq[d, first:first + T].reshape(R, H), H)
+                w, b = product(dghT[d * G:(d + 1) * G, :R], hpt, H)
+                dw_hh.append(w)
+                db_hh.append(b)
+            # LSTM: the hidden-side gate gradients ARE the input-side ones; bias_ih.grad and bias_hh.grad still get their
+            # own storage (two products), so an in-place op over all gradients hits each of them once
             # in the order of ctx.params: w_ih, w_hh, b_ih, b_hh, then the reverse direction's
-            return (dw_ih, dw_hh[0], db_ih_cat[:G], db_hh_cat[:G], dw_ih_r, dw_hh[1], db_ih_cat[G:], db_hh_cat[G:])
+            return (dw_ih, dw_hh[0], db_ih, db_hh[0], dw_ih_r, dw_hh[1], db_ih_r, db_hh[1])
 
         params = ctx.params
         overlap = (WGRAD_OVERLAP and dout.is_cuda and all(ctx.needs_input_grad[3:])

@@ -102,6 +102,12 @@ class DeepSpeech(nn.Module):
         output_lengths = self.get_seq_lens(lengths)
         x, _ = self.conv(x, output_lengths)
         x = F_.NchwToTnf.apply(x)
+        cb = getattr(self, "after_rnn_backward", None)
+        if cb is not None and x.requires_grad:
+            # fires when the gradient w.r.t. the recurrent stack's input exists, i.e. every gradient of the recurrent
+            # layers and the head has been issued: data-parallel training starts their all-reduce here, under the conv
+            # backward (asr_b200.distributed.OverlappedGradSync)
+            x.register_hook(lambda g, cb=cb: (cb(), g)[1])
         for rnn in self.rnns:
             x = rnn(x, output_lengths)
         if not self.bidirectional:

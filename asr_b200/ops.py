@@ -58,7 +58,7 @@ PROFILE = None   # set to a dict to collect (start, end) CUDA-event pairs per en
 # kernels launched per call of an entry point (memsets not counted); used for the `gpu_launches` claim
 KERNELS_PER_CALL = {
     "asrb_conv2d_mask_bwd_weight": 3, "asrb_bn2d_stats": 2, "asrb_bn_act_mask_bwd": 3, "asrb_bn_rows_fwd": 3,
-    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_ctc_bwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_conv32_bwd_weight": 2, "asrb_conv1_fwd": 3, "asrb_conv1_bwd_weight": 2,
+    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_ctc_bwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_rnn_fwd_sum": 2, "asrb_conv32_bwd_weight": 2, "asrb_conv1_fwd": 3, "asrb_conv1_bwd_weight": 2,
 }
 
 
@@ -472,8 +472,9 @@ def rnn_pack_weights(cell, w_hh_fwd, w_hh_rev, B, fwd=True, bwd=True):
     return pf, pb
 
 
-def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
-    """gi [T,B,2,G], b_hh [2,G] -> hseq [2,T+2,B,H], cseq (LSTM) or None, saved [2,T,B,4,H]"""
+def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H, want_sum=False):
+    """gi [T,B,2,G], b_hh [2,G] -> hseq [2,T+2,B,H], cseq (LSTM) or None, saved [2,T,B,4,H]
+    (+ out [T,B,H] = the sum of the two directions, blocks.py:92, when want_sum)"""
     _chk(gi, b_hh)
     _chk(lengths, dtype=torch.int32)
     dev = gi.device
@@ -483,6 +484,11 @@ def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
     cseq = torch.empty(2, T + 2, B, H, device=dev, dtype=torch.float32) if cell == LSTM else None
     saved = torch.empty(_lib.query("asrb_rnn_saved_floats", cell, H, B, int(bf16), T), device=dev, dtype=torch.float32)
     counters = torch.empty(128, device=dev, dtype=torch.int32)
+    if want_sum:
+        out = torch.empty(T, B, H, device=dev, dtype=torch.float32)
+        _call("asrb_rnn_fwd_sum", cell, int(bf16), _p(gi), _p(b_hh), _p(wpack_fwd), _p(lengths), _p(hseq), _p(hbf), _p(cseq),
+              _p(saved), _p(out), _p(counters), T, B, H)
+        return hseq, cseq, saved, out
     _call("asrb_rnn_fwd", cell, int(bf16), _p(gi), _p(b_hh), _p(wpack_fwd), _p(lengths), _p(hseq), _p(hbf), _p(cseq),
           _p(saved), _p(counters), T, B, H)
     return hseq, cseq, saved

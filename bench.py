@@ -227,6 +227,113 @@ def run_torch_cudnn(dev, steps, warmup, cfg=CFG):
     return out
 
 
+def ragged_dp_leg(model, bucket, sync, dev, rank, world, steps, warmup, cfg=CFG):
+    """BASELINE.json configs[3] as stated: global batch 64 x N, durations U(5, 20) s, the utterances dealt to the ranks by
+    `frame_balanced_shards` (equal counts, nearly equal frame sums), every rank's batch sorted by length and padded to its
+    own longest utterance like _collate_fn (functional.py:9-32).  Reports per-rank compute time (before the all-reduce),
+    the straggler ratio and the aggregate utterance-sec/s.  Extra key only: the metric line stays on the uniform config."""
+    import torch.distributed as dist
+
+    from asr_b200.distributed import frame_balanced_shards
+    from asr_b200.trainers import CTCLoss, fit
+    from oracle.make_golden import synth_batch
+
+    g = torch.Generator().manual_seed(4321)
+    secs = (5.0 + 15.0 * torch.rand(cfg["B"] * world, generator=g)).tolist()
+    frames = [int(100 * sec) + 1 for sec in secs]
+    shards = frame_balanced_shards(frames, world)
+    whole_bins = [sorted(frames, reverse=True)[r * cfg["B"]:(r + 1) * cfg["B"]] for r in range(world)]   # the reference's rule
+    mine = [frames[i] for i in shards[rank]]
+    tmax = mine[0]
+    U = [max(1, f // 10) for f in mine]                               # ~10 characters per second
+    host = synth_batch(1240 + rank, cfg["B"], tmax, U, cfg["C"], mine)
+    x = host[0].to(dev)
+    criterion = CTCLoss(reduction="sum")
+
+    def one():
+        bucket.zero()
+        _, loss, lv = fit(model, criterion, (x, host[1], host[2], host[3]), dev)
+        loss.backward()
+        mid = torch.cuda.Event(enable_timing=True)
+        mid.record()
+        sync.finish() if sync is not None else None
+        return mid
+
+    for _ in range(max(2, warmup)):
+        one()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    comp = 0.0
+    e0.record()
+    starts, mids = [], []
+    for _ in range(steps):
+        st = torch.cuda.Event(enable_timing=True)
+        st.record()
+        starts.append(st)
+        mids.append(one())
+    e1.record()
+    torch.cuda.synchronize()
+    total = e0.elapsed_time(e1) / steps
+    comp = sum(a.elapsed_time(b) for a, b in zip(starts, mids)) / steps
+    t = torch.tensor([total, comp, float(sum(mine)), float(tmax)], device=dev)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    rows = [v.tolist() for v in allt]
+    step_ms = max(r[0] for r in rows)
+    comps = [r[1] for r in rows]
+    audio = sum(secs)
+    return {"global_batch": cfg["B"] * world, "durations": "U(5,20) s, seed 4321", "sharding": "frame_balanced_shards",
+            "ms_per_step": step_ms, "value": audio / (step_ms * 1e-3), "unit": "utterance-sec/s",
+            "per_rank_compute_ms": [round(c, 2) for c in comps], "straggler_ratio": max(comps) / min(comps),
+            "per_rank_frames": [int(r[2]) for r in rows], "per_rank_longest": [int(r[3]) for r in rows],
+            "frame_imbalance_balanced": max(r[2] for r in rows) / min(r[2] for r in rows),
+            "frame_imbalance_whole_bins": max(sum(b) for b in whole_bins) / min(sum(b) for b in whole_bins),
+            "padded_frame_imbalance_whole_bins": max(b[0] * len(b) for b in whole_bins) / min(b[0] * len(b) for b in whole_bins)}
+
+
+def configs2_leg(dev, tf_peak):
+    """BASELINE.json configs[2] on one GPU, after the timed region: 7 x biLSTM-1024, batch 128, 15 s, 90 labels, U=150,
+    fwd + CTC + bwd (TF32 forward products, bf16 recurrent and backward-GEMM operands, fp32 accumulation)."""
+    from asr_b200.trainers import CTCLoss, fit
+    from oracle.make_golden import synth_batch
+
+    cfg = dict(rnn_type="lstm", hidden=1024, layers=7, C=90, B=128, seconds=15, T=1501, U=150, seed=1237)
+    model = build_model(cfg, dev)
+    host = synth_batch(cfg["seed"], cfg["B"], cfg["T"], cfg["U"], cfg["C"])
+    x = host[0].to(dev)
+    crit = CTCLoss(reduction="sum")
+
+    def one():
+        for p in model.parameters():
+            p.grad = None
+        _, loss, lv = fit(model, crit, (x, host[1], host[2], host[3]), dev)
+        loss.backward()
+        return lv
+
+    for _ in range(2):
+        lv = one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        lv = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    Tp, B, H, L, G = 751, 128, 1024, 7, 4096
+    rnn_flops = 3.0 * sum(2.0 * Tp * B * (1312 if l == 0 else H) * G * 2 + 2.0 * Tp * B * H * G * 2 for l in range(L))
+    floor_ms = rnn_flops / (tf_peak * 1e12) * 1e3
+    out = {"workload": "configs[2]: 7xbiLSTM-1024, batch 128, 15 s, 90 labels, U=150, fwd+CTC+bwd", "ms_per_step": ms,
+           "value": B * 15 / (ms * 1e-3), "unit": "utterance-sec/s", "loss": lv,
+           "rnn_gemm_floor_ms": floor_ms, "frac_of_rnn_gemm_roofline": floor_ms / ms,
+           "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9,
+           "parity": "tests/test_gpu_fullsize_golden.py::cfg3_lstm1024x7_b16 (same model, batch 16, against the unmodified reference)"}
+    del model, x
+    torch.cuda.empty_cache()
+    return out
+
+
 def isolation_rooflines(dev, hbm_peak):
     """The HBM-bound named kernels at the shapes BASELINE.json quotes them on, run AFTER the timed region (stated):
     CTC forward / backward at configs[4] (T=2000, N=256, C=5000, U=200) and the spectrogram chain at the configs[1]
@@ -307,7 +414,8 @@ def build_model(cfg, device):
     conf = SimpleNamespace(sample_rate=16000, window_size=0.02, window_stride=0.01, window="hamming")
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "labels.csv")
-        pd.DataFrame({"label": LABELS29[:cfg["C"]]}).to_csv(path, index=False)
+        labels = LABELS29[:cfg["C"]] if cfg["C"] <= 29 else [chr(0x3041 + i) for i in range(cfg["C"])]
+        pd.DataFrame({"label": labels}).to_csv(path, index=False)
         model = DeepSpeech(audio_conf=conf, decoder=None, label_path=path, rnn_type=f"nn.{cfg['rnn_type'].upper()}",
                            rnn_hidden_size=cfg["hidden"], rnn_hidden_layers=cfg["layers"])
     model.load_state_dict(torch_path.init_params(cfg["rnn_type"], cfg["hidden"], cfg["layers"], cfg["C"]), strict=True)
@@ -349,7 +457,7 @@ def main():
     import torch.distributed as dist
 
     from asr_b200 import ops
-    from asr_b200.distributed import FlatGradBucket
+    from asr_b200.distributed import FlatGradBucket, OverlappedGradSync
     from asr_b200.trainers import CTCLoss, fit
 
     torch.cuda.set_device(local_rank)
@@ -359,6 +467,8 @@ def main():
     model = build_model(cfg, dev)
     criterion = CTCLoss(reduction="sum")
     bucket = FlatGradBucket(model.parameters())
+    # N > 1: the all-reduce of the recurrent + head gradients starts under the conv backward, the conv gradients follow
+    sync = OverlappedGradSync(bucket, model) if world > 1 else None
     host = make_batch(cfg["B"])
     pinned = host[0].pin_memory()
     resident = host[0].to(dev)
@@ -368,7 +478,8 @@ def main():
         bucket.zero()
         valid, loss, loss_value = fit(model, criterion, (inputs, host[1], host[2], host[3]), dev)
         loss.backward()
-        bucket.all_reduce_mean()
+        if sync is not None:
+            sync.finish()
         return loss_value
 
     def barrier():
@@ -439,6 +550,12 @@ def main():
         step(resident)
     _, _, _, prof = timed(resident, args.steps, profile=True)
     F_.WGRAD_OVERLAP = overlap
+    ragged = None
+    if world > 1:
+        try:
+            ragged = ragged_dp_leg(model, bucket, sync, dev, rank, world, args.steps, args.warmup)
+        except Exception as e:
+            ragged = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -512,6 +629,8 @@ def main():
                                   "recurrence is a latency chain of T' grid-wide steps, see DESIGN.md section 6"},
                 rooflines=rooflines,
                 kernel_ms_per_step={k: round(v[0], 3) for k, v in sorted(per_op.items(), key=lambda kv: -kv[1][0])})
+    if ragged is not None:
+        line["ragged_dp"] = ragged
     if world == 1 and not args.no_isolation:
         # freed first: the isolation shapes need ~35 GB
         del model, bucket, resident, dev_buf
@@ -521,6 +640,10 @@ def main():
         except Exception as e:
             line["rooflines"]["isolation_error"] = f"{type(e).__name__}: {e}"[:200]
         line["torch_cudnn"] = run_torch_cudnn(dev, args.steps, args.warmup)
+        try:
+            line["configs2"] = configs2_leg(dev, tf_peak)
+        except Exception as e:
+            line["configs2"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     if not args.no_cpu_baseline and world == 1:
         v, dt, cores, sample = run_cpu_port(3, 1, best_of=True)
         line["cpu_baseline"] = {"value": v, "unit": "utterance-sec/s", "cores": cores, "kind": "port", "sample": sample,

@@ -97,6 +97,12 @@ int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fw
 int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
                  float* hseq, void* hseq_bf16, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream);
+/* The same with the direction sum of blocks.py:92 folded in: out_sum [T,B,H] = hseq[0][1..T] + hseq[1][1..T] (NULL: not
+ * wanted).  The tensor-memory kernel adds both directions' tiles into it with TMA reduce-adds; the other kernels run
+ * asrb_rnn_sum_dirs behind the recurrence. */
+int asrb_rnn_fwd_sum(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
+                     float* hseq, void* hseq_bf16, float* cseq, float* saved, float* out_sum, uint32_t* counters, int T, int B,
+                     int H, asrb_stream_t stream);
 /* dout [T,B,H] (gradient of the direction-summed output).  out: dgi [T,B,2,G] (for the input-gradient GEMM);
  * dgiT [2G, ldT] = its transpose (row = dir*G + gate*H + unit, column = t*B + b; ldT >= T*B, multiple of 4) and, for
  * GRU, dghT [2G, ldT] = the transposed hidden-side gate gradients (they differ from dgiT in the n gate; LSTM: NULL)

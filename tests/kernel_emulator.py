@@ -216,7 +216,7 @@ def rnn_pack_weights(cell, w_hh_fwd, w_hh_rev, B, fwd=True, bwd=True):
     return (w if fwd else None), (w if bwd else None)
 
 
-def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
+def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H, want_sum=False):
     gates = 3 if cell == GRU else 4
     G = gates * H
     gi = gi.view(T, B, 2, G)
@@ -255,6 +255,8 @@ def rnn_fwd(cell, gi, b_hh, wpack_fwd, lengths, T, B, H):
             if cell == LSTM:
                 cseq[d, t + 1] = c
             saved[d, t] = sv * act[:, None]
+    if want_sum:
+        return hseq, cseq, saved, hseq[0, 1:T + 1] + hseq[1, 1:T + 1]
     return hseq, cseq, saved
 
 

@@ -11,7 +11,7 @@ def test_library_exports_every_header_symbol():
 
     assert os.path.exists(_lib.LIBRARY), "run __graft_entry__.build() first"
     names = set(_lib.PROTOTYPES)
-    expected = {"asrb_version", "asrb_strerror", "asrb_set_debug_flags", "asrb_gemm_tn", "asrb_rnn_fwd",
+    expected = {"asrb_version", "asrb_strerror", "asrb_set_debug_flags", "asrb_gemm_tn", "asrb_rnn_fwd", "asrb_rnn_fwd_sum",
                 "asrb_rnn_bwd", "asrb_conv2d_mask_fwd", "asrb_bn_act_mask_fwd", "asrb_bn_rows_fwd",
                 "asrb_log_softmax_fwd", "asrb_ctc_fwd", "asrb_ctc_bwd", "asrb_spectrogram"}
     assert expected <= names

@@ -61,3 +61,52 @@ def test_frame_balanced_shards_beats_whole_bin_dealing():
     for s in shards:
         ls = [frames[i] for i in s]
         assert ls == sorted(ls, reverse=True)
+
+
+def _worker_split(rank, world, port, ret):
+    """OverlappedGradSync: the bucket reduced in two pieces (head = the conv stack's gradients, tail = the rest) equals the
+    one-piece mean.  On the CPU there is no communication stream, so the hook is a no-op and finish() does both pieces."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+
+        from asr_b200.distributed import OverlappedGradSync
+
+        g = torch.Generator().manual_seed(10 + rank)
+        conv = torch.nn.Conv2d(1, 2, 3)
+        rest = torch.nn.Linear(4, 3)
+        model = SimpleNamespace(conv=conv)
+        params = list(conv.parameters()) + list(rest.parameters())
+        bucket = FlatGradBucket(params)
+        sync = OverlappedGradSync(bucket, model)
+        assert sync.head == sum(p.numel() for p in conv.parameters()) and callable(model.after_rnn_backward)
+        bucket.zero()
+        for p in params:
+            p.grad.copy_(torch.randn(p.shape, generator=g))
+        local = bucket.flat.clone()
+        model.after_rnn_backward()          # CPU: nothing to overlap
+        sync.finish()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        ret[rank] = bool(torch.allclose(bucket.flat, sum(gathered) / world, atol=1e-7))
+        # second form: the tail already reduced by the hook (emulated), finish() completes the head and waits
+        bucket.zero()
+        for p in params:
+            p.grad.copy_(torch.randn(p.shape, generator=g))
+        local = bucket.flat.clone()
+        sync.work = dist.all_reduce(bucket.flat[sync.head:], op=dist.ReduceOp.SUM, async_op=True)
+        sync.work.wait()
+        bucket.flat[sync.head:].div_(world)
+        sync.finish()
+        dist.all_gather(gathered, local)
+        ret[rank] = ret[rank] and bool(torch.allclose(bucket.flat, sum(gathered) / world, atol=1e-7))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_grad_sync_two_ranks():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_split, args=(2, 30500 + os.getpid() % 1000, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -319,6 +319,8 @@ def test_rnn_fwd_bwd(ops, c, mode):
         pf, pb = ops.rnn_pack_weights(cell, w_hh[0].contiguous().to(DEV), w_hh[1].contiguous().to(DEV), B)
         hseq, cseq, saved = ops.rnn_fwd(cell, gi.to(DEV), b_hh.to(DEV), pf, ld, T, B, H)
         out = ops.rnn_sum_dirs(hseq, T, B, H)
+        h2, _, _, out2 = ops.rnn_fwd(cell, gi.to(DEV), b_hh.to(DEV), pf, ld, T, B, H, want_sum=True)   # asrb_rnn_fwd_sum
+        assert torch.equal(h2, hseq) and torch.equal(out2, out)
         torch.cuda.synchronize()
         tol = {"simt_debug": 1e-5, "tf32": 3e-3, "bf16": 1.2e-2}[mode]   # the product feeds back through T steps
         gtol = {"simt_debug": 5e-5, "tf32": 1e-2, "bf16": 4e-2}[mode]
