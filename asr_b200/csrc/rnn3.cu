@@ -356,7 +356,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         bulk_commit_group();
                     }
                 }
-                if (!staged) {
+                if (!staged && !(p.dbg & 1)) {     // (dbg bit 1: timing experiment without these stores, results incomplete)
                     // hold the other stores back until the release has been issued: its MEMBAR waits for every store in flight
                     named_bar_sync(12 + chain, kR3EpiThreads);
                     // (2) the stores nobody waits for

@@ -276,6 +276,10 @@ RNN_CASES = [
     dict(cell="gru", T=20, B=64, H=800, lens=None),
     dict(cell="lstm", T=10, B=33, H=800, lens=None),
     dict(cell="gru", T=6, B=128, H=160, lens=None),
+    # rnn3.cu corner cases: one whole chain (staged TMA outputs); a whole chain + a partial one (staged + direct stores in
+    # the same launch); K tail (H not a multiple of 64)
+    dict(cell="lstm", T=8, B=32, H=64, lens=None),
+    dict(cell="gru", T=9, B=48, H=272, lens=None),
 ]
 
 
