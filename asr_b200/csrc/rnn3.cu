@@ -44,7 +44,11 @@ constexpr int kR3CounterStride = 16;        // step counters [dir][chain], 64 by
 // NCH chains of 64 / NCH batch rows.  Warp c < NCH is chain c's control warp (polls the chain's step counter, issues its TMA
 // copies, then its MMAs -- the steps of a chain are sequential anyway); warps 4 .. 19 are the epilogue warps, 16 / NCH per
 // chain, with warp % 4 = TMEM lane quarter = gate.
-template <int CELL, int NCH>
+// CS > 1: clusters of CS neighbouring CTAs of a direction share the copies of the previous state -- each CTA issues every
+// CS-th K block as a TMA MULTICAST that lands in all CS shared memories (and completes on all CS barriers).  Experiment
+// (see rnn3_forward): the 2 x 50 CTAs of configs[1] read the same 100 KB per step, 10.6 MB per step through L2, but halving
+// that traffic does not speed the copies up.
+template <int CELL, int NCH, int CS>
 __global__ void __launch_bounds__(kRnnThreads, 1)
 rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmGi,
                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmC,
@@ -119,6 +123,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    if constexpr (CS > 1) cluster_sync_all();     // the peers' barriers exist before anybody's multicast completes on them
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_d = tmem_base + chain * kR3Rows;      // the chain's accumulator: kR3Rows columns
     const uint32_t tmem_w = tmem_base + kR3Chains * kR3Rows;  // weights: kpad/2 columns
@@ -155,8 +161,15 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int c = 0; c < nchunks; ++c) {
                         const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
                         mbar_arrive_expect_tx(&full_bar[c], (uint32_t)nblk * kSlotBytes);
-                        for (int i = 0; i < nblk; ++i)
-                            tma_load_3d(smem_a + (size_t)(kb0 + i) * kSlotBytes, &tmA, &full_bar[c], (kb0 + i) * KBE, row0, slab);
+                        for (int i = 0; i < nblk; ++i) {
+                            if constexpr (CS > 1) {      // our share of the blocks, to every CTA of the cluster
+                                if ((uint32_t)((kb0 + i) % CS) == crank)
+                                    tma_load_3d_mc(smem_a + (size_t)(kb0 + i) * kSlotBytes, &tmA, &full_bar[c], (kb0 + i) * KBE, row0, slab,
+                                                   (uint16_t)((1u << CS) - 1));
+                            } else {
+                                tma_load_3d(smem_a + (size_t)(kb0 + i) * kSlotBytes, &tmA, &full_bar[c], (kb0 + i) * KBE, row0, slab);
+                            }
+                        }
                     }
                     if (s + 1 < T) load_gi(s + 1);
                 }
@@ -384,9 +397,10 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after_sync();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
+    if constexpr (CS > 1) cluster_sync_all();   // nobody leaves while a peer's multicast may still land here
 }
 
-template <int CELL, int NCH>
+template <int CELL, int NCH, int CS>
 static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {
     constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
     constexpr int kR3Chains = NCH, kR3Rows = 64 / NCH, kR3DtStride = kR3Rows + 8;
@@ -451,7 +465,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return ASRB_ERR_TENSORMAP;
     }
-    auto kern = rnn_rec3_kernel<CELL, NCH>;
+    auto kern = rnn_rec3_kernel<CELL, NCH, CS>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {   // the step barrier spins: refuse the launch when the device cannot hold the whole grid at once
         int dev = 0, sms = 0, per_sm = 0;
@@ -466,6 +480,16 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     cfg.blockDim = dim3(kRnnThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = CS > 1 ? 1 : 0;
+    if (CS > 1) {
+        int nclusters = 0;
+        ASRB_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
+        if (2 * pl.P > CS * nclusters) return ASRB_ERR_UNSUPPORTED;
+    }
     prm.dbg = g_rnn_dbg;
     ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmGi, tmH, tmC, tmSaved, tmOut, prm));
     return 0;
@@ -913,12 +937,19 @@ int rnn3_forward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack,
     // Two chains of 32 rows.  Four chains of 16 (asrb_debug_rnn_dbg bit 512) measure the same: what a chain waits for is
     // shared -- the release's MEMBAR covers every store the SM has in flight, and the chains' copies share the TMA / L2
     // bandwidth -- and starting the chains staggered (0.25 .. 6 k cycles apart) changes nothing either: they couple.
+    // TMA multicast of the copies over CTA pairs (bit 8192) is built and measured SLOWER (8.5 k against 8.0 k cycles per
+    // step): the copies are not bound by L2 read bandwidth, and a CTA then waits for the slower of two issuers; off.
+    const bool mc = (pl.P % 2 == 0) && (g_rnn_dbg & 8192);
     if (g_rnn_dbg & 512) {
-        if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 4>(pl, prm, wpack, stream);
-        return rnn3_launch<ASRB_RNN_LSTM, 4>(pl, prm, wpack, stream);
+        if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 4, 1>(pl, prm, wpack, stream);
+        return rnn3_launch<ASRB_RNN_LSTM, 4, 1>(pl, prm, wpack, stream);
     }
-    if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 2>(pl, prm, wpack, stream);
-    return rnn3_launch<ASRB_RNN_LSTM, 2>(pl, prm, wpack, stream);
+    if (mc) {
+        if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 2, 2>(pl, prm, wpack, stream);
+        return rnn3_launch<ASRB_RNN_LSTM, 2, 2>(pl, prm, wpack, stream);
+    }
+    if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 2, 1>(pl, prm, wpack, stream);
+    return rnn3_launch<ASRB_RNN_LSTM, 2, 1>(pl, prm, wpack, stream);
 }
 
 }  // namespace asrb
