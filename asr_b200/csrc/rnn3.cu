@@ -248,11 +248,15 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const bool have = lane < 16 && c < NPAD;
                 const uint4* wrow = reinterpret_cast<const uint4*>(
                     reinterpret_cast<const __nv_bfloat16*>(p.wpack) + ((size_t)(dir * P + pidx) * NPAD + (have ? c : 0)) * p.kpad);
-                for (int k16 = 0; k16 < p.kpad / 16; ++k16) {
-                    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
-                    if (have) { lo = __ldg(wrow + 2 * k16); hi = __ldg(wrow + 2 * k16 + 1); }
-                    const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-                    tmem_st_32x8(tmem_w + (uint32_t(quad * 32) << 16) + k16 * 8, r);
+                for (int k0 = 0; k0 < p.kpad / 16; k0 += 4) {       // kpad is a multiple of 64: four stores per round,
+                    uint4 v[8];                                      // their eight loads in flight together
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = have ? __ldg(wrow + 2 * k0 + i) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t r[8] = {v[2 * i].x, v[2 * i].y, v[2 * i].z, v[2 * i].w, v[2 * i + 1].x, v[2 * i + 1].y, v[2 * i + 1].z, v[2 * i + 1].w};
+                        tmem_st_32x8(tmem_w + (uint32_t(quad * 32) << 16) + (k0 + i) * 8, r);
+                    }
                 }
                 tmem_st_wait();
             }
@@ -657,11 +661,15 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const bool have = lane < 16;
                 const uint4* wrow = reinterpret_cast<const uint4*>(
                     reinterpret_cast<const __nv_bfloat16*>(p.wpack) + ((size_t)(dir * P + pidx) * 64 + (have ? c : 0)) * p.kpad);
-                for (int k16 = 0; k16 < p.kpad / 16; ++k16) {
-                    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
-                    if (have) { lo = __ldg(wrow + 2 * k16); hi = __ldg(wrow + 2 * k16 + 1); }
-                    const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-                    tmem_st_32x8(tmem_w + (uint32_t(quad * 32) << 16) + k16 * 8, r);
+                for (int k0 = 0; k0 < p.kpad / 16; k0 += 4) {       // kpad is a multiple of 64: four stores per round,
+                    uint4 v[8];                                      // their eight loads in flight together
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = have ? __ldg(wrow + 2 * k0 + i) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t r[8] = {v[2 * i].x, v[2 * i].y, v[2 * i].z, v[2 * i].w, v[2 * i + 1].x, v[2 * i + 1].y, v[2 * i + 1].z, v[2 * i + 1].w};
+                        tmem_st_32x8(tmem_w + (uint32_t(quad * 32) << 16) + (k0 + i) * 8, r);
+                    }
                 }
                 tmem_st_wait();
             }
@@ -783,27 +791,45 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     dg[0][c] = d0; dg[1][c] = d1; dg[2][c] = d2; dg[3][c] = d3; eg2[c] = e2;
                 }
+                // All 2-byte outputs go out as 4-byte pairs: neighbouring lanes swap one value so that a thread holds two
+                // adjacent elements -- lane pairs (ul, ul^1) for the row-major tensors (two units of one row: the even lane
+                // takes row 0 of the pair's cells, the odd lane row 1), lane pairs (r, r^1) for the transposed ones (two rows
+                // of one unit).  Halves the store instructions of the busiest phase of the step.
+                const bool ev_u = (ul & 1) == 0, ev_r = ((lane >> 2) & 1) == 0;
+                auto pair_units = [&](float c0, float c1) {          // -> bf16x2 of (unit, unit+1) for our store row
+                    const float got = __shfl_xor_sync(0xffffffffu, ev_u ? c1 : c0, 1);
+                    const __nv_bfloat162 v = ev_u ? __floats2bfloat162_rn(c0, got) : __floats2bfloat162_rn(got, c1);
+                    return *reinterpret_cast<const uint32_t*>(&v);
+                };
+                auto pair_rows = [&](float c0, float c1) {           // -> bf16x2 of (row, row+1) for our store unit
+                    const float got = __shfl_xor_sync(0xffffffffu, ev_r ? c1 : c0, 4);
+                    const __nv_bfloat162 v = ev_r ? __floats2bfloat162_rn(c0, got) : __floats2bfloat162_rn(got, c1);
+                    return *reinterpret_cast<const uint32_t*>(&v);
+                };
+                const int cu = ev_u ? 0 : 1;                          // which of our two cells' rows the unit pair is stored for
+                const int unit2 = unit & ~1;
                 // (1) the next step's MMA operand (hidden-side gate gradients), published through the chain's step counter
+                {
+                    uint32_t* o = reinterpret_cast<uint32_t*>(p.dghbf + (((size_t)dir * T + t) * B + row[cu]) * p.Gp + unit2);
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (cellok[c]) {
-                        __nv_bfloat16* o = p.dghbf + (((size_t)dir * T + t) * B + row[c]) * p.Gp + unit;
-#pragma unroll
-                        for (int q = 0; q < kGates; ++q) o[(size_t)q * H] = __float2bfloat16_rn((q == 2) ? eg2[c] : dg[q][c]);
+                    for (int q = 0; q < kGates; ++q) {
+                        const uint32_t v = (q == 2) ? pair_units(eg2[0], eg2[1]) : pair_units(dg[q][0], dg[q][1]);
+                        if (cellok[cu]) o[(size_t)q * H / 2] = v;
                     }
                 }
                 if (staged) {
                     if (s == 0 && el == 0) bulk_wait_group_read<0>();
+                    const int rl_u = rl0 + 8 * cu;                                  // our row of the unit pairs
+                    const int rl_r = ev_r ? rl0 : rl0 - 1 + 8;                      // first row of our row pair
+                    uint32_t* s_dgi = reinterpret_cast<uint32_t*>(st_dgi);
+                    uint32_t* s_gT = reinterpret_cast<uint32_t*>(st_gT);
+                    uint32_t* s_hT = reinterpret_cast<uint32_t*>(st_hT);
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int rl = rl0 + 8 * c;
-#pragma unroll
-                        for (int q = 0; q < kGates; ++q) {
-                            const __nv_bfloat16 v = __float2bfloat16_rn(dg[q][c]);
-                            st_dgi[q * (kR3StageBytes / 2) + rl * NJ + ju] = v;
-                            st_gT[q * (kR3StageBytes / 2) + ju * kRows + rl] = v;
-                            if (p.dghT) st_hT[q * (kR3StageBytes / 2) + ju * kRows + rl] = (q == 2) ? __float2bfloat16_rn(eg2[c]) : v;
-                        }
+                    for (int q = 0; q < kGates; ++q) {
+                        s_dgi[(q * (kR3StageBytes / 2) + rl_u * NJ + (ju & ~1)) / 2] = pair_units(dg[q][0], dg[q][1]);
+                        const uint32_t vt = pair_rows(dg[q][0], dg[q][1]);
+                        s_gT[(q * (kR3StageBytes / 2) + ju * kRows + rl_r) / 2] = vt;
+                        if (p.dghT) s_hT[(q * (kR3StageBytes / 2) + ju * kRows + rl_r) / 2] = (q == 2) ? pair_rows(eg2[0], eg2[1]) : vt;
                     }
                     fence_proxy_async_smem();                  // generic stores -> the TMA stores' async-proxy reads
                 }

@@ -280,6 +280,8 @@ RNN_CASES = [
     # the same launch); K tail (H not a multiple of 64)
     dict(cell="lstm", T=8, B=32, H=64, lens=None),
     dict(cell="gru", T=9, B=48, H=272, lens=None),
+    dict(cell="gru", T=1, B=64, H=64, lens=None),      # a single step: no recurrent product at all
+    dict(cell="lstm", T=2, B=40, H=48, lens=[2] * 20 + [1] * 20),
 ]
 
 
