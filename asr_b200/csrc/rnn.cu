@@ -159,8 +159,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             for (int s = 1; s < T; ++s) {
                 // step barrier: every CTA of this direction has published step s-1
                 const uint32_t need = (uint32_t)P * (uint32_t)s;
-                while (ld_acquire_u32(counter) < need) {
-                }
+                poll_counter(counter, need);
                 if (lane == 0) ASRB_TRACE(0, s);
                 // other CTAs' generic-proxy stores (acquired above) -> visible to our async-proxy (TMA) reads.
                 // The .global form is a bare FENCE.VIEW.ASYNC.G; the unqualified one adds a MEMBAR.ALL.GPU.
@@ -386,8 +385,7 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     // DEBUG path (asrb_set_debug_flags bit 1): same algorithm, plain fp32 dot products
                     if (hl == 0) {
                         const uint32_t need = (uint32_t)P * (uint32_t)s;
-                        while (ld_acquire_u32(counter) < need) {
-                        }
+                        poll_counter(counter, need);
                     }
                     named_bar_sync(1, kRnnEpiThreads);
                     if (rowok) {

@@ -102,6 +102,28 @@ __device__ __forceinline__ void st4_bf16(__nv_bfloat16* dst, const float* v) {
         if (p.trace) p.trace[((size_t)blockIdx.x * p.T + (step)) * 16 + (slot)] = clock64();     \
     } while (0)
 
+// Step-barrier poll with a watchdog: the CTAs of a launch spin on counters the other CTAs bump, which needs the whole grid
+// resident at once (checked against the occupancy API before every launch).  Should that ever not hold -- another spinning
+// kernel on the device, a MIG slice smaller than reported -- the kernel traps after kRnnWatchdogNs instead of hanging the
+// stream forever: the launch then fails loudly with a CUDA error.
+constexpr unsigned long long kRnnWatchdogNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void poll_counter(const uint32_t* counter, uint32_t need) {
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_u32(counter) < need) {
+        if ((++spins & 0x3FFFu) == 0) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kRnnWatchdogNs) __trap();
+        }
+    }
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -50,7 +50,7 @@ constexpr int kR3CounterStride = 16;        // step counters [dir][chain], 64 by
 // that traffic does not speed the copies up.
 template <int CELL, int NCH, int CS>
 __global__ void __launch_bounds__(kRnnThreads, 1)
-rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmGi,
+rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmGi,
                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmC,
                 const __grid_constant__ CUtensorMap tmSaved, const __grid_constant__ CUtensorMap tmOut, const RnnParams p) {
     constexpr int kR3Chains = NCH;
@@ -108,6 +108,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp < NCH && lane == 0) {
         if (warp == 0) {
             tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmA2);
             tma_prefetch_desc(&tmGi);
             tma_prefetch_desc(&tmH);
             tma_prefetch_desc(&tmSaved);
@@ -151,24 +152,26 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int s = 1; s < T; ++s) {
                 // step barrier of the chain: every CTA of this direction has published step s-1 of these rows
                 const uint32_t need = (uint32_t)P * (uint32_t)s;
-                while (ld_acquire_u32(counter) < need) {
-                }
+                poll_counter(counter, need);
                 if (lane == 0 && chain == 0) ASRB_TRACE(0, s);
+                if (lane == 0 && chain == 1) ASRB_TRACE(12, s);
                 fence_proxy_async_global();      // the others' generic-proxy stores -> our async-proxy (TMA) reads
                 const int slab = dir * (T + 2) + t_of(s - 1) + 1;
                 // (our own arrival is part of `need`: our MMAs of step s-1 have read the tile, our epilogue its gate boxes)
                 if (elect_one()) {
                     for (int c = 0; c < nchunks; ++c) {
                         const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
+                        // ONE box per chunk: [4 K blocks][32 rows][128 B] (the tensor map walks the K blocks as its third
+                        // dimension; blocks past the last one are zero-filled).  A TMA request costs ~60 cycles on top of its
+                        // bytes: thirteen 4 KB boxes streamed at 31 B/clk, four 16 KB boxes do at twice that.
+                        // (tmA2: the same tensor with a box of nkb % 4 blocks, for the last chunk)
+                        const CUtensorMap* tm = nblk == kR3Chunk ? &tmA : &tmA2;
                         mbar_arrive_expect_tx(&full_bar[c], (uint32_t)nblk * kSlotBytes);
-                        for (int i = 0; i < nblk; ++i) {
-                            if constexpr (CS > 1) {      // our share of the blocks, to every CTA of the cluster
-                                if ((uint32_t)((kb0 + i) % CS) == crank)
-                                    tma_load_3d_mc(smem_a + (size_t)(kb0 + i) * kSlotBytes, &tmA, &full_bar[c], (kb0 + i) * KBE, row0, slab,
-                                                   (uint16_t)((1u << CS) - 1));
-                            } else {
-                                tma_load_3d(smem_a + (size_t)(kb0 + i) * kSlotBytes, &tmA, &full_bar[c], (kb0 + i) * KBE, row0, slab);
-                            }
+                        if constexpr (CS > 1) {          // (experiment) every CS-th chunk from us, to every CTA of the cluster
+                            if ((uint32_t)(c % CS) == crank)
+                                tma_load_4d_mc(smem_a + (size_t)kb0 * kSlotBytes, tm, &full_bar[c], 0, row0, kb0, slab, (uint16_t)((1u << CS) - 1));
+                        } else {
+                            tma_load_4d(smem_a + (size_t)kb0 * kSlotBytes, tm, &full_bar[c], 0, row0, kb0, slab);
                         }
                     }
                     if (s + 1 < T) load_gi(s + 1);
@@ -193,6 +196,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     __syncwarp();
                 }
                 if (lane == 0 && chain == 0) ASRB_TRACE(3, s);
+                if (lane == 0 && chain == 1) ASRB_TRACE(13, s);
             }
         }
     } else {
@@ -245,9 +249,9 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // gate row c = 16 * quarter + i sits in TMEM lane 32 * quarter + i (the M = 64 data path layout, like the
                 // accumulator rows); 16 bf16 = 8 columns per store
                 const int c = 16 * quad + lane;
-                const bool have = lane < 16 && c < NPAD;
+                const bool have = lane < 16 && c < NPAD && pidx < p.P_saved;      // (padding CTAs of a cluster own no slice)
                 const uint4* wrow = reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const __nv_bfloat16*>(p.wpack) + ((size_t)(dir * P + pidx) * NPAD + (have ? c : 0)) * p.kpad);
+                    reinterpret_cast<const __nv_bfloat16*>(p.wpack) + ((size_t)(dir * p.P_saved + (have ? pidx : 0)) * NPAD + (have ? c : 0)) * p.kpad);
                 for (int k0 = 0; k0 < p.kpad / 16; k0 += 4) {       // kpad is a multiple of 64: four stores per round,
                     uint4 v[8];                                      // their eight loads in flight together
 #pragma unroll
@@ -282,6 +286,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 2; ++c) active[c] = cellok[c] && (t < len[c]);
                 if (el == 0 && chain == 0) ASRB_TRACE(4, s);
+                if (el == 0 && chain == 1) ASRB_TRACE(14, s);
                 float acc[kGates][2];
 #pragma unroll
                 for (int g = 0; g < kGates; ++g) acc[g][0] = acc[g][1] = 0.f;
@@ -368,7 +373,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (staged) {
                         tma_store_3d(&tmH, st_h, j0, row0, dir * (T + 2) + t + 1);
                         if constexpr (CELL == ASRB_RNN_LSTM) tma_store_3d(&tmC, st_c, j0, row0, dir * (T + 2) + t + 1);
-                        tma_store_3d(&tmSaved, st_sv, 0, row0, (((dir * T + t) * P + pidx) * 4) * NV);
+                        tma_store_3d(&tmSaved, st_sv, 0, row0, (((dir * T + t) * p.P_saved + pidx) * 4) * NV);
                         if (p.out_sum) tma_reduce_add_3d(&tmOut, st_h, j0, row0, t);
                         bulk_commit_group();
                     }
@@ -381,7 +386,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int c = 0; c < 2; ++c) {
                         if (cellok[c]) {
                             const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)row[c] * H + unit;
-                            float* svp = p.saved + ((((size_t)dir * T + t) * P + pidx) * 4) * (size_t)(NV * B * 4) +
+                            float* svp = p.saved + ((((size_t)dir * T + t) * p.P_saved + pidx) * 4) * (size_t)(NV * B * 4) +
                                          (size_t)ug * (B * 4) + (size_t)row[c] * 4 + ul;
                             p.hseq[o] = hn[c];
                             if constexpr (CELL == ASRB_RNN_LSTM) p.cseq[o] = cn[c];
@@ -411,8 +416,9 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     const int kpad = pl.kpad_f, nkb = kpad / 64;
     const int B = prm.B;
     if (ceil_div(nkb, kR3Chunk) > kR3MaxChunks || kR3Chains * kR3Rows + kpad / 2 > 512) return ASRB_ERR_UNSUPPORTED;
+    const int Pk = (pl.P + CS - 1) / CS * CS;                // CTAs per direction: the slices, padded to whole clusters
     prm.P_saved = pl.P;
-    prm.P = pl.P;
+    prm.P = Pk;
     prm.kpad = kpad;
     prm.wpack = reinterpret_cast<const float*>(wpack);       // bf16 slices, read once into tensor memory
     const size_t st_bytes = (size_t)2 * kR3Rows * 16 * 4 + (size_t)16 * kR3Rows * 16;
@@ -423,7 +429,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     if (!enc) return ASRB_ERR_DRIVER;
     if (prm.out_sum)     // both directions add their h tiles into it
         ASRB_CUDA_OK(cudaMemsetAsync(prm.out_sum, 0, (size_t)prm.T * B * prm.H * sizeof(float), stream));
-    CUtensorMap tmA, tmGi, tmH, tmC, tmSaved, tmOut;
+    CUtensorMap tmA, tmA2, tmGi, tmH, tmC, tmSaved, tmOut;
     // staged outputs: whole tiles only (rows of a chain, 16 valid units)
     prm.stage_out = (B % kR3Rows == 0 && prm.H % 16 == 0 && (g_rnn_dbg & 4096)) ? 1 : 0;   // see asrb_rnn_fwd_sum: off
     if (prm.stage_out) {
@@ -452,12 +458,20 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         if (!ok) prm.stage_out = 0;
     }
     if (!prm.stage_out) tmH = tmC = tmSaved = tmOut = CUtensorMap{};
-    {   // hbf [2(T+2)][B][Hp] bf16, box = 64 columns x 32 rows (one chain), 128-byte swizzle; rows >= B, columns >= H: zero fill
-        uint64_t d[3] = {(uint64_t)prm.H, (uint64_t)B, (uint64_t)2 * (prm.T + 2)};
-        uint64_t s[2] = {(uint64_t)prm.Hp * 2, (uint64_t)B * prm.Hp * 2};
-        uint32_t bx[3] = {64, (uint32_t)kR3Rows, 1};
-        int rc = make_tmap_bf16(&tmA, prm.hbf, 3, d, s, bx);
+    {   // hbf [2(T+2)][B][Hp] bf16 seen as [slab][K block][row][64 columns]: box = 64 columns x rows of a chain x 4 K blocks,
+        // 128-byte swizzle; rows >= B and K blocks >= Hp/64 are zero-filled.  The columns H..Hp of the last K block are inside
+        // the tensor: they are zeroed once here (the weights' K padding is zero too, but 0 x NaN is NaN).
+        uint64_t d[4] = {64, (uint64_t)B, (uint64_t)prm.Hp / 64, (uint64_t)2 * (prm.T + 2)};
+        uint64_t s[3] = {(uint64_t)prm.Hp * 2, 128, (uint64_t)B * prm.Hp * 2};
+        uint32_t bx[4] = {64, (uint32_t)kR3Rows, (uint32_t)kR3Chunk, 1};
+        int rc = make_tmap_bf16(&tmA, prm.hbf, 4, d, s, bx);
         if (rc) return rc;
+        bx[2] = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;      // box of the last chunk
+        rc = make_tmap_bf16(&tmA2, prm.hbf, 4, d, s, bx);
+        if (rc) return rc;
+        if (prm.Hp > prm.H)
+            ASRB_CUDA_OK(cudaMemset2DAsync(prm.hbf + prm.H, (size_t)prm.Hp * 2, 0, (size_t)(prm.Hp - prm.H) * 2,
+                                           (size_t)2 * (prm.T + 2) * B, stream));
     }
     {   // gi [T][B][2G] fp32, box = 16 columns x 32 rows, 64-byte swizzle (conflict-free reads by (row, unit) threads)
         if ((reinterpret_cast<uintptr_t>(prm.gi) & 15) != 0) return ASRB_ERR_ALIGNMENT;
@@ -476,11 +490,11 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         ASRB_CUDA_OK(cudaGetDevice(&dev));
         ASRB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         ASRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRnnThreads, smem));
-        if (2 * pl.P > sms * per_sm) return ASRB_ERR_UNSUPPORTED;
+        if (2 * Pk > sms * per_sm) return ASRB_ERR_UNSUPPORTED;
     }
     ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * kR3Chains * kR3CounterStride * sizeof(uint32_t), stream));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pl.P);
+    cfg.gridDim = dim3(2 * Pk);
     cfg.blockDim = dim3(kRnnThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -492,10 +506,10 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     if (CS > 1) {
         int nclusters = 0;
         ASRB_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
-        if (2 * pl.P > CS * nclusters) return ASRB_ERR_UNSUPPORTED;
+        if (2 * Pk > CS * nclusters) return ASRB_ERR_UNSUPPORTED;
     }
     prm.dbg = g_rnn_dbg;
-    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmGi, tmH, tmC, tmSaved, tmOut, prm));
+    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmGi, tmH, tmC, tmSaved, tmOut, prm));
     return 0;
 }
 
@@ -516,7 +530,7 @@ constexpr int kR3StageBytes = 32 * 16 * 2;                  // one gate's [32 ro
 
 template <int CELL>
 __global__ void __launch_bounds__(kRnnThreads, 1)
-rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmDgi,
+rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmDgi,
                     const __grid_constant__ CUtensorMap tmGT, const __grid_constant__ CUtensorMap tmHT, const RnnParams p) {
     constexpr int NCH = 2, KS = 4;
     constexpr int kRows = 64 / NCH;             // batch rows of a chain = N of its MMAs
@@ -568,6 +582,7 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp < NCH && lane == 0) {
         if (warp == 0) {
             tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmA2);
             tma_prefetch_desc(&tmDgi);
             tma_prefetch_desc(&tmGT);
             tma_prefetch_desc(&tmHT);
@@ -597,17 +612,15 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after_sync();
             for (int s = 1; s < T; ++s) {
                 const uint32_t need = (uint32_t)P * (uint32_t)s;
-                while (ld_acquire_u32(counter) < need) {
-                }
+                poll_counter(counter, need);
                 if (lane == 0 && chain == 0) ASRB_TRACE(0, s);
                 fence_proxy_async_global();
                 const int slab = dir * T + t_of(s - 1);
                 if (elect_one()) {
-                    for (int c = 0; c < nchunks; ++c) {
+                    for (int c = 0; c < nchunks; ++c) {      // one box per chunk of 4 K blocks (see the forward kernel)
                         const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
                         mbar_arrive_expect_tx(&full_bar[c], (uint32_t)nblk * kSlotBytes);
-                        for (int i = 0; i < nblk; ++i)      // columns >= G and rows >= B: TMA zero fill
-                            tma_load_3d(smem_a + (size_t)(kb0 + i) * kSlotBytes, &tmA, &full_bar[c], kcol0 + (kb0 + i) * KBE, row0, slab);
+                        tma_load_4d(smem_a + (size_t)kb0 * kSlotBytes, nblk == kR3Chunk ? &tmA : &tmA2, &full_bar[c], 0, row0, kcol0 / KBE + kb0, slab);
                     }
                 }
                 __syncwarp();
@@ -897,7 +910,7 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
     if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return ASRB_ERR_DRIVER;
-    CUtensorMap tmA, tmDgi, tmGT, tmHT;
+    CUtensorMap tmA, tmA2, tmDgi, tmGT, tmHT;
     // staged outputs: whole 32-row x 16-unit tiles only, and 16-byte aligned tile rows in the transposed copies
     prm.stage_out = (B % 32 == 0 && prm.H % 16 == 0 && !(g_rnn_dbg & 2048)) ? 1 : 0;
     if (prm.stage_out) {
@@ -924,12 +937,17 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
         if (!ok) prm.stage_out = 0;
     }
     if (!prm.stage_out) tmDgi = tmGT = tmHT = CUtensorMap{};
-    {   // dghbf [2 T][B][Gp] bf16, box = 64 columns x 32 rows (one chain), 128-byte swizzle
-        uint64_t d[3] = {(uint64_t)prm.G, (uint64_t)B, (uint64_t)2 * prm.T};
-        uint64_t s[2] = {(uint64_t)prm.Gp * 2, (uint64_t)B * prm.Gp * 2};
-        uint32_t bx[3] = {64, 32, 1};
-        int rc = make_tmap_bf16(&tmA, prm.dghbf, 3, d, s, bx);
+    {   // dghbf [2 T][B][Gp] bf16 seen as [slab][K block][row][64 columns]: box = 64 columns x 32 rows (one chain) x 4 K blocks
+        uint64_t d[4] = {64, (uint64_t)B, (uint64_t)prm.Gp / 64, (uint64_t)2 * prm.T};
+        uint64_t s[3] = {(uint64_t)prm.Gp * 2, 128, (uint64_t)B * prm.Gp * 2};
+        uint32_t bx[4] = {64, 32, (uint32_t)kR3Chunk, 1};
+        int rc = make_tmap_bf16(&tmA, prm.dghbf, 4, d, s, bx);
         if (rc) return rc;
+        bx[2] = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;      // box of the last chunk of a K quarter
+        rc = make_tmap_bf16(&tmA2, prm.dghbf, 4, d, s, bx);
+        if (rc) return rc;
+        if (prm.Gp > prm.G)      // the columns G..Gp of the last K block are inside the tensor: zero them once (0 x NaN is NaN)
+            ASRB_CUDA_OK(cudaMemset2DAsync(prm.dghbf + prm.G, (size_t)prm.Gp * 2, 0, (size_t)(prm.Gp - prm.G) * 2, (size_t)2 * prm.T * B, stream));
     }
     auto kern = rnn_rec3_bwd_kernel<CELL>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -950,7 +968,7 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
         if (2 * pl.P_b > 4 * nclusters) return ASRB_ERR_UNSUPPORTED;
     }
     prm.dbg = g_rnn_dbg;
-    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmDgi, tmGT, tmHT, prm));
+    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmDgi, tmGT, tmHT, prm));
     return 0;
 }
 
@@ -966,6 +984,11 @@ int rnn3_forward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack,
     // TMA multicast of the copies over CTA pairs (bit 8192) is built and measured SLOWER (8.5 k against 8.0 k cycles per
     // step): the copies are not bound by L2 read bandwidth, and a CTA then waits for the slower of two issuers; off.
     const bool mc = (pl.P % 2 == 0) && (g_rnn_dbg & 8192);
+    if (g_rnn_dbg & 16384) {     // experiment: clusters of 8 (slice count padded), multicast over all 8
+        cudaFuncSetAttribute(rnn_rec3_kernel<ASRB_RNN_GRU, 2, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+        if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 2, 8>(pl, prm, wpack, stream);
+        return rnn3_launch<ASRB_RNN_LSTM, 2, 8>(pl, prm, wpack, stream);
+    }
     if (g_rnn_dbg & 512) {
         if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 4, 1>(pl, prm, wpack, stream);
         return rnn3_launch<ASRB_RNN_LSTM, 4, 1>(pl, prm, wpack, stream);

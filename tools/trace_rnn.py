@@ -20,7 +20,7 @@ dout = torch.randn(T, B, H, device=dev)
 # slot names of the exchange-by-data kernel (rnn2.cu)
 names2 = {4: "E:step top", 0: "P:canaries ok", 10: "E:go", 8: "E:deferred stores issued", 1: "P:copies issued", 2: "M:first K block",
           3: "M:last commit", 5: "E:tfull", 6: "E:ld+verdict", 11: "E:exchange done", 7: "E:operand stored"}
-names1 = {4: "E:step top", 0: "P:counter ok", 9: "P:fence done", 2: "M:first full", 1: "P:loads issued", 3: "M:commit",
+names1 = {4: "E:step top", 14: "chain1 step top", 12: "chain1 counter ok", 13: "chain1 commit", 0: "P:counter ok", 9: "P:fence done", 2: "M:first full", 1: "P:loads issued", 3: "M:commit",
           5: "E:tfull", 6: "E:ld done", 11: "E:exchange done", 7: "E:math+stores", 8: "E:bar done", 10: "E:red"}
 
 
@@ -35,7 +35,7 @@ def timed(fn, n=3):
 
 # outputs of every variant against the counter + TMA kernels of rnn.cu
 ref = None
-for dbg, label in ((8, "rnn.cu"), (0, "rnn3 forward + backward (TMEM weights, two chains)"), (1024, "rnn3 forward, rnn.cu backward"), (256, "rnn2")):
+for dbg, label in ((8, "rnn.cu"), (0, "rnn3 forward + backward (TMEM weights, two chains)"), (1024, "rnn3 forward, rnn.cu backward")):
     _lib.query("asrb_debug_rnn_dbg", dbg)
     pf, pb = ops.rnn_pack_weights(cell, w[0], w[1], B)
     hs, cs, sv = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
@@ -50,7 +50,7 @@ for dbg, label in ((8, "rnn.cu"), (0, "rnn3 forward + backward (TMEM weights, tw
             msg += f"; dghT {(dghT.float() - ref[3]).abs().max().item():.3e}"
         print(msg, flush=True)
 
-variants = [(0, "default: rnn3.cu forward and backward (weights in tensor memory, two chains of 32 rows)"), (8192, "rnn3 forward WITH TMA multicast over CTA pairs"), (8, "counter + TMA (rnn.cu)")]
+variants = [(0, "default: rnn3.cu forward and backward (weights in tensor memory, two chains of 32 rows)"), (8, "counter + TMA (rnn.cu)")]
 for dbg, label in variants:
     _lib.query("asrb_debug_rnn_dbg", dbg)
     _lib.query("asrb_debug_rnn_ksplit", ks)
@@ -76,8 +76,6 @@ for dbg, label in variants:
         s0, s1 = min(50, T // 4), max(T - 50, T // 2)
         tot = tr[0, T - 1, 4] - tr[0, 0, 4]
         print(f" {which}: first to last step top {tot:.0f} cycles = {tot / 1.965e6:.3f} ms @1965 MHz", flush=True)
-        if dbg >> 16:
-            continue
         for cta in (0, P):
             x = tr[cta, s0:s1]
             top = x[:, 4]

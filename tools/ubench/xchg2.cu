@@ -7,6 +7,7 @@
 //                 1 = 2-byte plain st (weak)
 //                 2 = 8-byte plain st, thread = (row, 4 units)       [32x32b mapping]
 //                 3 = 16-byte plain st, thread = (row, 8 units)
+//                 4 = 16-byte plain st, lane pairs cover a row's 32 bytes (chunk-major slab: still two half sectors)
 //   copy kinds  : 0 = cp.async.bulk per 64-column K block (chunk-major slab), 1 = one cp.async.bulk for the whole slab,
 //                 2 = per-thread 16-byte ld.volatile + st.shared
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o xchg2 xchg2.cu
@@ -70,6 +71,15 @@ xchg(uint16_t* buf, int K, int steps, int store_kind, int copy_kind, int canary,
                     uint16_t* dst = slab + ((size_t)(unit >> 3) * B + row) * 8 + (unit & 7);
                     const uint32_t v2 = val | ((uint32_t)val << 16);
                     if (unit < K) asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(v2), "r"(v2) : "memory");
+                }
+            } else if (store_kind == 4) {
+                // full 32-byte sectors: two adjacent lanes write the two 16-byte halves of a row's 16 units
+                const int e = wq * 32 + lane;
+                if (e < 128) {
+                    const int row = e >> 1, ch = e & 1, unit = 16 * me + 8 * ch;
+                    uint16_t* dst = slab + ((size_t)(unit >> 3) * B + row) * 8;
+                    const uint32_t v2 = val | ((uint32_t)val << 16);
+                    if (unit < K) asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v2), "r"(v2), "r"(v2), "r"(v2) : "memory");
                 }
             } else {
                 const int e = wq * 32 + lane;
@@ -170,7 +180,7 @@ int main(int argc, char** argv) {
         CK(cudaFuncSetAttribute(xchg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         for (int canary = 1; canary >= 0; --canary)
             for (int copy_kind = 0; copy_kind < 3; ++copy_kind)
-                for (int store_kind = 0; store_kind < 4; ++store_kind) {
+                for (int store_kind = 0; store_kind < 5; ++store_kind) {
                     if (!canary && (store_kind != 0 || copy_kind == 2)) continue;
                     for (int rep = 0; rep < 2; ++rep) {
                         CK(cudaMemset(buf, 0xFF, bytes));
