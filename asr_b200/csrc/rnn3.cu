@@ -31,6 +31,10 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  :: "l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 // global += shared (fp32), 3-D tile
 __device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
     asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -138,9 +142,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             auto load_gi = [&](int s) {   // the slice's gate pre-activations of step s, rows of this chain -> buffer s & 1
                 const int t = t_of(s);
                 mbar_arrive_expect_tx(&gi_bar[s & 1], (uint32_t)(kGates * kR3Rows * NJ * 4));
-#pragma unroll
-                for (int q = 0; q < kGates; ++q)
-                    tma_load_3d(smem_gi + (size_t)((s & 1) * kGates + q) * kGiRegion, &tmGi, &gi_bar[s & 1], dir * G + q * H + j0, row0, t);
+                // one box for all gates: [gate][row][16 columns] (the tensor map walks the gates, H columns apart, as its third dimension)
+                tma_load_4d(smem_gi + (size_t)((s & 1) * kGates) * kGiRegion, &tmGi, &gi_bar[s & 1], dir * G + j0, row0, 0, t);
             };
             if (elect_one()) {
                 load_gi(0);
@@ -475,10 +478,12 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     }
     {   // gi [T][B][2G] fp32, box = 16 columns x 32 rows, 64-byte swizzle (conflict-free reads by (row, unit) threads)
         if ((reinterpret_cast<uintptr_t>(prm.gi) & 15) != 0) return ASRB_ERR_ALIGNMENT;
-        cuuint64_t gdim[3] = {(cuuint64_t)2 * prm.G, (cuuint64_t)B, (cuuint64_t)prm.T};
-        cuuint64_t gstr[2] = {(cuuint64_t)2 * prm.G * 4, (cuuint64_t)B * 2 * prm.G * 4};
-        cuuint32_t bx[3] = {16, (cuuint32_t)kR3Rows, 1}, es[3] = {1, 1, 1};
-        CUresult r = enc(&tmGi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(prm.gi), gdim, gstr, bx, es,
+        // dims: column (within [dir*G + gate*H + unit]), batch row, gate (H columns apart), time.  The column extent is 2G - (gates-1)H
+        // so that column + gate*H never leaves the row.
+        cuuint64_t gdim[4] = {(cuuint64_t)2 * prm.G - (cuuint64_t)(kGates - 1) * prm.H, (cuuint64_t)B, (cuuint64_t)kGates, (cuuint64_t)prm.T};
+        cuuint64_t gstr[3] = {(cuuint64_t)2 * prm.G * 4, (cuuint64_t)prm.H * 4, (cuuint64_t)B * 2 * prm.G * 4};
+        cuuint32_t bx[4] = {16, (cuuint32_t)kR3Rows, (cuuint32_t)kGates, 1}, es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmGi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(prm.gi), gdim, gstr, bx, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return ASRB_ERR_TENSORMAP;
@@ -853,12 +858,10 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     red_release_add_u32(counter, 1u);
                     if (chain == 0) ASRB_TRACE(10, s);
                     if (staged) {
-#pragma unroll
-                        for (int q = 0; q < kGates; ++q) {
-                            tma_store_3d(&tmDgi, st_dgi + q * (kR3StageBytes / 2), dir * G + q * H + j0, row0, t);
-                            tma_store_2d(&tmGT, st_gT + q * (kR3StageBytes / 2), t * B + row0, dir * G + q * H + j0);
-                            if (p.dghT) tma_store_2d(&tmHT, st_hT + q * (kR3StageBytes / 2), t * B + row0, dir * G + q * H + j0);
-                        }
+                        // one store per tensor: the tiles of all gates (the tensor maps walk the gates as an extra dimension)
+                        tma_store_4d(&tmDgi, st_dgi, dir * G + j0, row0, 0, t);
+                        tma_store_3d(&tmGT, st_gT, t * B + row0, dir * G + j0, 0);
+                        if (p.dghT) tma_store_3d(&tmHT, st_hT, t * B + row0, dir * G + j0, 0);
                         bulk_commit_group();
                     }
                 }
@@ -915,24 +918,24 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
     prm.stage_out = (B % 32 == 0 && prm.H % 16 == 0 && !(g_rnn_dbg & 2048)) ? 1 : 0;
     if (prm.stage_out) {
         auto plain = [&](CUtensorMap* m, void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* bx) {
-            cuuint32_t es[3] = {1, 1, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
             if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
             return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         };
         bool ok = true;
-        {   // dgi [T][B][2G] bf16, box = 16 columns x 32 rows
-            cuuint64_t gdim[3] = {(cuuint64_t)2 * prm.G, (cuuint64_t)B, (cuuint64_t)prm.T};
-            cuuint64_t gstr[2] = {(cuuint64_t)2 * prm.G * 2, (cuuint64_t)B * 2 * prm.G * 2};
-            cuuint32_t bx[3] = {16, 32, 1};
-            ok = ok && plain(&tmDgi, prm.dgi, 3, gdim, gstr, bx);
+        {   // dgi [T][B][2G] bf16 as (column, row, gate, time): box = 16 columns x 32 rows x all gates
+            cuuint64_t gdim[4] = {(cuuint64_t)2 * prm.G - (cuuint64_t)(kGates - 1) * prm.H, (cuuint64_t)B, (cuuint64_t)kGates, (cuuint64_t)prm.T};
+            cuuint64_t gstr[3] = {(cuuint64_t)2 * prm.G * 2, (cuuint64_t)prm.H * 2, (cuuint64_t)B * 2 * prm.G * 2};
+            cuuint32_t bx[4] = {16, 32, (cuuint32_t)kGates, 1};
+            ok = ok && plain(&tmDgi, prm.dgi, 4, gdim, gstr, bx);
         }
-        {   // dgiT / dghT [2G][ldT] bf16, box = 32 columns (batch rows of one time step) x 16 rows (units)
-            cuuint64_t gdim[2] = {(cuuint64_t)prm.ldT, (cuuint64_t)2 * prm.G};
-            cuuint64_t gstr[1] = {(cuuint64_t)prm.ldT * 2};
-            cuuint32_t bx[2] = {32, 16};
-            ok = ok && plain(&tmGT, prm.dgiT, 2, gdim, gstr, bx);
-            ok = ok && plain(&tmHT, prm.dghT ? prm.dghT : prm.dgiT, 2, gdim, gstr, bx);
+        {   // dgiT / dghT [2G][ldT] bf16 as (column, unit row, gate): box = 32 columns (batch rows of one time step) x 16 rows x all gates
+            cuuint64_t gdim[3] = {(cuuint64_t)prm.ldT, (cuuint64_t)2 * prm.G - (cuuint64_t)(kGates - 1) * prm.H, (cuuint64_t)kGates};
+            cuuint64_t gstr[2] = {(cuuint64_t)prm.ldT * 2, (cuuint64_t)prm.H * prm.ldT * 2};
+            cuuint32_t bx[3] = {32, 16, (cuuint32_t)kGates};
+            ok = ok && plain(&tmGT, prm.dgiT, 3, gdim, gstr, bx);
+            ok = ok && plain(&tmHT, prm.dghT ? prm.dghT : prm.dgiT, 3, gdim, gstr, bx);
         }
         if (!ok) prm.stage_out = 0;
     }
