@@ -43,6 +43,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Non-suspending probe loop, for a SINGLE waiting thread on a latency-critical path (one probe every few tens of cycles
+// is harmless; many warps doing this clog the MIO queue -- use mbar_wait there).
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
 // cluster-scope variants (the data guarded by the barrier was written by a peer CTA through distributed shared memory)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
@@ -296,6 +311,9 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------ host: tensor-map encoding

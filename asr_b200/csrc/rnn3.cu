@@ -56,7 +56,8 @@ template <int CELL, int NCH, int CS>
 __global__ void __launch_bounds__(kRnnThreads, 1)
 rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmGi,
                 const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmC,
-                const __grid_constant__ CUtensorMap tmSaved, const __grid_constant__ CUtensorMap tmOut, const RnnParams p) {
+                const __grid_constant__ CUtensorMap tmSaved, const __grid_constant__ CUtensorMap tmOut,
+                const __grid_constant__ CUtensorMap tmOp, const RnnParams p) {
     constexpr int kR3Chains = NCH;
     constexpr int kR3Rows = 64 / NCH;           // batch rows of a chain = N of its MMAs
     constexpr int kR3EpiWarps = 16 / NCH;       // per chain
@@ -82,7 +83,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const size_t dt_bytes = (size_t)64 * kR3DtStride * 4;
     // staged outputs (TMA stores): h and c tiles [rows][16 units] fp32, saved activations [4 gates x 4 unit groups][rows][4]
     const size_t hc_bytes = (size_t)kR3Rows * NJ * 4, sv_bytes = (size_t)16 * kR3Rows * 16;
-    const size_t st_bytes = 2 * hc_bytes + sv_bytes;
+    const size_t op_bytes = (size_t)kR3Rows * NJ * 2;          // the chain's operand tile [rows][16 units] bf16 (one TMA store a step)
+    const size_t st_bytes = 2 * hc_bytes + sv_bytes + op_bytes;
     const size_t chain_bytes = (a_bytes + gi_bytes + dt_bytes + st_bytes + 256 + 1023) & ~size_t(1023);   // operand tiles: 1 KB aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -98,6 +100,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* st_h = reinterpret_cast<float*>(cs + a_bytes + gi_bytes + dt_bytes);      // [rows][16]
     float* st_c = st_h + kR3Rows * NJ;                                               // [rows][16]
     float* st_sv = st_c + kR3Rows * NJ;                                              // [gate * 4 + unit group][rows][4]
+    __nv_bfloat16* st_op = reinterpret_cast<__nv_bfloat16*>(st_sv + 16 * kR3Rows * 4);   // [rows][16]
     uint64_t* bars = reinterpret_cast<uint64_t*>(cs + a_bytes + gi_bytes + dt_bytes + st_bytes);
     uint64_t* full_bar = bars;                                // [kR3MaxChunks]
     uint64_t* tfull_bar = bars + kR3MaxChunks;
@@ -105,6 +108,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + (size_t)kR3Chains * chain_bytes);   // weights are in tensor memory
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
     float* s_bias = reinterpret_cast<float*>(w_bar + 2);      // [kGates][NJ]
+    uint32_t* mma_lock = reinterpret_cast<uint32_t*>(s_bias + kGates * NJ);   // tensor pipe: one chain's MMA sequence at a time
 
     uint32_t* counter = p.counters + (dir * kR3Chains + (chain < NCH ? chain : 0)) * kR3CounterStride;
     auto t_of = [&](int s) { return dir == 1 ? (T - 1 - s) : s; };
@@ -116,7 +120,10 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_prefetch_desc(&tmGi);
             tma_prefetch_desc(&tmH);
             tma_prefetch_desc(&tmSaved);
+            tma_prefetch_desc(&tmOp);
             mbar_init(w_bar, 1);
+            mma_lock[0] = 0u;
+            mma_lock[1] = 0u;
         }
         for (int i = 0; i < kR3MaxChunks; ++i) mbar_init(&full_bar[i], 1);
         mbar_init(tfull_bar, 1);
@@ -145,29 +152,30 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // one box for all gates: [gate][row][16 columns] (the tensor map walks the gates, H columns apart, as its third dimension)
                 tma_load_4d(smem_gi + (size_t)((s & 1) * kGates) * kGiRegion, &tmGi, &gi_bar[s & 1], dir * G + j0, row0, 0, t);
             };
+            // ONE elected thread runs the chain's whole control loop: poll, copies, MMAs.  (Per-chunk elect / __syncwarp
+            // rounds of the whole warp cost ~250 cycles a chunk on the chain's critical path -- more than the chunk's 16 MMAs
+            // at ~20 cycles each, which therefore never overlapped the copies still in flight.)
             if (elect_one()) {
                 load_gi(0);
                 if (T > 1) load_gi(1);
-            }
-            __syncwarp();
-            mbar_wait(w_bar, 0);           // the weight slice is in tensor memory
-            tc_fence_after_sync();
-            for (int s = 1; s < T; ++s) {
-                // step barrier of the chain: every CTA of this direction has published step s-1 of these rows
-                const uint32_t need = (uint32_t)P * (uint32_t)s;
-                poll_counter(counter, need);
-                if (lane == 0 && chain == 0) ASRB_TRACE(0, s);
-                if (lane == 0 && chain == 1) ASRB_TRACE(12, s);
-                fence_proxy_async_global();      // the others' generic-proxy stores -> our async-proxy (TMA) reads
-                const int slab = dir * (T + 2) + t_of(s - 1) + 1;
-                // (our own arrival is part of `need`: our MMAs of step s-1 have read the tile, our epilogue its gate boxes)
-                if (elect_one()) {
+                mbar_wait(w_bar, 0);           // the weight slice is in tensor memory
+                tc_fence_after_sync();
+                const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_a));
+                const int first = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;     // K blocks of the first chunk
+                const bool use_lock = B > kR3Rows && (p.dbg & 32768);     // (measured: helps the backward kernel only)
+                for (int s = 1; s < T; ++s) {
+                    // step barrier of the chain: every CTA of this direction has published step s-1 of these rows
+                    poll_counter(counter, (uint32_t)P * (uint32_t)s);
+                    if (chain == 0) ASRB_TRACE(0, s);
+                    if (chain == 1) ASRB_TRACE(12, s);
+                    fence_proxy_async_global();      // the others' generic-proxy stores -> our async-proxy (TMA) reads
+                    const int slab = dir * (T + 2) + t_of(s - 1) + 1;
+                    // (our own arrival is part of `need`: our MMAs of step s-1 have read the tile, our epilogue its gate boxes)
                     for (int c = 0; c < nchunks; ++c) {
-                        const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
+                        const int kb0 = c ? first + (c - 1) * kR3Chunk : 0, nblk = c ? kR3Chunk : first;
                         // ONE box per chunk: [4 K blocks][32 rows][128 B] (the tensor map walks the K blocks as its third
-                        // dimension; blocks past the last one are zero-filled).  A TMA request costs ~60 cycles on top of its
-                        // bytes: thirteen 4 KB boxes streamed at 31 B/clk, four 16 KB boxes do at twice that.
-                        // (tmA2: the same tensor with a box of nkb % 4 blocks, for the last chunk)
+                        // dimension).  A TMA request costs ~60 cycles on top of its bytes.
+                        // (tmA2: the same tensor with a box of nkb % 4 blocks -- the FIRST chunk: the small box lands soonest)
                         const CUtensorMap* tm = nblk == kR3Chunk ? &tmA : &tmA2;
                         mbar_arrive_expect_tx(&full_bar[c], (uint32_t)nblk * kSlotBytes);
                         if constexpr (CS > 1) {          // (experiment) every CS-th chunk from us, to every CTA of the cluster
@@ -178,29 +186,50 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                     if (s + 1 < T) load_gi(s + 1);
-                }
-                __syncwarp();
-                if (lane == 0 && chain == 0) ASRB_TRACE(1, s);
-                const uint32_t ph = (uint32_t)((s - 1) & 1);
-                for (int c = 0; c < nchunks; ++c) {
-                    const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
-                    mbar_wait(&full_bar[c], ph);
-                    if (c == 0 && lane == 0 && chain == 0) ASRB_TRACE(2, s);
-                    tc_fence_after_sync();
-                    if (elect_one()) {
-                        for (int i = 0; i < nblk; ++i) {
-                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_a + (size_t)(kb0 + i) * kSlotBytes));
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)   // 8 TMEM columns of weights per K = 16 step
-                                umma_f16_ts(tmem_d, tmem_w + ((kb0 + i) * 4 + k) * 8, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                    if (chain == 0) ASRB_TRACE(1, s);
+                    const uint32_t ph = (uint32_t)((s - 1) & 1);
+                    for (int c = 0; c < nchunks; ++c) {
+                        const int kb0 = c ? first + (c - 1) * kR3Chunk : 0, nblk = c ? kR3Chunk : first;
+                        mbar_wait(&full_bar[c], ph);
+                        if (c == 0) {
+                            if (chain == 0) ASRB_TRACE(2, s);
+                            // one chain's MMA sequence at a time: interleaved in the tensor pipe both chains finish late, and
+                            // stay in lockstep; first come first served lets one run ahead until the phases no longer overlap
+                            if (use_lock) while (atomicCAS(mma_lock, 0u, 1u) != 0u) {}
                         }
-                        if (c == nchunks - 1) umma_commit(tfull_bar);
+                        if (chain == 0 && c > 0) ASRB_TRACE(c == 1 ? 9 : (c == 2 ? 11 : 15), s);      // chunk c has landed
+                        tc_fence_after_sync();
+                        if ((p.dbg & 524288) && c > 0) continue;      // (experiment) no MMAs after the first chunk: landing times alone
+                        // (constant offsets from the chunk's base descriptor / weight column: the issue loop stays in the
+                        // uniform datapath -- a runtime K-block loop re-derives them through R2UR, ~70 cycles per block)
+                        const uint64_t cdesc = bdesc0 + (uint64_t)kb0 * (kSlotBytes >> 4);
+                        const uint32_t cw = tmem_w + (uint32_t)kb0 * 32;
+#pragma unroll
+                        for (int i = 0; i < kR3Chunk; ++i) {
+                            if (i < nblk) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)   // 8 TMEM columns of weights per K = 16 step
+                                    umma_f16_ts(tmem_d, cw + (i * 4 + k) * 8, cdesc + (uint64_t)(i * (kSlotBytes >> 4) + 2 * k), idesc, (c | i | k) != 0);
+                            }
+                        }
+                        if (p.dbg & 262144) {
+#pragma unroll
+                        for (int i = 0; i < kR3Chunk; ++i) {
+                            if (i < nblk) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f16_ts(tmem_d, cw + (i * 4 + k) * 8, cdesc + (uint64_t)(i * (kSlotBytes >> 4) + 2 * k), idesc, 1);
+                            }
+                        }
+                        }
                     }
-                    __syncwarp();
+                    umma_commit(tfull_bar);
+                    if (use_lock) atomicExch(mma_lock, 0u);
+                    if (chain == 0) ASRB_TRACE(3, s);
+                    if (chain == 1) ASRB_TRACE(13, s);
                 }
-                if (lane == 0 && chain == 0) ASRB_TRACE(3, s);
-                if (lane == 0 && chain == 1) ASRB_TRACE(13, s);
             }
+            __syncwarp();
         }
     } else {
         // ===================== epilogue warps of the chain: 8 warps =====================
@@ -352,10 +381,22 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     state_h[c] = h_;
                     state_c[c] = c_;
                 }
-                // (1) the next step's MMA operand, published through the chain's step counter
+                // (1) the next step's MMA operand, published through the chain's step counter.  It leaves as ONE TMA store of
+                // the chain's [rows][16 units] tile, whose completion (cp.async.bulk.wait_group) the publishing thread waits for
+                // before a RELAXED counter increment: a release here is a MEMBAR.GPU, and that was measured to wait for every
+                // memory operation the SM has in flight -- the OTHER chain's TMA copies included (tools/ubench/membar_tma.cu:
+                // 870 cycles alone, the rest of the copies' ~3 k when they are in flight), which chained the two chains together.
+                // (rows >= B are clipped by the tensor map; units >= H hold 0 and land in the zero K padding.)
+                const bool tma_op = !(p.dbg & 2);
+                if (tma_op) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
-                    if (cellok[c]) p.hbf[(((size_t)dir * (T + 2) + t + 1) * B + row[c]) * p.Hp + unit] = __float2bfloat16_rn(hn[c]);
+                    for (int c = 0; c < 2; ++c) st_op[(rl0 + 8 * c) * NJ + ju] = __float2bfloat16_rn(hn[c]);
+                    if (!staged) fence_proxy_async_smem();
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if (cellok[c]) p.hbf[(((size_t)dir * (T + 2) + t + 1) * B + row[c]) * p.Hp + unit] = __float2bfloat16_rn(hn[c]);
+                }
                 if (staged) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -371,7 +412,14 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 named_bar_sync(8 + chain, kR3EpiThreads);
                 if (el == 0) {
                     if (chain == 0) ASRB_TRACE(8, s);
-                    red_release_add_u32(counter, 1u);
+                    if (tma_op) {
+                        tma_store_3d(&tmOp, st_op, j0, row0, dir * (T + 2) + t + 1);
+                        bulk_commit_group();
+                        bulk_wait_group<0>();            // written (not just read): the tile is in L2, where the consumers' TMA reads it
+                        red_relaxed_add_u32(counter, 1u);
+                    } else {
+                        red_release_add_u32(counter, 1u);
+                    }
                     if (chain == 0) ASRB_TRACE(10, s);
                     if (staged) {
                         tma_store_3d(&tmH, st_h, j0, row0, dir * (T + 2) + t + 1);
@@ -401,6 +449,14 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
             if (staged && el == 0) bulk_wait_group<0>();      // the last TMA stores have been written
+            if ((p.dbg & 65536) && el == 0) atomicExch(mma_lock + 1, 1u);
+        } else if ((p.dbg & 65536) && chain == 1 && el == 0) {
+            // (experiment) an idle chain's thread keeps a store + MEMBAR.GPU in flight while the other chain runs
+            uint32_t n = 0;
+            while (atomicAdd(mma_lock + 1, 0u) == 0u) {
+                p.counters[3 * kR3CounterStride + 8] = ++n;
+                __threadfence();
+            }
         }
     }
     tc_fence_before_sync();
@@ -424,7 +480,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     prm.P = Pk;
     prm.kpad = kpad;
     prm.wpack = reinterpret_cast<const float*>(wpack);       // bf16 slices, read once into tensor memory
-    const size_t st_bytes = (size_t)2 * kR3Rows * 16 * 4 + (size_t)16 * kR3Rows * 16;
+    const size_t st_bytes = (size_t)2 * kR3Rows * 16 * 4 + (size_t)16 * kR3Rows * 16 + (size_t)kR3Rows * 16 * 2;
     const size_t chain_bytes = ((size_t)nkb * kR3Rows * 128 + (size_t)2 * kGates * kR3Rows * 64 + (size_t)64 * kR3DtStride * 4 + st_bytes + 256 + 1023) & ~size_t(1023);
     const size_t smem = 1024 + kR3Chains * chain_bytes + 16 + kGates * 16 * 4 + 64;
     if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
@@ -432,7 +488,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     if (!enc) return ASRB_ERR_DRIVER;
     if (prm.out_sum)     // both directions add their h tiles into it
         ASRB_CUDA_OK(cudaMemsetAsync(prm.out_sum, 0, (size_t)prm.T * B * prm.H * sizeof(float), stream));
-    CUtensorMap tmA, tmA2, tmGi, tmH, tmC, tmSaved, tmOut;
+    CUtensorMap tmA, tmA2, tmGi, tmH, tmC, tmSaved, tmOut, tmOp;
     // staged outputs: whole tiles only (rows of a chain, 16 valid units)
     prm.stage_out = (B % kR3Rows == 0 && prm.H % 16 == 0 && (g_rnn_dbg & 4096)) ? 1 : 0;   // see asrb_rnn_fwd_sum: off
     if (prm.stage_out) {
@@ -475,6 +531,13 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         if (prm.Hp > prm.H)
             ASRB_CUDA_OK(cudaMemset2DAsync(prm.hbf + prm.H, (size_t)prm.Hp * 2, 0, (size_t)(prm.Hp - prm.H) * 2,
                                            (size_t)2 * (prm.T + 2) * B, stream));
+        // the same tensor as plain [slab][row][column] for the epilogue's operand stores: box = 16 units x rows of a chain
+        cuuint64_t gdim[3] = {(cuuint64_t)prm.Hp, (cuuint64_t)B, (cuuint64_t)2 * (prm.T + 2)};
+        cuuint64_t gstr[2] = {(cuuint64_t)prm.Hp * 2, (cuuint64_t)B * prm.Hp * 2};
+        cuuint32_t bxo[3] = {16, (cuuint32_t)kR3Rows, 1}, es[3] = {1, 1, 1};
+        if (enc(&tmOp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, prm.hbf, gdim, gstr, bxo, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return ASRB_ERR_TENSORMAP;
     }
     {   // gi [T][B][2G] fp32, box = 16 columns x 32 rows, 64-byte swizzle (conflict-free reads by (row, unit) threads)
         if ((reinterpret_cast<uintptr_t>(prm.gi) & 15) != 0) return ASRB_ERR_ALIGNMENT;
@@ -514,7 +577,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         if (2 * Pk > CS * nclusters) return ASRB_ERR_UNSUPPORTED;
     }
     prm.dbg = g_rnn_dbg;
-    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmGi, tmH, tmC, tmSaved, tmOut, prm));
+    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmGi, tmH, tmC, tmSaved, tmOut, tmOp, prm));
     return 0;
 }
 
@@ -536,7 +599,8 @@ constexpr int kR3StageBytes = 32 * 16 * 2;                  // one gate's [32 ro
 template <int CELL>
 __global__ void __launch_bounds__(kRnnThreads, 1)
 rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmDgi,
-                    const __grid_constant__ CUtensorMap tmGT, const __grid_constant__ CUtensorMap tmHT, const RnnParams p) {
+                    const __grid_constant__ CUtensorMap tmGT, const __grid_constant__ CUtensorMap tmHT,
+                    const __grid_constant__ CUtensorMap tmOp, const RnnParams p) {
     constexpr int NCH = 2, KS = 4;
     constexpr int kRows = 64 / NCH;             // batch rows of a chain = N of its MMAs
     constexpr int kEpiWarps = 16 / NCH, kEpiThreads = kEpiWarps * 32;
@@ -554,7 +618,9 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // per chain: operand tile | own quarter [16][40] | staging [2 parities][4 peers][16][40] | receive [2][4 sources][16][40] | barriers
     const size_t a_bytes = (size_t)nkb * kSlotBytes;
     const size_t x_bytes = (size_t)(1 + 2 * KS + 2 * KS) * kR3XBytes;
-    const size_t st_bytes = (size_t)3 * kGates * kR3StageBytes;     // staged outputs: dgi, dgiT, dghT tiles of every gate
+    // staged outputs: dgi, dgiT, dghT tiles of every gate; GRU: plus the operand tiles (LSTM: the operand IS the dgi tile)
+    constexpr int kStTiles = (CELL == ASRB_RNN_GRU) ? 4 : 3;
+    const size_t st_bytes = (size_t)kStTiles * kGates * kR3StageBytes;
     const size_t chain_bytes = (a_bytes + x_bytes + st_bytes + 256 + 1023) & ~size_t(1023);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -573,12 +639,14 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __nv_bfloat16* st_dgi = reinterpret_cast<__nv_bfloat16*>(cs + a_bytes + x_bytes);
     __nv_bfloat16* st_gT = st_dgi + kGates * (kR3StageBytes / 2);
     __nv_bfloat16* st_hT = st_gT + kGates * (kR3StageBytes / 2);
+    __nv_bfloat16* st_op = (CELL == ASRB_RNN_GRU) ? st_hT + kGates * (kR3StageBytes / 2) : st_dgi;   // [gate][32 rows][16 units]
     uint64_t* bars = reinterpret_cast<uint64_t*>(cs + a_bytes + x_bytes + st_bytes);
     uint64_t* full_bar = bars;                                // [kR3MaxChunks]
     uint64_t* tfull_bar = bars + kR3MaxChunks;
     uint64_t* x_bar = bars + kR3MaxChunks + 1;                // [2] the peers' quarters of step parity 0 / 1 have arrived
     uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + (size_t)NCH * chain_bytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    uint32_t* mma_lock = tmem_slot + 1;                       // tensor pipe: one chain's MMA sequence at a time
 
     uint32_t* counter = p.counters + (dir * NCH + (chain < NCH ? chain : 0)) * kR3CounterStride;
     const int kcol0 = (int)crank * p.kpad;                    // first gate column of our K quarter
@@ -591,7 +659,9 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_prefetch_desc(&tmDgi);
             tma_prefetch_desc(&tmGT);
             tma_prefetch_desc(&tmHT);
+            tma_prefetch_desc(&tmOp);
             mbar_init(w_bar, 1);
+            *mma_lock = 0u;
         }
         for (int i = 0; i < kR3MaxChunks; ++i) mbar_init(&full_bar[i], 1);
         mbar_init(tfull_bar, 1);
@@ -613,42 +683,51 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         //   D[64 units of the cluster, kRows batch rows] = W_hh^T[our K quarter, tensor memory] x dgates^T[shared memory]
         if (chain_on) {
             constexpr uint32_t idesc = umma_idesc(kFmtBF16, 64, kRows);
-            mbar_wait(w_bar, 0);
-            tc_fence_after_sync();
-            for (int s = 1; s < T; ++s) {
-                const uint32_t need = (uint32_t)P * (uint32_t)s;
-                poll_counter(counter, need);
-                if (lane == 0 && chain == 0) ASRB_TRACE(0, s);
-                fence_proxy_async_global();
-                const int slab = dir * T + t_of(s - 1);
-                if (elect_one()) {
+            if (elect_one()) {               // one thread runs the chain's control loop (see the forward kernel)
+                mbar_wait(w_bar, 0);
+                tc_fence_after_sync();
+                const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_a));
+                const int first = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;     // K blocks of the first chunk
+                const bool use_lock = B > kRows && !(p.dbg & 32768);
+                for (int s = 1; s < T; ++s) {
+                    poll_counter(counter, (uint32_t)P * (uint32_t)s);
+                    if (chain == 0) ASRB_TRACE(0, s);
+                    fence_proxy_async_global();
+                    const int slab = dir * T + t_of(s - 1);
                     for (int c = 0; c < nchunks; ++c) {      // one box per chunk of 4 K blocks (see the forward kernel)
-                        const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
+                        const int kb0 = c ? first + (c - 1) * kR3Chunk : 0, nblk = c ? kR3Chunk : first;
                         mbar_arrive_expect_tx(&full_bar[c], (uint32_t)nblk * kSlotBytes);
                         tma_load_4d(smem_a + (size_t)kb0 * kSlotBytes, nblk == kR3Chunk ? &tmA : &tmA2, &full_bar[c], 0, row0, kcol0 / KBE + kb0, slab);
                     }
-                }
-                __syncwarp();
-                if (lane == 0 && chain == 0) ASRB_TRACE(1, s);
-                const uint32_t ph = (uint32_t)((s - 1) & 1);
-                for (int c = 0; c < nchunks; ++c) {
-                    const int kb0 = c * kR3Chunk, nblk = min(kR3Chunk, nkb - kb0);
-                    mbar_wait(&full_bar[c], ph);
-                    if (c == 0 && lane == 0 && chain == 0) ASRB_TRACE(2, s);
-                    tc_fence_after_sync();
-                    if (elect_one()) {
-                        for (int i = 0; i < nblk; ++i) {
-                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_a + (size_t)(kb0 + i) * kSlotBytes));
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_f16_ts(tmem_d, tmem_w + ((kb0 + i) * 4 + k) * 8, bdesc + 2 * k, idesc, (c | i | k) != 0);
+                    if (chain == 0) ASRB_TRACE(1, s);
+                    const uint32_t ph = (uint32_t)((s - 1) & 1);
+                    for (int c = 0; c < nchunks; ++c) {
+                        const int kb0 = c ? first + (c - 1) * kR3Chunk : 0, nblk = c ? kR3Chunk : first;
+                        mbar_wait(&full_bar[c], ph);
+                        if (c == 0) {
+                            if (chain == 0) ASRB_TRACE(2, s);
+                            // one chain's MMA sequence at a time: interleaved in the tensor pipe both chains finish late, and
+                            // stay in lockstep; first come first served lets one run ahead until the phases no longer overlap
+                            if (use_lock) while (atomicCAS(mma_lock, 0u, 1u) != 0u) {}
                         }
-                        if (c == nchunks - 1) umma_commit(tfull_bar);
+                        tc_fence_after_sync();
+                        const uint64_t cdesc = bdesc0 + (uint64_t)kb0 * (kSlotBytes >> 4);
+                        const uint32_t cw = tmem_w + (uint32_t)kb0 * 32;
+#pragma unroll
+                        for (int i = 0; i < kR3Chunk; ++i) {
+                            if (i < nblk) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_f16_ts(tmem_d, cw + (i * 4 + k) * 8, cdesc + (uint64_t)(i * (kSlotBytes >> 4) + 2 * k), idesc, (c | i | k) != 0);
+                            }
+                        }
                     }
-                    __syncwarp();
+                    umma_commit(tfull_bar);
+                    if (use_lock) atomicExch(mma_lock, 0u);
+                    if (chain == 0) ASRB_TRACE(3, s);
                 }
-                if (lane == 0 && chain == 0) ASRB_TRACE(3, s);
             }
+            __syncwarp();
         }
     } else {
         // ===================== epilogue warps of the chain =====================
@@ -826,8 +905,11 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 };
                 const int cu = ev_u ? 0 : 1;                          // which of our two cells' rows the unit pair is stored for
                 const int unit2 = unit & ~1;
-                // (1) the next step's MMA operand (hidden-side gate gradients), published through the chain's step counter
-                {
+                // (1) the next step's MMA operand (hidden-side gate gradients), published through the chain's step counter:
+                // with whole tiles, one TMA store + its completion + a relaxed increment instead of stores + a release (see the
+                // forward kernel: the release's MEMBAR waits for the other chain's TMA copies)
+                const bool tma_op = staged && !(p.dbg & 2);
+                if (!tma_op) {
                     uint32_t* o = reinterpret_cast<uint32_t*>(p.dghbf + (((size_t)dir * T + t) * B + row[cu]) * p.Gp + unit2);
 #pragma unroll
                     for (int q = 0; q < kGates; ++q) {
@@ -844,7 +926,11 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint32_t* s_hT = reinterpret_cast<uint32_t*>(st_hT);
 #pragma unroll
                     for (int q = 0; q < kGates; ++q) {
-                        s_dgi[(q * (kR3StageBytes / 2) + rl_u * NJ + (ju & ~1)) / 2] = pair_units(dg[q][0], dg[q][1]);
+                        const uint32_t vu = pair_units(dg[q][0], dg[q][1]);
+                        s_dgi[(q * (kR3StageBytes / 2) + rl_u * NJ + (ju & ~1)) / 2] = vu;
+                        if constexpr (CELL == ASRB_RNN_GRU)
+                            if (tma_op) reinterpret_cast<uint32_t*>(st_op)[(q * (kR3StageBytes / 2) + rl_u * NJ + (ju & ~1)) / 2] =
+                                (q == 2) ? pair_units(eg2[0], eg2[1]) : vu;
                         const uint32_t vt = pair_rows(dg[q][0], dg[q][1]);
                         s_gT[(q * (kR3StageBytes / 2) + ju * kRows + rl_r) / 2] = vt;
                         if (p.dghT) s_hT[(q * (kR3StageBytes / 2) + ju * kRows + rl_r) / 2] = (q == 2) ? pair_rows(eg2[0], eg2[1]) : vt;
@@ -855,7 +941,14 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 named_bar_sync(8 + chain, kEpiThreads);
                 if (el == 0) {
                     if (chain == 0) ASRB_TRACE(8, s);
-                    red_release_add_u32(counter, 1u);
+                    if (tma_op) {
+                        tma_store_4d(&tmOp, st_op, j0, row0, 0, dir * T + t);
+                        bulk_commit_group();
+                        bulk_wait_group<0>();            // written: the tiles are in L2, where the consumers' TMA reads them
+                        red_relaxed_add_u32(counter, 1u);
+                    } else {
+                        red_release_add_u32(counter, 1u);
+                    }
                     if (chain == 0) ASRB_TRACE(10, s);
                     if (staged) {
                         // one store per tensor: the tiles of all gates (the tensor maps walk the gates as an extra dimension)
@@ -908,12 +1001,12 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
     prm.kpad = kpad;
     prm.wpack = reinterpret_cast<const float*>(wpack);
     constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
-    const size_t chain_bytes = ((size_t)nkb * 32 * 128 + (size_t)(1 + 4 * 4) * kR3XBytes + (size_t)3 * kGates * kR3StageBytes + 256 + 1023) & ~size_t(1023);
+    const size_t chain_bytes = ((size_t)nkb * 32 * 128 + (size_t)(1 + 4 * 4) * kR3XBytes + (size_t)(CELL == ASRB_RNN_GRU ? 4 : 3) * kGates * kR3StageBytes + 256 + 1023) & ~size_t(1023);
     const size_t smem = 1024 + 2 * chain_bytes + 64;
     if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return ASRB_ERR_DRIVER;
-    CUtensorMap tmA, tmA2, tmDgi, tmGT, tmHT;
+    CUtensorMap tmA, tmA2, tmDgi, tmGT, tmHT, tmOp;
     // staged outputs: whole 32-row x 16-unit tiles only, and 16-byte aligned tile rows in the transposed copies
     prm.stage_out = (B % 32 == 0 && prm.H % 16 == 0 && !(g_rnn_dbg & 2048)) ? 1 : 0;
     if (prm.stage_out) {
@@ -937,9 +1030,15 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
             ok = ok && plain(&tmGT, prm.dgiT, 3, gdim, gstr, bx);
             ok = ok && plain(&tmHT, prm.dghT ? prm.dghT : prm.dgiT, 3, gdim, gstr, bx);
         }
+        {   // dghbf [2 T][B][Gp] bf16 (the recurrence's own operand) as (column, row, gate, slab): box = 16 columns x 32 rows x all gates
+            cuuint64_t gdim[4] = {(cuuint64_t)prm.Gp - (cuuint64_t)(kGates - 1) * prm.H, (cuuint64_t)B, (cuuint64_t)kGates, (cuuint64_t)2 * prm.T};
+            cuuint64_t gstr[3] = {(cuuint64_t)prm.Gp * 2, (cuuint64_t)prm.H * 2, (cuuint64_t)B * prm.Gp * 2};
+            cuuint32_t bx[4] = {16, 32, (cuuint32_t)kGates, 1};
+            ok = ok && plain(&tmOp, prm.dghbf, 4, gdim, gstr, bx);
+        }
         if (!ok) prm.stage_out = 0;
     }
-    if (!prm.stage_out) tmDgi = tmGT = tmHT = CUtensorMap{};
+    if (!prm.stage_out) tmDgi = tmGT = tmHT = tmOp = CUtensorMap{};
     {   // dghbf [2 T][B][Gp] bf16 seen as [slab][K block][row][64 columns]: box = 64 columns x 32 rows (one chain) x 4 K blocks
         uint64_t d[4] = {64, (uint64_t)B, (uint64_t)prm.Gp / 64, (uint64_t)2 * prm.T};
         uint64_t s[3] = {(uint64_t)prm.Gp * 2, 128, (uint64_t)B * prm.Gp * 2};
@@ -971,7 +1070,7 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
         if (2 * pl.P_b > 4 * nclusters) return ASRB_ERR_UNSUPPORTED;
     }
     prm.dbg = g_rnn_dbg;
-    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmDgi, tmGT, tmHT, prm));
+    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmDgi, tmGT, tmHT, tmOp, prm));
     return 0;
 }
 

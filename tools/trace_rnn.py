@@ -19,9 +19,9 @@ lens = torch.full((B,), T, dtype=torch.int32, device=dev)
 dout = torch.randn(T, B, H, device=dev)
 # slot names of the exchange-by-data kernel (rnn2.cu)
 names2 = {4: "E:step top", 0: "P:canaries ok", 10: "E:go", 8: "E:deferred stores issued", 1: "P:copies issued", 2: "M:first K block",
-          3: "M:last commit", 5: "E:tfull", 6: "E:ld+verdict", 11: "E:exchange done", 7: "E:operand stored"}
-names1 = {4: "E:step top", 14: "chain1 step top", 12: "chain1 counter ok", 13: "chain1 commit", 0: "P:counter ok", 9: "P:fence done", 2: "M:first full", 1: "P:loads issued", 3: "M:commit",
-          5: "E:tfull", 6: "E:ld done", 11: "E:exchange done", 7: "E:math+stores", 8: "E:bar done", 10: "E:red"}
+          3: "M:last commit", 5: "E:tfull", 6: "E:ld+verdict", 15: "chunk3 landed", 11: "E:exchange done / chunk2 landed", 7: "E:operand stored"}
+names1 = {4: "E:step top", 14: "chain1 step top", 12: "chain1 counter ok", 13: "chain1 commit", 0: "P:counter ok", 9: "P:fence done / chunk1 landed", 2: "M:first full", 1: "P:loads issued", 3: "M:commit",
+          5: "E:tfull", 6: "E:ld done", 15: "chunk3 landed", 11: "E:exchange done / chunk2 landed", 7: "E:math+stores", 8: "E:bar done", 10: "E:red"}
 
 
 def timed(fn, n=3):
@@ -50,7 +50,7 @@ for dbg, label in ((8, "rnn.cu"), (0, "rnn3 forward + backward (TMEM weights, tw
             msg += f"; dghT {(dghT.float() - ref[3]).abs().max().item():.3e}"
         print(msg, flush=True)
 
-variants = [(0, "default: rnn3.cu forward and backward (weights in tensor memory, two chains of 32 rows)"), (8, "counter + TMA (rnn.cu)")]
+variants = [(0, "default: rnn3.cu forward and backward (weights in tensor memory, two chains of 32 rows)"), (4096, "rnn3 forward with staged outputs (TMA stores)"),  (8, "counter + TMA (rnn.cu)")]
 for dbg, label in variants:
     _lib.query("asrb_debug_rnn_dbg", dbg)
     _lib.query("asrb_debug_rnn_ksplit", ks)
