@@ -166,6 +166,18 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
 }
 
+// the same, issued only when `enable` != 0 (a predicated instruction: no branch around it, so a run of MMAs with constant
+// operand offsets stays straight-line code in the uniform datapath)
+__device__ __forceinline__ void umma_f16_ts_if(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t enable) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(enable)
+        : "memory");
+}
+
 struct RnnPlan {
     int nj, P, npad_f, npad_b, kpad_f, kpad_b, stages_f, stages_b, chunk_f, chunk_b, mrows, bf16, ksplit, P_b;   // ksplit: 0, 2, 4
     int ts_bwd;   // the backward recurrence runs rnn3.cu (weights in tensor memory, clusters of 4): packed layout of ks = 4

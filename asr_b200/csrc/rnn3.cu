@@ -52,6 +52,27 @@ constexpr int kR3CounterStride = 16;        // step counters [dir][chain], 64 by
 // CS-th K block as a TMA MULTICAST that lands in all CS shared memories (and completes on all CS barriers).  Experiment
 // (see rnn3_forward): the 2 x 50 CTAs of configs[1] read the same 100 KB per step, 10.6 MB per step through L2, but halving
 // that traffic does not speed the copies up.
+// zero the K-padding columns [col0, col0 + ncols) of every row of a bf16 matrix (ncols even, 4-byte aligned): one 4-byte
+// store per thread.  (cudaMemset2DAsync on 64-byte rows costs ~0.1 ms per call; this is a few microseconds.)
+__global__ void rnn3_zero_pad_cols_kernel(__nv_bfloat16* base, size_t rows, int pitch, int col0, int ncols) {
+    const int per_row = ncols / 2;
+    const size_t n = rows * (size_t)per_row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / per_row;
+        const int c = (int)(i % per_row);
+        *reinterpret_cast<uint32_t*>(base + r * pitch + col0 + 2 * c) = 0u;
+    }
+}
+static int rnn3_zero_pad_cols(__nv_bfloat16* base, size_t rows, int pitch, int col0, int ncols, asrb_stream_t stream) {
+    if (ncols <= 0) return 0;
+    if ((ncols | col0 | pitch) & 1) return ASRB_ERR_ALIGNMENT;
+    const size_t n = rows * (size_t)(ncols / 2);
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    rnn3_zero_pad_cols_kernel<<<blocks, 256, 0, stream>>>(base, rows, pitch, col0, ncols);
+    ASRB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <int CELL, int NCH, int CS>
 __global__ void __launch_bounds__(kRnnThreads, 1)
 rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmGi,
@@ -74,6 +95,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr int NV = NJ / 4;
 
     extern __shared__ uint8_t smem_raw[];
+    const long long t_entry = clock64();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int T = p.T, B = p.B, H = p.H, G = p.G, P = p.P;
     const int nkb = p.kpad / KBE;
@@ -197,30 +219,18 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             // stay in lockstep; first come first served lets one run ahead until the phases no longer overlap
                             if (use_lock) while (atomicCAS(mma_lock, 0u, 1u) != 0u) {}
                         }
-                        if (chain == 0 && c > 0) ASRB_TRACE(c == 1 ? 9 : (c == 2 ? 11 : 15), s);      // chunk c has landed
-                        tc_fence_after_sync();
-                        if ((p.dbg & 524288) && c > 0) continue;      // (experiment) no MMAs after the first chunk: landing times alone
+                        // (no tcgen05.fence here: the mbarrier wait orders the TMA's writes before the MMAs' reads, and a
+                        // fence per chunk was measured to drain the MMAs in flight -- ~250 cycles a chunk)
+                        if (c == 0) tc_fence_after_sync();   // after the poll: the epilogue's reads of D are done
                         // (constant offsets from the chunk's base descriptor / weight column: the issue loop stays in the
                         // uniform datapath -- a runtime K-block loop re-derives them through R2UR, ~70 cycles per block)
                         const uint64_t cdesc = bdesc0 + (uint64_t)kb0 * (kSlotBytes >> 4);
                         const uint32_t cw = tmem_w + (uint32_t)kb0 * 32;
 #pragma unroll
                         for (int i = 0; i < kR3Chunk; ++i) {
-                            if (i < nblk) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)   // 8 TMEM columns of weights per K = 16 step
-                                    umma_f16_ts(tmem_d, cw + (i * 4 + k) * 8, cdesc + (uint64_t)(i * (kSlotBytes >> 4) + 2 * k), idesc, (c | i | k) != 0);
-                            }
-                        }
-                        if (p.dbg & 262144) {
-#pragma unroll
-                        for (int i = 0; i < kR3Chunk; ++i) {
-                            if (i < nblk) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_f16_ts(tmem_d, cw + (i * 4 + k) * 8, cdesc + (uint64_t)(i * (kSlotBytes >> 4) + 2 * k), idesc, 1);
-                            }
-                        }
+                            for (int k = 0; k < 4; ++k)   // 8 TMEM columns of weights per K = 16 step
+                                umma_f16_ts_if(tmem_d, cw + (i * 4 + k) * 8, cdesc + (uint64_t)(i * (kSlotBytes >> 4) + 2 * k), idesc, (c | i | k) != 0, i < nblk);
                         }
                     }
                     umma_commit(tfull_bar);
@@ -319,6 +329,9 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int c = 0; c < 2; ++c) active[c] = cellok[c] && (t < len[c]);
                 if (el == 0 && chain == 0) ASRB_TRACE(4, s);
                 if (el == 0 && chain == 1) ASRB_TRACE(14, s);
+                if (s == 0 && el == 0 && chain == 0 && p.trace) p.trace[((size_t)blockIdx.x * p.T) * 16 + 15] = t_entry;
+                if ((s == 0 || s == T - 1) && el == 0 && chain == 0 && p.trace)      // wall clock (ns) next to the SM clock: the real SM frequency
+                    p.trace[((size_t)blockIdx.x * p.T + s) * 16 + 11] = (long long)globaltimer_ns();
                 float acc[kGates][2];
 #pragma unroll
                 for (int g = 0; g < kGates; ++g) acc[g][0] = acc[g][1] = 0.f;
@@ -449,14 +462,6 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
             if (staged && el == 0) bulk_wait_group<0>();      // the last TMA stores have been written
-            if ((p.dbg & 65536) && el == 0) atomicExch(mma_lock + 1, 1u);
-        } else if ((p.dbg & 65536) && chain == 1 && el == 0) {
-            // (experiment) an idle chain's thread keeps a store + MEMBAR.GPU in flight while the other chain runs
-            uint32_t n = 0;
-            while (atomicAdd(mma_lock + 1, 0u) == 0u) {
-                p.counters[3 * kR3CounterStride + 8] = ++n;
-                __threadfence();
-            }
         }
     }
     tc_fence_before_sync();
@@ -528,9 +533,8 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         bx[2] = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;      // box of the last chunk
         rc = make_tmap_bf16(&tmA2, prm.hbf, 4, d, s, bx);
         if (rc) return rc;
-        if (prm.Hp > prm.H)
-            ASRB_CUDA_OK(cudaMemset2DAsync(prm.hbf + prm.H, (size_t)prm.Hp * 2, 0, (size_t)(prm.Hp - prm.H) * 2,
-                                           (size_t)2 * (prm.T + 2) * B, stream));
+        rc = rnn3_zero_pad_cols(prm.hbf, (size_t)2 * (prm.T + 2) * B, prm.Hp, prm.H, prm.Hp - prm.H, stream);
+        if (rc) return rc;
         // the same tensor as plain [slab][row][column] for the epilogue's operand stores: box = 16 units x rows of a chain
         cuuint64_t gdim[3] = {(cuuint64_t)prm.Hp, (cuuint64_t)B, (cuuint64_t)2 * (prm.T + 2)};
         cuuint64_t gstr[2] = {(cuuint64_t)prm.Hp * 2, (cuuint64_t)B * prm.Hp * 2};
@@ -710,16 +714,14 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             // stay in lockstep; first come first served lets one run ahead until the phases no longer overlap
                             if (use_lock) while (atomicCAS(mma_lock, 0u, 1u) != 0u) {}
                         }
-                        tc_fence_after_sync();
+                        if (c == 0) tc_fence_after_sync();
                         const uint64_t cdesc = bdesc0 + (uint64_t)kb0 * (kSlotBytes >> 4);
                         const uint32_t cw = tmem_w + (uint32_t)kb0 * 32;
 #pragma unroll
                         for (int i = 0; i < kR3Chunk; ++i) {
-                            if (i < nblk) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_f16_ts(tmem_d, cw + (i * 4 + k) * 8, cdesc + (uint64_t)(i * (kSlotBytes >> 4) + 2 * k), idesc, (c | i | k) != 0);
-                            }
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16_ts_if(tmem_d, cw + (i * 4 + k) * 8, cdesc + (uint64_t)(i * (kSlotBytes >> 4) + 2 * k), idesc, (c | i | k) != 0, i < nblk);
                         }
                     }
                     umma_commit(tfull_bar);
@@ -1048,8 +1050,9 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
         bx[2] = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;      // box of the last chunk of a K quarter
         rc = make_tmap_bf16(&tmA2, prm.dghbf, 4, d, s, bx);
         if (rc) return rc;
-        if (prm.Gp > prm.G)      // the columns G..Gp of the last K block are inside the tensor: zero them once (0 x NaN is NaN)
-            ASRB_CUDA_OK(cudaMemset2DAsync(prm.dghbf + prm.G, (size_t)prm.Gp * 2, 0, (size_t)(prm.Gp - prm.G) * 2, (size_t)2 * prm.T * B, stream));
+        // the columns G..Gp of the last K block are inside the tensor: zero them once (0 x NaN is NaN)
+        rc = rnn3_zero_pad_cols(prm.dghbf, (size_t)2 * prm.T * B, prm.Gp, prm.G, prm.Gp - prm.G, stream);
+        if (rc) return rc;
     }
     auto kern = rnn_rec3_bwd_kernel<CELL>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

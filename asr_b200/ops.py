@@ -58,7 +58,8 @@ PROFILE = None   # set to a dict to collect (start, end) CUDA-event pairs per en
 # kernels launched per call of an entry point (memsets not counted); used for the `gpu_launches` claim
 KERNELS_PER_CALL = {
     "asrb_conv2d_mask_bwd_weight": 3, "asrb_bn2d_stats": 2, "asrb_bn_act_mask_bwd": 3, "asrb_bn_rows_fwd": 3,
-    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_ctc_bwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_rnn_fwd_sum": 2, "asrb_conv32_bwd_weight": 2, "asrb_conv1_fwd": 3, "asrb_conv1_bwd_weight": 2,
+    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_ctc_bwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_rnn_fwd": 2, "asrb_rnn_bwd": 2, "asrb_rnn_fwd_sum": 3,   # (+1: the K-padding columns of the operand are zeroed by a small kernel)
+    "asrb_conv32_bwd_weight": 2, "asrb_conv1_fwd": 3, "asrb_conv1_bwd_weight": 2,
 }
 
 
