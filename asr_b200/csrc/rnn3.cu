@@ -45,13 +45,16 @@ constexpr int kR3Chunk = 4;                 // K blocks per TMA barrier
 constexpr int kR3MaxChunks = 4;             // kpad <= 1024
 constexpr int kR3CounterStride = 16;        // step counters [dir][chain], 64 bytes apart (8 of them in the 512-byte block)
 
-// NCH chains of 64 / NCH batch rows.  Warp c < NCH is chain c's control warp (polls the chain's step counter, issues its TMA
-// copies, then its MMAs -- the steps of a chain are sequential anyway); warps 4 .. 19 are the epilogue warps, 16 / NCH per
-// chain, with warp % 4 = TMEM lane quarter = gate.
-// CS > 1: clusters of CS neighbouring CTAs of a direction share the copies of the previous state -- each CTA issues every
-// CS-th K block as a TMA MULTICAST that lands in all CS shared memories (and completes on all CS barriers).  Experiment
-// (see rnn3_forward): the 2 x 50 CTAs of configs[1] read the same 100 KB per step, 10.6 MB per step through L2, but halving
-// that traffic does not speed the copies up.
+// Two chains of 32 batch rows.  Warp c < 2 is chain c's control warp (one elected thread polls the chain's step counter,
+// issues its TMA copies, then its MMAs -- the steps of a chain are sequential anyway); warps 4 .. 19 are the epilogue warps,
+// 8 per chain.
+//
+// Accumulator rows: the CTA's 16 units x 4 gate slots are laid out so that TMEM lane quarter q holds ALL gates of units
+// 4q .. 4q+3 (lane 32q + 4*gate + u).  An epilogue warp (quarter q = warp % 4, batch columns 16*half .. +15 of the chain)
+// reads its quarter with one tcgen05.ld.16x256b.x2 -- thread t gets rows t/4 and t/4+8, i.e. gates (0, 2) of unit t/4 for
+// t/4 < 4 and gates (1, 3) of unit t/4-4 otherwise, for four batch columns -- and one round of lane^16 swaps leaves every
+// thread with all gates of one unit for two batch rows: no shared-memory transpose, no barrier between the accumulator read
+// and the gate math.
 // zero the K-padding columns [col0, col0 + ncols) of every row of a bf16 matrix (ncols even, 4-byte aligned): one 4-byte
 // store per thread.  (cudaMemset2DAsync on 64-byte rows costs ~0.1 ms per call; this is a few microseconds.)
 __global__ void rnn3_zero_pad_cols_kernel(__nv_bfloat16* base, size_t rows, int pitch, int col0, int ncols) {
@@ -73,18 +76,14 @@ static int rnn3_zero_pad_cols(__nv_bfloat16* base, size_t rows, int pitch, int c
     return 0;
 }
 
-template <int CELL, int NCH, int CS>
+template <int CELL>
 __global__ void __launch_bounds__(kRnnThreads, 1)
 rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmGi,
-                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmC,
-                const __grid_constant__ CUtensorMap tmSaved, const __grid_constant__ CUtensorMap tmOut,
                 const __grid_constant__ CUtensorMap tmOp, const RnnParams p) {
-    constexpr int kR3Chains = NCH;
+    constexpr int NCH = 2;
     constexpr int kR3Rows = 64 / NCH;           // batch rows of a chain = N of its MMAs
     constexpr int kR3EpiWarps = 16 / NCH;       // per chain
     constexpr int kR3EpiThreads = kR3EpiWarps * 32;
-    constexpr int kR3DtStride = kR3Rows + 8;    // floats per gate row of a chain's transposed accumulator tile (2-way conflicts
-                                                // on the 256-byte float2 stores = the minimum; conflict-free reads)
     constexpr int NJ = 16;
     constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
     constexpr int NPAD = ((kGates * NJ + 15) / 16) * 16;      // rows of the packed forward slice
@@ -100,14 +99,10 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int T = p.T, B = p.B, H = p.H, G = p.G, P = p.P;
     const int nkb = p.kpad / KBE;
     const int nchunks = ceil_div(nkb, kR3Chunk);
-    // per chain: operand tile, gate boxes (2 step parities), transposed accumulator tile, barriers
+    // per chain: operand tile | gate boxes (2 step parities) | the chain's output operand tile [rows][16 units] bf16 | barriers
     const size_t a_bytes = (size_t)nkb * kSlotBytes, gi_bytes = (size_t)2 * kGates * kGiRegion;
-    const size_t dt_bytes = (size_t)64 * kR3DtStride * 4;
-    // staged outputs (TMA stores): h and c tiles [rows][16 units] fp32, saved activations [4 gates x 4 unit groups][rows][4]
-    const size_t hc_bytes = (size_t)kR3Rows * NJ * 4, sv_bytes = (size_t)16 * kR3Rows * 16;
-    const size_t op_bytes = (size_t)kR3Rows * NJ * 2;          // the chain's operand tile [rows][16 units] bf16 (one TMA store a step)
-    const size_t st_bytes = 2 * hc_bytes + sv_bytes + op_bytes;
-    const size_t chain_bytes = (a_bytes + gi_bytes + dt_bytes + st_bytes + 256 + 1023) & ~size_t(1023);   // operand tiles: 1 KB aligned
+    const size_t op_bytes = (size_t)kR3Rows * NJ * 2;
+    const size_t chain_bytes = (a_bytes + gi_bytes + op_bytes + 256 + 1023) & ~size_t(1023);   // operand tiles: 1 KB aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.x / P, pidx = blockIdx.x % P;
@@ -118,21 +113,16 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint8_t* cs = smem + (size_t)(chain < NCH ? chain : 0) * chain_bytes;
     uint8_t* smem_a = cs;                                     // [nkb][32 rows x 128 B]
     uint8_t* smem_gi = cs + a_bytes;                          // [2][kGates][kGiRegion]
-    float* dt = reinterpret_cast<float*>(cs + a_bytes + gi_bytes);   // [64 gate rows][kR3DtStride]
-    float* st_h = reinterpret_cast<float*>(cs + a_bytes + gi_bytes + dt_bytes);      // [rows][16]
-    float* st_c = st_h + kR3Rows * NJ;                                               // [rows][16]
-    float* st_sv = st_c + kR3Rows * NJ;                                              // [gate * 4 + unit group][rows][4]
-    __nv_bfloat16* st_op = reinterpret_cast<__nv_bfloat16*>(st_sv + 16 * kR3Rows * 4);   // [rows][16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cs + a_bytes + gi_bytes + dt_bytes + st_bytes);
+    __nv_bfloat16* st_op = reinterpret_cast<__nv_bfloat16*>(cs + a_bytes + gi_bytes);   // [rows][16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cs + a_bytes + gi_bytes + op_bytes);
     uint64_t* full_bar = bars;                                // [kR3MaxChunks]
     uint64_t* tfull_bar = bars + kR3MaxChunks;
     uint64_t* gi_bar = bars + kR3MaxChunks + 1;               // [2]
-    uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + (size_t)kR3Chains * chain_bytes);   // weights are in tensor memory
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + (size_t)NCH * chain_bytes);   // weights are in tensor memory
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
-    float* s_bias = reinterpret_cast<float*>(w_bar + 2);      // [kGates][NJ]
-    uint32_t* mma_lock = reinterpret_cast<uint32_t*>(s_bias + kGates * NJ);   // tensor pipe: one chain's MMA sequence at a time
+    float* s_bias = reinterpret_cast<float*>(w_bar + 2);      // [4][NJ]
 
-    uint32_t* counter = p.counters + (dir * kR3Chains + (chain < NCH ? chain : 0)) * kR3CounterStride;
+    uint32_t* counter = p.counters + (dir * NCH + (chain < NCH ? chain : 0)) * kR3CounterStride;
     auto t_of = [&](int s) { return dir == 1 ? (T - 1 - s) : s; };
 
     if (warp < NCH && lane == 0) {
@@ -140,12 +130,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmA2);
             tma_prefetch_desc(&tmGi);
-            tma_prefetch_desc(&tmH);
-            tma_prefetch_desc(&tmSaved);
             tma_prefetch_desc(&tmOp);
             mbar_init(w_bar, 1);
-            mma_lock[0] = 0u;
-            mma_lock[1] = 0u;
         }
         for (int i = 0; i < kR3MaxChunks; ++i) mbar_init(&full_bar[i], 1);
         mbar_init(tfull_bar, 1);
@@ -157,11 +143,9 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    if constexpr (CS > 1) cluster_sync_all();     // the peers' barriers exist before anybody's multicast completes on them
-    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_d = tmem_base + chain * kR3Rows;      // the chain's accumulator: kR3Rows columns
-    const uint32_t tmem_w = tmem_base + kR3Chains * kR3Rows;  // weights: kpad/2 columns
+    const uint32_t tmem_w = tmem_base + NCH * kR3Rows;        // weights: kpad/2 columns
 
     if (warp < kRnnCtrlWarps) {
         // ===================== control warp of the chain: TMA copies, then the MMAs =====================
@@ -175,8 +159,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tma_load_4d(smem_gi + (size_t)((s & 1) * kGates) * kGiRegion, &tmGi, &gi_bar[s & 1], dir * G + j0, row0, 0, t);
             };
             // ONE elected thread runs the chain's whole control loop: poll, copies, MMAs.  (Per-chunk elect / __syncwarp
-            // rounds of the whole warp cost ~250 cycles a chunk on the chain's critical path -- more than the chunk's 16 MMAs
-            // at ~20 cycles each, which therefore never overlapped the copies still in flight.)
+            // rounds of the whole warp cost ~250 cycles a chunk on the chain's critical path.)  The loop is kept SMALL: this
+            // path runs once a step next to sixteen epilogue warps, and its instruction fetches sit on the critical path.
             if (elect_one()) {
                 load_gi(0);
                 if (T > 1) load_gi(1);
@@ -184,13 +168,12 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc_fence_after_sync();
                 const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_a));
                 const int first = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;     // K blocks of the first chunk
-                const bool use_lock = B > kR3Rows && (p.dbg & 32768);     // (measured: helps the backward kernel only)
                 for (int s = 1; s < T; ++s) {
                     // step barrier of the chain: every CTA of this direction has published step s-1 of these rows
                     poll_counter(counter, (uint32_t)P * (uint32_t)s);
                     if (chain == 0) ASRB_TRACE(0, s);
                     if (chain == 1) ASRB_TRACE(12, s);
-                    fence_proxy_async_global();      // the others' generic-proxy stores -> our async-proxy (TMA) reads
+                    fence_proxy_async_global();      // (fallback path: the others' generic-proxy stores -> our async-proxy reads)
                     const int slab = dir * (T + 2) + t_of(s - 1) + 1;
                     // (our own arrival is part of `need`: our MMAs of step s-1 have read the tile, our epilogue its gate boxes)
                     for (int c = 0; c < nchunks; ++c) {
@@ -198,14 +181,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         // ONE box per chunk: [4 K blocks][32 rows][128 B] (the tensor map walks the K blocks as its third
                         // dimension).  A TMA request costs ~60 cycles on top of its bytes.
                         // (tmA2: the same tensor with a box of nkb % 4 blocks -- the FIRST chunk: the small box lands soonest)
-                        const CUtensorMap* tm = nblk == kR3Chunk ? &tmA : &tmA2;
                         mbar_arrive_expect_tx(&full_bar[c], (uint32_t)nblk * kSlotBytes);
-                        if constexpr (CS > 1) {          // (experiment) every CS-th chunk from us, to every CTA of the cluster
-                            if ((uint32_t)(c % CS) == crank)
-                                tma_load_4d_mc(smem_a + (size_t)kb0 * kSlotBytes, tm, &full_bar[c], 0, row0, kb0, slab, (uint16_t)((1u << CS) - 1));
-                        } else {
-                            tma_load_4d(smem_a + (size_t)kb0 * kSlotBytes, tm, &full_bar[c], 0, row0, kb0, slab);
-                        }
+                        tma_load_4d(smem_a + (size_t)kb0 * kSlotBytes, nblk == kR3Chunk ? &tmA : &tmA2, &full_bar[c], 0, row0, kb0, slab);
                     }
                     if (s + 1 < T) load_gi(s + 1);
                     if (chain == 0) ASRB_TRACE(1, s);
@@ -213,17 +190,14 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int c = 0; c < nchunks; ++c) {
                         const int kb0 = c ? first + (c - 1) * kR3Chunk : 0, nblk = c ? kR3Chunk : first;
                         mbar_wait(&full_bar[c], ph);
+                        // (one tcgen05.fence per step, after the poll: the epilogue's reads of D are done.  None per chunk: the
+                        // mbarrier wait orders the TMA's writes before the MMAs' reads.)
                         if (c == 0) {
                             if (chain == 0) ASRB_TRACE(2, s);
-                            // one chain's MMA sequence at a time: interleaved in the tensor pipe both chains finish late, and
-                            // stay in lockstep; first come first served lets one run ahead until the phases no longer overlap
-                            if (use_lock) while (atomicCAS(mma_lock, 0u, 1u) != 0u) {}
+                            tc_fence_after_sync();
                         }
-                        // (no tcgen05.fence here: the mbarrier wait orders the TMA's writes before the MMAs' reads, and a
-                        // fence per chunk was measured to drain the MMAs in flight -- ~250 cycles a chunk)
-                        if (c == 0) tc_fence_after_sync();   // after the poll: the epilogue's reads of D are done
-                        // (constant offsets from the chunk's base descriptor / weight column: the issue loop stays in the
-                        // uniform datapath -- a runtime K-block loop re-derives them through R2UR, ~70 cycles per block)
+                        // constant offsets from the chunk's base descriptor / weight column, predicated instead of branched:
+                        // straight-line code in the uniform datapath
                         const uint64_t cdesc = bdesc0 + (uint64_t)kb0 * (kSlotBytes >> 4);
                         const uint32_t cw = tmem_w + (uint32_t)kb0 * 32;
 #pragma unroll
@@ -234,7 +208,6 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                     umma_commit(tfull_bar);
-                    if (use_lock) atomicExch(mma_lock, 0u);
                     if (chain == 0) ASRB_TRACE(3, s);
                     if (chain == 1) ASRB_TRACE(13, s);
                 }
@@ -243,30 +216,26 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else {
         // ===================== epilogue warps of the chain: 8 warps =====================
-        // accumulator role: lane quarter q = warp % 4 holds gate q of the 16 units (rows), this warp takes the chain's
-        // batch columns 16*half .. +15.  cell role: thread = unit 4*ug + lane%4 of two batch rows of the chain.
-        constexpr int kRp16 = kR3Rows / 16;                    // 16-row groups of the chain
         const int wl = (warp - kRnnCtrlWarps) % kR3EpiWarps;
-        const int quad = warp & 3, half = wl >> 2;
-        const int ug = wl / kRp16, ul = lane & 3;
+        const int quad = warp & 3, half = wl >> 2;             // TMEM lane quarter = unit group; batch columns 16*half .. +15
+        const int r8 = lane >> 2, hi = r8 >> 2;                // accumulator row pair of the lane; hi: keeps the odd columns
+        const int ug = quad, ul = r8 & 3;
         const int el = wl * 32 + lane;                         // 0..255 within the chain
         const int ju = 4 * ug + ul, unit = j0 + ju;
         const bool uvalid = unit < H;
-        int row[2], len[2];
+        int rl[2], row[2], len[2];                             // our two cells: (unit, batch rows rl[0], rl[0] + 8 of the chain)
         bool cellok[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            row[c] = row0 + 16 * (wl % kRp16) + (lane >> 2) + 8 * c;
+            rl[c] = 16 * half + 2 * (lane & 3) + hi + 8 * c;
+            row[c] = row0 + rl[c];
             cellok[c] = uvalid && row[c] < B;
             len[c] = cellok[c] ? p.lengths[row[c]] : 0;
         }
         const size_t slotHB = (size_t)B * H;
         uint32_t gi_off[2];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int rl = row[c] - row0;
-            gi_off[c] = (uint32_t)(rl * 64 + ((ug ^ ((rl >> 1) & 3)) << 4) + ul * 4);
-        }
+        for (int c = 0; c < 2; ++c) gi_off[c] = (uint32_t)(rl[c] * 64 + ((ug ^ ((rl[c] >> 1) & 3)) << 4) + ul * 4);
         const uint32_t smem_gi_u32 = smem_u32(smem_gi);
 
         // ---- once: zero boundary slots, biases, the weight slice -> tensor memory ----
@@ -283,15 +252,15 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
         if (chain == 0) {
-            for (int i = el; i < kGates * NJ; i += kR3EpiThreads) {
+            for (int i = el; i < 4 * NJ; i += kR3EpiThreads) {
                 const int g = i / NJ, jj = i % NJ;
-                s_bias[i] = (j0 + jj < H) ? p.b_hh[(size_t)dir * G + g * H + j0 + jj] : 0.f;
+                s_bias[i] = (g < kGates && j0 + jj < H) ? p.b_hh[(size_t)dir * G + g * H + j0 + jj] : 0.f;
             }
             if (wl < 4) {
-                // gate row c = 16 * quarter + i sits in TMEM lane 32 * quarter + i (the M = 64 data path layout, like the
-                // accumulator rows); 16 bf16 = 8 columns per store
-                const int c = 16 * quad + lane;
-                const bool have = lane < 16 && c < NPAD && pidx < p.P_saved;      // (padding CTAs of a cluster own no slice)
+                // TMEM lane 32 * quarter + 4 * gate + u holds packed row gate * 16 + 4 * quarter + u (the M = 64 data path
+                // uses lanes 0..15 of each quarter); 16 bf16 = 8 columns per store
+                const int g = lane >> 2, c = g * NJ + 4 * quad + (lane & 3);
+                const bool have = lane < 16 && g < kGates && c < NPAD && pidx < p.P_saved;
                 const uint4* wrow = reinterpret_cast<const uint4*>(
                     reinterpret_cast<const __nv_bfloat16*>(p.wpack) + ((size_t)(dir * p.P_saved + (have ? pidx : 0)) * NPAD + (have ? c : 0)) * p.kpad);
                 for (int k0 = 0; k0 < p.kpad / 16; k0 += 4) {       // kpad is a multiple of 64: four stores per round,
@@ -310,18 +279,32 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         named_bar_sync(3, kRnnEpiThreads);                      // all 16 epilogue warps
         if (warp == kRnnCtrlWarps && lane == 0) mbar_arrive(w_bar);
-        float bias[kGates];
+        float bias[4];
 #pragma unroll
-        for (int g = 0; g < kGates; ++g) bias[g] = s_bias[g * NJ + ju];
+        for (int g = 0; g < 4; ++g) bias[g] = s_bias[g * NJ + ju];
 
         if (chain_on) {
             float state_h[2] = {0.f, 0.f}, state_c[2] = {0.f, 0.f};
-            // The stores nobody waits for (fp32 state, saved activations: 10 scattered 4-byte stores per thread and step)
-            // go through shared-memory tiles and TMA stores when the tiles are whole (32 / 16 batch rows, 16 valid units):
-            // no LSU issue time, and the release's MEMBAR does not wait for them.  The direction sum the next layer reads
-            // (blocks.py:92) is a TMA reduce-add of the same h tile into the zero-filled output.
-            const bool staged = p.stage_out && j0 + NJ <= H && row0 + kR3Rows <= B;
-            const int rl0 = 16 * (wl % kRp16) + (lane >> 2);
+            const bool tma_op = !(p.dbg & 2);
+            // per-step addresses advance by constants (t moves by +-1): bases for step 0, strides in elements
+            const int t0 = t_of(0);
+            const long long tstep = dir == 1 ? -1 : 1;
+            float* hq[2];
+            float* cq[2];
+            float* svq[2];
+            __nv_bfloat16* opq[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const size_t o = ((size_t)dir * (T + 2) + t0 + 1) * slotHB + (size_t)row[c] * H + unit;
+                hq[c] = p.hseq + o;
+                cq[c] = (CELL == ASRB_RNN_LSTM) ? p.cseq + o : nullptr;
+                svq[c] = p.saved + ((((size_t)dir * T + t0) * p.P_saved + pidx) * 4) * (size_t)(NV * B * 4) + (size_t)ug * (B * 4) + (size_t)row[c] * 4 + ul;
+                opq[c] = p.hbf + (((size_t)dir * (T + 2) + t0 + 1) * B + row[c]) * p.Hp + unit;
+            }
+            const long long h_stride = tstep * (long long)slotHB;
+            const long long sv_stride = tstep * (long long)p.P_saved * 4 * (long long)(NV * B * 4);
+            const long long op_stride = tstep * (long long)B * p.Hp;
+            const size_t sv_gate = (size_t)NV * (B * 4);
             for (int s = 0; s < T; ++s) {
                 const int t = t_of(s);
                 bool active[2];
@@ -332,30 +315,33 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (s == 0 && el == 0 && chain == 0 && p.trace) p.trace[((size_t)blockIdx.x * p.T) * 16 + 15] = t_entry;
                 if ((s == 0 || s == T - 1) && el == 0 && chain == 0 && p.trace)      // wall clock (ns) next to the SM clock: the real SM frequency
                     p.trace[((size_t)blockIdx.x * p.T + s) * 16 + 11] = (long long)globaltimer_ns();
-                float acc[kGates][2];
+                float acc[4][2];
 #pragma unroll
-                for (int g = 0; g < kGates; ++g) acc[g][0] = acc[g][1] = 0.f;
+                for (int g = 0; g < 4; ++g) acc[g][0] = acc[g][1] = 0.f;
                 if (s > 0) {
                     mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
                     if (el == 0 && chain == 0) ASRB_TRACE(5, s);
                     tc_fence_after_sync();
-                    if (quad < kGates) {
-                        float v[8];
-                        tmem_ld_16x256b_x2(tmem_d + (uint32_t(quad * 32) << 16) + 16 * half, v);
-                        tmem_ld_wait();
-                        float* d = dt + (quad * 16 + (lane >> 2)) * kR3DtStride + 16 * half + 2 * ul;
-                        *reinterpret_cast<float2*>(d) = make_float2(v[0], v[1]);
-                        *reinterpret_cast<float2*>(d + 8 * kR3DtStride) = make_float2(v[2], v[3]);
-                        *reinterpret_cast<float2*>(d + 8) = make_float2(v[4], v[5]);
-                        *reinterpret_cast<float2*>(d + 8 * kR3DtStride + 8) = make_float2(v[6], v[7]);
-                    }
+                    float v[8];
+                    tmem_ld_16x256b_x2(tmem_d + (uint32_t(quad * 32) << 16) + 16 * half, v);
+                    tmem_ld_wait();
                     tc_fence_before_sync();    // the counter arrival below orders these reads before the next step's MMAs
-                    if (staged && el == 0) bulk_wait_group_read<0>();   // the previous step's TMA stores have read their tiles
-                    named_bar_sync(4 + chain, kR3EpiThreads);
+                    // v[0..1]: row r8, columns 2*(lane&3) + {0, 1}; v[2..3]: row r8 + 8; v[4..7]: the same, columns + 8.
+                    // lo lanes (r8 < 4) hold gates 0 / 2 and keep the even columns; hi lanes hold gates 1 / 3 and keep the odd.
+                    // send what the partner keeps, keep ours: cell c uses column 2*(lane&3) + hi + 8*c
 #pragma unroll
-                    for (int g = 0; g < kGates; ++g)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) acc[g][c] = dt[(g * 16 + ju) * kR3DtStride + (row[c] - row0)];
+                    for (int c = 0; c < 2; ++c) {
+                        const float mine_a = hi ? v[4 * c + 1] : v[4 * c + 0];      // gate (hi ? 1 : 0) of our column
+                        const float mine_b = hi ? v[4 * c + 3] : v[4 * c + 2];      // gate (hi ? 3 : 2)
+                        const float send_a = hi ? v[4 * c + 0] : v[4 * c + 1];
+                        const float send_b = hi ? v[4 * c + 2] : v[4 * c + 3];
+                        const float got_a = __shfl_xor_sync(0xffffffffu, send_a, 16);   // partner's gate (hi ? 0 : 1) of our column
+                        const float got_b = __shfl_xor_sync(0xffffffffu, send_b, 16);   // partner's gate (hi ? 2 : 3)
+                        acc[0][c] = hi ? got_a : mine_a;
+                        acc[1][c] = hi ? mine_a : got_a;
+                        acc[2][c] = hi ? got_b : mine_b;
+                        acc[3][c] = hi ? mine_b : got_b;
+                    }
                     if (el == 0 && chain == 0) ASRB_TRACE(6, s);
                 }
                 // gate pre-activations of this step (TMA, a step ahead)
@@ -383,7 +369,7 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const float gi_ = fsigmoid(in[0][c] + acc[0][c] + bias[0]);
                             const float gf = fsigmoid(in[1][c] + acc[1][c] + bias[1]);
                             const float gg = ftanh(in[2][c] + acc[2][c] + bias[2]);
-                            const float go = fsigmoid(in[3][c] + acc[kGates - 1][c] + bias[kGates - 1]);
+                            const float go = fsigmoid(in[3][c] + acc[3][c] + bias[3]);
                             c_ = gf * state_c[c] + gi_ * gg;
                             h_ = go * ftanh(c_);
                             s0 = gi_; s1 = gf; s2 = gg; s3 = go;
@@ -400,26 +386,14 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // memory operation the SM has in flight -- the OTHER chain's TMA copies included (tools/ubench/membar_tma.cu:
                 // 870 cycles alone, the rest of the copies' ~3 k when they are in flight), which chained the two chains together.
                 // (rows >= B are clipped by the tensor map; units >= H hold 0 and land in the zero K padding.)
-                const bool tma_op = !(p.dbg & 2);
                 if (tma_op) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) st_op[(rl0 + 8 * c) * NJ + ju] = __float2bfloat16_rn(hn[c]);
-                    if (!staged) fence_proxy_async_smem();
+                    for (int c = 0; c < 2; ++c) st_op[rl[c] * NJ + ju] = __float2bfloat16_rn(hn[c]);
+                    fence_proxy_async_smem();
                 } else {
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
-                        if (cellok[c]) p.hbf[(((size_t)dir * (T + 2) + t + 1) * B + row[c]) * p.Hp + unit] = __float2bfloat16_rn(hn[c]);
-                }
-                if (staged) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int rl = rl0 + 8 * c;
-                        st_h[rl * NJ + ju] = hn[c];
-                        if constexpr (CELL == ASRB_RNN_LSTM) st_c[rl * NJ + ju] = cn[c];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) st_sv[((q * NV + ug) * kR3Rows + rl) * 4 + ul] = sv[q][c];
-                    }
-                    fence_proxy_async_smem();                  // generic stores -> the TMA stores' async-proxy reads
+                        if (cellok[c]) *opq[c] = __float2bfloat16_rn(hn[c]);
                 }
                 if (el == 0 && chain == 0) ASRB_TRACE(7, s);
                 named_bar_sync(8 + chain, kR3EpiThreads);
@@ -434,34 +408,29 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         red_release_add_u32(counter, 1u);
                     }
                     if (chain == 0) ASRB_TRACE(10, s);
-                    if (staged) {
-                        tma_store_3d(&tmH, st_h, j0, row0, dir * (T + 2) + t + 1);
-                        if constexpr (CELL == ASRB_RNN_LSTM) tma_store_3d(&tmC, st_c, j0, row0, dir * (T + 2) + t + 1);
-                        tma_store_3d(&tmSaved, st_sv, 0, row0, (((dir * T + t) * p.P_saved + pidx) * 4) * NV);
-                        if (p.out_sum) tma_reduce_add_3d(&tmOut, st_h, j0, row0, t);
-                        bulk_commit_group();
-                    }
                 }
-                if (!staged && !(p.dbg & 1)) {     // (dbg bit 1: timing experiment without these stores, results incomplete)
-                    // hold the other stores back until the release has been issued: its MEMBAR waits for every store in flight
+                if (!(p.dbg & 1)) {     // (dbg bit 1: timing experiment without these stores, results incomplete)
+                    // hold the other stores back until the operand tile has been read: they would sit in the LSU queue ahead of it
                     named_bar_sync(12 + chain, kR3EpiThreads);
                     // (2) the stores nobody waits for
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         if (cellok[c]) {
-                            const size_t o = ((size_t)dir * (T + 2) + t + 1) * slotHB + (size_t)row[c] * H + unit;
-                            float* svp = p.saved + ((((size_t)dir * T + t) * p.P_saved + pidx) * 4) * (size_t)(NV * B * 4) +
-                                         (size_t)ug * (B * 4) + (size_t)row[c] * 4 + ul;
-                            p.hseq[o] = hn[c];
-                            if constexpr (CELL == ASRB_RNN_LSTM) p.cseq[o] = cn[c];
-                            if (p.out_sum) atomicAdd(p.out_sum + (size_t)t * slotHB + (size_t)row[c] * H + unit, hn[c]);
+                            *hq[c] = hn[c];
+                            if constexpr (CELL == ASRB_RNN_LSTM) *cq[c] = cn[c];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) svp[(size_t)q * NV * (B * 4)] = sv[q][c];
+                            for (int q = 0; q < 4; ++q) svq[c][(size_t)q * sv_gate] = sv[q][c];
                         }
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    hq[c] += h_stride;
+                    if constexpr (CELL == ASRB_RNN_LSTM) cq[c] += h_stride;
+                    svq[c] += sv_stride;
+                    opq[c] += op_stride;
+                }
             }
-            if (staged && el == 0) bulk_wait_group<0>();      // the last TMA stores have been written
         }
     }
     tc_fence_before_sync();
@@ -470,58 +439,27 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after_sync();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
-    if constexpr (CS > 1) cluster_sync_all();   // nobody leaves while a peer's multicast may still land here
 }
 
-template <int CELL, int NCH, int CS>
+template <int CELL>
 static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {
     constexpr int kGates = (CELL == ASRB_RNN_GRU) ? 3 : 4;
-    constexpr int kR3Chains = NCH, kR3Rows = 64 / NCH, kR3DtStride = kR3Rows + 8;
+    constexpr int NCH = 2, kR3Rows = 64 / NCH;
     const int kpad = pl.kpad_f, nkb = kpad / 64;
     const int B = prm.B;
-    if (ceil_div(nkb, kR3Chunk) > kR3MaxChunks || kR3Chains * kR3Rows + kpad / 2 > 512) return ASRB_ERR_UNSUPPORTED;
-    const int Pk = (pl.P + CS - 1) / CS * CS;                // CTAs per direction: the slices, padded to whole clusters
+    if (ceil_div(nkb, kR3Chunk) > kR3MaxChunks || NCH * kR3Rows + kpad / 2 > 512) return ASRB_ERR_UNSUPPORTED;
     prm.P_saved = pl.P;
-    prm.P = Pk;
+    prm.P = pl.P;
     prm.kpad = kpad;
     prm.wpack = reinterpret_cast<const float*>(wpack);       // bf16 slices, read once into tensor memory
-    const size_t st_bytes = (size_t)2 * kR3Rows * 16 * 4 + (size_t)16 * kR3Rows * 16 + (size_t)kR3Rows * 16 * 2;
-    const size_t chain_bytes = ((size_t)nkb * kR3Rows * 128 + (size_t)2 * kGates * kR3Rows * 64 + (size_t)64 * kR3DtStride * 4 + st_bytes + 256 + 1023) & ~size_t(1023);
-    const size_t smem = 1024 + kR3Chains * chain_bytes + 16 + kGates * 16 * 4 + 64;
+    prm.out_sum = nullptr;                                   // (the direction sum is a separate kernel: see asrb_rnn_fwd_sum)
+    prm.stage_out = 0;
+    const size_t chain_bytes = ((size_t)nkb * kR3Rows * 128 + (size_t)2 * kGates * kR3Rows * 64 + (size_t)kR3Rows * 16 * 2 + 256 + 1023) & ~size_t(1023);
+    const size_t smem = 1024 + NCH * chain_bytes + 16 + 4 * 16 * 4 + 64;
     if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return ASRB_ERR_DRIVER;
-    if (prm.out_sum)     // both directions add their h tiles into it
-        ASRB_CUDA_OK(cudaMemsetAsync(prm.out_sum, 0, (size_t)prm.T * B * prm.H * sizeof(float), stream));
-    CUtensorMap tmA, tmA2, tmGi, tmH, tmC, tmSaved, tmOut, tmOp;
-    // staged outputs: whole tiles only (rows of a chain, 16 valid units)
-    prm.stage_out = (B % kR3Rows == 0 && prm.H % 16 == 0 && (g_rnn_dbg & 4096)) ? 1 : 0;   // see asrb_rnn_fwd_sum: off
-    if (prm.stage_out) {
-        auto plain = [&](CUtensorMap* m, const void* base, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* bx) {
-            cuuint32_t es[3] = {1, 1, 1};
-            if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
-            return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-        };
-        bool ok = true;
-        {   // hseq / cseq [2(T+2)][B][H] fp32 and the direction sum [T][B][H]: box = 16 units x rows of a chain
-            cuuint64_t gdim[3] = {(cuuint64_t)prm.H, (cuuint64_t)B, (cuuint64_t)2 * (prm.T + 2)};
-            cuuint64_t gstr[2] = {(cuuint64_t)prm.H * 4, (cuuint64_t)B * prm.H * 4};
-            cuuint32_t bx[3] = {16, (cuuint32_t)kR3Rows, 1};
-            ok = ok && plain(&tmH, prm.hseq, gdim, gstr, bx);
-            ok = ok && plain(&tmC, prm.cseq ? prm.cseq : prm.hseq, gdim, gstr, bx);
-            gdim[2] = (cuuint64_t)prm.T;
-            ok = ok && plain(&tmOut, prm.out_sum ? prm.out_sum : prm.hseq, gdim, gstr, bx);
-        }
-        {   // saved [2 T P 16 (gate, unit group)][B][4] fp32: box = one step's 16 (gate, group) planes x rows of a chain
-            cuuint64_t gdim[3] = {4, (cuuint64_t)B, (cuuint64_t)2 * prm.T * pl.P * 16};
-            cuuint64_t gstr[2] = {16, (cuuint64_t)B * 16};
-            cuuint32_t bx[3] = {4, (cuuint32_t)kR3Rows, 16};
-            ok = ok && plain(&tmSaved, prm.saved, gdim, gstr, bx);
-        }
-        if (!ok) prm.stage_out = 0;
-    }
-    if (!prm.stage_out) tmH = tmC = tmSaved = tmOut = CUtensorMap{};
+    CUtensorMap tmA, tmA2, tmGi, tmOp;
     {   // hbf [2(T+2)][B][Hp] bf16 seen as [slab][K block][row][64 columns]: box = 64 columns x rows of a chain x 4 K blocks,
         // 128-byte swizzle; rows >= B and K blocks >= Hp/64 are zero-filled.  The columns H..Hp of the last K block are inside
         // the tensor: they are zeroed once here (the weights' K padding is zero too, but 0 x NaN is NaN).
@@ -530,7 +468,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         uint32_t bx[4] = {64, (uint32_t)kR3Rows, (uint32_t)kR3Chunk, 1};
         int rc = make_tmap_bf16(&tmA, prm.hbf, 4, d, s, bx);
         if (rc) return rc;
-        bx[2] = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;      // box of the last chunk
+        bx[2] = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;      // box of the first chunk
         rc = make_tmap_bf16(&tmA2, prm.hbf, 4, d, s, bx);
         if (rc) return rc;
         rc = rnn3_zero_pad_cols(prm.hbf, (size_t)2 * (prm.T + 2) * B, prm.Hp, prm.H, prm.Hp - prm.H, stream);
@@ -555,33 +493,19 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return ASRB_ERR_TENSORMAP;
     }
-    auto kern = rnn_rec3_kernel<CELL, NCH, CS>;
+    auto kern = rnn_rec3_kernel<CELL>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {   // the step barrier spins: refuse the launch when the device cannot hold the whole grid at once
         int dev = 0, sms = 0, per_sm = 0;
         ASRB_CUDA_OK(cudaGetDevice(&dev));
         ASRB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         ASRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRnnThreads, smem));
-        if (2 * Pk > sms * per_sm) return ASRB_ERR_UNSUPPORTED;
+        if (2 * pl.P > sms * per_sm) return ASRB_ERR_UNSUPPORTED;
     }
-    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * kR3Chains * kR3CounterStride * sizeof(uint32_t), stream));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * Pk);
-    cfg.blockDim = dim3(kRnnThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attrs[1];
-    attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-    cfg.attrs = attrs;
-    cfg.numAttrs = CS > 1 ? 1 : 0;
-    if (CS > 1) {
-        int nclusters = 0;
-        ASRB_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
-        if (2 * Pk > CS * nclusters) return ASRB_ERR_UNSUPPORTED;
-    }
+    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * NCH * kR3CounterStride * sizeof(uint32_t), stream));
     prm.dbg = g_rnn_dbg;
-    ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmGi, tmH, tmC, tmSaved, tmOut, tmOp, prm));
+    kern<<<dim3(2 * pl.P), dim3(kRnnThreads), smem, stream>>>(tmA, tmA2, tmGi, tmOp, prm);
+    ASRB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -1083,27 +1007,11 @@ int rnn3_backward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack
 }
 
 int rnn3_forward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {
-    // Two chains of 32 rows.  Four chains of 16 (asrb_debug_rnn_dbg bit 512) measure the same: what a chain waits for is
-    // shared -- the release's MEMBAR covers every store the SM has in flight, and the chains' copies share the TMA / L2
-    // bandwidth -- and starting the chains staggered (0.25 .. 6 k cycles apart) changes nothing either: they couple.
-    // TMA multicast of the copies over CTA pairs (bit 8192) is built and measured SLOWER (8.5 k against 8.0 k cycles per
-    // step): the copies are not bound by L2 read bandwidth, and a CTA then waits for the slower of two issuers; off.
-    const bool mc = (pl.P % 2 == 0) && (g_rnn_dbg & 8192);
-    if (g_rnn_dbg & 16384) {     // experiment: clusters of 8 (slice count padded), multicast over all 8
-        cudaFuncSetAttribute(rnn_rec3_kernel<ASRB_RNN_GRU, 2, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
-        if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 2, 8>(pl, prm, wpack, stream);
-        return rnn3_launch<ASRB_RNN_LSTM, 2, 8>(pl, prm, wpack, stream);
-    }
-    if (g_rnn_dbg & 512) {
-        if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 4, 1>(pl, prm, wpack, stream);
-        return rnn3_launch<ASRB_RNN_LSTM, 4, 1>(pl, prm, wpack, stream);
-    }
-    if (mc) {
-        if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 2, 2>(pl, prm, wpack, stream);
-        return rnn3_launch<ASRB_RNN_LSTM, 2, 2>(pl, prm, wpack, stream);
-    }
-    if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU, 2, 1>(pl, prm, wpack, stream);
-    return rnn3_launch<ASRB_RNN_LSTM, 2, 1>(pl, prm, wpack, stream);
+    // Two chains of 32 rows.  Measured and dropped: four chains of 16; TMA multicast of the copies over
+    // CTA pairs and clusters of 8 (the copies are not bound by L2 read bandwidth); h / c / saved activations staged through
+    // shared memory and TMA stores, with the direction sum as a TMA reduce-add (more L2 time than the separate sum kernel).
+    if (cell == ASRB_RNN_GRU) return rnn3_launch<ASRB_RNN_GRU>(pl, prm, wpack, stream);
+    return rnn3_launch<ASRB_RNN_LSTM>(pl, prm, wpack, stream);
 }
 
 }  // namespace asrb
