@@ -755,19 +755,20 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     tc_fence_before_sync();
                     fence_proxy_async_smem();                  // generic stores -> the bulk copies' async-proxy reads
-                    if (staged && el == 0) bulk_wait_group_read<0>();   // the previous step's TMA stores have read their tiles
-                    named_bar_sync(4 + chain, kEpiThreads);
-                    if (el == 0) {
-                        if (chain == 0) ASRB_TRACE(6, s);
-#pragma unroll
-                        for (int q = 1; q < KS; ++q) {
-                            const uint32_t peer = (crank + q) % KS;
-                            // lands in slot [par][source = our rank] of the peer's receive buffer of this chain
-                            dsmem_bulk_copy(map_to_cta(xr + ((size_t)par * KS + crank) * 16 * kR3XStride, peer),
-                                            xs + ((size_t)par * KS + peer) * 16 * kR3XStride, (uint32_t)kR3XBytes,
-                                            map_to_cta(&x_bar[par], peer));
+                    if ((uint32_t)quad != crank) {
+                        // the two warps of a quarter sync among themselves (64 threads) and send it: no wait for the other quarters
+                        constexpr int kQBar[2][4] = {{1, 2, 6, 7}, {10, 11, 14, 15}};
+                        named_bar_sync(kQBar[chain][quad], 64);
+                        if (half == 0 && lane == 0) {
+                            // lands in slot [par][source = our rank] of the owner's receive buffer of this chain
+                            dsmem_bulk_copy(map_to_cta(xr + ((size_t)par * KS + crank) * 16 * kR3XStride, (uint32_t)quad),
+                                            xs + ((size_t)par * KS + quad) * 16 * kR3XStride, (uint32_t)kR3XBytes,
+                                            map_to_cta(&x_bar[par], (uint32_t)quad));
                         }
                     }
+                    if (staged && el == 0) bulk_wait_group_read<0>();   // the previous step's TMA stores have read their tiles
+                    named_bar_sync(4 + chain, kEpiThreads);    // our own quarter is in `dt`
+                    if (el == 0 && chain == 0) ASRB_TRACE(6, s);
                     mbar_wait_cluster(&x_bar[par], xphase[par]);
                     xphase[par] ^= 1u;
 #pragma unroll
@@ -835,33 +836,23 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // with whole tiles, one TMA store + its completion + a relaxed increment instead of stores + a release (see the
                 // forward kernel: the release's MEMBAR waits for the other chain's TMA copies)
                 const bool tma_op = staged && !(p.dbg & 2);
-                if (!tma_op) {
+                uint32_t vu[kGates];                                   // (unit, unit+1) pairs of the input-side gate gradients
+#pragma unroll
+                for (int q = 0; q < kGates; ++q) vu[q] = pair_units(dg[q][0], dg[q][1]);
+                const uint32_t ve2 = (CELL == ASRB_RNN_GRU) ? pair_units(eg2[0], eg2[1]) : vu[2];   // gate 2 of the hidden side
+                const int rl_u = rl0 + 8 * cu;                                  // our row of the unit pairs
+                if (tma_op) {
+                    // phase A, on the chain's critical path: only the operand tile ([gate][32 rows][16 units]; LSTM: it IS the
+                    // dgi tile).  The other output tiles are filled after the hand-over, in the shadow of its latency.
+                    uint32_t* s_op = reinterpret_cast<uint32_t*>(st_op);
+#pragma unroll
+                    for (int q = 0; q < kGates; ++q) s_op[(q * (kR3StageBytes / 2) + rl_u * NJ + (ju & ~1)) / 2] = (q == 2) ? ve2 : vu[q];
+                    fence_proxy_async_smem();                  // generic stores -> the TMA store's async-proxy reads
+                } else {
                     uint32_t* o = reinterpret_cast<uint32_t*>(p.dghbf + (((size_t)dir * T + t) * B + row[cu]) * p.Gp + unit2);
 #pragma unroll
-                    for (int q = 0; q < kGates; ++q) {
-                        const uint32_t v = (q == 2) ? pair_units(eg2[0], eg2[1]) : pair_units(dg[q][0], dg[q][1]);
-                        if (cellok[cu]) o[(size_t)q * H / 2] = v;
-                    }
-                }
-                if (staged) {
-                    if (s == 0 && el == 0) bulk_wait_group_read<0>();
-                    const int rl_u = rl0 + 8 * cu;                                  // our row of the unit pairs
-                    const int rl_r = ev_r ? rl0 : rl0 - 1 + 8;                      // first row of our row pair
-                    uint32_t* s_dgi = reinterpret_cast<uint32_t*>(st_dgi);
-                    uint32_t* s_gT = reinterpret_cast<uint32_t*>(st_gT);
-                    uint32_t* s_hT = reinterpret_cast<uint32_t*>(st_hT);
-#pragma unroll
-                    for (int q = 0; q < kGates; ++q) {
-                        const uint32_t vu = pair_units(dg[q][0], dg[q][1]);
-                        s_dgi[(q * (kR3StageBytes / 2) + rl_u * NJ + (ju & ~1)) / 2] = vu;
-                        if constexpr (CELL == ASRB_RNN_GRU)
-                            if (tma_op) reinterpret_cast<uint32_t*>(st_op)[(q * (kR3StageBytes / 2) + rl_u * NJ + (ju & ~1)) / 2] =
-                                (q == 2) ? pair_units(eg2[0], eg2[1]) : vu;
-                        const uint32_t vt = pair_rows(dg[q][0], dg[q][1]);
-                        s_gT[(q * (kR3StageBytes / 2) + ju * kRows + rl_r) / 2] = vt;
-                        if (p.dghT) s_hT[(q * (kR3StageBytes / 2) + ju * kRows + rl_r) / 2] = (q == 2) ? pair_rows(eg2[0], eg2[1]) : vt;
-                    }
-                    fence_proxy_async_smem();                  // generic stores -> the TMA stores' async-proxy reads
+                    for (int q = 0; q < kGates; ++q)
+                        if (cellok[cu]) o[(size_t)q * H / 2] = (q == 2) ? ve2 : vu[q];
                 }
                 if (el == 0 && chain == 0) ASRB_TRACE(7, s);
                 named_bar_sync(8 + chain, kEpiThreads);
@@ -876,7 +867,23 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         red_release_add_u32(counter, 1u);
                     }
                     if (chain == 0) ASRB_TRACE(10, s);
-                    if (staged) {
+                }
+                if (staged) {
+                    // phase B: the tiles only later kernels read
+                    const int rl_r = ev_r ? rl0 : rl0 - 1 + 8;                      // first row of our row pair
+                    uint32_t* s_dgi = reinterpret_cast<uint32_t*>(st_dgi);
+                    uint32_t* s_gT = reinterpret_cast<uint32_t*>(st_gT);
+                    uint32_t* s_hT = reinterpret_cast<uint32_t*>(st_hT);
+#pragma unroll
+                    for (int q = 0; q < kGates; ++q) {
+                        if (CELL == ASRB_RNN_GRU || !tma_op) s_dgi[(q * (kR3StageBytes / 2) + rl_u * NJ + (ju & ~1)) / 2] = vu[q];
+                        const uint32_t vt = pair_rows(dg[q][0], dg[q][1]);
+                        s_gT[(q * (kR3StageBytes / 2) + ju * kRows + rl_r) / 2] = vt;
+                        if (p.dghT) s_hT[(q * (kR3StageBytes / 2) + ju * kRows + rl_r) / 2] = (q == 2) ? pair_rows(eg2[0], eg2[1]) : vt;
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(12 + chain, kEpiThreads);
+                    if (el == 0) {
                         // one store per tensor: the tiles of all gates (the tensor maps walk the gates as an extra dimension)
                         tma_store_4d(&tmDgi, st_dgi, dir * G + j0, row0, 0, t);
                         tma_store_3d(&tmGT, st_gT, t * B + row0, dir * G + j0, 0);
