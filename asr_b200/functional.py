@@ -226,7 +226,9 @@ def _transpose_padded(a):
 import os as _os
 
 WGRAD_OVERLAP = _os.environ.get("ASRB_WGRAD_OVERLAP", "1") != "0"
-WGRAD_CTAS = int(_os.environ.get("ASRB_WGRAD_CTAS", "44"))   # the backward recurrence holds 104 of the 148 SMs (13 clusters of 4 per direction)
+WGRAD_CTAS = int(_os.environ.get("ASRB_WGRAD_CTAS", "64"))   # the backward recurrence holds 104 of the 148 SMs (13 clusters of 4 per direction)
+# (end of round 2, recurrence at 1.8 ms per layer: cap 44 / 64 / 96 / 148 -> 34.1-34.3 / 33.6-33.9 / 34.4 / 35.1 ms per step,
+# overlap off 35.5; lifting the cap for the stack's first layer, whose products run after the last recurrence: no change)
 # measured ms/step at configs[1], same box, two runs each: overlap off 48.5; on with cap 0 / 16 / 32 / 48:
 # 47.0 / 50.3 / 47.4 / 46.9.  The chain itself slows by ~8 % under the extra L2 traffic, which is why the gain is
 # 1.6 ms and not the 5 ms of work that moved off the critical path.
