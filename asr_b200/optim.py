@@ -16,6 +16,13 @@ import torch
 from . import ops
 
 
+def _bump_versions(params):
+    """The kernel writes the parameters behind autograd's back: bump their version counters like an in-place op would, so
+    that anything keyed on `_version` (functional._cached: packed / concatenated weights) sees the update."""
+    for p in params:
+        torch.autograd.graph.increment_version(p)
+
+
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, bucket=None):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
@@ -70,6 +77,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 self.state[p]["step"] = st["step"]
             ops.adamw_step(self.bucket.flat_params, self.bucket.flat, st["exp_avg"], st["exp_avg_sq"], g["lr"], g["betas"][0],
                            g["betas"][1], g["eps"], g["weight_decay"], st["step"], inv_scale)
+            _bump_versions(self.bucket.params)
             return loss
         for g in self.param_groups:
             for p in g["params"]:
@@ -86,4 +94,5 @@ class FusedAdamW(torch.optim.Optimizer):
                     raise ValueError("FusedAdamW needs contiguous parameters and gradients")
                 ops.adamw_step(p, p.grad, st["exp_avg"], st["exp_avg_sq"], g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                                g["weight_decay"], st["step"], inv_scale)
+                _bump_versions((p,))
         return loss

@@ -338,3 +338,41 @@ def test_amp_branch_of_the_training_loop(tmp_path, golden, name):
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) <= 1e-3 * abs(a), (losses[False], losses[True])
     assert abs(losses[True][0] - g["loss"].item()) <= 1e-4 * abs(g["loss"].item())
+
+
+def test_weight_cache_does_not_change_training(tmp_path, golden, monkeypatch):
+    """functional._cached (packed / concatenated weights reused while their parameters are unchanged): four optimizer
+    steps with FusedAdamW -- whose kernel writes the parameters behind autograd's back -- give the same losses with the
+    cache on and off, and a repeated forward without an update launches fewer kernels than one that rebuilds the packs."""
+    from asr_b200 import functional as F_
+    from asr_b200 import ops
+    from asr_b200.optim import FusedAdamW
+    from asr_b200.trainers import CTCLoss, DeepSpeechStep
+
+    g = golden("gru_small")
+    batch = synth_batch(g["seed"], g["B"], g["T"], g["U"], g["C"], g["lengths"])
+    runs = {}
+    for cache in (True, False):
+        monkeypatch.setattr(F_, "WEIGHT_CACHE", cache)
+        model, _ = build_model(tmp_path, g)
+        model.train()
+        step = DeepSpeechStep(model, CTCLoss(), FusedAdamW(model.parameters(), lr=1e-3), DEV)
+        runs[cache] = [step(batch)[1] for _ in range(4)]
+    # (not bit-identical from the third step on: the conv weight gradients are sums of fp32 atomics, so two runs of the same
+    # configuration already differ in the last digits; a stale pack would repeat the previous step's loss)
+    for a, b in zip(runs[True], runs[False]):
+        assert abs(a - b) <= 1e-4 * abs(b), runs
+    assert runs[True][-1] < 0.6 * runs[True][0]
+    # unchanged parameters: the second forward builds nothing
+    monkeypatch.setattr(F_, "WEIGHT_CACHE", True)
+    model.eval()
+    x, sizes = batch[0].to(DEV), (batch[2] * g["T"]).int()
+    with torch.no_grad():
+        model.forward(x, sizes)
+        n0 = ops.LAUNCHES
+        model.forward(x, sizes)
+        n1 = ops.LAUNCHES
+        monkeypatch.setattr(F_, "WEIGHT_CACHE", False)
+        model.forward(x, sizes)
+        n2 = ops.LAUNCHES
+    assert (n1 - n0) < (n2 - n1)

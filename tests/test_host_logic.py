@@ -558,3 +558,48 @@ def test_fused_adamw_flat_state_survives_a_checkpoint(monkeypatch):
     for a, c, r in zip(ps_a, ps_c, ref_p):
         assert torch.allclose(a, c, rtol=0, atol=1e-8)
         assert torch.allclose(a, r, atol=1e-7)
+
+
+def test_weight_cache_is_keyed_on_version_and_storage(monkeypatch):
+    """functional._cached: packed / concatenated weights are rebuilt after ANY in-place update of a source tensor (what an
+    optimizer step does), after the storage moved (FlatGradBucket(flatten_params=True)), and kept otherwise."""
+    from asr_b200 import functional as F_
+
+    monkeypatch.setattr(F_, "WEIGHT_CACHE", True)
+    w = torch.nn.Parameter(torch.randn(6, 4))
+    w_r = torch.nn.Parameter(torch.randn(6, 4))
+    calls = []
+
+    def build():
+        calls.append(1)
+        return torch.cat([w.detach(), w_r.detach()])
+
+    a = F_._cached((w, w_r), "cat", build)
+    b = F_._cached((w, w_r), "cat", build)
+    assert a is b and len(calls) == 1
+    with torch.no_grad():
+        w_r.add_(1.0)                                   # in-place update of the SECOND source: still a miss
+    c = F_._cached((w, w_r), "cat", build)
+    assert len(calls) == 2 and torch.equal(c, torch.cat([w.detach(), w_r.detach()]))
+    torch.autograd.graph.increment_version(w)           # what FusedAdamW does after its kernel wrote the parameters
+    F_._cached((w, w_r), "cat", build)
+    assert len(calls) == 3
+    w.data = w.data.clone()                             # storage moved
+    F_._cached((w, w_r), "cat", build)
+    assert len(calls) == 4
+    F_._cached((w, w_r), "other kind", build)           # kinds do not share entries
+    F_._cached((w, w_r), "cat", build)
+    assert len(calls) == 5
+    monkeypatch.setattr(F_, "WEIGHT_CACHE", False)
+    F_._cached((w, w_r), "cat", build)
+    assert len(calls) == 6
+
+
+def test_fused_adamw_bumps_the_version_counters(monkeypatch):
+    """the optimizer kernel writes the parameters through raw pointers: the version counters must move all the same."""
+    from asr_b200 import optim
+
+    p = torch.nn.Parameter(torch.randn(5))
+    v0 = p._version
+    optim._bump_versions((p,))
+    assert p._version == v0 + 1
