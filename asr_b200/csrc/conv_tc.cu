@@ -217,6 +217,264 @@ conv_row_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// NR output rows per work item
+// ------------------------------------------------------------------------------------------------
+// conv_row_tc_kernel above is bound by shared-memory operand reads: every MMA re-reads a 16 KB strip tile for N = 32
+// output channels (20 KB per 64 cycles of tensor work against 128 B/clk).  A source row feeds up to KH/SH output rows, through
+// different kernel rows: rows d0 + j * rowstep (j < NR) see source row hs through kernel rows kh_j = kh_a -/+ j * SH.  Stacking
+// their tap matrices along N gives one MMA of N = 32 * NR per (strip, tap, K step): the strip tile is read once for NR output
+// rows (NR = 4: 16 KB + 16 KB per 64-cycle MMA -- tensor pipe and SMEM port balanced).  The stacked tap matrices
+// ([entry e = kh_a - kh_lo][kw][32 NR rows][32], zero blocks where kh_j falls outside the kernel) come from
+// asrb_conv32_pack_rows.  Two rings: strips (2 pixel tiles per stage) and tap tiles (16 KB each).
+struct ConvRowsParams {
+    int B, Hs, Ws, Ho, Wo, KH, KW, SH, PH, PW, mode;   // mode 0 = forward, 1 = data gradient
+    const float* bias;
+    const int* lengths;
+    float* out;                                        // NCHW [B][32][Ho][Wo]
+    int num_items, tpairs, groups, n_e;
+};
+
+// output row 0 of group g, and the source row that pack entry e holds for it (or -1)
+__device__ __forceinline__ int conv_rows_d0(const ConvRowsParams& p, int g, int NR) {
+    if (p.mode == 0) return g * NR;
+    return (g / p.SH) * p.SH * NR + g % p.SH;
+}
+__device__ __forceinline__ int conv_rows_src(const ConvRowsParams& p, int d0, int e, int NR) {
+    if (p.mode == 0) {
+        const int hs = d0 * p.SH + e - p.PH;                       // kh_a = e
+        return (hs >= 0 && hs < p.Hs) ? hs : -1;
+    }
+    const int kh_a = e - p.SH * (NR - 1);
+    const int num = d0 + p.PH - kh_a;
+    if (num < 0 || num % p.SH != 0) return -1;
+    const int hs = num / p.SH;
+    return hs < p.Hs ? hs : -1;
+}
+
+template <int NR>
+__global__ void __launch_bounds__(kCtThreads, 1)
+conv_rows_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmW, const ConvRowsParams p) {
+    constexpr int N = 32 * NR;
+    constexpr int kWTile = N * 128;                    // one tap: [N rows][32 tf32]
+    constexpr int kSStages = 2;                        // strip ring (2 pixel tiles each)
+    constexpr int kWStages = (NR == 4) ? 6 : 10;       // tap-tile ring
+    constexpr int kTmemCols = 4 * N;                   // 2 accumulator buffers x 2 pixel tiles x N columns
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_strip = smem;                                        // [kSStages][2][kCtStrip]
+    uint8_t* s_w = smem + kSStages * 2 * kCtStrip;                  // [kWStages][kWTile]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kWStages * kWTile);
+    uint64_t* sfull = bars;
+    uint64_t* sempty = sfull + kSStages;
+    uint64_t* wfull = sempty + kSStages;
+    uint64_t* wempty = wfull + kWStages;
+    uint64_t* tfull_bar = wempty + kWStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmS);
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < kSStages; ++i) { mbar_init(&sfull[i], 1); mbar_init(&sempty[i], 1); }
+        for (int i = 0; i < kWStages; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t strip_bytes = (uint32_t)(128 + p.KW - 1) * 128u;
+
+    auto decode = [&](int item, int& b, int& d0, int& t0, int& n_mt) {
+        const int tp = item % p.tpairs;
+        const int r = item / p.tpairs;
+        d0 = conv_rows_d0(p, r % p.groups, NR);
+        b = r / p.groups;
+        t0 = tp * 256;
+        n_mt = (t0 + 128 < p.Wo) ? 2 : 1;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer: one elected thread =====================
+        if (elect_one()) {
+            int ss = 0, ws = 0;
+            uint32_t sph = 0, wph = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                int b, d0, t0, n_mt;
+                decode(item, b, d0, t0, n_mt);
+                if (d0 >= p.Ho) continue;
+                // first source column of the strip: forward x col = t + kw - PW ; dgrad dy col = t + PW - kw
+                const int col0 = p.mode == 0 ? t0 - p.PW : t0 + p.PW - (p.KW - 1);
+                for (int e = 0; e < p.n_e; ++e) {
+                    const int hs = conv_rows_src(p, d0, e, NR);
+                    if (hs < 0) continue;
+                    mbar_wait(&sempty[ss], sph ^ 1);
+                    mbar_arrive_expect_tx(&sfull[ss], n_mt * strip_bytes);
+                    for (int mt = 0; mt < n_mt; ++mt)
+                        tma_load_4d(s_strip + (ss * 2 + mt) * kCtStrip, &tmS, &sfull[ss], 0, col0 + mt * 128, hs, b);
+                    if (++ss == kSStages) { ss = 0; sph ^= 1; }
+                    for (int kw = 0; kw < p.KW; ++kw) {
+                        mbar_wait(&wempty[ws], wph ^ 1);
+                        mbar_arrive_expect_tx(&wfull[ws], (uint32_t)kWTile);
+                        tma_load_2d(s_w + ws * kWTile, &tmW, &wfull[ws], 0, (e * p.KW + kw) * N);
+                        if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer: one elected thread =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc(kFmtTF32, 128, N);
+            int ss = 0, ws = 0, acc = 0;
+            uint32_t sph = 0, wph = 0, acc_phase = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                int b, d0, t0, n_mt;
+                decode(item, b, d0, t0, n_mt);
+                if (d0 >= p.Ho) continue;
+                int nstrips = 0;
+                for (int e = 0; e < p.n_e; ++e) nstrips += conv_rows_src(p, d0, e, NR) >= 0;
+                if (nstrips == 0) continue;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * 2 * N;
+                int done = 0;
+                for (int e = 0; e < p.n_e; ++e) {
+                    if (conv_rows_src(p, d0, e, NR) < 0) continue;
+                    mbar_wait(&sfull[ss], sph);
+                    const uint32_t a0 = smem_u32(s_strip + (ss * 2) * kCtStrip);
+                    for (int kw = 0; kw < p.KW; ++kw) {
+                        const int shift = p.mode == 0 ? kw : p.KW - 1 - kw;
+                        mbar_wait(&wfull[ws], wph);
+                        tc_fence_after_sync();
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(s_w + ws * kWTile));
+                        for (int mt = 0; mt < n_mt; ++mt) {
+                            const uint64_t adesc = umma_desc_sw128(a0 + mt * kCtStrip + shift * 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_tf32(d_tmem + mt * N, adesc + 2 * k, bdesc + 2 * k, idesc, (done | kw | k) != 0);
+                        }
+                        umma_commit(&wempty[ws]);
+                        if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                    }
+                    umma_commit(&sempty[ss]);
+                    if (++ss == kSStages) { ss = 0; sph ^= 1; }
+                    ++done;
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..5): thread = pixel, 32 channels of one output row at a time =====================
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int rowstep = p.mode == 0 ? 1 : p.SH;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            int b, d0, t0, n_mt;
+            decode(item, b, d0, t0, n_mt);
+            if (d0 >= p.Ho) continue;
+            int nstrips = 0;
+            for (int e = 0; e < p.n_e; ++e) nstrips += conv_rows_src(p, d0, e, NR) >= 0;
+            const bool have = nstrips > 0;
+            if (have) {
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after_sync();
+            }
+            const int len = (p.mode == 0 && p.lengths) ? p.lengths[b] : p.Wo;
+            for (int mt = 0; mt < n_mt; ++mt) {
+                const int t = t0 + mt * 128 + quad * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const int drow = d0 + j * rowstep;
+                    if (drow >= p.Ho) break;                       // (warp-uniform)
+                    float v[32];
+                    if (have) {
+                        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * 2 * N + mt * N + j * 32, v);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = 0.f;
+                    }
+                    if (t < p.Wo) {
+                        float* o = p.out + (((size_t)b * kCtC) * p.Ho + drow) * p.Wo + t;
+                        const size_t cstride = (size_t)p.Ho * p.Wo;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            float r = v[c];
+                            if (p.mode == 0) r = t < len ? r + (p.bias ? __ldg(p.bias + c) : 0.f) : 0.f;
+                            o[c * cstride] = r;
+                        }
+                    }
+                }
+            }
+            if (have) {
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// stacked tap matrices: out[e][kw][j * 32 + n][k] = pack[(kh_j * KW + kw)][n][k] with kh_j = e - j * SH (forward) or
+// e - SH (NR - 1) + j * SH (data gradient), zero where kh_j is outside [0, KH)
+__global__ void conv_pack_rows_kernel(const float* __restrict__ pack, float* __restrict__ out, int KH, int KW, int SH, int NR, int mode) {
+    const int n_e = KH + SH * (NR - 1);
+    const size_t total = (size_t)n_e * KW * NR * 1024;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % 32), n = (int)((i / 32) % 32), j = (int)((i / 1024) % NR);
+        const int kw = (int)((i / ((size_t)1024 * NR)) % KW), e = (int)(i / ((size_t)1024 * NR * KW));
+        const int kh = mode == 0 ? e - j * SH : e - SH * (NR - 1) + j * SH;
+        out[i] = (kh >= 0 && kh < KH) ? pack[((size_t)(kh * KW + kw) * 32 + n) * 32 + k] : 0.f;
+    }
+}
+
+template <int NR>
+static int conv_rows_launch(const float* src_nhwc, const float* wpack_rows, ConvRowsParams& p, asrb_stream_t stream) {
+    constexpr int N = 32 * NR;
+    constexpr int kWStages = (NR == 4) ? 6 : 10;
+    CUtensorMap tmS, tmW;
+    p.n_e = p.KH + p.SH * (NR - 1);
+    {
+        uint64_t d[4] = {32, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
+        uint64_t s[3] = {128, (uint64_t)p.Ws * 128, (uint64_t)p.Hs * p.Ws * 128};
+        uint32_t bx[4] = {32, (uint32_t)(128 + p.KW - 1), 1, 1};
+        int rc = make_tmap_f32(&tmS, src_nhwc, 4, d, s, bx);
+        if (rc) return rc;
+    }
+    {
+        uint64_t d[2] = {32, (uint64_t)p.n_e * p.KW * N}, s[1] = {128};
+        uint32_t bx[2] = {32, (uint32_t)N};
+        int rc = make_tmap_f32(&tmW, wpack_rows, 2, d, s, bx);
+        if (rc) return rc;
+    }
+    p.tpairs = ceil_div(p.Wo, 256);
+    p.groups = p.mode == 0 ? ceil_div(p.Ho, NR) : ceil_div(p.Ho, p.SH * NR) * p.SH;
+    p.num_items = p.B * p.groups * p.tpairs;
+    const size_t smem = (size_t)2 * 2 * kCtStrip + (size_t)kWStages * N * 128 + 1024 + 512;
+    auto kern = conv_rows_tc_kernel<NR>;
+    ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = p.num_items < kNumSMs ? p.num_items : kNumSMs;
+    kern<<<grid, kCtThreads, smem, stream>>>(tmS, tmW, p);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------------
 struct ConvWgradParams {
@@ -463,6 +721,34 @@ int asrb_conv32_bwd_data(const float* dy_nhwc, const float* pack_dgrad, float* d
     ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
     ConvRowParams p = {B, Hout, Wout, Hin, Win, KH, KW, SH, PH, PW, 1, nullptr, nullptr, dx, 0, 0};
     return conv_row_launch(dy_nhwc, pack_dgrad, p, stream);
+}
+
+/* Row-grouped variants (NR = 2 or 4 output rows per work item share every source strip: see conv_rows_tc_kernel).
+ * pack_rows: [KH + SH (NR-1)][KW][32 NR][32] floats, built by asrb_conv32_pack_rows from the plain pack of the same mode. */
+int asrb_conv32_pack_rows(const float* pack, float* pack_rows, int KH, int KW, int SH, int NR, int mode, asrb_stream_t stream) {
+    ASRB_REQUIRE(pack && pack_rows && KH > 0 && KW > 0 && SH > 0 && (NR == 2 || NR == 4) && (mode == 0 || mode == 1), ASRB_ERR_BAD_ARG);
+    conv_pack_rows_kernel<<<kNumSMs, 256, 0, stream>>>(pack, pack_rows, KH, KW, SH, NR, mode);
+    ASRB_LAUNCH_OK();
+    return 0;
+}
+
+int asrb_conv32_fwd_rows(const float* x_nhwc, const float* pack_rows, const float* bias, const int32_t* lengths, float* y,
+                         int B, int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW, int NR,
+                         asrb_stream_t stream) {
+    ASRB_REQUIRE(x_nhwc && pack_rows && y && B > 0 && (NR == 2 || NR == 4), ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(asrb_conv32_supported(32, 32, KH, KW, SH, 1, PH, PW), ASRB_ERR_UNSUPPORTED);
+    ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
+    ConvRowsParams p = {B, Hin, Win, Hout, Wout, KH, KW, SH, PH, PW, 0, bias, lengths, y, 0, 0, 0, 0};
+    return NR == 4 ? conv_rows_launch<4>(x_nhwc, pack_rows, p, stream) : conv_rows_launch<2>(x_nhwc, pack_rows, p, stream);
+}
+
+int asrb_conv32_bwd_data_rows(const float* dy_nhwc, const float* pack_rows, float* dx, int B, int Hin, int Win, int Hout,
+                              int Wout, int KH, int KW, int SH, int PH, int PW, int NR, asrb_stream_t stream) {
+    ASRB_REQUIRE(dy_nhwc && pack_rows && dx && B > 0 && (NR == 2 || NR == 4), ASRB_ERR_BAD_ARG);
+    ASRB_REQUIRE(asrb_conv32_supported(32, 32, KH, KW, SH, 1, PH, PW), ASRB_ERR_UNSUPPORTED);
+    ASRB_REQUIRE(Hout == (Hin + 2 * PH - KH) / SH + 1 && Wout == Win + 2 * PW - KW + 1, ASRB_ERR_BAD_ARG);
+    ConvRowsParams p = {B, Hout, Wout, Hin, Win, KH, KW, SH, PH, PW, 1, nullptr, nullptr, dx, 0, 0, 0, 0};
+    return NR == 4 ? conv_rows_launch<4>(dy_nhwc, pack_rows, p, stream) : conv_rows_launch<2>(dy_nhwc, pack_rows, p, stream);
 }
 
 static int g_conv_wgrad_bf16 = 1;

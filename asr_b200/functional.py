@@ -64,8 +64,14 @@ class Conv2dMask(Function):
             1 if ops.conv1_supported(x.shape, weight.shape, stride, padding) else 0)
         ctx.conf = (stride, padding, bias is not None, tc)
         if tc == 2:   # implicit GEMM over an NHWC source
-            pack_f = _cached((weight,), "conv32_fwd", lambda: ops.conv32_pack_weights(weight, fwd=True, dgrad=False)[0])
-            return ops.conv32_fwd(ops.nchw_to_nhwc(x), pack_f, bias, lengths_dev, weight.shape, stride, padding)
+            nr = ops.CONV_ROWS if ops.CONV_ROWS in (2, 4) else 0
+
+            def pack_fwd():
+                pf = ops.conv32_pack_weights(weight, fwd=True, dgrad=False)[0]
+                return ops.conv32_pack_rows(pf, weight.shape, stride[0], 0, nr) if nr else pf
+
+            pack_f = _cached((weight,), f"conv32_fwd_{nr}", pack_fwd)
+            return ops.conv32_fwd(ops.nchw_to_nhwc(x), pack_f, bias, lengths_dev, weight.shape, stride, padding, rows=nr)
         if tc == 1:   # polyphase implicit GEMM
             return ops.conv1_fwd(x, weight, bias, lengths_dev, stride, padding)
         return ops.conv2d_mask_fwd(x, weight, bias, lengths_dev, stride, padding)
@@ -82,8 +88,14 @@ class Conv2dMask(Function):
             dym = ops.mask_time(dy, lengths_dev)
             if ctx.needs_input_grad[0]:
                 if tc == 2:
-                    pack_d = _cached((weight,), "conv32_dgrad", lambda: ops.conv32_pack_weights(weight, fwd=False, dgrad=True)[1])
-                    dx = ops.conv32_bwd_data(ops.nchw_to_nhwc(dym), pack_d, x.shape, weight.shape, stride, padding)
+                    nr = ops.CONV_ROWS if ops.CONV_ROWS in (2, 4) else 0
+
+                    def pack_dgrad():
+                        pd = ops.conv32_pack_weights(weight, fwd=False, dgrad=True)[1]
+                        return ops.conv32_pack_rows(pd, weight.shape, stride[0], 1, nr) if nr else pd
+
+                    pack_d = _cached((weight,), f"conv32_dgrad_{nr}", pack_dgrad)
+                    dx = ops.conv32_bwd_data(ops.nchw_to_nhwc(dym), pack_d, x.shape, weight.shape, stride, padding, rows=nr)
                 else:     # a gradient w.r.t. the spectrogram is never needed on the training path: generic kernel
                     dx = ops.conv2d_mask_bwd_data(dym, weight, None, x.shape, stride, padding)
             if ctx.needs_input_grad[1]:

@@ -8,6 +8,7 @@ stream.  `LAUNCHES` counts kernel-launching calls (bench.py reports it as `gpu_l
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -282,25 +283,48 @@ def conv32_pack_weights(w, fwd=True, dgrad=True):
     return pf, pd
 
 
-def conv32_fwd(x_nhwc, pack_fwd, bias, lengths, w_shape, stride, padding):
+# output rows per work item of the 32->32 conv's forward / data-gradient kernels (1 = the one-row kernel, 2, 4)
+CONV_ROWS = int(os.environ.get("ASRB_CONV_ROWS", "4"))
+
+
+def conv32_pack_rows(pack, w_shape, stride_h, mode, rows=None):
+    """plain pack of conv32_pack_weights (mode 0: forward, 1: data gradient) -> tap matrices stacked for `rows` output rows"""
+    rows = CONV_ROWS if rows is None else rows
+    _chk(pack)
+    _, _, KH, KW = w_shape
+    out = torch.empty((KH + stride_h * (rows - 1)) * KW * rows * 1024, device=pack.device, dtype=torch.float32)
+    _call("asrb_conv32_pack_rows", _p(pack), _p(out), KH, KW, stride_h, rows, mode)
+    return out
+
+
+def conv32_fwd(x_nhwc, pack_fwd, bias, lengths, w_shape, stride, padding, rows=0):
+    """rows = 0: pack_fwd is the plain pack; rows = 2 / 4: pack_fwd comes from conv32_pack_rows(..., mode 0, rows)"""
     _chk(x_nhwc, pack_fwd, bias)
     B, Hin, Win, _ = x_nhwc.shape
     _, _, KH, KW = w_shape
     Hout, Wout = conv_out_size(Hin, KH, stride[0], padding[0]), conv_out_size(Win, KW, 1, padding[1])
     y = torch.empty(B, 32, Hout, Wout, device=x_nhwc.device, dtype=torch.float32)
-    _call("asrb_conv32_fwd", _p(x_nhwc), _p(pack_fwd), _p(bias), _p(lengths), _p(y), B, Hin, Win, Hout, Wout, KH, KW,
-          stride[0], padding[0], padding[1])
+    if rows > 1:
+        _call("asrb_conv32_fwd_rows", _p(x_nhwc), _p(pack_fwd), _p(bias), _p(lengths), _p(y), B, Hin, Win, Hout, Wout, KH, KW,
+              stride[0], padding[0], padding[1], rows)
+    else:
+        _call("asrb_conv32_fwd", _p(x_nhwc), _p(pack_fwd), _p(bias), _p(lengths), _p(y), B, Hin, Win, Hout, Wout, KH, KW,
+              stride[0], padding[0], padding[1])
     return y
 
 
-def conv32_bwd_data(dy_nhwc, pack_dgrad, x_shape, w_shape, stride, padding):
+def conv32_bwd_data(dy_nhwc, pack_dgrad, x_shape, w_shape, stride, padding, rows=0):
     _chk(dy_nhwc, pack_dgrad)
     B, _, Hin, Win = x_shape
     _, Hout, Wout, _ = dy_nhwc.shape
     _, _, KH, KW = w_shape
     dx = torch.empty(x_shape, device=dy_nhwc.device, dtype=torch.float32)
-    _call("asrb_conv32_bwd_data", _p(dy_nhwc), _p(pack_dgrad), _p(dx), B, Hin, Win, Hout, Wout, KH, KW, stride[0],
-          padding[0], padding[1])
+    if rows > 1:
+        _call("asrb_conv32_bwd_data_rows", _p(dy_nhwc), _p(pack_dgrad), _p(dx), B, Hin, Win, Hout, Wout, KH, KW, stride[0],
+              padding[0], padding[1], rows)
+    else:
+        _call("asrb_conv32_bwd_data", _p(dy_nhwc), _p(pack_dgrad), _p(dx), B, Hin, Win, Hout, Wout, KH, KW, stride[0],
+              padding[0], padding[1])
     return dx
 
 

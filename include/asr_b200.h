@@ -170,6 +170,16 @@ int asrb_conv32_fwd(const float* x_nhwc, const float* pack_fwd, const float* bia
                     asrb_stream_t stream);
 int asrb_conv32_bwd_data(const float* dy_nhwc, const float* pack_dgrad, float* dx, int B, int Hin, int Win, int Hout,
                          int Wout, int KH, int KW, int SH, int PH, int PW, asrb_stream_t stream);
+/* Row-grouped variants: NR = 2 or 4 output rows (forward: consecutive; data gradient: SH apart) share every source strip
+ * in one work item, their tap matrices stacked along N = 32 NR, so the strip tile is read from shared memory once for NR
+ * rows.  pack_rows holds [KH + SH (NR-1)][KW][32 NR][32] floats, built from the plain pack of the same mode (0 forward,
+ * 1 data gradient). */
+int asrb_conv32_pack_rows(const float* pack, float* pack_rows, int KH, int KW, int SH, int NR, int mode, asrb_stream_t stream);
+int asrb_conv32_fwd_rows(const float* x_nhwc, const float* pack_rows, const float* bias, const int32_t* lengths, float* y,
+                         int B, int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW, int NR,
+                         asrb_stream_t stream);
+int asrb_conv32_bwd_data_rows(const float* dy_nhwc, const float* pack_rows, float* dx, int B, int Hin, int Win, int Hout,
+                              int Wout, int KH, int KW, int SH, int PH, int PW, int NR, asrb_stream_t stream);
 size_t asrb_conv32_bwd_weight_workspace_bytes(int B, int Hin, int Win, int Hout, int Wout);
 /* operands of the weight-gradient product: 1 (default) bf16 copies, 0 TF32 (then lddy % 4 == 0); v < 0 queries */
 int asrb_debug_conv_wgrad_bf16(int v);

@@ -111,11 +111,18 @@ def conv32_pack_weights(w, fwd=True, dgrad=True):
     return (w if fwd else None), (w if dgrad else None)
 
 
-def conv32_fwd(x_nhwc, pack_fwd, bias, lengths, w_shape, stride, padding):
+CONV_ROWS = 4
+
+
+def conv32_pack_rows(pack, w_shape, stride_h, mode, rows=None):
+    return pack
+
+
+def conv32_fwd(x_nhwc, pack_fwd, bias, lengths, w_shape, stride, padding, rows=0):
     return conv2d_mask_fwd(x_nhwc.permute(0, 3, 1, 2), pack_fwd, bias, lengths, stride, padding)
 
 
-def conv32_bwd_data(dy_nhwc, pack_dgrad, x_shape, w_shape, stride, padding):
+def conv32_bwd_data(dy_nhwc, pack_dgrad, x_shape, w_shape, stride, padding, rows=0):
     return torch.nn.grad.conv2d_input(x_shape, pack_dgrad, dy_nhwc.permute(0, 3, 1, 2), stride=stride, padding=padding)
 
 

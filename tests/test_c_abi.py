@@ -45,6 +45,12 @@ def test_error_contract_without_a_gpu():
         _lib.call("asrb_lookahead_bwd", None, None, None, None, None, None, 4, 2, 8, 0, 0, 0.0, 0.0, None)
     with pytest.raises(ValueError):
         _lib.call("asrb_adamw_step", None, None, None, None, 16, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None, None)
+    with pytest.raises(ValueError):           # row-grouped conv entry points: NULL pointers, rows per item other than 2 / 4
+        _lib.call("asrb_conv32_pack_rows", None, None, 21, 11, 2, 4, 0, None)
+    with pytest.raises(ValueError):
+        _lib.call("asrb_conv32_fwd_rows", None, None, None, None, None, 1, 81, 100, 41, 100, 21, 11, 2, 10, 5, 3, None)
+    with pytest.raises(ValueError):
+        _lib.call("asrb_conv32_bwd_data_rows", None, None, None, 1, 81, 100, 41, 100, 21, 11, 2, 10, 5, 4, None)
     assert _lib.query("asrb_gemm_cta_limit", -1) == 0 and _lib.query("asrb_debug_gemm_tma_store", -1) == 1
     assert _lib.query("asrb_debug_conv_wgrad_bf16", -1) == 1
     assert _lib.query("asrb_conv32_bwd_weight_workspace_bytes", 64, 81, 501, 41, 501) >= 8 * 64 * 32 * 81 * 504 * 2

@@ -167,6 +167,17 @@ def test_conv32_tensor_core_fwd_bwd(ops, c):
     dx = ops.conv32_bwd_data(ops.nchw_to_nhwc(dy.to(DEV)), pd, tuple(x.shape), tuple(w.shape), c["s"], c["p"])
     torch.cuda.synchronize()
     assert report("conv32 dgrad", dx, x.grad) <= 2e-3 * math.sqrt(K) * 0.05
+    # row-grouped kernels (2 / 4 output rows per work item share every source strip): same products, other summation order
+    for rows in (2, 4):
+        pfr = ops.conv32_pack_rows(pf, tuple(w.shape), c["s"][0], 0, rows)
+        pdr = ops.conv32_pack_rows(pd, tuple(w.shape), c["s"][0], 1, rows)
+        yr = ops.conv32_fwd(ops.nchw_to_nhwc(xd), pfr, b.detach().to(DEV), ld, tuple(w.shape), c["s"], c["p"], rows=rows)
+        dxr = ops.conv32_bwd_data(ops.nchw_to_nhwc(dy.to(DEV)), pdr, tuple(x.shape), tuple(w.shape), c["s"], c["p"], rows=rows)
+        torch.cuda.synchronize()
+        assert report(f"conv32 fwd rows={rows}", yr, y_ref.detach()) <= 2e-3 * math.sqrt(K) * 0.05
+        assert report(f"conv32 dgrad rows={rows}", dxr, x.grad) <= 2e-3 * math.sqrt(K) * 0.05
+        assert (yr - y).abs().max().item() <= 1e-5 * max(1.0, y.abs().max().item())
+        assert (dxr - dx).abs().max().item() <= 1e-5 * max(1.0, dx.abs().max().item())
     from asr_b200 import _lib
     npix = c["B"] * y_ref.shape[2] * y_ref.shape[3]
     try:
