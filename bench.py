@@ -590,6 +590,8 @@ def main():
                               "the bf16 GEMM launches of a step (gradient-only products): in-proj dgrad + wgrad, dW_hh"),
         "asrb_conv32_fwd": ("tensor", fl["conv2"], "conv2 forward"),
         "asrb_conv32_bwd_data": ("tensor", fl["conv2"], "conv2 input gradient"),
+        "asrb_conv32_fwd_rows": ("tensor", fl["conv2"], "conv2 forward, 4 output rows per work item (tf32 operands: half the bf16 peak quoted)"),
+        "asrb_conv32_bwd_data_rows": ("tensor", fl["conv2"], "conv2 input gradient, 4 output rows per work item (tf32 operands)"),
         "asrb_conv32_bwd_weight": ("tensor", fl["conv2"], "conv2 weight gradient"),
         "asrb_conv1_fwd": ("tensor", fl["conv1"], "conv1 forward"),
         "asrb_conv1_bwd_weight": ("tensor", fl["conv1"], "conv1 weight gradient"),
