@@ -609,17 +609,161 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
 }
 
+/* Weight gradient, one CTA per (kernel-row class, M tile, chunk of source rows).  conv_wgrad_tc_kernel above fixes kh per
+ * CTA, so every x row is fetched KH times (and each of its KW shifted copies once): 23 GB of L2 -> SM traffic per launch at
+ * configs[1], the L2 bandwidth cap.  Here a CTA walks the SOURCE rows: x row hi meets the gradient rows y = (hi + PH - kh) / SH
+ * of every kh of its residue class c = (hi + PH) mod SH -- kh = c + SH j, up to NKH = ceil(KH / SH) of them -- and those rows
+ * are consecutive in y: ONE TMA box [NKH rows of y][32 co][64 t] is the stacked B operand (N = 32 NKH <= 352, zero-filled
+ * outside the image), the x taps of an M tile (4 kernel columns x 32 ci) are read once per stage for all of them, and the
+ * accumulators of all NKH kernel rows stay in tensor memory (352 columns).  bf16 operands only. */
+struct ConvWgradClsParams {
+    int B, Hin, Win, Hout, Wout, KH, KW, SH, PH, PW;
+    int m_tiles, nkh, chunks;
+    float* dw;                                          // [32][32][KH][KW]
+};
+
+__global__ void __launch_bounds__(kCtThreads, 1)
+conv_wgrad_cls_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                      const ConvWgradClsParams p) {
+    constexpr int KT = 64, NQ = 8;
+    constexpr int kStages = 3;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int ntot = 32 * p.nkh;                           // stacked N
+    const int b_bytes = ntot * 128;
+    const int stage_bytes = 16384 + ((b_bytes + 1023) & ~1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tfull_bar = bars + 2 * kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+    constexpr int kTmemCols = 512;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // blockIdx.x = (class * m_tiles + mt) * chunks + chunk
+    const int chunk = blockIdx.x % p.chunks;
+    const int mt = (blockIdx.x / p.chunks) % p.m_tiles;
+    const int c = blockIdx.x / (p.chunks * p.m_tiles);
+    const int hi0 = (((c - p.PH) % p.SH) + p.SH) % p.SH;   // first source row of the class
+    const int nhi = hi0 < p.Hin ? (p.Hin - hi0 + p.SH - 1) / p.SH : 0;
+    const int nrows = p.B * nhi;
+    const int per = (nrows + p.chunks - 1) / p.chunks;
+    const int r0 = chunk * per, r1 = min(nrows, r0 + per);
+    const int n_kb = ceil_div(p.Wout, KT);
+    const int steps = max(0, r1 - r0) * n_kb;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmDy);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int r = r0; r < r1; ++r) {
+                const int b = r / nhi, hi = hi0 + (r % nhi) * p.SH;
+                const int ybase = (hi + p.PH - c) / p.SH;          // the gradient row that kh = c pairs with x row hi
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    uint8_t* st = smem + stage * stage_bytes;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(16384 + b_bytes));
+                    for (int jw = 0; jw < 4; ++jw) {              // kernel column 4 mt + jw (columns >= KW are never read back)
+                        const int off = 4 * mt + jw - p.PW;       // time shift; copy q holds x delayed by q samples
+                        const int q = (((-off) % NQ) + NQ) % NQ;  // so that the box start kb*KT + off + q is 16-byte aligned
+                        tma_load_5d(st + jw * kCtWTile, &tmX, &full_bar[stage], kb * KT + off + q, hi, 0, b, q);
+                    }
+                    // rows y = ybase - (nkh - 1) .. ybase, 32 co each: column block jj <-> kh = c + SH (nkh - 1 - jj)
+                    tma_load_4d(st + 16384, &tmDy, &full_bar[stage], kb * KT, 0, ybase - (p.nkh - 1), b);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one() && steps > 0) {
+            const int n1 = ntot > 256 ? 256 : ntot, n2 = ntot - n1;
+            const uint32_t idesc1 = umma_idesc(kFmtBF16, 128, n1), idesc2 = umma_idesc(kFmtBF16, 128, n2 > 0 ? n2 : 16);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int s = 0; s < steps; ++s) {
+                uint8_t* st = smem + stage * stage_bytes;
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after_sync();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(st));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(st + 16384));
+                const uint64_t bdesc2 = umma_desc_sw128(smem_u32(st + 16384 + 256 * 128));     // rows 256.. of the stacked tile
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc1, (s | k) != 0);
+                    if (n2 > 0) umma_f16(tmem_base + 256, adesc + 2 * k, bdesc2 + 2 * k, idesc2, (s | k) != 0);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull_bar);
+        }
+        __syncwarp();
+    } else {
+        const int quad = warp & 3;
+        if (steps > 0) {
+            mbar_wait(tfull_bar, 0);
+            tc_fence_after_sync();
+            const int kw = mt * 4 + quad, ci = lane;           // accumulator row = (kernel column, input channel)
+            for (int jj = 0; jj < p.nkh; ++jj) {
+                const int kh = c + p.SH * (p.nkh - 1 - jj);
+                float v[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + jj * 32, v);
+                tmem_ld_wait();
+                if (kw < p.KW && kh < p.KH) {
+#pragma unroll
+                    for (int co = 0; co < 32; ++co)
+                        atomicAdd(p.dw + (((size_t)co * kCtC + ci) * p.KH + kh) * p.KW + kw, v[co]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
 // bf16 forms: xs[r][row][w] = x[row][w - r], r = 0..7, row stride ldo >= W + 7 (multiple of 8)
 __global__ void conv_shift_copies_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xs, long long rows,
                                               int W, int ldo) {
-    const long long per = rows * ldo;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
-        const long long row = i / ldo;
-        const int w = (int)(i - row * ldo);
+    // one thread = 8 consecutive output samples of a row, for all 8 copies: 15 loads, eight 16-byte stores
+    const int gpr = ldo / 8;                                  // groups per row (ldo is a multiple of 8)
+    const long long per = rows * ldo, ngroups = rows * gpr;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
+        const long long row = g / gpr;
+        const int w0 = (int)(g - row * gpr) * 8;
         const float* xr = x + row * W;
+        float v[15];                                          // x[w0 - 7 .. w0 + 7]
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-            xs[r * per + i] = __float2bfloat16((w - r >= 0 && w - r < W) ? xr[w - r] : 0.f);
+        for (int i = 0; i < 15; ++i) {
+            const int w = w0 - 7 + i;
+            v[i] = (w >= 0 && w < W) ? __ldg(xr + w) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {                         // copy r, sample w0 + e = x[w0 + e - r] = v[7 + e - r]
+            uint4 o;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[7 - r], v[8 - r]), p1 = __floats2bfloat162_rn(v[9 - r], v[10 - r]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[11 - r], v[12 - r]), p3 = __floats2bfloat162_rn(v[13 - r], v[14 - r]);
+            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+            o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(xs + r * per + row * ldo + w0) = o;
+        }
     }
 }
 
@@ -752,6 +896,13 @@ int asrb_conv32_bwd_data_rows(const float* dy_nhwc, const float* pack_rows, floa
 }
 
 static int g_conv_wgrad_bf16 = 1;
+static int g_conv_wgrad_cls = 1;      // bf16 weight gradient: 1 = one CTA per (kernel-row class, M tile, chunk), 0 = per kernel row
+/* debug/tuning: the work split of the bf16 weight gradient (see conv_wgrad_cls_kernel); v < 0 queries */
+int asrb_debug_conv_wgrad_cls(int v) {
+    const int old = g_conv_wgrad_cls;
+    if (v >= 0) g_conv_wgrad_cls = v;
+    return old;
+}
 /* debug/tuning: 1 (default) bf16 operand copies for the 32->32 weight gradient, 0 TF32 operands */
 int asrb_debug_conv_wgrad_bf16(int v) {
     const int old = g_conv_wgrad_bf16;
@@ -783,7 +934,7 @@ int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw,
     const long long xrows = (long long)B * 32 * Hin, yrows = (long long)B * 32 * Hout;
     const void* dy_src = dy;
     {
-        const long long n = xrows * ldx;
+        const long long n = bf16 ? xrows * (ldx / 8) : xrows * ldx;      // (bf16: one thread per 8 samples)
         const int g = (int)((n + 255) / 256 < kNumSMs * 8 ? (n + 255) / 256 : kNumSMs * 8);
         if (bf16) {
             __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(ws);
@@ -814,6 +965,31 @@ int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw,
         uint32_t bx[4] = {bf16 ? 64u : 32u, 1, 32, 1};
         int rc = bf16 ? make_tmap_bf16(&tmDy, dy_src, 4, d, s, bx) : make_tmap_f32(&tmDy, dy_src, 4, d, s, bx);
         if (rc) return rc;
+    }
+    const int nkh = ceil_div(KH, SH);
+    if (bf16 && g_conv_wgrad_cls && nkh * 32 <= 352 && nkh <= 256 && 3 * (16384 + round_up(nkh * 32 * 128, 1024)) + 2048 <= 227 * 1024) {
+        // one CTA per (kernel-row class, M tile, chunk of source rows): conv_wgrad_cls_kernel
+        CUtensorMap tmDy2;
+        {   // dy as (t, co, ho, b): a box of nkh consecutive gradient rows is the stacked B operand [ho][co][64 t]
+            uint64_t d[4] = {(uint64_t)Wout, 32, (uint64_t)Hout, (uint64_t)B};
+            uint64_t s[3] = {(uint64_t)Hout * ldy * es, (uint64_t)ldy * es, (uint64_t)32 * Hout * ldy * es};
+            uint32_t bx[4] = {64u, 32, (uint32_t)nkh, 1};
+            int rc = make_tmap_bf16(&tmDy2, dy_src, 4, d, s, bx);
+            if (rc) return rc;
+        }
+        ConvWgradClsParams pc = {B, Hin, Win, Hout, Wout, KH, KW, SH, PH, PW, ceil_div(KW, 4), nkh, 1, dw};
+        const int combos = SH * pc.m_tiles;
+        int chunks = kNumSMs / combos;
+        if (chunks < 1) chunks = 1;
+        const int max_rows = B * ceil_div(Hin, SH);
+        if (chunks > max_rows) chunks = max_rows;
+        pc.chunks = chunks;
+        ASRB_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)32 * 32 * KH * KW * sizeof(float), stream));
+        const size_t smem = (size_t)3 * (16384 + round_up(nkh * 32 * 128, 1024)) + 1024 + 256;
+        ASRB_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_wgrad_cls_kernel<<<combos * chunks, kCtThreads, smem, stream>>>(tmX, tmDy2, pc);
+        ASRB_LAUNCH_OK();
+        return 0;
     }
     ConvWgradParams p = {B, Hin, Win, Hout, Wout, KH, KW, SH, PH, PW, 0, ceil_div(KW, 4), dw};
     int chunks = kNumSMs / KH;

@@ -183,6 +183,9 @@ int asrb_conv32_bwd_data_rows(const float* dy_nhwc, const float* pack_rows, floa
 size_t asrb_conv32_bwd_weight_workspace_bytes(int B, int Hin, int Win, int Hout, int Wout);
 /* operands of the weight-gradient product: 1 (default) bf16 copies, 0 TF32 (then lddy % 4 == 0); v < 0 queries */
 int asrb_debug_conv_wgrad_bf16(int v);
+/* work split of the bf16 weight gradient: 1 (default) one CTA per (kernel-row class, M tile, chunk of source rows), 0 one
+ * CTA per (kernel row, chunk); v < 0 queries */
+int asrb_debug_conv_wgrad_cls(int v);
 int asrb_conv32_bwd_weight(const float* x, const float* dy, int lddy, float* dw, float* ws, size_t ws_bytes, int B,
                            int Hin, int Win, int Hout, int Wout, int KH, int KW, int SH, int PH, int PW,
                            asrb_stream_t stream);

@@ -181,14 +181,18 @@ def test_conv32_tensor_core_fwd_bwd(ops, c):
     from asr_b200 import _lib
     npix = c["B"] * y_ref.shape[2] * y_ref.shape[3]
     try:
-        for bf16, tol in ((1, 1.5e-2), (0, 2e-3)):    # bf16 operand copies (default): rounding sigma 1.6e-3*sqrt(npix) per
-            # entry, worst of 2e5 entries ~5 sigma; TF32 operands: a quarter of that
+        for bf16, cls, tol in ((1, 1, 1.5e-2), (1, 0, 1.5e-2), (0, 0, 2e-3)):
+            # bf16 operand copies (default): rounding sigma 1.6e-3*sqrt(npix) per entry, worst of 2e5 entries ~5 sigma; TF32
+            # operands: a quarter of that.  cls: one CTA per (kernel-row class, M tile, chunk of source rows) -- the default
+            # -- or per (kernel row, chunk)
             _lib.query("asrb_debug_conv_wgrad_bf16", bf16)
+            _lib.query("asrb_debug_conv_wgrad_cls", cls)
             dw = ops.conv32_bwd_weight(xd, dy.to(DEV), tuple(w.shape), c["s"], c["p"])
             torch.cuda.synchronize()
-            assert report(f"conv32 wgrad bf16={bf16}", dw, w.grad) <= tol * math.sqrt(npix)
+            assert report(f"conv32 wgrad bf16={bf16} cls={cls}", dw, w.grad) <= tol * math.sqrt(npix)
     finally:
         _lib.query("asrb_debug_conv_wgrad_bf16", 1)
+        _lib.query("asrb_debug_conv_wgrad_cls", 1)
     assert report("channel sums", ops.nchw_channel_sums(dy.to(DEV), ld), b.grad) <= 1e-4 * max(1.0, b.grad.abs().max().item())
 
 
