@@ -315,6 +315,15 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (s == 0 && el == 0 && chain == 0 && p.trace) p.trace[((size_t)blockIdx.x * p.T) * 16 + 15] = t_entry;
                 if ((s == 0 || s == T - 1) && el == 0 && chain == 0 && p.trace)      // wall clock (ns) next to the SM clock: the real SM frequency
                     p.trace[((size_t)blockIdx.x * p.T + s) * 16 + 11] = (long long)globaltimer_ns();
+                // gate pre-activations of this step (TMA, a step ahead): read BEFORE the wait for the accumulator -- the box
+                // landed long ago, and the barrier probe + six shared-memory loads (~280 cycles) are off the critical path here
+                mbar_wait(&gi_bar[s & 1], (uint32_t)((s >> 1) & 1));
+                float in[kGates][2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int q = 0; q < kGates; ++q)
+                        in[q][c] = active[c] ? ld_shared_f32(smem_gi_u32 + (uint32_t)(((s & 1) * kGates + q) * kGiRegion) + gi_off[c]) : 0.f;
                 float acc[4][2];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) acc[g][0] = acc[g][1] = 0.f;
@@ -344,15 +353,6 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     if (el == 0 && chain == 0) ASRB_TRACE(6, s);
                 }
-                // gate pre-activations of this step (TMA, a step ahead)
-                mbar_wait(&gi_bar[s & 1], (uint32_t)((s >> 1) & 1));
-                float in[kGates][2];
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int q = 0; q < kGates; ++q)
-                        in[q][c] = active[c] ? ld_shared_f32(smem_gi_u32 + (uint32_t)(((s & 1) * kGates + q) * kGiRegion) + gi_off[c]) : 0.f;
-
                 float hn[2], cn[2], sv[4][2];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
