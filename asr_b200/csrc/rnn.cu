@@ -146,42 +146,40 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        // ===================== TMA producer: ONE elected thread runs the whole loop =====================
+        // (per-chunk elect / __syncwarp rounds of the whole warp cost ~250 cycles each on the step's critical path: rnn3.cu)
         if (tc) {
             if (elect_one()) {
                 mbar_arrive_expect_tx(w_bar, (uint32_t)(nkb * NPAD * 128));
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(smem_w + (size_t)kb * NPAD * 128, &tmW, w_bar, kb * KBE, (dir * P + pidx) * NPAD);
-            }
-            __syncwarp();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int s = 1; s < T; ++s) {
-                // step barrier: every CTA of this direction has published step s-1
-                const uint32_t need = (uint32_t)P * (uint32_t)s;
-                poll_counter(counter, need);
-                if (lane == 0) ASRB_TRACE(0, s);
-                // other CTAs' generic-proxy stores (acquired above) -> visible to our async-proxy (TMA) reads.
-                // The .global form is a bare FENCE.VIEW.ASYNC.G; the unqualified one adds a MEMBAR.ALL.GPU.
-                fence_proxy_async_global();
-                if (lane == 0) ASRB_TRACE(9, s);
-                const int tp = t_of(s - 1);
-                const int slab = BWD ? (dir * T + tp) : (dir * (T + 2) + tp + 1);
-                for (int c = 0; c < nchunks; ++c) {
-                    const int kb0 = c * p.chunk;
-                    const int nblk = min(p.chunk, nkb - kb0);
-                    uint8_t* st = smem_a + (size_t)stage * stage_bytes;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (elect_one()) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int s = 1; s < T; ++s) {
+                    // step barrier: every CTA of this direction has published step s-1
+                    const uint32_t need = (uint32_t)P * (uint32_t)s;
+                    poll_counter(counter, need);
+                    ASRB_TRACE(0, s);
+                    // other CTAs' generic-proxy stores (acquired above) -> visible to our async-proxy (TMA) reads.
+                    // The .global form is a bare FENCE.VIEW.ASYNC.G; the unqualified one adds a MEMBAR.ALL.GPU.
+                    fence_proxy_async_global();
+                    ASRB_TRACE(9, s);
+                    const int tp = t_of(s - 1);
+                    const int slab = BWD ? (dir * T + tp) : (dir * (T + 2) + tp + 1);
+                    for (int c = 0; c < nchunks; ++c) {
+                        const int kb0 = c * p.chunk;
+                        const int nblk = min(p.chunk, nkb - kb0);
+                        uint8_t* st = smem_a + (size_t)stage * stage_bytes;
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nblk * kStageBytes));
                         for (int i = 0; i < nblk; ++i)
                             tma_load_3d(st + (size_t)i * kStageBytes, &tmA, &full_bar[stage], (kb_off + kb0 + i) * KBE, 0, slab);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    ASRB_TRACE(1, s);
                 }
-                if (lane == 0) ASRB_TRACE(1, s);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
@@ -192,20 +190,20 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         // time) and not by the number of MMAs (two half-batch passes cost the same as one).
         if (tc) {
             constexpr uint32_t idesc = umma_idesc(BF16 ? kFmtBF16 : kFmtTF32, MROWS, NPAD);
-            mbar_wait(w_bar, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int s = 1; s < T; ++s) {
-                const uint32_t it = (uint32_t)(s - 1);
-                mbar_wait(tempty_bar, (it & 1) ^ 1);
-                tc_fence_after_sync();
-                for (int c = 0; c < nchunks; ++c) {
-                    const int kb0 = c * p.chunk;
-                    const int nblk = min(p.chunk, nkb - kb0);
-                    mbar_wait(&full_bar[stage], phase);
-                    if (c == 0 && lane == 0) ASRB_TRACE(2, s);
+            if (elect_one()) {               // one elected thread runs the whole loop
+                mbar_wait(w_bar, 0);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int s = 1; s < T; ++s) {
+                    const uint32_t it = (uint32_t)(s - 1);
+                    mbar_wait(tempty_bar, (it & 1) ^ 1);
                     tc_fence_after_sync();
-                    if (elect_one()) {
+                    for (int c = 0; c < nchunks; ++c) {
+                        const int kb0 = c * p.chunk;
+                        const int nblk = min(p.chunk, nkb - kb0);
+                        mbar_wait(&full_bar[stage], phase);
+                        if (c == 0) ASRB_TRACE(2, s);
+                        tc_fence_after_sync();
                         const uint32_t a0 = smem_u32(smem_a + (size_t)stage * stage_bytes);
                         const uint32_t b0 = smem_u32(smem_w + (size_t)kb0 * NPAD * 128);
                         for (int i = 0; i < nblk; ++i) {
@@ -219,12 +217,12 @@ rnn_rec_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         }
                         umma_commit(&empty_bar[stage]);
                         if (c == nchunks - 1) umma_commit(tfull_bar);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    ASRB_TRACE(3, s);
                 }
-                if (lane == 0) ASRB_TRACE(3, s);
             }
+            __syncwarp();
         }
     } else if (warp >= kRnnCtrlWarps) {
         // ===================== epilogue: thread = (batch row, one 4-wide group of the slice's hidden units) ==========
