@@ -719,6 +719,10 @@ static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void*
 //   backward, batch <= 64, G/4 <= 896: rnn3.cu (weights in tensor memory, clusters of 4, two chains) -- default;
 //     bit 1024: the backward of this file instead;
 //   bit 256: the experimental exchange-by-data kernel (rnn2.cu), forward and backward.
+// Inside rnn3.cu: bit 2: publish the operand with generic stores + red.release (MEMBAR) instead of a TMA store + relaxed
+// increment; bit 1: forward without the stores nobody waits for (timing only, results incomplete); bit 2048: backward
+// outputs through direct stores instead of shared-memory tiles + TMA stores; bit 32768: forward with / backward without
+// the tensor-pipe lock between the two chains' MMA sequences.
 static inline bool rnn2_eligible(const RnnPlan& pl, const RnnParams& prm) {
     return pl.bf16 && !prm.use_simt && (g_rnn_dbg & 256) && pl.nj == 16 && prm.H % 16 == 0;
 }
@@ -798,11 +802,11 @@ int asrb_rnn_fwd_sum(int cell, int bf16, const float* gi, const float* b_hh, con
     prm.Hp = round_up(H, 64);
     prm.trace = g_rnn_trace;
     if (rnn3_eligible(pl, prm)) {
-        // DEBUG bit 4096: the kernel itself adds both directions' h tiles into out_sum with TMA reduce-adds and stores the
-        // fp32 state / saved activations through shared-memory tiles.  Measured at configs[1]: 12.45 ms per step for the
-        // five forward launches against 11.46 + 0.27 (separate sum kernel) -- the reduce-adds cost more L2 time than the
-        // streaming sum, and the 11 staging stores per thread more issue slots than the scattered global ones; off.
-        prm.out_sum = (g_rnn_dbg & 4096) ? out_sum : nullptr;
+        // (A variant in which the kernel itself added both directions' h tiles into out_sum with TMA reduce-adds and stored the
+        // fp32 state / saved activations through shared-memory tiles was built and measured: 12.45 ms per step for the five
+        // forward launches against 11.46 + 0.27 with the separate sum kernel -- the reduce-adds cost more L2 time than the
+        // streaming sum; removed.)
+        prm.out_sum = nullptr;
         rc = rnn3_forward(cell, pl, prm, wpack_fwd, stream);
         if (rc == 0 && out_sum && !prm.out_sum) rc = asrb_rnn_sum_dirs(hseq, out_sum, T, B, H, stream);
         return rc;
