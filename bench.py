@@ -52,37 +52,74 @@ def flops_per_step(B, Tp, H, L, C, layers_in=1312):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe: the nvidia-smi clocks line).
+    Read through NVML in-process (nvidia_ml_py: the library nvidia-smi itself sits on) every 50 ms: spawning `nvidia-smi`
+    from a thread initialises NVML anew on every call, which was measured to stall this process's kernel launches for
+    ~15 ms now and then -- 1-2 ms per step on a 30 ms step over a handful of timed steps.  Falls back to the nvidia-smi
+    subprocess (every 0.5 s) when the NVML bindings are missing."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-relative index -> NVML handle through the PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.handle = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.handle = h
+                        break
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.rows.append((mhz, self.max_mhz, mask))
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            r = [x.strip() for x in out.split(",")]
+            mask = sum(bit for (_, bit), v in zip(self.REASONS, r[2:6]) if v.lower().startswith("active"))
+            self.rows.append((float(r[0]), float(r[1]), mask))
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05 if self.nvml is not None else 0.5)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        reasons = []
-        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
-            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(self.rows[0][1]) if self.rows and self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [name for name, bit in self.REASONS if any(r[2] & bit for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.rows[0][1] if self.rows else None,
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_batch(B, cfg=CFG):
@@ -538,7 +575,14 @@ def main():
     if sampler:
         sampler.start()
     ms_dev, loss_value, launches, _ = timed(resident, args.steps)
+    # the host-input form has its own warm-up (copy stream, staging buffers, the allocator's blocks for that tensor pattern):
+    # measured without it, its first leg ran 1.7 ms/step slower than a second one (32.1 against 30.4)
+    timed(pinned, max(2, min(args.warmup, 3)))
     ms_e2e, _, _, _ = timed(pinned, args.steps)          # host buffers: pinned H2D + loss D2H inside the region
+    if os.environ.get("ASRB_BENCH_DIAG"):                # diagnostic: the two legs again, in the other order
+        ms_e2e_b, _, _, _ = timed(pinned, args.steps)
+        ms_dev_b, _, _, _ = timed(resident, args.steps)
+        print(f"[diag] resident {ms_dev:.2f}, host {ms_e2e:.2f}, host again {ms_e2e_b:.2f}, resident again {ms_dev_b:.2f} ms/step", file=sys.stderr, flush=True)
     # the clock sampler covers the two timed regions above and stops here: its periodic nvidia-smi spawn stalls the
     # launching thread for ~15 ms now and then, which is noise in `value` but lands on ONE kernel's event pair below
     clocks = sampler.stop() if sampler else None
