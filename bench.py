@@ -513,10 +513,16 @@ def main():
     resident = host[0].to(dev)
     stream = torch.cuda.current_stream()
 
+    diag = [] if os.environ.get("ASRB_BENCH_DIAG") else None
+
     def step(inputs):
+        t0 = time.perf_counter()
         bucket.zero()
         valid, loss, loss_value = fit(model, criterion, (inputs, host[1], host[2], host[3]), dev)
+        t1 = time.perf_counter()
         loss.backward()
+        if diag is not None:
+            diag.append((t1 - t0, time.perf_counter() - t1))
         if sync is not None:
             sync.finish()
         return loss_value
@@ -583,6 +589,9 @@ def main():
         ms_e2e_b, _, _, _ = timed(pinned, args.steps)
         ms_dev_b, _, _, _ = timed(resident, args.steps)
         print(f"[diag] resident {ms_dev:.2f}, host {ms_e2e:.2f}, host again {ms_e2e_b:.2f}, resident again {ms_dev_b:.2f} ms/step", file=sys.stderr, flush=True)
+        tail = diag[-args.steps:]
+        print(f"[diag] host time per step: fit() incl. the loss read-back {1e3 * sum(a for a, _ in tail) / len(tail):.2f} ms, "
+              f"backward() enqueue {1e3 * sum(b for _, b in tail) / len(tail):.2f} ms", file=sys.stderr, flush=True)
     # the clock sampler covers the two timed regions above and stops here: its periodic nvidia-smi spawn stalls the
     # launching thread for ~15 ms now and then, which is noise in `value` but lands on ONE kernel's event pair below
     clocks = sampler.stop() if sampler else None
