@@ -377,6 +377,43 @@ def test_rnn_fwd_bwd(ops, c, mode):
         ops.RNN_BF16_MIN_HIDDEN = old_min
 
 
+@pytest.mark.parametrize("cellname", ["gru", "lstm"])
+def test_rnn3_publish_protocols_agree(ops, cellname):
+    """rnn3.cu hands a step over with ONE TMA store of the operand tile + its completion + a RELAXED counter increment (a
+    release is a MEMBAR.GPU, which waits for the other chain's TMA copies: DESIGN.md section 6).  The fallback --
+    generic stores + red.release, `asrb_debug_rnn_dbg(2)` -- must give bit-identical outputs over a few hundred steps at
+    the benchmarked width: a consumer that read a tile before it was complete would show up here."""
+    from asr_b200 import _lib
+
+    T, B, H = 300, 64, 800
+    cell = ops.GRU if cellname == "gru" else ops.LSTM
+    G = (3 if cellname == "gru" else 4) * H
+    k = 1.0 / math.sqrt(H)
+    gi = rnd(T, B, 2, G, seed=140).to(DEV)
+    w_hh = ((torch.rand(2, G, H, generator=torch.Generator().manual_seed(141)) * 2 - 1) * k).to(DEV)
+    b_hh = ((torch.rand(2, G, generator=torch.Generator().manual_seed(142)) * 2 - 1) * k).to(DEV)
+    dout = rnd(T, B, H, seed=143).to(DEV)
+    lens = torch.tensor(sorted([max(1, T - (i * 7) % T) for i in range(B)], reverse=True), dtype=torch.int32).to(DEV)
+    old_bf16, ops.RNN_BF16 = ops.RNN_BF16, True
+    outs = {}
+    try:
+        pf, pb = ops.rnn_pack_weights(cell, w_hh[0].contiguous(), w_hh[1].contiguous(), B)
+        for dbg in (0, 2, 0):
+            _lib.query("asrb_debug_rnn_dbg", dbg)
+            hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
+            dgi, dgiT, dghT = ops.rnn_bwd(cell, dout, pb, lens, hseq, cseq, saved, T, B, H)
+            torch.cuda.synchronize()
+            cur = (hseq.clone(), dgi.clone(), dgiT.clone())
+            assert torch.isfinite(cur[0]).all() and torch.isfinite(cur[1].float()).all()
+            if dbg in outs:
+                assert all(torch.equal(a, b) for a, b in zip(outs[dbg], cur))       # run-to-run: deterministic
+            outs[dbg] = cur
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[2]))
+    finally:
+        _lib.query("asrb_debug_rnn_dbg", 0)
+        ops.RNN_BF16 = old_bf16
+
+
 # ----------------------------------------------------------------------------- softmax / argmax / CTC
 @pytest.mark.parametrize("R,C", [(100, 29), (33, 90), (17, 5000), (5, 1)])
 def test_log_softmax_argmax(ops, R, C):
