@@ -18,6 +18,8 @@ LIBRARY = os.path.join(_HERE, "libasr_b200.so")
 _CTYPES = {
     "int": ctypes.c_int,
     "unsigned": ctypes.c_uint,
+    "uint32_t": ctypes.c_uint32,
+    "int32_t": ctypes.c_int32,
     "float": ctypes.c_float,
     "double": ctypes.c_double,
     "size_t": ctypes.c_size_t,
