@@ -27,8 +27,6 @@
 namespace asrb {
 
 long long* g_rnn_trace = nullptr;
-const uint32_t* g_rnn_gi_ready = nullptr;
-int g_rnn_gi_block = 0, g_rnn_gi_nblocks = 0;
 int g_rnn_dbg = 0;
 int g_rnn_ksplit = 2;
 int g_rnn_chunk = 0;
@@ -803,10 +801,6 @@ int asrb_rnn_fwd_sum(int cell, int bf16, const float* gi, const float* b_hh, con
     prm.hbf = reinterpret_cast<__nv_bfloat16*>(hseq_bf16);
     prm.Hp = round_up(H, 64);
     prm.trace = g_rnn_trace;
-    // (one-shot: set by asrb_rnn_gi_progress for THIS launch)
-    prm.gi_ready = g_rnn_gi_ready; prm.gi_block = g_rnn_gi_block; prm.gi_nblocks = g_rnn_gi_nblocks;
-    g_rnn_gi_ready = nullptr; g_rnn_gi_block = g_rnn_gi_nblocks = 0;
-    if (prm.gi_ready && !rnn3_eligible(pl, prm)) return ASRB_ERR_UNSUPPORTED;     // only rnn3.cu's forward polls it
     if (rnn3_eligible(pl, prm)) {
         // (A variant in which the kernel itself added both directions' h tiles into out_sum with TMA reduce-adds and stored the
         // fp32 state / saved activations through shared-memory tiles was built and measured: 12.45 ms per step for the five
@@ -870,39 +864,6 @@ int asrb_debug_rnn_chunk(int blocks) {
 /* DEBUG: per-step SM-clock stamps of the next asrb_rnn_fwd / asrb_rnn_bwd launches into trace[grid][T][12] (NULL = off) */
 int asrb_debug_rnn_trace(long long* trace) {
     g_rnn_trace = trace;
-    return 0;
-}
-
-/* The NEXT asrb_rnn_fwd / asrb_rnn_fwd_sum launch (rnn3.cu's forward only: asrb_rnn3_fwd_eligible) may start while gi is
- * still being written by other streams: gi is produced in nblocks blocks of frames_per_block frames, block pairs
- * (b, nblocks-1-b) from both ends inwards, and *ready (device word, written with asrb_stream_write_u32 after each pair)
- * counts the complete pairs.  The kernel polls it before it fetches a frame of a later pair.  ready = NULL switches it off. */
-int asrb_rnn_gi_progress(const uint32_t* ready, int frames_per_block, int nblocks) {
-    ASRB_REQUIRE(!ready || (frames_per_block > 0 && nblocks > 0), ASRB_ERR_BAD_ARG);
-    g_rnn_gi_ready = ready;
-    g_rnn_gi_block = ready ? frames_per_block : 0;
-    g_rnn_gi_nblocks = ready ? nblocks : 0;
-    return 0;
-}
-
-int asrb_rnn3_fwd_eligible(int cell, int H, int B, int bf16) {
-    RnnPlan pl;
-    if (rnn_make_plan(cell, H, B, rnn_effective_bf16(bf16), &pl) != 0) return 0;
-    RnnParams prm = {};
-    prm.B = B; prm.H = H;
-    prm.use_simt = (g_debug_flags & ASRB_DEBUG_SIMT_RNN) ? 1 : 0;
-    return rnn3_eligible(pl, prm) ? 1 : 0;
-}
-
-__global__ void stream_write_u32_kernel(uint32_t* p, uint32_t v) {
-    __threadfence();
-    *reinterpret_cast<volatile uint32_t*>(p) = v;
-}
-/* *p = v in stream order (after everything queued on `stream` before it has completed) */
-int asrb_stream_write_u32(uint32_t* p, uint32_t v, asrb_stream_t stream) {
-    ASRB_REQUIRE(p, ASRB_ERR_BAD_ARG);
-    stream_write_u32_kernel<<<1, 1, 0, stream>>>(p, v);
-    ASRB_LAUNCH_OK();
     return 0;
 }
 

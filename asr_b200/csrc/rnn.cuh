@@ -37,10 +37,6 @@ struct RnnParams {
     __nv_bfloat16* dghbf; // [2,T,B,Gp]  bf16 copy of dgh  (backward, bf16 mode)
     int Hp, Gp;
     long long* trace;     // DEBUG: [gridDim][T][16] SM-clock stamps per step (asrb_debug_rnn_trace), else NULL
-    // forward, optional (asrb_rnn_gi_progress): the gate pre-activations are still being produced, in blocks of gi_block
-    // frames, from both ends of the sequence inwards: *gi_ready = number of block PAIRS (b, nblocks-1-b) that are complete
-    const uint32_t* gi_ready;
-    int gi_block, gi_nblocks;
     // forward
     const float* gi;     // [T,B,2,G]
     const float* b_hh;   // [2,G]
@@ -70,8 +66,6 @@ struct RnnShape {
 // the recurrence
 // ------------------------------------------------------------------------------------------------
 extern long long* g_rnn_trace;
-extern const uint32_t* g_rnn_gi_ready;
-extern int g_rnn_gi_block, g_rnn_gi_nblocks;
 extern int g_rnn_dbg;
 extern int g_rnn_ksplit;   // largest backward K split allowed: 0 none, 2 CTA pairs (default), 4 clusters of four -- the
                         // 1.5 k cycles the MMA phase gains with four are lost again in the longer exchange (measured)

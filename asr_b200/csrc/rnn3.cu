@@ -152,18 +152,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         //   D[64 gate rows, kR3Rows batch rows] = W[tensor memory] x h^T[shared memory]
         if (chain_on) {
             constexpr uint32_t idesc = umma_idesc(kFmtBF16, 64, kR3Rows);
-            uint32_t gi_seen = 0;
             auto load_gi = [&](int s) {   // the slice's gate pre-activations of step s, rows of this chain -> buffer s & 1
                 const int t = t_of(s);
-                if (p.gi_ready) {          // gi is still being produced on another stream, block pairs from both ends inwards
-                    const int blk = t / p.gi_block;
-                    const uint32_t need = (uint32_t)min(blk, p.gi_nblocks - 1 - blk) + 1u;
-                    if (gi_seen < need) {
-                        poll_counter(p.gi_ready, need);
-                        gi_seen = need;
-                        fence_proxy_async_global();     // the producer kernel's stores -> our async-proxy (TMA) read
-                    }
-                }
                 mbar_arrive_expect_tx(&gi_bar[s & 1], (uint32_t)(kGates * kR3Rows * NJ * 4));
                 // one box for all gates: [gate][row][16 columns] (the tensor map walks the gates, H columns apart, as its third dimension)
                 tma_load_4d(smem_gi + (size_t)((s & 1) * kGates) * kGiRegion, &tmGi, &gi_bar[s & 1], dir * G + j0, row0, 0, t);

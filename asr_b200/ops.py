@@ -479,22 +479,6 @@ def rnn_use_bf16(H):
     return bool(RNN_BF16 and H % 8 == 0 and H >= RNN_BF16_MIN_HIDDEN and not (DEBUG_FLAGS & 2))
 
 
-def rnn3_fwd_eligible(cell, H, B):
-    """True when asrb_rnn_fwd will run rnn3.cu's forward kernel (the one that can poll a gi-progress word)"""
-    return bool(_lib.query("asrb_rnn3_fwd_eligible", cell, H, B, int(rnn_use_bf16(H))))
-
-
-def rnn_gi_progress(ready, frames_per_block, nblocks):
-    """one-shot, for the next rnn_fwd call: gi is still being produced in block pairs from both ends inwards (see
-    include/asr_b200.h); ready = int32 device word counting the complete pairs, or None to switch it off"""
-    _lib.call("asrb_rnn_gi_progress", _p(ready), int(frames_per_block), int(nblocks))
-
-
-def stream_write_u32(word, value):
-    """word[0] = value, in stream order on the current stream"""
-    _call("asrb_stream_write_u32", _p(word), int(value))
-
-
 def rnn_plan(cell, H, B, bf16):
     nj, P = ctypes.c_int(), ctypes.c_int()
     wf, wb = ctypes.c_size_t(), ctypes.c_size_t()

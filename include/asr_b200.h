@@ -116,13 +116,6 @@ int asrb_rnn_bwd(int cell, int bf16, const float* dout, const void* wpack_bwd, c
                  asrb_stream_t stream);
 /* floats in the saved-gates buffer (slice-major layout private to asrb_rnn_fwd / asrb_rnn_bwd) */
 size_t asrb_rnn_saved_floats(int cell, int H, int B, int bf16, int T);
-/* Overlap of the input projection with the recurrence (rnn3.cu's forward only: asrb_rnn3_fwd_eligible != 0): the NEXT
- * asrb_rnn_fwd / asrb_rnn_fwd_sum launch may start while gi is still being written on other streams, in nblocks blocks of
- * frames_per_block frames, block pairs (b, nblocks-1-b) from both ends inwards; *ready (device word, bumped with
- * asrb_stream_write_u32 after each pair) counts the complete pairs and is polled before a frame of a later pair is fetched. */
-int asrb_rnn_gi_progress(const uint32_t* ready, int frames_per_block, int nblocks);
-int asrb_rnn3_fwd_eligible(int cell, int H, int B, int bf16);
-int asrb_stream_write_u32(uint32_t* p, uint32_t v, asrb_stream_t stream);
 int asrb_debug_rnn_trace(long long* trace);
 int asrb_debug_rnn_chunk(int blocks);
 int asrb_debug_rnn_ksplit(int on);
