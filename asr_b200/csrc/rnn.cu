@@ -719,8 +719,11 @@ static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void*
 //   backward, batch <= 64, G/4 <= 896: rnn3.cu (weights in tensor memory, clusters of 4, two chains) -- default;
 //     bit 1024: the backward of this file instead;
 //   bit 256: the experimental exchange-by-data kernel (rnn2.cu), forward and backward.
-// Inside rnn3.cu: bit 2: publish the operand with generic stores + red.release (MEMBAR) instead of a TMA store + relaxed
-// increment; bit 1: forward without the stores nobody waits for (timing only, results incomplete); bit 2048: backward
+// Inside rnn3.cu: the step hand-over is generic stores + red.release (default).  bit 16: ONE TMA store of the operand tile +
+// cp.async.bulk.wait_group + a relaxed increment -- 0.3 / 0.5 ms per layer faster (the release's MEMBAR.GPU waits for the
+// other chain's TMA copies), but the completion does NOT mean the data is in L2: about one hand-over in 10^7 was consumed too
+// early (tools/stress_fullsize.py), so it is an experiment only; bit 4: the same + an L2 read-back of the tile before the
+// increment.  bit 1: forward without the stores nobody waits for (timing only, results incomplete); bit 2048: backward
 // outputs through direct stores instead of shared-memory tiles + TMA stores; bit 32768: forward with / backward without
 // the tensor-pipe lock between the two chains' MMA sequences.
 static inline bool rnn2_eligible(const RnnPlan& pl, const RnnParams& prm) {

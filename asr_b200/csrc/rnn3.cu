@@ -285,7 +285,10 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
         if (chain_on) {
             float state_h[2] = {0.f, 0.f}, state_c[2] = {0.f, 0.f};
+            // hand-over protocol (asrb_debug_rnn_dbg): the launcher SETS bit 2 (generic stores + red.release) unless bit 16
+            // (TMA store + completion + relaxed increment) or bit 4 (the same + L2 read-back) asks for a TMA-store form
             const bool tma_op = !(p.dbg & 2);
+            const bool readback = (p.dbg & 4) != 0;
             // per-step addresses advance by constants (t moves by +-1): bases for step 0, strides in elements
             const int t0 = t_of(0);
             const long long tstep = dir == 1 ? -1 : 1;
@@ -397,17 +400,27 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 if (el == 0 && chain == 0) ASRB_TRACE(7, s);
                 named_bar_sync(8 + chain, kR3EpiThreads);
-                if (el == 0) {
-                    if (chain == 0) ASRB_TRACE(8, s);
+                if (wl == 0) {          // the chain's first epilogue warp publishes
+                    if (lane == 0 && chain == 0) ASRB_TRACE(8, s);
                     if (tma_op) {
-                        tma_store_3d(&tmOp, st_op, j0, row0, dir * (T + 2) + t + 1);
-                        bulk_commit_group();
-                        bulk_wait_group<0>();            // written (not just read): the tile is in L2, where the consumers' TMA reads it
-                        red_relaxed_add_u32(counter, 1u);
-                    } else {
+                        if (lane == 0) {
+                            tma_store_3d(&tmOp, st_op, j0, row0, dir * (T + 2) + t + 1);
+                            bulk_commit_group();
+                            bulk_wait_group<0>();        // the bulk store has "completed" -- which is NOT "its data is in L2"
+                        }
+                        __syncwarp();
+                        if (readback && row0 + lane < B) {   // lane l: first word of row l of the tile, from L2, until it is there
+                            const uint32_t want = *reinterpret_cast<const uint32_t*>(st_op + lane * NJ);
+                            const __nv_bfloat16* g = p.hbf + (((size_t)dir * (T + 2) + t + 1) * B + row0 + lane) * p.Hp + j0;
+                            uint32_t spins = 0;
+                            while (ld_relaxed_gpu_u32(g) != want && ++spins < (1u << 22)) {}
+                        }
+                        __syncwarp();
+                        if (lane == 0) red_relaxed_add_u32(counter, 1u);
+                    } else if (lane == 0) {
                         red_release_add_u32(counter, 1u);
                     }
-                    if (chain == 0) ASRB_TRACE(10, s);
+                    if (lane == 0 && chain == 0) ASRB_TRACE(10, s);
                 }
                 if (!(p.dbg & 1)) {     // (dbg bit 1: timing experiment without these stores, results incomplete)
                     // hold the other stores back until the operand tile has been read: they would sit in the LSU queue ahead of it
@@ -503,7 +516,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         if (2 * pl.P > sms * per_sm) return ASRB_ERR_UNSUPPORTED;
     }
     ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * NCH * kR3CounterStride * sizeof(uint32_t), stream));
-    prm.dbg = g_rnn_dbg;
+    prm.dbg = (g_rnn_dbg & (16 | 4)) ? (g_rnn_dbg & ~2) : (g_rnn_dbg | 2);      // hand-over: release unless a TMA-store form is asked for
     kern<<<dim3(2 * pl.P), dim3(kRnnThreads), smem, stream>>>(tmA, tmA2, tmGi, tmOp, prm);
     ASRB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -836,6 +849,7 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // with whole tiles, one TMA store + its completion + a relaxed increment instead of stores + a release (see the
                 // forward kernel: the release's MEMBAR waits for the other chain's TMA copies)
                 const bool tma_op = staged && !(p.dbg & 2);
+                const bool readback = (p.dbg & 4) != 0;
                 uint32_t vu[kGates];                                   // (unit, unit+1) pairs of the input-side gate gradients
 #pragma unroll
                 for (int q = 0; q < kGates; ++q) vu[q] = pair_units(dg[q][0], dg[q][1]);
@@ -856,17 +870,38 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (el == 0 && chain == 0) ASRB_TRACE(7, s);
                 named_bar_sync(8 + chain, kEpiThreads);
-                if (el == 0) {
-                    if (chain == 0) ASRB_TRACE(8, s);
+                if (wl == 0) {          // the chain's first epilogue warp publishes
+                    if (lane == 0 && chain == 0) ASRB_TRACE(8, s);
                     if (tma_op) {
-                        tma_store_4d(&tmOp, st_op, j0, row0, 0, dir * T + t);
-                        bulk_commit_group();
-                        bulk_wait_group<0>();            // written: the tiles are in L2, where the consumers' TMA reads them
-                        red_relaxed_add_u32(counter, 1u);
-                    } else {
+                        if (lane == 0) {
+                            tma_store_4d(&tmOp, st_op, j0, row0, 0, dir * T + t);
+                            bulk_commit_group();
+                            bulk_wait_group<0>();
+                        }
+                        __syncwarp();
+                        if (readback) {      // lane l: first word of row l of every gate's tile, from L2, until they are there
+                            const __nv_bfloat16* g = p.dghbf + (((size_t)dir * T + t) * B + row0 + lane) * p.Gp + j0;
+                            uint32_t want[kGates];
+#pragma unroll
+                            for (int q = 0; q < kGates; ++q)
+                                want[q] = *reinterpret_cast<const uint32_t*>(st_op + q * (kR3StageBytes / 2) + lane * NJ);
+                            uint32_t spins = 0;
+                            bool ok = false;
+                            while (!ok && ++spins < (1u << 22)) {
+                                uint32_t got[kGates];
+#pragma unroll
+                                for (int q = 0; q < kGates; ++q) got[q] = ld_relaxed_gpu_u32(g + (size_t)q * H);
+                                ok = true;
+#pragma unroll
+                                for (int q = 0; q < kGates; ++q) ok = ok && (got[q] == want[q]);
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) red_relaxed_add_u32(counter, 1u);
+                    } else if (lane == 0) {
                         red_release_add_u32(counter, 1u);
                     }
-                    if (chain == 0) ASRB_TRACE(10, s);
+                    if (lane == 0 && chain == 0) ASRB_TRACE(10, s);
                 }
                 if (staged) {
                     // phase B: the tiles only later kernels read
@@ -1003,7 +1038,7 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
         ASRB_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
         if (2 * pl.P_b > 4 * nclusters) return ASRB_ERR_UNSUPPORTED;
     }
-    prm.dbg = g_rnn_dbg;
+    prm.dbg = (g_rnn_dbg & (16 | 4)) ? (g_rnn_dbg & ~2) : (g_rnn_dbg | 2);      // hand-over: release unless a TMA-store form is asked for
     ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmDgi, tmGT, tmHT, tmOp, prm));
     return 0;
 }
