@@ -719,7 +719,9 @@ static int rnn_dispatch(int cell, const RnnPlan& pl, RnnParams& prm, const void*
 //   backward, batch <= 64, G/4 <= 896: rnn3.cu (weights in tensor memory, clusters of 4, two chains) -- default;
 //     bit 1024: the backward of this file instead;
 //   bit 256: the experimental exchange-by-data kernel (rnn2.cu), forward and backward.
-// Inside rnn3.cu: the step hand-over is generic stores + red.release (default).  bit 16: ONE TMA store of the operand tile +
+// Inside rnn3.cu: the step hand-over is VERIFIED by default (a fast first pass that detects a stale operand + a release
+// second pass that runs only then; bit 8192 forces the second pass: see rnn3.cu); bit 4096: generic stores + red.release in
+// one pass.  bit 16: ONE TMA store of the operand tile +
 // cp.async.bulk.wait_group + a relaxed increment -- 0.3 / 0.5 ms per layer faster (the release's MEMBAR.GPU waits for the
 // other chain's TMA copies), but the completion does NOT mean the data is in L2: about one hand-over in 10^7 was consumed too
 // early (tools/stress_fullsize.py), so it is an experiment only; bit 4: the same + an L2 read-back of the tile before the
@@ -858,6 +860,10 @@ int asrb_debug_rnn_ksplit(int on) { g_rnn_ksplit = on == 1 ? 2 : on; return 0; }
 
 /* DEBUG / timing experiments: K blocks per pipeline barrier (0 = automatic) */
 int asrb_debug_rnn_dbg(int bits) { g_rnn_dbg = bits; return 0; }
+int asrb_debug_rnn_redos(void) {
+    const long long v = asrb::rnn3_redo_count();
+    return v < 0 ? -1 : (int)(v & 0x7fffffff);
+}
 int asrb_debug_rnn_chunk(int blocks) {
     ASRB_REQUIRE(blocks >= 0 && blocks <= 8, ASRB_ERR_BAD_ARG);
     g_rnn_chunk = blocks;

@@ -191,5 +191,6 @@ int rnn2_dispatch(bool bwd, int cell, const RnnPlan& pl, RnnParams& prm, const v
 int rnn3_forward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream);
 // rnn3.cu: backward recurrence, weights in tensor memory, K split over clusters of 4, two chains (plan.ts_bwd)
 int rnn3_backward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream);
+long long rnn3_redo_count();      // launches whose second pass had to run (verified hand-over, rnn3.cu); < 0: CUDA error
 
 }  // namespace asrb

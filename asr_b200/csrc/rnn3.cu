@@ -66,6 +66,50 @@ __global__ void rnn3_zero_pad_cols_kernel(__nv_bfloat16* base, size_t rows, int 
         *reinterpret_cast<uint32_t*>(base + r * pitch + col0 + 2 * c) = 0u;
     }
 }
+// Verified hand-over (see rnn3_launch): kernel-internal bits of RnnParams::dbg, the flag word and the second pass's counters
+constexpr int kR3Check = 1 << 20;           // first pass: look for the sentinel in every operand tile that arrives
+constexpr int kR3Redo = 1 << 21;            // second pass: leave at once unless the first pass raised the flag
+constexpr int kR3Sabotage = 1 << 22;        // TEST: CTA 0 withholds the operand tile of step 5 (its counter arrival stays)
+constexpr int kR3FlagWord = 8;              // counters[8]: "a stale operand sector was consumed"
+constexpr int kR3RedoCounters = 64;         // the second pass counts in counters[64..128)
+__device__ unsigned long long g_rnn3_redos = 0;   // launches repeated so far (asrb_debug_rnn_redos)
+
+// rows of a bf16 matrix: columns [0, valid) <- 0xFFFF (a NaN no cell ever produces: the sentinel), [valid, pitch) <- 0 (the
+// K padding).  pitch is a multiple of 8 elements; 16 bytes per thread.
+__global__ void rnn3_fill_sentinel_kernel(__nv_bfloat16* base, size_t rows, int pitch, int valid) {
+    const int per_row = pitch / 8;
+    const size_t n = rows * (size_t)per_row;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % per_row) * 8;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            w[k] = (c0 + 2 * k < valid ? 0xFFFFu : 0u) | (c0 + 2 * k + 1 < valid ? 0xFFFF0000u : 0u);
+        reinterpret_cast<uint4*>(base)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+static int rnn3_fill_sentinel(__nv_bfloat16* base, size_t rows, int pitch, int valid, asrb_stream_t stream) {
+    if ((pitch & 7) || (reinterpret_cast<uintptr_t>(base) & 15)) return ASRB_ERR_ALIGNMENT;
+    const size_t n = rows * (size_t)(pitch / 8);
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    rnn3_fill_sentinel_kernel<<<blocks, 256, 0, stream>>>(base, rows, pitch, valid);
+    ASRB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+// one word of every 32-byte sector of a landed operand tile [nkb][32 rows][128 B, 128-byte swizzle]: is any the sentinel?
+// (a sector is written whole by one TMA store, so one word stands for it; word `sec` of chunk 2*sec keeps the 32 lanes of a
+// warp on 32 different banks)
+__device__ __forceinline__ bool rnn3_tile_has_sentinel(const uint8_t* tile, int nkb, int el, int nthreads) {
+    const uint32_t base = smem_u32(tile);
+    bool bad = false;
+    for (int i = el; i < nkb * 128; i += nthreads) {
+        const int kb = i >> 7, r = (i >> 2) & 31, sec = i & 3;
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)(kb * 4096 + r * 128 + (((2 * sec) ^ (r & 7)) << 4) + sec * 4)));
+        bad = bad || (v == 0xFFFFFFFFu);
+    }
+    return bad;
+}
 static int rnn3_zero_pad_cols(__nv_bfloat16* base, size_t rows, int pitch, int col0, int ncols, asrb_stream_t stream) {
     if (ncols <= 0) return 0;
     if ((ncols | col0 | pitch) & 1) return ASRB_ERR_ALIGNMENT;
@@ -75,6 +119,23 @@ static int rnn3_zero_pad_cols(__nv_bfloat16* base, size_t rows, int pitch, int c
     ASRB_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+// Step hand-over of a launch (asrb_debug_rnn_dbg):
+//   default: VERIFIED hand-over.  Pass 1 hands the operand tile over with a TMA store + its completion + a relaxed counter
+//     increment.  That is fast -- a release is a MEMBAR.GPU that waits for the other chain's TMA copies -- but "completed" is
+//     not "visible in L2": about one hand-over in 10^7 is consumed too early.  So every operand slab starts as a sentinel
+//     (bf16 0xFFFF, a NaN no cell produces), each consumer looks for it in every tile that lands (one word per 32-byte
+//     sector, in the shadow of the MMAs), and raises a flag.  Pass 2 is the same kernel with the release hand-over: it
+//     leaves at once when the flag is down and recomputes the whole launch when it is up.  Both passes write the same
+//     outputs from the same inputs, so the result is the release protocol's, bit for bit.
+//     bit 8192 (TEST): CTA 0 withholds its tile of step 5 in pass 1, so pass 2 must run.
+//   bit 4096: generic stores + red.release in one pass.  bit 16 / bit 4: the unverified TMA-store forms (experiments).
+static inline bool rnn3_verified_handover() { return !(g_rnn_dbg & (4096 | 16 | 4)); }
+static inline int rnn3_first_pass_dbg(bool verified) {
+    if (verified) return (g_rnn_dbg & ~2) | kR3Check | ((g_rnn_dbg & 8192) ? kR3Sabotage : 0);
+    return (g_rnn_dbg & (16 | 4)) ? (g_rnn_dbg & ~2) : (g_rnn_dbg | 2);      // release unless a TMA-store form is asked for
+}
+static inline int rnn3_second_pass_dbg() { return ((g_rnn_dbg | 2) & ~(16 | 4)) | kR3Redo; }
 
 template <int CELL>
 __global__ void __launch_bounds__(kRnnThreads, 1)
@@ -122,8 +183,12 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
     float* s_bias = reinterpret_cast<float*>(w_bar + 2);      // [4][NJ]
 
-    uint32_t* counter = p.counters + (dir * NCH + (chain < NCH ? chain : 0)) * kR3CounterStride;
+    uint32_t* counter = p.counters + ((p.dbg & kR3Redo) ? kR3RedoCounters : 0) + (dir * NCH + (chain < NCH ? chain : 0)) * kR3CounterStride;
     auto t_of = [&](int s) { return dir == 1 ? (T - 1 - s) : s; };
+    if (p.dbg & kR3Redo) {       // second pass of a verified launch: nothing to do unless the first pass consumed a stale sector
+        if (ld_relaxed_gpu_u32(p.counters + kR3FlagWord) == 0u) return;
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rnn3_redos, 1ull);
+    }
 
     if (warp < NCH && lane == 0) {
         if (warp == 0) {
@@ -331,6 +396,11 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int g = 0; g < 4; ++g) acc[g][0] = acc[g][1] = 0.f;
                 if (s > 0) {
+                    if (p.dbg & kR3Check) {
+                        // verified hand-over: the operand tile has landed long before its MMAs finish -- look at it meanwhile
+                        for (int c = 0; c < nchunks; ++c) mbar_wait(&full_bar[c], (uint32_t)((s - 1) & 1));
+                        if (rnn3_tile_has_sentinel(smem_a, nkb, el, kR3EpiThreads)) atomicOr(p.counters + kR3FlagWord, 1u);
+                    }
                     mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
                     if (el == 0 && chain == 0) ASRB_TRACE(5, s);
                     tc_fence_after_sync();
@@ -404,7 +474,8 @@ rnn_rec3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (lane == 0 && chain == 0) ASRB_TRACE(8, s);
                     if (tma_op) {
                         if (lane == 0) {
-                            tma_store_3d(&tmOp, st_op, j0, row0, dir * (T + 2) + t + 1);
+                            if (!((p.dbg & kR3Sabotage) && blockIdx.x == 0 && s == 5))
+                                tma_store_3d(&tmOp, st_op, j0, row0, dir * (T + 2) + t + 1);
                             bulk_commit_group();
                             bulk_wait_group<0>();        // the bulk store has "completed" -- which is NOT "its data is in L2"
                         }
@@ -472,6 +543,7 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return ASRB_ERR_DRIVER;
+    const bool verified = rnn3_verified_handover();
     CUtensorMap tmA, tmA2, tmGi, tmOp;
     {   // hbf [2(T+2)][B][Hp] bf16 seen as [slab][K block][row][64 columns]: box = 64 columns x rows of a chain x 4 K blocks,
         // 128-byte swizzle; rows >= B and K blocks >= Hp/64 are zero-filled.  The columns H..Hp of the last K block are inside
@@ -484,7 +556,9 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         bx[2] = nkb % kR3Chunk ? nkb % kR3Chunk : kR3Chunk;      // box of the first chunk
         rc = make_tmap_bf16(&tmA2, prm.hbf, 4, d, s, bx);
         if (rc) return rc;
-        rc = rnn3_zero_pad_cols(prm.hbf, (size_t)2 * (prm.T + 2) * B, prm.Hp, prm.H, prm.Hp - prm.H, stream);
+        // verified hand-over: every operand slab starts as the sentinel (K padding zero); otherwise only the padding is written
+        rc = verified ? rnn3_fill_sentinel(prm.hbf, (size_t)2 * (prm.T + 2) * B, prm.Hp, prm.H, stream)
+                      : rnn3_zero_pad_cols(prm.hbf, (size_t)2 * (prm.T + 2) * B, prm.Hp, prm.H, prm.Hp - prm.H, stream);
         if (rc) return rc;
         // the same tensor as plain [slab][row][column] for the epilogue's operand stores: box = 16 units x rows of a chain
         cuuint64_t gdim[3] = {(cuuint64_t)prm.Hp, (cuuint64_t)B, (cuuint64_t)2 * (prm.T + 2)};
@@ -515,10 +589,15 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
         ASRB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRnnThreads, smem));
         if (2 * pl.P > sms * per_sm) return ASRB_ERR_UNSUPPORTED;
     }
-    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * NCH * kR3CounterStride * sizeof(uint32_t), stream));
-    prm.dbg = (g_rnn_dbg & (16 | 4)) ? (g_rnn_dbg & ~2) : (g_rnn_dbg | 2);      // hand-over: release unless a TMA-store form is asked for
+    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 128 * sizeof(uint32_t), stream));     // both passes' counters and the flag word
+    prm.dbg = rnn3_first_pass_dbg(verified);
     kern<<<dim3(2 * pl.P), dim3(kRnnThreads), smem, stream>>>(tmA, tmA2, tmGi, tmOp, prm);
     ASRB_CUDA_OK(cudaGetLastError());
+    if (verified) {      // second pass: the release hand-over, run only if the first pass saw a sentinel (else it leaves at once)
+        prm.dbg = rnn3_second_pass_dbg();
+        kern<<<dim3(2 * pl.P), dim3(kRnnThreads), smem, stream>>>(tmA, tmA2, tmGi, tmOp, prm);
+        ASRB_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -589,7 +668,11 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
     uint32_t* mma_lock = tmem_slot + 1;                       // tensor pipe: one chain's MMA sequence at a time
 
-    uint32_t* counter = p.counters + (dir * NCH + (chain < NCH ? chain : 0)) * kR3CounterStride;
+    uint32_t* counter = p.counters + ((p.dbg & kR3Redo) ? kR3RedoCounters : 0) + (dir * NCH + (chain < NCH ? chain : 0)) * kR3CounterStride;
+    if (p.dbg & kR3Redo) {       // second pass of a verified launch (see the forward kernel); every CTA of every cluster leaves
+        if (ld_relaxed_gpu_u32(p.counters + kR3FlagWord) == 0u) return;
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_rnn3_redos, 1ull);
+    }
     const int kcol0 = (int)crank * p.kpad;                    // first gate column of our K quarter
     auto t_of = [&](int s) { return dir == 0 ? (T - 1 - s) : s; };     // the backward pass walks each direction in reverse
 
@@ -751,6 +834,10 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float acc[2] = {0.f, 0.f};
                 if (s > 0) {
                     const int par = s & 1;
+                    if (p.dbg & kR3Check) {      // verified hand-over: see the forward kernel
+                        for (int c = 0; c < nchunks; ++c) mbar_wait(&full_bar[c], (uint32_t)((s - 1) & 1));
+                        if (rnn3_tile_has_sentinel(smem_a, nkb, el, kEpiThreads)) atomicOr(p.counters + kR3FlagWord, 1u);
+                    }
                     mbar_wait(tfull_bar, (uint32_t)((s - 1) & 1));
                     if (el == 0 && chain == 0) ASRB_TRACE(5, s);
                     tc_fence_after_sync();
@@ -874,7 +961,8 @@ rnn_rec3_bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (lane == 0 && chain == 0) ASRB_TRACE(8, s);
                     if (tma_op) {
                         if (lane == 0) {
-                            tma_store_4d(&tmOp, st_op, j0, row0, 0, dir * T + t);
+                            if (!((p.dbg & kR3Sabotage) && blockIdx.x == 0 && s == 5))
+                                tma_store_4d(&tmOp, st_op, j0, row0, 0, dir * T + t);
                             bulk_commit_group();
                             bulk_wait_group<0>();
                         }
@@ -977,6 +1065,7 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
     CUtensorMap tmA, tmA2, tmDgi, tmGT, tmHT, tmOp;
     // staged outputs: whole 32-row x 16-unit tiles only, and 16-byte aligned tile rows in the transposed copies
     prm.stage_out = (B % 32 == 0 && prm.H % 16 == 0 && !(g_rnn_dbg & 2048)) ? 1 : 0;
+    bool verified = rnn3_verified_handover();
     if (prm.stage_out) {
         auto plain = [&](CUtensorMap* m, void* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* bx) {
             cuuint32_t es[4] = {1, 1, 1, 1};
@@ -1007,6 +1096,7 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
         if (!ok) prm.stage_out = 0;
     }
     if (!prm.stage_out) tmDgi = tmGT = tmHT = tmOp = CUtensorMap{};
+    if (!prm.stage_out) verified = false;       // without whole tiles every CTA hands over with a release anyway
     {   // dghbf [2 T][B][Gp] bf16 seen as [slab][K block][row][64 columns]: box = 64 columns x 32 rows (one chain) x 4 K blocks
         uint64_t d[4] = {64, (uint64_t)B, (uint64_t)prm.Gp / 64, (uint64_t)2 * prm.T};
         uint64_t s[3] = {(uint64_t)prm.Gp * 2, 128, (uint64_t)B * prm.Gp * 2};
@@ -1017,12 +1107,14 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
         rc = make_tmap_bf16(&tmA2, prm.dghbf, 4, d, s, bx);
         if (rc) return rc;
         // the columns G..Gp of the last K block are inside the tensor: zero them once (0 x NaN is NaN)
-        rc = rnn3_zero_pad_cols(prm.dghbf, (size_t)2 * prm.T * B, prm.Gp, prm.G, prm.Gp - prm.G, stream);
+        // (verified hand-over: every operand slab starts as the sentinel, see rnn3_launch)
+        rc = verified ? rnn3_fill_sentinel(prm.dghbf, (size_t)2 * prm.T * B, prm.Gp, prm.G, stream)
+                      : rnn3_zero_pad_cols(prm.dghbf, (size_t)2 * prm.T * B, prm.Gp, prm.G, prm.Gp - prm.G, stream);
         if (rc) return rc;
     }
     auto kern = rnn_rec3_bwd_kernel<CELL>;
     ASRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 2 * 2 * kR3CounterStride * sizeof(uint32_t), stream));
+    ASRB_CUDA_OK(cudaMemsetAsync(prm.counters, 0, 128 * sizeof(uint32_t), stream));     // both passes' counters and the flag word
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pl.P_b);
     cfg.blockDim = dim3(kRnnThreads);
@@ -1038,9 +1130,19 @@ static int rnn3_bwd_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack,
         ASRB_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg));
         if (2 * pl.P_b > 4 * nclusters) return ASRB_ERR_UNSUPPORTED;
     }
-    prm.dbg = (g_rnn_dbg & (16 | 4)) ? (g_rnn_dbg & ~2) : (g_rnn_dbg | 2);      // hand-over: release unless a TMA-store form is asked for
+    prm.dbg = rnn3_first_pass_dbg(verified);
     ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmDgi, tmGT, tmHT, tmOp, prm));
+    if (verified) {      // second pass, see rnn3_launch
+        prm.dbg = rnn3_second_pass_dbg();
+        ASRB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmDgi, tmGT, tmHT, tmOp, prm));
+    }
     return 0;
+}
+
+long long rnn3_redo_count() {
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_rnn3_redos, sizeof(v)) != cudaSuccess) return -1;
+    return (long long)v;
 }
 
 int rnn3_backward(int cell, const RnnPlan& pl, RnnParams& prm, const void* wpack, asrb_stream_t stream) {

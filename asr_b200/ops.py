@@ -59,7 +59,7 @@ PROFILE = None   # set to a dict to collect (start, end) CUDA-event pairs per en
 # kernels launched per call of an entry point (memsets not counted); used for the `gpu_launches` claim
 KERNELS_PER_CALL = {
     "asrb_conv2d_mask_bwd_weight": 3, "asrb_bn2d_stats": 2, "asrb_bn_act_mask_bwd": 3, "asrb_bn_rows_fwd": 3,
-    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_ctc_bwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_rnn_fwd": 2, "asrb_rnn_bwd": 2, "asrb_rnn_fwd_sum": 3,   # (+1: the K-padding columns of the operand are zeroed by a small kernel)
+    "asrb_bn_rows_bwd": 3, "asrb_col_sums": 2, "asrb_ctc_fwd": 2, "asrb_ctc_bwd": 2, "asrb_spectrogram": 4, "asrb_rnn_pack_weights": 1, "asrb_rnn_fwd": 3, "asrb_rnn_bwd": 3, "asrb_rnn_fwd_sum": 4,   # (sentinel fill of the operand slabs + two passes of the recurrence, the second leaving at once: csrc/rnn3.cu)
     "asrb_conv32_bwd_weight": 2, "asrb_conv1_fwd": 3, "asrb_conv1_bwd_weight": 2,
 }
 
@@ -285,6 +285,11 @@ def conv32_pack_weights(w, fwd=True, dgrad=True):
 
 # output rows per work item of the 32->32 conv's forward / data-gradient kernels (1 = the one-row kernel, 2, 4)
 CONV_ROWS = int(os.environ.get("ASRB_CONV_ROWS", "4"))
+
+# Step hand-over of the tensor-memory recurrent kernels (asrb_debug_rnn_dbg bits, csrc/rnn.cu): set once at import when the
+# environment asks for something else than the library's default (A/B timing of whole steps through bench.py).
+if os.environ.get("ASRB_RNN_DBG"):
+    _lib.query("asrb_debug_rnn_dbg", int(os.environ["ASRB_RNN_DBG"]))
 
 
 def conv32_pack_rows(pack, w_shape, stride_h, mode, rows=None):

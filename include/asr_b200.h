@@ -93,7 +93,7 @@ int asrb_rnn_pack_weights(int cell, int H, int B, int bf16, const float* w_hh_fw
 /* gi [T,B,2,G] = x W_ih^T + b_ih for both directions; b_hh [2,G]; lengths int32[B];
  * out: hseq [2,T+2,B,H] (slot t+1 = step t; slots 0,T+1 zero), hseq_bf16 [2,T+2,B,Hp] bf16 with Hp = H rounded up to 64 (bf16 mode, else NULL),
  * cseq like hseq (LSTM only, else NULL), saved: asrb_rnn_saved_floats floats (GRU: r,z,n,W_hn h+b_hn ; LSTM: i,f,g,o);
- * counters: uint32[64] scratch (one step counter per direction, 128 bytes apart). */
+ * counters: uint32[128] scratch (step counters per direction and chain, 64 bytes apart, for two passes; one flag word). */
 int asrb_rnn_fwd(int cell, int bf16, const float* gi, const float* b_hh, const void* wpack_fwd, const int32_t* lengths,
                  float* hseq, void* hseq_bf16, float* cseq, float* saved, uint32_t* counters, int T, int B, int H,
                  asrb_stream_t stream);
@@ -120,6 +120,9 @@ int asrb_debug_rnn_trace(long long* trace);
 int asrb_debug_rnn_chunk(int blocks);
 int asrb_debug_rnn_ksplit(int on);
 int asrb_debug_rnn_dbg(int bits);
+/* launches of the tensor-memory recurrent kernels whose second (release) pass had to run since the library was loaded
+ * (verified hand-over, asrb_debug_rnn_dbg bit 4096); synchronises the device; -1 on a CUDA error */
+int asrb_debug_rnn_redos(void);
 /* out[T,B,H] = hseq[0][1..T] + hseq[1][1..T] */
 int asrb_rnn_sum_dirs(const float* hseq, float* out, int T, int B, int H, asrb_stream_t stream);
 

@@ -379,11 +379,13 @@ def test_rnn_fwd_bwd(ops, c, mode):
 
 @pytest.mark.parametrize("cellname", ["gru", "lstm"])
 def test_rnn3_publish_protocols_agree(ops, cellname):
-    """rnn3.cu's default hand-over is generic stores + `red.release` (formally a release/acquire pair).  Two faster forms exist
-    behind `asrb_debug_rnn_dbg`: bit 16 = ONE TMA store of the operand tile + its completion + a RELAXED counter increment
-    (a release is a MEMBAR.GPU, which waits for the other chain's TMA copies: DESIGN.md section 6) -- measured to lose about one
-    hand-over in 10^7 (tools/stress_fullsize.py), hence not the default -- and bit 4 = the same + an L2 read-back of the tile
-    before the increment.  All three must give bit-identical outputs over a few hundred steps at the benchmarked width."""
+    """Step hand-over of rnn3.cu (asrb_debug_rnn_dbg).  Bit 4096 = generic stores + `red.release`, formally a release/acquire
+    pair.  Bit 16 = ONE TMA store of the operand tile + its completion + a RELAXED counter increment (a release is a
+    MEMBAR.GPU, which waits for the other chain's TMA copies: DESIGN.md section 6) -- measured to lose about one hand-over in
+    10^7 (tools/stress_fullsize.py); bit 4 = the same + an L2 read-back of the tile before the increment.  The DEFAULT is the
+    VERIFIED hand-over: the bit-16 form as a first pass that looks for a sentinel in every operand tile it consumes, and a
+    release second pass that recomputes the launch only when one was seen (bit 8192 withholds one tile so that it must).
+    All must give bit-identical outputs over a few hundred steps at the benchmarked width."""
     from asr_b200 import _lib
 
     T, B, H = 300, 64, 800
@@ -399,18 +401,23 @@ def test_rnn3_publish_protocols_agree(ops, cellname):
     outs = {}
     try:
         pf, pb = ops.rnn_pack_weights(cell, w_hh[0].contiguous(), w_hh[1].contiguous(), B)
-        for dbg in (0, 16, 4, 0):
+        for dbg in (0, 4096, 16, 4, 8192, 0):
             _lib.query("asrb_debug_rnn_dbg", dbg)
+            redos = _lib.query("asrb_debug_rnn_redos")
             hseq, cseq, saved = ops.rnn_fwd(cell, gi, b_hh, pf, lens, T, B, H)
             dgi, dgiT, dghT = ops.rnn_bwd(cell, dout, pb, lens, hseq, cseq, saved, T, B, H)
             torch.cuda.synchronize()
+            redos = _lib.query("asrb_debug_rnn_redos") - redos
+            # verified hand-over: a withheld tile (bit 8192) must send both launches through their second pass; otherwise a
+            # second pass is a one-in-10^7-hand-overs event (1.2e5 hand-overs here)
+            assert redos == (2 if dbg & 8192 else 0) or (dbg == 0 and redos <= 2), (dbg, redos)
             cur = (hseq.clone(), dgi.clone(), dgiT.clone())
             assert torch.isfinite(cur[0]).all() and torch.isfinite(cur[1].float()).all()
             if dbg in outs:
                 assert all(torch.equal(a, b) for a, b in zip(outs[dbg], cur))       # run-to-run: deterministic
             outs[dbg] = cur
-        assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[16]))
-        assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[4]))
+        for other in (0, 16, 4, 8192):
+            assert all(torch.equal(a, b) for a, b in zip(outs[4096], outs[other])), other
     finally:
         _lib.query("asrb_debug_rnn_dbg", 0)
         ops.RNN_BF16 = old_bf16

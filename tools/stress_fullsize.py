@@ -26,6 +26,7 @@ def poison():
 
 
 bad = 0
+redos0 = _lib.query("asrb_debug_rnn_redos")
 for r in range(reps):
     if r % 8 == 0:
         poison()
@@ -37,4 +38,4 @@ for r in range(reps):
         if nf or loss != loss:
             bad += 1
             print(f"rep {r} B={hb[0].shape[0]}: loss {loss}, non-finite grads in {len(nf)} tensors, first {nf[:3]}", flush=True)
-print(f"dbg={dbg}: {bad} bad of {3 * reps} steps", flush=True)
+print(f"dbg={dbg}: {bad} bad of {3 * reps} steps; second passes run by the verified hand-over: {_lib.query('asrb_debug_rnn_redos') - redos0}", flush=True)

@@ -50,7 +50,11 @@ for dbg, label in ((8, "rnn.cu"), (0, "rnn3 forward + backward (TMEM weights, tw
             msg += f"; dghT {(dghT.float() - ref[3]).abs().max().item():.3e}"
         print(msg, flush=True)
 
-variants = [(0, "default: rnn3.cu forward and backward (weights in tensor memory, two chains of 32 rows), release hand-over"), (32768, "rnn3 backward without the tensor-pipe lock"), (16, "rnn3, hand-over = TMA store + completion + relaxed increment (UNSAFE: 1e-7 race)"), (4, "rnn3, hand-over = TMA store + completion + L2 read-back + relaxed increment"),      (8, "counter + TMA (rnn.cu)")]
+variants = [(0, "default: rnn3.cu forward and backward (weights in tensor memory, two chains of 32 rows), VERIFIED hand-over (TMA-store first pass with sentinel check + conditional release second pass)"),
+            (8192, "rnn3, verified hand-over with a withheld tile: both passes run"),
+            (4096, "rnn3, hand-over = generic stores + red.release, one pass"),
+            (16, "rnn3, hand-over = TMA store + completion + relaxed increment, unverified (UNSAFE: 1e-7 race)"),
+            (8, "counter + TMA (rnn.cu)")]
 for dbg, label in variants:
     _lib.query("asrb_debug_rnn_dbg", dbg)
     _lib.query("asrb_debug_rnn_ksplit", ks)
