@@ -543,7 +543,9 @@ static int rnn3_launch(const RnnPlan& pl, RnnParams& prm, const void* wpack, asr
     if (smem > (size_t)kRnnMaxSmem) return ASRB_ERR_UNSUPPORTED;
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return ASRB_ERR_DRIVER;
-    const bool verified = rnn3_verified_handover();
+    // (the sentinel check reads ONE word per 32-byte sector: a sector that is part K padding could show a zero there while its
+    // valid columns are stale, so widths that are not whole sectors keep the one-pass release hand-over)
+    const bool verified = rnn3_verified_handover() && prm.H % 16 == 0;
     CUtensorMap tmA, tmA2, tmGi, tmOp;
     {   // hbf [2(T+2)][B][Hp] bf16 seen as [slab][K block][row][64 columns]: box = 64 columns x rows of a chain x 4 K blocks,
         // 128-byte swizzle; rows >= B and K blocks >= Hp/64 are zero-filled.  The columns H..Hp of the last K block are inside
