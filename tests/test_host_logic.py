@@ -603,3 +603,37 @@ def test_fused_adamw_bumps_the_version_counters(monkeypatch):
     v0 = p._version
     optim._bump_versions((p,))
     assert p._version == v0 + 1
+
+
+def test_sentinel_check_word_pattern_of_the_verified_hand_over():
+    """csrc/rnn3.cu: rnn3_tile_has_sentinel reads ONE word per 32-byte sector of a landed operand tile
+    [K block][32 rows][128 B, 128-byte swizzle].  Restated here: every sector is visited once, the 32 loads of a warp hit 32
+    different banks, the word read is a VALID column whenever the width is whole sectors (H % 16 == 0) -- and can be K padding
+    when it is not, which is why rnn3_launch keeps the one-pass release hand-over for those widths."""
+    nkb = 13                                     # H = 800 -> 832 columns
+    seen = set()
+    for w0 in range(0, nkb * 128, 32):
+        banks = set()
+        for i in range(w0, w0 + 32):
+            kb, r, sec = i >> 7, (i >> 2) & 31, i & 3
+            addr = kb * 4096 + r * 128 + (((2 * sec) ^ (r & 7)) << 4) + sec * 4
+            banks.add((addr >> 2) & 31)
+            chunk = ((addr >> 4) & 7) ^ (r & 7)               # undo the swizzle: logical 16-byte chunk of the row
+            assert chunk == 2 * sec                           # first chunk of sector `sec`
+            seen.add((kb, r, sec))
+        assert len(banks) == 32
+    assert len(seen) == nkb * 32 * 4
+
+    def checked_columns(H):
+        """logical columns (bf16 elements) the check reads in row 0, for sectors that hold at least one valid column"""
+        cols = []
+        for kb in range((H + 63) // 64):
+            for sec in range(4):
+                first = kb * 64 + 16 * sec
+                if first < H:
+                    cols.append(first + 2 * sec)              # word `sec` of the sector's first chunk = elements 2 sec, 2 sec + 1
+        return cols
+
+    for H in (16, 32, 800, 1024, 1760):
+        assert all(c + 1 < H for c in checked_columns(H))
+    assert any(c >= 36 for c in checked_columns(36))          # a partly padded sector: the word read is padding
